@@ -1,0 +1,238 @@
+/*
+ * rslf_b200.h — C ABI of the B200-native EPI depth-estimation path.
+ *
+ * This is the drop-in boundary behind the reference's C++ depth-computer /
+ * fine-to-coarse classes (RSLightFields).  Every entry point names the reference
+ * interface it replaces (paths relative to /root/reference/RSLightFields).
+ * Plain pointers and sizes only; no C++ / torch types cross this boundary.
+ *
+ * Conventions
+ *   - all functions return 0 on success or a negative rslf error code
+ *     (rslf_cuda_strerror turns it into text); there is NO CPU fallback:
+ *     without a usable CUDA device every compute call fails with RSLF_ERR_CUDA.
+ *   - dimension names follow the reference: s = view, v = image row, u = column,
+ *     d = disparity hypothesis, C = channels (1 or 3).
+ *   - host images use OpenCV's Mat layout: row-major, interleaved channels,
+ *     `step` bytes between rows (cv::Mat::data / cv::Mat::step).
+ *   - per-(s,v,u) maps are S planes of V x U, densely packed ([S][V][U]),
+ *     float32 or uint8 (masks are 0 / 255 like OpenCV comparison results).
+ *   - one host thread per rslf_ctx; a ctx owns one CUDA device + one stream.
+ */
+#ifndef RSLF_B200_H
+#define RSLF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* OpenCV depth codes accepted by rslf_cuda_upload_epis (CV_8U = 0, CV_32F = 5). */
+#define RSLF_DEPTH_8U  0
+#define RSLF_DEPTH_32F 5
+
+enum {
+    RSLF_OK             =  0,
+    RSLF_ERR_CUDA       = -1,   /* CUDA runtime error; see rslf_cuda_last_error_text */
+    RSLF_ERR_ARG        = -2,   /* invalid argument                                   */
+    RSLF_ERR_STATE      = -3,   /* call order violated (e.g. run before upload)       */
+    RSLF_ERR_UNSUPPORTED= -4,   /* valid in the reference, not implemented here       */
+    RSLF_ERR_NCCL       = -5,   /* NCCL error                                         */
+    RSLF_ERR_NOMEM      = -6
+};
+
+/*
+ * Algorithm parameters.  Mirrors rslf::Depth1DParameters<T>
+ * (include/rslf_depth_computation_core.hpp:66-142; defaults :16-31).
+ * The interpolation class is always Interpolation1DLinear and the kernel class
+ * BandwidthKernel(h) (core.hpp:76-78) — the only ones the reference selects.
+ */
+typedef struct rslf_params {
+    float edge_score_threshold;      /* par_edge_score_threshold   0.02 */
+    float line_score_threshold;      /* par_line_score_threshold   0.02 (unused: flag off) */
+    float disp_score_threshold;      /* par_disp_score_threshold   0.01 (unused: flag off) */
+    float raw_score_threshold;       /* par_raw_score_threshold    0    */
+    int   mean_shift_max_iter;       /* par_mean_shift_max_iter    10   */
+    int   edge_confidence_filter_size;   /* 9 */
+    int   edge_confidence_opening_type;  /* cv::MORPH_ELLIPSE = 2 */
+    int   edge_confidence_opening_size;  /* 1 => opening disabled (core.hpp:759) */
+    int   median_filter_size;        /* par_median_filter_size     5    */
+    float median_filter_epsilon;     /* 0.1  */
+    float propagation_epsilon;       /* 0.1  */
+    float slope_factor;              /* par_slope_factor 1.0 (set per pyramid level, ftc.hpp:139) */
+    int   cut_shadows;               /* par_cut_shadows true */
+    float shadow_level;              /* (float)(0.05 * 1.73205080757) */
+    float kernel_h;                  /* _BANDWIDTH_KERNEL_PARAMETER 0.2 (kern.hpp:43) */
+} rslf_params;
+
+/* Fills *p with the reference defaults (core.hpp:16-31, 74-99). */
+void rslf_params_default(rslf_params* p);
+
+/* Per-call stage timings (CUDA events on the ctx stream) and work counters. */
+typedef struct rslf_timing {
+    float  ms_total;          /* whole run() on the device                      */
+    float  ms_edge;           /* edge-confidence kernels                         */
+    float  ms_depth;          /* sampling + mean-shift + score kernels           */
+    float  ms_reduce;         /* argmax / confidence kernels                     */
+    float  ms_median;         /* selective median                                */
+    float  ms_propagate;      /* propagation                                     */
+    float  ms_pyramid;        /* downsample + normalise + bounds + fuse + median */
+    float  ms_h2d;            /* upload (host->device copies + normalisation)    */
+    float  ms_d2h;            /* result download                                 */
+    double computed_pixels;   /* sum over levels and passes of pixels evaluated  */
+    double samples;           /* computed_pixels x D x S  (the BASELINE metric)  */
+    double depth_launches;    /* launches of the dominant (mean-shift) kernel    */
+    double kernel_launches;   /* all kernel launches of the call                 */
+    int    levels;            /* pyramid levels run                              */
+    int    passes;            /* s_hat passes run (all levels)                   */
+} rslf_timing;
+
+typedef struct rslf_ctx rslf_ctx;
+
+/* ---- lifetime ------------------------------------------------------------ */
+int  rslf_cuda_create(int device, rslf_ctx** out);
+void rslf_cuda_destroy(rslf_ctx* ctx);
+const char* rslf_cuda_strerror(int code);
+/* Text of the last CUDA/NCCL failure seen by this ctx ("" if none). */
+const char* rslf_cuda_last_error_text(const rslf_ctx* ctx);
+int  rslf_cuda_last_timing(const rslf_ctx* ctx, rslf_timing* out);
+/* ABI version, bumped on any signature change. */
+int  rslf_cuda_abi_version(void);
+
+/* ---- input ---------------------------------------------------------------
+ * Replaces the input handling of the computers' constructors
+ * (rslf_depth_computation.hpp:425-477 Depth1DComputer_pile,
+ *  :651-704 Depth2DComputer; rslf_fine_to_coarse.hpp:103-159 FineToCoarse):
+ * deep-copies the V EPIs (each S rows x U cols x C channels) to the device and
+ * normalises to float32: 8U -> x*(1/255); otherwise x*(1/scale) with
+ * scale = epi_scale_factor if >= 0 else the global max over the stack.
+ * epi_ptrs[v] = cv::Mat::data of EPI v, row_step_bytes = cv::Mat::step.
+ */
+int rslf_cuda_upload_epis(rslf_ctx* ctx, const void* const* epi_ptrs,
+                          int V, int S, int U, int C, int cv_depth,
+                          size_t row_step_bytes, float epi_scale_factor);
+/* Same, but the raw stack already lives on this ctx's device as one dense
+ * [V][S][U][C] array (used to time the path with HBM-resident inputs). */
+int rslf_cuda_set_epis_device(rslf_ctx* ctx, const void* d_epis,
+                              int V, int S, int U, int C, int cv_depth,
+                              float epi_scale_factor);
+/* Device-side EPI building: replaces rslf::build_epis_from_imgs
+ * (src/rslf_io.cpp:194-227).  img_ptrs[s] = one V x U x C image per view. */
+int rslf_cuda_upload_images(rslf_ctx* ctx, const void* const* img_ptrs,
+                            int S, int V, int U, int C, int cv_depth,
+                            size_t row_step_bytes, float epi_scale_factor);
+
+/* ---- Depth1DComputer_pile<T>::run() --------------------------------------
+ * (rslf_depth_computation.hpp:513-565): edge confidence of line s_hat,
+ * per-pixel depth on confident pixels, selective median.  s_hat < 0 or >= S
+ * selects floor(S/2) (dc.hpp:489-498).  Output pointers are host buffers
+ * (V x U, dense); any of them may be NULL.  best_depth is the median-filtered
+ * map (core.hpp:892 rebinds the member).  rbar is V x U x C.
+ */
+int rslf_cuda_depth1d_pile(rslf_ctx* ctx, float dmin, float dmax, int dim_d,
+                           int s_hat, const rslf_params* params,
+                           float* best_depth_vu, float* edge_conf_vu,
+                           uint8_t* edge_mask_vu, float* disp_conf_vu,
+                           float* rbar_vuc);
+/* compute only / copy only halves of the call above */
+int rslf_cuda_depth1d_pile_run(rslf_ctx* ctx, float dmin, float dmax, int dim_d,
+                               int s_hat, const rslf_params* params);
+int rslf_cuda_depth1d_pile_get(rslf_ctx* ctx, float* best_depth_vu,
+                               float* edge_conf_vu, uint8_t* edge_mask_vu,
+                               float* disp_conf_vu, float* rbar_vuc);
+
+/* ---- Depth2DComputer<T>::run() -------------------------------------------
+ * (rslf_depth_computation.hpp:748-805 -> core.hpp:901-1133): edge confidence on
+ * all lines, then the sequential s_hat passes with propagation.  dmin_svu /
+ * dmax_svu are optional per-(s,v,u) host maps (edit_dmin()/edit_dmax(),
+ * dc.hpp:211-213); NULL means the constant dmin / dmax.
+ * Outputs = the public members m_best_depth_s_v_u, m_edge_confidence_s_v_u,
+ * m_edge_confidence_mask_s_v_u, m_disp_confidence_s_v_u, m_rbar_s_v_u
+ * (dc.hpp:217-224); any may be NULL.
+ */
+int rslf_cuda_depth2d(rslf_ctx* ctx, float dmin, float dmax, int dim_d,
+                      const rslf_params* params,
+                      const float* dmin_svu, const float* dmax_svu,
+                      float* best_depth_svu, float* edge_conf_svu,
+                      uint8_t* edge_mask_svu, float* disp_conf_svu,
+                      float* rbar_svuc);
+int rslf_cuda_depth2d_run(rslf_ctx* ctx, float dmin, float dmax, int dim_d,
+                          const rslf_params* params,
+                          const float* dmin_svu, const float* dmax_svu);
+int rslf_cuda_depth2d_get(rslf_ctx* ctx, float* best_depth_svu,
+                          float* edge_conf_svu, uint8_t* edge_mask_svu,
+                          float* disp_conf_svu, float* rbar_svuc);
+/* Depth2DComputer::get_valid_depths_mask_s_v_u (dc.hpp:893-915). */
+int rslf_cuda_depth2d_get_valid_mask(rslf_ctx* ctx, int accept_all,
+                                     const rslf_params* params,
+                                     uint8_t* valid_svu);
+
+/* ---- FineToCoarse<T>::run() + get_results() ------------------------------
+ * (rslf_fine_to_coarse.hpp:103-322, src/rslf_fine_to_coarse_core.cpp:14-135):
+ * builds the pyramid (while V > 10 && U > 10 && level < max_pyr_depth), runs a
+ * Depth2D computation per level fine -> coarse, derives per-pixel [dmin,dmax]
+ * of the next level, fuses coarse -> fine and applies the 3x3 median.
+ * out_map_svu: S x V x U float32; out_valid_svu: S x V x U uint8.
+ */
+int rslf_cuda_fine_to_coarse(rslf_ctx* ctx, float dmin, float dmax, int dim_d,
+                             const rslf_params* params, int max_pyr_depth,
+                             int accept_all_last_scale,
+                             float* out_map_svu, uint8_t* out_valid_svu);
+int rslf_cuda_fine_to_coarse_run(rslf_ctx* ctx, float dmin, float dmax, int dim_d,
+                                 const rslf_params* params, int max_pyr_depth,
+                                 int accept_all_last_scale);
+int rslf_cuda_fine_to_coarse_get(rslf_ctx* ctx, float* out_map_svu,
+                                 uint8_t* out_valid_svu);
+/* Number of levels of the last fine-to-coarse run and the size of level p. */
+int rslf_cuda_fine_to_coarse_level_dims(const rslf_ctx* ctx, int level,
+                                        int* V, int* U);
+/* Per-level Depth2D results of the last fine-to-coarse run (for parity tests;
+ * the reference exposes them through m_computers[p]'s public members). */
+int rslf_cuda_fine_to_coarse_get_level(rslf_ctx* ctx, int level,
+                                       float* best_depth_svu, float* edge_conf_svu,
+                                       uint8_t* edge_mask_svu, float* disp_conf_svu,
+                                       float* dmin_svu, float* dmax_svu);
+
+/* ---- free functions of the reference (each one its own entry point) ------ */
+/* rslf::downsample_EPIs (src/rslf_fine_to_coarse_core.cpp:14-60), float32 stacks.
+ * in: dense [V][S][U][C]; out: dense [V2][S][U2][C], V2 = cvRound(V/2). */
+int rslf_cuda_downsample_epis(rslf_ctx* ctx, const float* in_epis, int V, int S,
+                              int U, int C, float* out_epis, int* V2, int* U2);
+/* rslf::fuse_disp_maps (src/rslf_fine_to_coarse_core.cpp:69-135).  disp_p[p] and
+ * valid_p[p] are dense [S][V_p][U_p] host maps, finest first. */
+int rslf_cuda_fuse_disp_maps(rslf_ctx* ctx, int levels, int S, const int* Vp,
+                             const int* Up, const float* const* disp_p,
+                             const uint8_t* const* valid_p,
+                             float* out_map_svu, uint8_t* out_valid_svu);
+/* rslf::selective_median_filter (core.hpp:663-718) on the uploaded EPIs. */
+int rslf_cuda_selective_median(rslf_ctx* ctx, const float* src_vu,
+                               const uint8_t* mask_vu, int s_hat, int size,
+                               float epsilon, float* dst_vu);
+/* rslf::compute_1D_edge_confidence_pile (core.hpp:728-770) for one line s. */
+int rslf_cuda_edge_confidence(rslf_ctx* ctx, int s, const rslf_params* params,
+                              float* edge_conf_vu, uint8_t* edge_mask_vu);
+
+/* ---- multi-GPU (row sharding, one process per GPU) -----------------------
+ * Rows are split in contiguous blocks; every rank uploads only its block plus
+ * halo rows.  The only exchange on the path is the +-2-row halo of the
+ * selective median (core.hpp:698-709), done with NCCL send/recv.
+ */
+int rslf_cuda_nccl_unique_id(void* id128 /* 128 bytes out */);
+int rslf_cuda_comm_init(rslf_ctx* ctx, const void* id128, int rank, int world);
+/* Declares which global rows [v0, v0+V) of a V_total-row light field the
+ * uploaded stack holds (default: the whole field). */
+int rslf_cuda_set_row_shard(rslf_ctx* ctx, int v0, int V_total);
+
+/* ---- measurement helpers -------------------------------------------------- */
+/* Measured FP32 FADD/FMUL issue rate of this device in Gop/s (non-FMA, the
+ * instruction mix of the mean-shift kernel); used as roofline denominator. */
+int rslf_cuda_measure_fp32_peak(rslf_ctx* ctx, double* gops_nofma, double* gflops_fma);
+/* Writes >126 MB on the device so the next timed step starts with a cold L2. */
+int rslf_cuda_flush_l2(rslf_ctx* ctx);
+int rslf_cuda_sync(rslf_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSLF_B200_H */
