@@ -141,6 +141,9 @@ int rslf_cuda_depth1d_pile_run(rslf_ctx* ctx, float dmin, float dmax, int dim_d,
 int rslf_cuda_depth1d_pile_get(rslf_ctx* ctx, float* best_depth_vu,
                                float* edge_conf_vu, uint8_t* edge_mask_vu,
                                float* disp_conf_vu, float* rbar_vuc);
+/* The unfiltered argmax depths of the last pile run: m_best_depth_v_u as it is
+ * before core.hpp:881-892 replaces it by the median-filtered map (diagnostic). */
+int rslf_cuda_depth1d_pile_get_raw_depth(rslf_ctx* ctx, float* raw_depth_vu);
 
 /* ---- Depth2DComputer<T>::run() -------------------------------------------
  * (rslf_depth_computation.hpp:748-805 -> core.hpp:901-1133): edge confidence on
@@ -205,6 +208,13 @@ int rslf_cuda_fuse_disp_maps(rslf_ctx* ctx, int levels, int S, const int* Vp,
                              const int* Up, const float* const* disp_p,
                              const uint8_t* const* valid_p,
                              float* out_map_svu, uint8_t* out_valid_svu);
+/* The bound-propagation step of FineToCoarse<T>::run (rslf_fine_to_coarse.hpp:201-294):
+ * per-pixel [dmin, dmax] of level p+1 (Vd x Ud) from the depths and validity of
+ * level p (Vu x Uu).  dmin_map / dmax_map are in/out ([S][Vd][Ud], pre-filled
+ * with the global bounds; pixels without two valid neighbours keep them). */
+int rslf_cuda_set_bounds(rslf_ctx* ctx, const float* depth_up_svu,
+                         const uint8_t* valid_up_svu, int S, int Vu, int Uu,
+                         int Vd, int Ud, float* dmin_map_svu, float* dmax_map_svu);
 /* rslf::selective_median_filter (core.hpp:663-718) on the uploaded EPIs. */
 int rslf_cuda_selective_median(rslf_ctx* ctx, const float* src_vu,
                                const uint8_t* mask_vu, int s_hat, int size,

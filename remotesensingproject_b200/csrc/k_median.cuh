@@ -1,0 +1,87 @@
+/*
+ * k_median.cuh — selective median filter of the depth plane of line s_hat.
+ *
+ * Replaces selective_median_filter (rslf_depth_computation_core.hpp:663-718):
+ * for every masked pixel, the element of rank n/2 (std::nth_element, i.e. the
+ * upper median) of src(k,l) over the (2w+1)^2 window clipped at the image
+ * borders, restricted to masked neighbours whose colour on line s_hat is within
+ * epsilon (norm) of the centre pixel's; unmasked outputs are 0.
+ *
+ * One thread per pixel; the window values sit in registers (fully unrolled) and
+ * the rank-n/2 element is found by counting, which needs no data-dependent
+ * indexing.  Colours are addressed through (colour, row_stride) so that a
+ * row-sharded run can pass the gathered colour plane of line s_hat.
+ */
+#pragma once
+#include "rslf_common.cuh"
+#include <math_constants.h>
+
+template <int C, int WIDTH>
+__global__ void __launch_bounds__(128)
+selective_median_kernel(const float* __restrict__ src, const uint8_t* __restrict__ mask,
+                        const float* __restrict__ colour, size_t colour_row_stride,
+                        int V, int U, float eps, double eps_T, float* __restrict__ dst)
+{
+    constexpr int N = (2 * WIDTH + 1) * (2 * WIDTH + 1);
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    const int v = blockIdx.y;
+    if (u >= U) return;
+    const size_t o = (size_t)v * U + u;
+    if (!mask[o]) { dst[o] = 0.f; return; }
+    float pc[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) pc[c] = __ldg(colour + (size_t)v * colour_row_stride + (size_t)u * C + c);
+    float val[N];
+    int n = 0;
+#pragma unroll
+    for (int dk = -WIDTH; dk <= WIDTH; ++dk) {
+#pragma unroll
+        for (int dl = -WIDTH; dl <= WIDTH; ++dl) {
+            const int k = v + dk, l = u + dl;
+            float x = CUDART_INF_F;
+            if (k >= 0 && k < V && l >= 0 && l < U && mask[(size_t)k * U + l]) {
+                float q[C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) q[c] = __ldg(colour + (size_t)k * colour_row_stride + (size_t)l * C + c);
+                if (rslf_norm_diff_lt<C>(pc, q, eps, eps_T)) { x = src[(size_t)k * U + l]; ++n; }
+            }
+            val[(dk + WIDTH) * (2 * WIDTH + 1) + (dl + WIDTH)] = x;
+        }
+    }
+    /* rank n/2 among the n selected values (the rejected ones are +inf and sort last).
+     * A depth of +inf itself cannot be told from a rejected slot; depths are finite. */
+    const int rank = n / 2;
+    float out = val[WIDTH * (2 * WIDTH + 1) + WIDTH];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        int less = 0, eq = 0;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            less += (val[j] < val[i]) ? 1 : 0;
+            eq += (val[j] == val[i]) ? 1 : 0;
+        }
+        if (less <= rank && rank < less + eq) out = val[i];
+    }
+    dst[o] = out;
+}
+
+static int launch_selective_median(rslf_ctx* ctx, const float* src, const uint8_t* mask, const float* colour,
+                                   size_t colour_row_stride, int V, int U, int C, int size, float eps, float* dst)
+{
+    const int width = (size - 1) / 2;
+    dim3 grid(rslf_div_up(U, 128), V);
+    const double T = rslf_sq_threshold(eps);
+#define RSLF_MED_CASE(CC, WW)                                                                             \
+    if (C == CC && width == WW) {                                                                         \
+        selective_median_kernel<CC, WW><<<grid, 128, 0, ctx->stream>>>(src, mask, colour, colour_row_stride, \
+                                                                       V, U, eps, T, dst);                \
+        RSLF_CUDA_TRY(ctx, cudaGetLastError());                                                           \
+        ctx->timing.kernel_launches += 1;                                                                 \
+        return RSLF_OK;                                                                                   \
+    }
+    RSLF_MED_CASE(1, 0) RSLF_MED_CASE(1, 1) RSLF_MED_CASE(1, 2) RSLF_MED_CASE(1, 3)
+    RSLF_MED_CASE(3, 0) RSLF_MED_CASE(3, 1) RSLF_MED_CASE(3, 2) RSLF_MED_CASE(3, 3)
+#undef RSLF_MED_CASE
+    snprintf(ctx->err, sizeof(ctx->err), "median_filter_size %d (window > 7x7) or C=%d not implemented", size, C);
+    return RSLF_ERR_UNSUPPORTED;
+}

@@ -1,0 +1,1025 @@
+/*
+ * rslf_api.cu — C ABI (include/rslf_b200.h) and host orchestration of the
+ * B200-native EPI depth path: streams, device buffers, the s_hat pass loop and
+ * the fine-to-coarse level loop.  No CPU fallback: every entry point needs a
+ * CUDA device.
+ */
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <limits>
+
+#include "rslf_common.cuh"
+#include "k_edge.cuh"
+#include "k_depth.cuh"
+#include "k_median.cuh"
+#include "k_propagate.cuh"
+#include "k_pyramid.cuh"
+#include "rslf_comm.cuh"
+#include "k_peak.cuh"
+
+#define RSLF_ABI_VERSION 2
+#define RSLF_COUNT_SLOTS 65536
+
+/* ------------------------------------------------------------------ helpers */
+template <typename T>
+static int dev_alloc(rslf_ctx* ctx, T** p, size_t n)
+{
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    if (n == 0) return RSLF_OK;
+    cudaError_t e = cudaMalloc((void**)p, n * sizeof(T));
+    if (e != cudaSuccess) {
+        snprintf(ctx->err, sizeof(ctx->err), "cudaMalloc(%zu bytes): %s", n * sizeof(T), cudaGetErrorString(e));
+        *p = nullptr;
+        return e == cudaErrorMemoryAllocation ? RSLF_ERR_NOMEM : RSLF_ERR_CUDA;
+    }
+    return RSLF_OK;
+}
+template <typename T> static void dev_free(T** p) { if (*p) { cudaFree(*p); *p = nullptr; } }
+
+static int stream_grid(const rslf_ctx* ctx, size_t n, int threads = 256)
+{
+    size_t b = (n + threads - 1) / threads;
+    size_t cap = (size_t)ctx->num_sm * 16;
+    return (int)std::max<size_t>(1, std::min(b, cap));
+}
+
+/* stage clock: CUDA events on the ctx stream, resolved after the final sync */
+static void clk_reset(rslf_ctx* ctx) { ctx->clk.used = 0; ctx->clk.spans.clear(); }
+static size_t clk_mark(rslf_ctx* ctx)
+{
+    rslf_stage_clock& c = ctx->clk;
+    if (c.used == c.pool.size()) {
+        cudaEvent_t e; cudaEventCreate(&e); c.pool.push_back(e);
+    }
+    cudaEventRecord(c.pool[c.used], ctx->stream);
+    return c.used++;
+}
+struct stage_scope {
+    rslf_ctx* ctx; int stage; size_t a; bool on;
+    stage_scope(rslf_ctx* c, int st) : ctx(c), stage(st), a(0), on(c->stage_timing != 0) { if (on) a = clk_mark(ctx); }
+    ~stage_scope() { if (on) { size_t b = clk_mark(ctx); ctx->clk.spans.push_back({stage, a, b}); } }
+};
+static void clk_resolve(rslf_ctx* ctx)
+{
+    float acc[ST_COUNT] = {0};
+    for (auto& sp : ctx->clk.spans) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->clk.pool[sp.a], ctx->clk.pool[sp.b]) == cudaSuccess) acc[sp.stage] += ms;
+    }
+    ctx->timing.ms_edge = acc[ST_EDGE]; ctx->timing.ms_depth = acc[ST_DEPTH]; ctx->timing.ms_reduce = acc[ST_REDUCE];
+    ctx->timing.ms_median = acc[ST_MEDIAN]; ctx->timing.ms_propagate = acc[ST_PROP]; ctx->timing.ms_pyramid = acc[ST_PYR];
+}
+
+static void free_level(rslf_level& L, bool keep_raw_borrowed_ptr = false)
+{
+    (void)keep_raw_borrowed_ptr;
+    dev_free(&L.raw); dev_free(&L.epi); dev_free(&L.ce); dev_free(&L.cd); dev_free(&L.depth); dev_free(&L.rbar);
+    dev_free(&L.dmin); dev_free(&L.dmax); dev_free(&L.emask); dev_free(&L.remaining); dev_free(&L.valid);
+    L.cap_px = 0; L.V = L.U = 0; L.have_bounds = false;
+}
+
+static void free_scratch(rslf_ctx* ctx)
+{
+    dev_free(&ctx->items); dev_free(&ctx->filtered); dev_free(&ctx->winner); dev_free(&ctx->arrive);
+    if (ctx->partials) { cudaFree(ctx->partials); ctx->partials = nullptr; }
+    ctx->partials_cap = 0;
+    dev_free(&ctx->nearest_l); dev_free(&ctx->nearest_r);
+    dev_free(&ctx->fuse_a); dev_free(&ctx->fuse_b); dev_free(&ctx->fuse_ma); dev_free(&ctx->fuse_mb);
+    dev_free(&ctx->out_map); dev_free(&ctx->out_valid); dev_free(&ctx->pile_depth_raw);
+    ctx->scratch_px = 0;
+}
+
+/* scratch shared by all levels, sized for level 0 */
+static int ensure_scratch(rslf_ctx* ctx, bool need_2d, bool need_ftc)
+{
+    const size_t plane = (size_t)ctx->V * ctx->U;
+    const size_t px = plane * ctx->S;
+    if (ctx->scratch_px != px) {
+        free_scratch(ctx);
+        RSLF_TRY(dev_alloc(ctx, &ctx->items, plane));
+        RSLF_TRY(dev_alloc(ctx, &ctx->filtered, plane));
+        RSLF_TRY(dev_alloc(ctx, &ctx->arrive, plane));
+        RSLF_TRY(dev_alloc(ctx, &ctx->pile_depth_raw, plane));
+        RSLF_CUDA_TRY(ctx, cudaMemsetAsync(ctx->arrive, 0, plane * sizeof(int), ctx->stream));
+        ctx->scratch_px = px;
+    }
+    if (need_2d && !ctx->winner) {
+        RSLF_TRY(dev_alloc(ctx, &ctx->winner, px));
+        RSLF_CUDA_TRY(ctx, cudaMemsetAsync(ctx->winner, 0x7f, px * sizeof(int), ctx->stream));  /* >= any u */
+    }
+    if (need_ftc && !ctx->out_map) {
+        RSLF_TRY(dev_alloc(ctx, &ctx->nearest_l, px));
+        RSLF_TRY(dev_alloc(ctx, &ctx->nearest_r, px));
+        RSLF_TRY(dev_alloc(ctx, &ctx->fuse_a, px));
+        RSLF_TRY(dev_alloc(ctx, &ctx->fuse_b, px));
+        RSLF_TRY(dev_alloc(ctx, &ctx->fuse_ma, px));
+        RSLF_TRY(dev_alloc(ctx, &ctx->fuse_mb, px));
+        RSLF_TRY(dev_alloc(ctx, &ctx->out_map, px));
+        RSLF_TRY(dev_alloc(ctx, &ctx->out_valid, px));
+    }
+    return RSLF_OK;
+}
+
+static int ensure_partials(rslf_ctx* ctx, size_t n)
+{
+    if (ctx->partials_cap >= n) return RSLF_OK;
+    if (ctx->partials) { cudaFree(ctx->partials); ctx->partials = nullptr; }
+    cudaError_t e = cudaMalloc(&ctx->partials, n * sizeof(rslf_partial));
+    if (e != cudaSuccess) {
+        snprintf(ctx->err, sizeof(ctx->err), "cudaMalloc(partials %zu): %s", n, cudaGetErrorString(e));
+        return RSLF_ERR_NOMEM;
+    }
+    ctx->partials_cap = n;
+    return RSLF_OK;
+}
+
+/* per-level maps; `full` = all S lines (2D), else one plane (pile) */
+static int ensure_level(rslf_ctx* ctx, int p, int V, int U, bool full, bool with_bounds)
+{
+    rslf_level& L = ctx->lv[p];
+    const size_t planes = full ? (size_t)ctx->S : 1;
+    const size_t px = planes * V * U;
+    const size_t stack = (size_t)V * ctx->S * U * ctx->C;
+    if (L.V != V || L.U != U || L.cap_px != px) {
+        float* raw = L.raw; float* epi = L.epi;            /* stacks survive a map re-allocation */
+        bool same_stack = (L.V == V && L.U == U);
+        L.raw = nullptr; L.epi = nullptr;
+        free_level(L);
+        if (same_stack) { L.raw = raw; L.epi = epi; } else { if (raw) cudaFree(raw); if (epi) cudaFree(epi); }
+        L.V = V; L.U = U;
+        RSLF_TRY(dev_alloc(ctx, &L.ce, px)); RSLF_TRY(dev_alloc(ctx, &L.cd, px));
+        RSLF_TRY(dev_alloc(ctx, &L.depth, px)); RSLF_TRY(dev_alloc(ctx, &L.rbar, px * ctx->C));
+        RSLF_TRY(dev_alloc(ctx, &L.emask, px)); RSLF_TRY(dev_alloc(ctx, &L.remaining, px));
+        RSLF_TRY(dev_alloc(ctx, &L.valid, px));
+        L.cap_px = px;
+    }
+    if (!L.epi) RSLF_TRY(dev_alloc(ctx, &L.epi, stack));
+    if (with_bounds && !L.dmin) {
+        RSLF_TRY(dev_alloc(ctx, &L.dmin, px)); RSLF_TRY(dev_alloc(ctx, &L.dmax, px));
+    }
+    return RSLF_OK;
+}
+
+static int check_params(rslf_ctx* ctx, const rslf_params* P, int dim_d)
+{
+    if (!ctx || !P) return RSLF_ERR_ARG;
+    if (!ctx->have_input) { snprintf(ctx->err, sizeof(ctx->err), "no EPIs uploaded"); return RSLF_ERR_STATE; }
+    if (dim_d < 2) { snprintf(ctx->err, sizeof(ctx->err), "dim_d must be >= 2"); return RSLF_ERR_ARG; }
+    if (ctx->C != 1 && ctx->C != 3) { snprintf(ctx->err, sizeof(ctx->err), "C must be 1 or 3"); return RSLF_ERR_ARG; }
+    return RSLF_OK;
+}
+
+/* kern.hpp:43: inv_m_h_sq = 1.0 / (h*h); the 1-channel kernel uses 3 * inv (kern.cpp:21) */
+static float kernel_inv(const rslf_params& P, int C)
+{
+    float hh = P.kernel_h * P.kernel_h;
+    float inv = (float)(1.0 / (double)hh);
+    if (C == 1) inv = (float)(3 * inv);
+    return inv;
+}
+
+/* Normalises the raw stack of level p into L.epi (ctor scaling, dc.hpp:442-477). */
+static int normalise_level(rslf_ctx* ctx, int p, const void* raw, int cv_depth)
+{
+    rslf_level& L = ctx->lv[p];
+    stage_scope sc(ctx, ST_PYR);
+    const size_t n = (size_t)L.V * ctx->S * L.U * ctx->C;
+    if (cv_depth == RSLF_DEPTH_8U) {
+        normalise_u8_kernel<<<stream_grid(ctx, n), 256, 0, ctx->stream>>>((const uint8_t*)raw, n, L.epi);
+        L.nonneg = 1;
+        ctx->timing.kernel_launches += 1;
+    } else {
+        /* max (start value = the scale factor, dc.hpp:445) and min of the stack */
+        float init[2] = {ctx->scale_factor, std::numeric_limits<float>::infinity()};
+        RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->minmax, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+        stack_minmax_kernel<<<stream_grid(ctx, n), 256, 0, ctx->stream>>>((const float*)raw, n, ctx->minmax);
+        float mm[2];
+        RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(mm, ctx->minmax, sizeof(mm), cudaMemcpyDeviceToHost, ctx->stream));
+        RSLF_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        float sf = ctx->scale_factor;
+        if (sf < 0.f) {
+            if (ctx->world > 1) RSLF_TRY(comm_allreduce_max(ctx, ctx->minmax, 1, &mm[0]));
+            sf = mm[0];
+        }
+        if (ctx->world > 1) { /* a shard may hold no negative value while another does: agree */
+            float neg = (mm[1] < 0.f) ? 1.f : 0.f, out = neg;
+            RSLF_TRY(comm_allreduce_max_host(ctx, neg, &out));
+            if (out > 0.f) mm[1] = -1.f;
+        }
+        /* sign of a normalised value: sign(x) * sign(1/sf) */
+        L.nonneg = ((mm[1] >= 0.f && sf > 0.f)) ? 1 : 0;
+        normalise_f32_kernel<<<stream_grid(ctx, n), 256, 0, ctx->stream>>>((const float*)raw, n, nullptr, sf, L.epi);
+        ctx->timing.kernel_launches += 2;
+    }
+    RSLF_CUDA_TRY(ctx, cudaGetLastError());
+    return RSLF_OK;
+}
+
+/* ------------------------------------------------------------------ lifetime */
+extern "C" int rslf_cuda_abi_version(void) { return RSLF_ABI_VERSION; }
+
+extern "C" void rslf_params_default(rslf_params* p)
+{
+    if (!p) return;
+    p->edge_score_threshold = 0.02f; p->line_score_threshold = 0.02f;
+    p->disp_score_threshold = 0.01f; p->raw_score_threshold = 0.f;
+    p->mean_shift_max_iter = 10; p->edge_confidence_filter_size = 9;
+    p->edge_confidence_opening_type = 2; p->edge_confidence_opening_size = 1;
+    p->median_filter_size = 5; p->median_filter_epsilon = 0.1f; p->propagation_epsilon = 0.1f;
+    p->slope_factor = 1.0f; p->cut_shadows = 1; p->shadow_level = (float)(0.05 * 1.73205080757);
+    p->kernel_h = 0.2f;
+}
+
+extern "C" const char* rslf_cuda_strerror(int code)
+{
+    switch (code) {
+        case RSLF_OK: return "ok";
+        case RSLF_ERR_CUDA: return "CUDA runtime error";
+        case RSLF_ERR_ARG: return "invalid argument";
+        case RSLF_ERR_STATE: return "call order violated";
+        case RSLF_ERR_UNSUPPORTED: return "not implemented in the CUDA path";
+        case RSLF_ERR_NCCL: return "NCCL error";
+        case RSLF_ERR_NOMEM: return "out of device memory";
+        default: return "unknown error";
+    }
+}
+
+extern "C" int rslf_cuda_create(int device, rslf_ctx** out)
+{
+    if (!out) return RSLF_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return RSLF_ERR_CUDA;
+    if (cudaSetDevice(device) != cudaSuccess) return RSLF_ERR_CUDA;
+    rslf_ctx* ctx = new rslf_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { delete ctx; return RSLF_ERR_CUDA; }
+    ctx->num_sm = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return RSLF_ERR_CUDA; }
+    cudaEventCreate(&ctx->ev_a); cudaEventCreate(&ctx->ev_b);
+    if (cudaMalloc((void**)&ctx->count, RSLF_COUNT_SLOTS * sizeof(int)) != cudaSuccess ||
+        cudaMalloc((void**)&ctx->total_px, sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMalloc((void**)&ctx->minmax, 4 * sizeof(float)) != cudaSuccess) {
+        rslf_cuda_destroy(ctx); return RSLF_ERR_CUDA;
+    }
+    memset(&ctx->timing, 0, sizeof(ctx->timing));
+    const char* st = getenv("RSLF_STAGE_TIMING");
+    if (st) ctx->stage_timing = atoi(st);
+    *out = ctx;
+    return RSLF_OK;
+}
+
+extern "C" void rslf_cuda_destroy(rslf_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    comm_destroy(ctx);
+    for (int p = 0; p < RSLF_MAX_LEVELS; ++p) free_level(ctx->lv[p]);
+    free_scratch(ctx);
+    if (ctx->raw_in && !ctx->raw_borrowed) cudaFree(ctx->raw_in);
+    dev_free(&ctx->count); dev_free(&ctx->total_px); dev_free(&ctx->minmax);
+    if (ctx->l2_flush) cudaFree(ctx->l2_flush);
+    for (auto e : ctx->clk.pool) cudaEventDestroy(e);
+    if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
+    if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" const char* rslf_cuda_last_error_text(const rslf_ctx* ctx) { return ctx ? ctx->err : "null ctx"; }
+
+extern "C" int rslf_cuda_last_timing(const rslf_ctx* ctx, rslf_timing* out)
+{
+    if (!ctx || !out) return RSLF_ERR_ARG;
+    *out = ctx->timing;
+    return RSLF_OK;
+}
+
+extern "C" int rslf_cuda_set_stage_timing(rslf_ctx* ctx, int on)
+{
+    if (!ctx) return RSLF_ERR_ARG;
+    ctx->stage_timing = on;
+    return RSLF_OK;
+}
+
+extern "C" int rslf_cuda_sync(rslf_ctx* ctx)
+{
+    if (!ctx) return RSLF_ERR_ARG;
+    RSLF_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    RSLF_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return RSLF_OK;
+}
+
+extern "C" int rslf_cuda_flush_l2(rslf_ctx* ctx)
+{
+    if (!ctx) return RSLF_ERR_ARG;
+    RSLF_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t bytes = 256u << 20;           /* > 126 MB L2 */
+    if (!ctx->l2_flush) RSLF_CUDA_TRY(ctx, cudaMalloc(&ctx->l2_flush, bytes));
+    RSLF_CUDA_TRY(ctx, cudaMemsetAsync(ctx->l2_flush, 0x5a, bytes, ctx->stream));
+    return RSLF_OK;
+}
+
+/* ------------------------------------------------------------------ input */
+static int set_dims(rslf_ctx* ctx, int V, int S, int U, int C, int cv_depth, float scale)
+{
+    if (V < 1 || S < 1 || U < 1 || (C != 1 && C != 3)) { snprintf(ctx->err, sizeof(ctx->err), "bad dimensions"); return RSLF_ERR_ARG; }
+    if (cv_depth != RSLF_DEPTH_8U && cv_depth != RSLF_DEPTH_32F) {
+        snprintf(ctx->err, sizeof(ctx->err), "only CV_8U and CV_32F inputs are implemented"); return RSLF_ERR_UNSUPPORTED;
+    }
+    if ((size_t)S * 2 > RSLF_COUNT_SLOTS / RSLF_MAX_LEVELS) { snprintf(ctx->err, sizeof(ctx->err), "S too large"); return RSLF_ERR_UNSUPPORTED; }
+    ctx->V = V; ctx->S = S; ctx->U = U; ctx->C = C; ctx->cv_depth = cv_depth; ctx->scale_factor = scale;
+    if (ctx->V_total == 0 || ctx->world == 1) { ctx->v0 = 0; ctx->V_total = V; }
+    return RSLF_OK;
+}
+
+static int own_raw(rslf_ctx* ctx, size_t bytes)
+{
+    if (ctx->raw_borrowed) { ctx->raw_in = nullptr; ctx->raw_borrowed = false; ctx->raw_cap = 0; }
+    if (ctx->raw_cap < bytes) {
+        if (ctx->raw_in) cudaFree(ctx->raw_in);
+        ctx->raw_in = nullptr; ctx->raw_cap = 0;
+        cudaError_t e = cudaMalloc(&ctx->raw_in, bytes);
+        if (e != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "cudaMalloc(raw %zu): %s", bytes, cudaGetErrorString(e)); return RSLF_ERR_NOMEM; }
+        ctx->raw_cap = bytes;
+    }
+    return RSLF_OK;
+}
+
+extern "C" int rslf_cuda_upload_epis(rslf_ctx* ctx, const void* const* epi_ptrs, int V, int S, int U, int C,
+                                     int cv_depth, size_t row_step_bytes, float epi_scale_factor)
+{
+    if (!ctx || !epi_ptrs) return RSLF_ERR_ARG;
+    RSLF_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    RSLF_TRY(set_dims(ctx, V, S, U, C, cv_depth, epi_scale_factor));
+    const size_t esz = (cv_depth == RSLF_DEPTH_8U) ? 1 : 4;
+    const size_t row = (size_t)U * C * esz;
+    if (row_step_bytes < row) { snprintf(ctx->err, sizeof(ctx->err), "row step smaller than a row"); return RSLF_ERR_ARG; }
+    const size_t epi_bytes = row * S;
+    RSLF_TRY(own_raw(ctx, epi_bytes * V));
+    cudaEventRecord(ctx->ev_a, ctx->stream);
+    /* one dense copy when the V Mats are continuous and back to back, else one 2D copy per EPI */
+    bool dense = (row_step_bytes == row);
+    for (int v = 1; dense && v < V; ++v)
+        dense = ((const char*)epi_ptrs[v] == (const char*)epi_ptrs[0] + (size_t)v * epi_bytes);
+    if (dense) {
+        RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->raw_in, epi_ptrs[0], epi_bytes * V, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        for (int v = 0; v < V; ++v)
+            RSLF_CUDA_TRY(ctx, cudaMemcpy2DAsync((char*)ctx->raw_in + (size_t)v * epi_bytes, row, epi_ptrs[v], row_step_bytes,
+                                                 row, S, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    cudaEventRecord(ctx->ev_b, ctx->stream);
+    RSLF_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ctx->timing.ms_h2d, ctx->ev_a, ctx->ev_b);
+    ctx->have_input = true;
+    return RSLF_OK;
+}
+
+extern "C" int rslf_cuda_set_epis_device(rslf_ctx* ctx, const void* d_epis, int V, int S, int U, int C,
+                                         int cv_depth, float epi_scale_factor)
+{
+    if (!ctx || !d_epis) return RSLF_ERR_ARG;
+    RSLF_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    RSLF_TRY(set_dims(ctx, V, S, U, C, cv_depth, epi_scale_factor));
+    if (ctx->raw_in && !ctx->raw_borrowed) cudaFree(ctx->raw_in);
+    ctx->raw_in = const_cast<void*>(d_epis);
+    ctx->raw_borrowed = true; ctx->raw_cap = 0;
+    ctx->have_input = true;
+    ctx->timing.ms_h2d = 0.f;
+    return RSLF_OK;
+}
+
+/* [S][V][U][C] -> [V][S][U][C] (rslf::build_epis_from_imgs, src/rslf_io.cpp:194-227) */
+template <typename T>
+__global__ void build_epis_kernel(const T* __restrict__ imgs, int S, int V, size_t rowlen, T* __restrict__ epis)
+{
+    const int s = blockIdx.y, v = blockIdx.z;
+    const T* src = imgs + ((size_t)s * V + v) * rowlen;
+    T* dst = epis + ((size_t)v * S + s) * rowlen;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < rowlen; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+extern "C" int rslf_cuda_upload_images(rslf_ctx* ctx, const void* const* img_ptrs, int S, int V, int U, int C,
+                                       int cv_depth, size_t row_step_bytes, float epi_scale_factor)
+{
+    if (!ctx || !img_ptrs) return RSLF_ERR_ARG;
+    RSLF_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    RSLF_TRY(set_dims(ctx, V, S, U, C, cv_depth, epi_scale_factor));
+    const size_t esz = (cv_depth == RSLF_DEPTH_8U) ? 1 : 4;
+    const size_t row = (size_t)U * C * esz;
+    if (row_step_bytes < row) return RSLF_ERR_ARG;
+    const size_t img_bytes = row * V;
+    RSLF_TRY(own_raw(ctx, img_bytes * S));
+    void* staging = nullptr;
+    RSLF_CUDA_TRY(ctx, cudaMalloc(&staging, img_bytes * S));
+    cudaEventRecord(ctx->ev_a, ctx->stream);
+    for (int s = 0; s < S; ++s) {
+        cudaError_t e = cudaMemcpy2DAsync((char*)staging + (size_t)s * img_bytes, row, img_ptrs[s], row_step_bytes, row, V,
+                                          cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) { cudaFree(staging); RSLF_CUDA_TRY(ctx, e); }
+    }
+    dim3 grid(std::max(1, std::min(8, rslf_div_up((long long)U * C, 256))), S, V);
+    if (esz == 1) build_epis_kernel<uint8_t><<<grid, 256, 0, ctx->stream>>>((const uint8_t*)staging, S, V, (size_t)U * C, (uint8_t*)ctx->raw_in);
+    else build_epis_kernel<float><<<grid, 256, 0, ctx->stream>>>((const float*)staging, S, V, (size_t)U * C, (float*)ctx->raw_in);
+    cudaEventRecord(ctx->ev_b, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(staging);
+    RSLF_CUDA_TRY(ctx, e);
+    cudaEventElapsedTime(&ctx->timing.ms_h2d, ctx->ev_a, ctx->ev_b);
+    ctx->have_input = true;
+    return RSLF_OK;
+}
+
+/* ------------------------------------------------------------------ one s_hat pass */
+struct pass_io {
+    int level; int s_hat; int D; float dmin, dmax; bool use_bound_maps;
+    bool pile;                /* 1D pile: single-plane maps, no remaining mask */
+    int count_slot;
+};
+
+/* compute_1D_depth_epi_pile (core.hpp:772-893) on line s_hat of level L: compaction,
+ * depth kernel, selective median into ctx->filtered. */
+static int run_depth_pass(rslf_ctx* ctx, const rslf_params& P, const pass_io& io)
+{
+    rslf_level& L = ctx->lv[io.level];
+    const int V = L.V, U = L.U, S = ctx->S, C = ctx->C;
+    const size_t plane = (size_t)V * U;
+    const size_t po = io.pile ? 0 : (size_t)io.s_hat * plane;
+    int* count = ctx->count + io.count_slot;
+    {
+        stage_scope sc(ctx, ST_REDUCE);
+        compact_kernel<<<stream_grid(ctx, plane), 256, 0, ctx->stream>>>(
+            L.emask + po, io.pile ? nullptr : L.remaining + po, (int)plane, ctx->items, count, ctx->total_px);
+        RSLF_CUDA_TRY(ctx, cudaGetLastError());
+        ctx->timing.kernel_launches += 1;
+    }
+    depth_plan plan = plan_depth(ctx, S, C, io.D);
+    if (plan.chunks > 1) RSLF_TRY(ensure_partials(ctx, plane * plan.chunks));
+    depth_args a;
+    a.epi = L.epi; a.V = V; a.S = S; a.U = U; a.D = io.D; a.s_hat = io.s_hat; a.slope = P.slope_factor;
+    a.inv = kernel_inv(P, C); a.iters = P.mean_shift_max_iter;
+    a.items = ctx->items; a.count = count;
+    a.dmin_map = io.use_bound_maps ? L.dmin + po : nullptr;
+    a.dmax_map = io.use_bound_maps ? L.dmax + po : nullptr;
+    a.dmin_c = io.dmin; a.dmax_c = io.dmax;
+    a.ce = L.ce + po; a.emask = L.emask + po; a.cd = L.cd + po;
+    a.depth = io.pile ? ctx->pile_depth_raw : L.depth + po;
+    a.rbar = L.rbar + po * C;
+    a.raw_thr = P.raw_score_threshold;
+    a.chunks = plan.chunks; a.partials = (rslf_partial*)ctx->partials; a.arrive = ctx->arrive;
+    {
+        stage_scope sc(ctx, ST_DEPTH);
+        RSLF_TRY(launch_depth(ctx, C, L.nonneg != 0, a, plan));
+    }
+    {
+        stage_scope sc(ctx, ST_MEDIAN);
+        /* colours of line s_hat: row v starts at epi + (v*S + s_hat)*U*C */
+        RSLF_TRY(launch_selective_median(ctx, a.depth, L.emask + po, L.epi + (size_t)io.s_hat * U * C, (size_t)S * U * C,
+                                         V, U, C, P.median_filter_size, P.median_filter_epsilon, ctx->filtered));
+    }
+    return RSLF_OK;
+}
+
+static std::vector<int> visiting_order(int S)
+{
+    /* core.hpp:953, 981-990 */
+    int s_hat = (int)std::floor(S / 2.0);
+    std::vector<int> order;
+    order.push_back(s_hat);
+    for (int off = 1; off < S - s_hat; ++off) {
+        order.push_back(s_hat + off);
+        if (s_hat - off > -1) order.push_back(s_hat - off);
+    }
+    return order;
+}
+
+/* Depth2DComputer::run (dc.hpp:748-805) on level p (stack already normalised in L.epi). */
+static int run_depth2d_level(rslf_ctx* ctx, int p, const rslf_params& P, float dmin, float dmax, int D, bool use_bound_maps)
+{
+    rslf_level& L = ctx->lv[p];
+    const int V = L.V, U = L.U, S = ctx->S, C = ctx->C;
+    const size_t plane = (size_t)V * U, px = plane * S;
+    /* result maps start from zero (dc.hpp:741-744; C_e / C_d: fresh zero pages) */
+    RSLF_CUDA_TRY(ctx, cudaMemsetAsync(L.depth, 0, px * sizeof(float), ctx->stream));
+    RSLF_CUDA_TRY(ctx, cudaMemsetAsync(L.cd, 0, px * sizeof(float), ctx->stream));
+    RSLF_CUDA_TRY(ctx, cudaMemsetAsync(L.rbar, 0, px * C * sizeof(float), ctx->stream));
+    {
+        stage_scope sc(ctx, ST_EDGE);
+        RSLF_TRY(launch_edge_confidence(ctx, L.epi, V, S, U, C, 0, S, P, L.ce, L.emask));
+    }
+    RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(L.remaining, L.emask, px, cudaMemcpyDeviceToDevice, ctx->stream));   /* core.hpp:958-963 */
+    std::vector<int> order = visiting_order(S);
+    int pass = 0;
+    for (int s_hat : order) {
+        pass_io io;
+        io.level = p; io.s_hat = s_hat; io.D = D; io.dmin = dmin; io.dmax = dmax; io.use_bound_maps = use_bound_maps;
+        io.pile = false; io.count_slot = p * 2 * S + pass;
+        RSLF_TRY(run_depth_pass(ctx, P, io));
+        {
+            stage_scope sc(ctx, ST_PROP);
+            prop_args a;
+            a.epi = L.epi; a.V = V; a.S = S; a.U = U; a.s_hat = s_hat; a.slope = P.slope_factor;
+            a.eps = P.propagation_epsilon; a.eps_T = rslf_sq_threshold(P.propagation_epsilon);
+            a.emask_p = L.emask + (size_t)s_hat * plane; a.filtered = ctx->filtered;
+            a.rbar_p = L.rbar + (size_t)s_hat * plane * C; a.cd_p = L.cd + (size_t)s_hat * plane;
+            a.depth = L.depth; a.cd = L.cd; a.remaining = L.remaining; a.winner = ctx->winner;
+            RSLF_TRY(launch_propagate(ctx, C, a));
+        }
+        ++pass;
+        ctx->timing.passes += 1;
+    }
+    return RSLF_OK;
+}
+
+static int begin_run(rslf_ctx* ctx)
+{
+    RSLF_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    float h2d = ctx->timing.ms_h2d;
+    memset(&ctx->timing, 0, sizeof(ctx->timing));
+    ctx->timing.ms_h2d = h2d;
+    clk_reset(ctx);
+    RSLF_CUDA_TRY(ctx, cudaMemsetAsync(ctx->count, 0, RSLF_COUNT_SLOTS * sizeof(int), ctx->stream));
+    RSLF_CUDA_TRY(ctx, cudaMemsetAsync(ctx->total_px, 0, sizeof(unsigned long long), ctx->stream));
+    RSLF_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
+    return RSLF_OK;
+}
+
+static int end_run(rslf_ctx* ctx, int D)
+{
+    RSLF_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_b, ctx->stream));
+    unsigned long long total = 0;
+    RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(&total, ctx->total_px, sizeof(total), cudaMemcpyDeviceToHost, ctx->stream));
+    RSLF_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    RSLF_CUDA_TRY(ctx, cudaEventElapsedTime(&ctx->timing.ms_total, ctx->ev_a, ctx->ev_b));
+    if (ctx->stage_timing) clk_resolve(ctx);
+    ctx->timing.computed_pixels = (double)total;
+    ctx->timing.samples = (double)total * D * ctx->S;
+    return RSLF_OK;
+}
+
+static int copy_out(rslf_ctx* ctx, void* host, const void* dev, size_t bytes)
+{
+    if (!host) return RSLF_OK;
+    RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return RSLF_OK;
+}
+
+/* ------------------------------------------------------------------ Depth1DComputer_pile */
+extern "C" int rslf_cuda_depth1d_pile_run(rslf_ctx* ctx, float dmin, float dmax, int dim_d, int s_hat,
+                                          const rslf_params* params)
+{
+    RSLF_TRY(check_params(ctx, params, dim_d));
+    const rslf_params& P = *params;
+    RSLF_TRY(begin_run(ctx));
+    const int V = ctx->V, U = ctx->U, S = ctx->S, C = ctx->C;
+    if (s_hat < 0 || s_hat > S - 1) s_hat = (int)std::floor((0.0 + S) / 2);      /* dc.hpp:489-498 */
+    RSLF_TRY(ensure_scratch(ctx, false, false));
+    RSLF_TRY(ensure_level(ctx, 0, V, U, false, false));
+    ctx->n_levels = 1;
+    rslf_level& L = ctx->lv[0];
+    L.slope = P.slope_factor;
+    RSLF_TRY(normalise_level(ctx, 0, ctx->raw_in, ctx->cv_depth));
+    const size_t plane = (size_t)V * U;
+    RSLF_CUDA_TRY(ctx, cudaMemsetAsync(ctx->pile_depth_raw, 0, plane * sizeof(float), ctx->stream));
+    RSLF_CUDA_TRY(ctx, cudaMemsetAsync(L.cd, 0, plane * sizeof(float), ctx->stream));
+    RSLF_CUDA_TRY(ctx, cudaMemsetAsync(L.rbar, 0, plane * C * sizeof(float), ctx->stream));
+    {
+        stage_scope sc(ctx, ST_EDGE);
+        RSLF_TRY(launch_edge_confidence(ctx, L.epi, V, S, U, C, s_hat, 1, P, L.ce, L.emask));
+    }
+    pass_io io;
+    io.level = 0; io.s_hat = s_hat; io.D = dim_d; io.dmin = dmin; io.dmax = dmax; io.use_bound_maps = false;
+    io.pile = true; io.count_slot = 0;
+    RSLF_TRY(run_depth_pass(ctx, P, io));
+    ctx->timing.passes = 1; ctx->timing.levels = 1;
+    ctx->last_kind = 1; ctx->pile_s_hat = s_hat;
+    return end_run(ctx, dim_d);
+}
+
+extern "C" int rslf_cuda_depth1d_pile_get(rslf_ctx* ctx, float* best_depth_vu, float* edge_conf_vu,
+                                          uint8_t* edge_mask_vu, float* disp_conf_vu, float* rbar_vuc)
+{
+    if (!ctx) return RSLF_ERR_ARG;
+    if (ctx->last_kind != 1) { snprintf(ctx->err, sizeof(ctx->err), "no pile result"); return RSLF_ERR_STATE; }
+    RSLF_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    rslf_level& L = ctx->lv[0];
+    const size_t plane = (size_t)L.V * L.U;
+    cudaEventRecord(ctx->ev_a, ctx->stream);
+    RSLF_TRY(copy_out(ctx, best_depth_vu, ctx->filtered, plane * 4));          /* the filtered map (core.hpp:892) */
+    RSLF_TRY(copy_out(ctx, edge_conf_vu, L.ce, plane * 4));
+    RSLF_TRY(copy_out(ctx, edge_mask_vu, L.emask, plane));
+    RSLF_TRY(copy_out(ctx, disp_conf_vu, L.cd, plane * 4));
+    RSLF_TRY(copy_out(ctx, rbar_vuc, L.rbar, plane * 4 * ctx->C));
+    cudaEventRecord(ctx->ev_b, ctx->stream);
+    RSLF_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ctx->timing.ms_d2h, ctx->ev_a, ctx->ev_b);
+    return RSLF_OK;
+}
+
+extern "C" int rslf_cuda_depth1d_pile(rslf_ctx* ctx, float dmin, float dmax, int dim_d, int s_hat,
+                                      const rslf_params* params, float* best_depth_vu, float* edge_conf_vu,
+                                      uint8_t* edge_mask_vu, float* disp_conf_vu, float* rbar_vuc)
+{
+    RSLF_TRY(rslf_cuda_depth1d_pile_run(ctx, dmin, dmax, dim_d, s_hat, params));
+    return rslf_cuda_depth1d_pile_get(ctx, best_depth_vu, edge_conf_vu, edge_mask_vu, disp_conf_vu, rbar_vuc);
+}
+
+/* unfiltered argmax depths of the last pile run (diagnostic; m_best_depth_v_u before core.hpp:881-892) */
+extern "C" int rslf_cuda_depth1d_pile_get_raw_depth(rslf_ctx* ctx, float* raw_depth_vu)
+{
+    if (!ctx || !raw_depth_vu) return RSLF_ERR_ARG;
+    if (ctx->last_kind != 1) return RSLF_ERR_STATE;
+    RSLF_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    RSLF_TRY(copy_out(ctx, raw_depth_vu, ctx->pile_depth_raw, (size_t)ctx->lv[0].V * ctx->lv[0].U * 4));
+    RSLF_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return RSLF_OK;
+}
+
+/* ------------------------------------------------------------------ Depth2DComputer */
+extern "C" int rslf_cuda_depth2d_run(rslf_ctx* ctx, float dmin, float dmax, int dim_d, const rslf_params* params,
+                                     const float* dmin_svu, const float* dmax_svu)
+{
+    RSLF_TRY(check_params(ctx, params, dim_d));
+    if ((dmin_svu == nullptr) != (dmax_svu == nullptr)) return RSLF_ERR_ARG;
+    const rslf_params& P = *params;
+    const int V = ctx->V, U = ctx->U, S = ctx->S;
+    RSLF_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    RSLF_TRY(ensure_scratch(ctx, true, false));
+    RSLF_TRY(ensure_level(ctx, 0, V, U, true, dmin_svu != nullptr));
+    ctx->n_levels = 1;
+    rslf_level& L = ctx->lv[0];
+    const size_t px = (size_t)S * V * U;
+    if (dmin_svu) {
+        RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(L.dmin, dmin_svu, px * 4, cudaMemcpyHostToDevice, ctx->stream));
+        RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(L.dmax, dmax_svu, px * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    RSLF_TRY(begin_run(ctx));
+    RSLF_TRY(normalise_level(ctx, 0, ctx->raw_in, ctx->cv_depth));
+    RSLF_TRY(run_depth2d_level(ctx, 0, P, dmin, dmax, dim_d, dmin_svu != nullptr));
+    ctx->timing.levels = 1;
+    ctx->last_kind = 2;
+    return end_run(ctx, dim_d);
+}
+
+static int get_level_maps(rslf_ctx* ctx, int p, float* best_depth, float* edge_conf, uint8_t* edge_mask,
+                          float* disp_conf, float* rbar, float* dmin_svu, float* dmax_svu)
+{
+    rslf_level& L = ctx->lv[p];
+    const size_t px = (size_t)ctx->S * L.V * L.U;
+    cudaEventRecord(ctx->ev_a, ctx->stream);
+    RSLF_TRY(copy_out(ctx, best_depth, L.depth, px * 4));
+    RSLF_TRY(copy_out(ctx, edge_conf, L.ce, px * 4));
+    RSLF_TRY(copy_out(ctx, edge_mask, L.emask, px));
+    RSLF_TRY(copy_out(ctx, disp_conf, L.cd, px * 4));
+    RSLF_TRY(copy_out(ctx, rbar, L.rbar, px * 4 * ctx->C));
+    if (L.dmin) { RSLF_TRY(copy_out(ctx, dmin_svu, L.dmin, px * 4)); RSLF_TRY(copy_out(ctx, dmax_svu, L.dmax, px * 4)); }
+    cudaEventRecord(ctx->ev_b, ctx->stream);
+    RSLF_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ctx->timing.ms_d2h, ctx->ev_a, ctx->ev_b);
+    return RSLF_OK;
+}
+
+extern "C" int rslf_cuda_depth2d_get(rslf_ctx* ctx, float* best_depth_svu, float* edge_conf_svu,
+                                     uint8_t* edge_mask_svu, float* disp_conf_svu, float* rbar_svuc)
+{
+    if (!ctx) return RSLF_ERR_ARG;
+    if (ctx->last_kind != 2) { snprintf(ctx->err, sizeof(ctx->err), "no depth2d result"); return RSLF_ERR_STATE; }
+    RSLF_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    return get_level_maps(ctx, 0, best_depth_svu, edge_conf_svu, edge_mask_svu, disp_conf_svu, rbar_svuc, nullptr, nullptr);
+}
+
+extern "C" int rslf_cuda_depth2d(rslf_ctx* ctx, float dmin, float dmax, int dim_d, const rslf_params* params,
+                                 const float* dmin_svu, const float* dmax_svu, float* best_depth_svu,
+                                 float* edge_conf_svu, uint8_t* edge_mask_svu, float* disp_conf_svu, float* rbar_svuc)
+{
+    RSLF_TRY(rslf_cuda_depth2d_run(ctx, dmin, dmax, dim_d, params, dmin_svu, dmax_svu));
+    return rslf_cuda_depth2d_get(ctx, best_depth_svu, edge_conf_svu, edge_mask_svu, disp_conf_svu, rbar_svuc);
+}
+
+extern "C" int rslf_cuda_depth2d_get_valid_mask(rslf_ctx* ctx, int accept_all, const rslf_params* params,
+                                                uint8_t* valid_svu)
+{
+    if (!ctx || !params || !valid_svu) return RSLF_ERR_ARG;
+    if (ctx->last_kind != 2) return RSLF_ERR_STATE;
+    RSLF_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    rslf_level& L = ctx->lv[0];
+    const size_t px = (size_t)ctx->S * L.V * L.U;
+    valid_mask_kernel<<<stream_grid(ctx, px), 256, 0, ctx->stream>>>(L.ce, px, params->edge_score_threshold, accept_all, L.valid);
+    RSLF_CUDA_TRY(ctx, cudaGetLastError());
+    RSLF_TRY(copy_out(ctx, valid_svu, L.valid, px));
+    RSLF_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return RSLF_OK;
+}
+
+/* ------------------------------------------------------------------ FineToCoarse */
+static inline int cv_round_half(int n) { return (int)std::nearbyint(n * 0.5); }   /* cvRound: half to even */
+
+static int launch_downsample(rslf_ctx* ctx, const float* in, int V, int S, int U, int C, float* out, int V2, int U2)
+{
+    dim3 grid(rslf_div_up(U2, DS_TU), rslf_div_up(V2, DS_TV), S);
+    if (C == 1) downsample_kernel<1><<<grid, DS_THREADS, 0, ctx->stream>>>(in, V, S, U, out, V2, U2);
+    else downsample_kernel<3><<<grid, DS_THREADS, 0, ctx->stream>>>(in, V, S, U, out, V2, U2);
+    RSLF_CUDA_TRY(ctx, cudaGetLastError());
+    ctx->timing.kernel_launches += 1;
+    return RSLF_OK;
+}
+
+static int launch_fuse(rslf_ctx* ctx, int levels, const int* Vp, const int* Up, const float* const* disp,
+                       const uint8_t* const* valid, float* out_map, uint8_t* out_valid)
+{
+    const int S = ctx->S;
+    const float* map_down = disp[levels - 1];
+    const uint8_t* mask_down = valid[levels - 1];
+    float* fa = ctx->fuse_a; float* fb = ctx->fuse_b; uint8_t* ma = ctx->fuse_ma; uint8_t* mb = ctx->fuse_mb;
+    for (int p = levels - 1; p > 0; --p) {
+        const int Vn = Vp[p - 1], Un = Up[p - 1];
+        dim3 grid(rslf_div_up(Un, 128), Vn, S);
+        uint8_t* mout = (p == 1) ? out_valid : ma;
+        fuse_level_kernel<<<grid, 128, 0, ctx->stream>>>(map_down, mask_down, Vp[p], Up[p], disp[p - 1], valid[p - 1], Vn, Un, fa, mout);
+        RSLF_CUDA_TRY(ctx, cudaGetLastError());
+        ctx->timing.kernel_launches += 1;
+        map_down = fa; mask_down = mout;
+        std::swap(fa, fb); std::swap(ma, mb);
+    }
+    const size_t px = (size_t)S * Vp[0] * Up[0];
+    if (levels == 1) RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(out_valid, mask_down, px, cudaMemcpyDeviceToDevice, ctx->stream));
+    dim3 grid(rslf_div_up(Up[0], 128), Vp[0], S);
+    median3x3_kernel<<<grid, 128, 0, ctx->stream>>>(map_down, Vp[0], Up[0], out_map);
+    RSLF_CUDA_TRY(ctx, cudaGetLastError());
+    ctx->timing.kernel_launches += 1;
+    return RSLF_OK;
+}
+
+extern "C" int rslf_cuda_fine_to_coarse_run(rslf_ctx* ctx, float dmin, float dmax, int dim_d,
+                                            const rslf_params* params, int max_pyr_depth, int accept_all_last_scale)
+{
+    RSLF_TRY(check_params(ctx, params, dim_d));
+    RSLF_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int S = ctx->S, C = ctx->C;
+    /* pyramid sizes: while (V > 10 && U > 10 && depth < max) (ftc.hpp:130), dsize = cvRound(n * 0.5) */
+    int Vp[RSLF_MAX_LEVELS], Up[RSLF_MAX_LEVELS];
+    int levels = 0;
+    {
+        int V = ctx->V, U = ctx->U;
+        int maxd = (max_pyr_depth < 1) ? RSLF_MAX_LEVELS : std::min(max_pyr_depth, RSLF_MAX_LEVELS);
+        while (V > 10 && U > 10 && levels < maxd) {
+            Vp[levels] = V; Up[levels] = U; ++levels;
+            V = cv_round_half(V); U = cv_round_half(U);
+        }
+    }
+    if (levels == 0) { snprintf(ctx->err, sizeof(ctx->err), "light field smaller than the minimum pyramid size"); return RSLF_ERR_ARG; }
+    if (ctx->cv_depth != RSLF_DEPTH_32F && levels > 1) {
+        snprintf(ctx->err, sizeof(ctx->err), "8-bit pyramids (OpenCV integer blur) are not implemented; convert to float32 or use max_pyr_depth=1");
+        return RSLF_ERR_UNSUPPORTED;
+    }
+    RSLF_TRY(ensure_scratch(ctx, true, true));
+    for (int p = 0; p < levels; ++p) {
+        RSLF_TRY(ensure_level(ctx, p, Vp[p], Up[p], true, true));
+        if (p > 0 && !ctx->lv[p].raw) RSLF_TRY(dev_alloc(ctx, &ctx->lv[p].raw, (size_t)Vp[p] * S * Up[p] * C));
+    }
+    ctx->n_levels = levels;
+    RSLF_TRY(begin_run(ctx));
+    const rslf_params& P0 = *params;
+    for (int p = 0; p < levels; ++p) {
+        rslf_level& L = ctx->lv[p];
+        const size_t px = (size_t)S * Vp[p] * Up[p];
+        const void* raw = (p == 0) ? ctx->raw_in : (const void*)L.raw;
+        RSLF_TRY(normalise_level(ctx, p, raw, p == 0 ? ctx->cv_depth : RSLF_DEPTH_32F));
+        rslf_params P = P0;
+        P.slope_factor = (float)((0.0 + Up[p]) / Up[0]);                        /* ftc.hpp:139 */
+        L.slope = P.slope_factor;
+        if (p == 0) {
+            stage_scope sc(ctx, ST_PYR);
+            fill_f32_kernel<<<stream_grid(ctx, px), 256, 0, ctx->stream>>>(L.dmin, px, dmin);
+            fill_f32_kernel<<<stream_grid(ctx, px), 256, 0, ctx->stream>>>(L.dmax, px, dmax);
+            ctx->timing.kernel_launches += 2;
+        }
+        RSLF_TRY(run_depth2d_level(ctx, p, P, dmin, dmax, dim_d, true));
+        {
+            stage_scope sc(ctx, ST_PYR);
+            const int accept_all = (accept_all_last_scale && p == levels - 1) ? 1 : 0;   /* ftc.hpp:157-158 */
+            valid_mask_kernel<<<stream_grid(ctx, px), 256, 0, ctx->stream>>>(L.ce, px, P.edge_score_threshold, accept_all, L.valid);
+            ctx->timing.kernel_launches += 1;
+            if (p + 1 < levels) {
+                rslf_level& N = ctx->lv[p + 1];
+                RSLF_TRY(launch_downsample(ctx, (const float*)raw, Vp[p], S, Up[p], C, N.raw, Vp[p + 1], Up[p + 1]));
+                const size_t npx = (size_t)S * Vp[p + 1] * Up[p + 1];
+                fill_f32_kernel<<<stream_grid(ctx, npx), 256, 0, ctx->stream>>>(N.dmin, npx, dmin);
+                fill_f32_kernel<<<stream_grid(ctx, npx), 256, 0, ctx->stream>>>(N.dmax, npx, dmax);
+                const int rows = S * Vp[p];
+                nearest_valid_kernel<<<rslf_div_up((long long)rows * 32, 256), 256, 0, ctx->stream>>>(L.valid, rows, Up[p], ctx->nearest_l, ctx->nearest_r);
+                dim3 grid(rslf_div_up(Up[p + 1], 128), Vp[p + 1], S);
+                set_bounds_kernel<<<grid, 128, 0, ctx->stream>>>(L.depth, ctx->nearest_l, ctx->nearest_r, S, Vp[p], Up[p],
+                                                                 Vp[p + 1], Up[p + 1], N.dmin, N.dmax);
+                ctx->timing.kernel_launches += 4;
+            }
+            RSLF_CUDA_TRY(ctx, cudaGetLastError());
+        }
+        ctx->timing.levels += 1;
+    }
+    {
+        stage_scope sc(ctx, ST_PYR);
+        const float* dp[RSLF_MAX_LEVELS]; const uint8_t* vp[RSLF_MAX_LEVELS];
+        for (int p = 0; p < levels; ++p) { dp[p] = ctx->lv[p].depth; vp[p] = ctx->lv[p].valid; }
+        RSLF_TRY(launch_fuse(ctx, levels, Vp, Up, dp, vp, ctx->out_map, ctx->out_valid));
+    }
+    ctx->last_kind = 3;
+    return end_run(ctx, dim_d);
+}
+
+extern "C" int rslf_cuda_fine_to_coarse_get(rslf_ctx* ctx, float* out_map_svu, uint8_t* out_valid_svu)
+{
+    if (!ctx) return RSLF_ERR_ARG;
+    if (ctx->last_kind != 3) { snprintf(ctx->err, sizeof(ctx->err), "no fine-to-coarse result"); return RSLF_ERR_STATE; }
+    RSLF_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t px = (size_t)ctx->S * ctx->V * ctx->U;
+    cudaEventRecord(ctx->ev_a, ctx->stream);
+    RSLF_TRY(copy_out(ctx, out_map_svu, ctx->out_map, px * 4));
+    RSLF_TRY(copy_out(ctx, out_valid_svu, ctx->out_valid, px));
+    cudaEventRecord(ctx->ev_b, ctx->stream);
+    RSLF_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ctx->timing.ms_d2h, ctx->ev_a, ctx->ev_b);
+    return RSLF_OK;
+}
+
+extern "C" int rslf_cuda_fine_to_coarse(rslf_ctx* ctx, float dmin, float dmax, int dim_d, const rslf_params* params,
+                                        int max_pyr_depth, int accept_all_last_scale, float* out_map_svu,
+                                        uint8_t* out_valid_svu)
+{
+    RSLF_TRY(rslf_cuda_fine_to_coarse_run(ctx, dmin, dmax, dim_d, params, max_pyr_depth, accept_all_last_scale));
+    return rslf_cuda_fine_to_coarse_get(ctx, out_map_svu, out_valid_svu);
+}
+
+extern "C" int rslf_cuda_fine_to_coarse_level_dims(const rslf_ctx* ctx, int level, int* V, int* U)
+{
+    if (!ctx) return RSLF_ERR_ARG;
+    if (ctx->last_kind != 3) return RSLF_ERR_STATE;
+    if (level >= 0 && level < ctx->n_levels) {
+        if (V) *V = ctx->lv[level].V;
+        if (U) *U = ctx->lv[level].U;
+    }
+    return ctx->n_levels;
+}
+
+extern "C" int rslf_cuda_fine_to_coarse_get_level(rslf_ctx* ctx, int level, float* best_depth_svu,
+                                                  float* edge_conf_svu, uint8_t* edge_mask_svu, float* disp_conf_svu,
+                                                  float* dmin_svu, float* dmax_svu)
+{
+    if (!ctx) return RSLF_ERR_ARG;
+    if (ctx->last_kind != 3 || level < 0 || level >= ctx->n_levels) return RSLF_ERR_STATE;
+    RSLF_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    return get_level_maps(ctx, level, best_depth_svu, edge_conf_svu, edge_mask_svu, disp_conf_svu, nullptr, dmin_svu, dmax_svu);
+}
+
+/* ------------------------------------------------------------------ free functions */
+extern "C" int rslf_cuda_edge_confidence(rslf_ctx* ctx, int s, const rslf_params* params, float* edge_conf_vu,
+                                         uint8_t* edge_mask_vu)
+{
+    if (!ctx || !params) return RSLF_ERR_ARG;
+    if (!ctx->have_input) return RSLF_ERR_STATE;
+    if (s < 0 || s >= ctx->S) return RSLF_ERR_ARG;
+    RSLF_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    RSLF_TRY(ensure_scratch(ctx, false, false));
+    RSLF_TRY(ensure_level(ctx, 0, ctx->V, ctx->U, false, false));
+    ctx->last_kind = 0;
+    RSLF_TRY(normalise_level(ctx, 0, ctx->raw_in, ctx->cv_depth));
+    rslf_level& L = ctx->lv[0];
+    RSLF_TRY(launch_edge_confidence(ctx, L.epi, ctx->V, ctx->S, ctx->U, ctx->C, s, 1, *params, L.ce, L.emask));
+    const size_t plane = (size_t)ctx->V * ctx->U;
+    RSLF_TRY(copy_out(ctx, edge_conf_vu, L.ce, plane * 4));
+    RSLF_TRY(copy_out(ctx, edge_mask_vu, L.emask, plane));
+    RSLF_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return RSLF_OK;
+}
+
+extern "C" int rslf_cuda_selective_median(rslf_ctx* ctx, const float* src_vu, const uint8_t* mask_vu, int s_hat,
+                                          int size, float epsilon, float* dst_vu)
+{
+    if (!ctx || !src_vu || !mask_vu || !dst_vu) return RSLF_ERR_ARG;
+    if (!ctx->have_input) return RSLF_ERR_STATE;
+    if (s_hat < 0 || s_hat >= ctx->S) return RSLF_ERR_ARG;
+    RSLF_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    RSLF_TRY(ensure_scratch(ctx, false, false));
+    RSLF_TRY(ensure_level(ctx, 0, ctx->V, ctx->U, false, false));
+    ctx->last_kind = 0;
+    RSLF_TRY(normalise_level(ctx, 0, ctx->raw_in, ctx->cv_depth));
+    rslf_level& L = ctx->lv[0];
+    const size_t plane = (size_t)ctx->V * ctx->U;
+    RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->pile_depth_raw, src_vu, plane * 4, cudaMemcpyHostToDevice, ctx->stream));
+    RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(L.emask, mask_vu, plane, cudaMemcpyHostToDevice, ctx->stream));
+    RSLF_TRY(launch_selective_median(ctx, ctx->pile_depth_raw, L.emask, L.epi + (size_t)s_hat * ctx->U * ctx->C,
+                                     (size_t)ctx->S * ctx->U * ctx->C, ctx->V, ctx->U, ctx->C, size, epsilon, ctx->filtered));
+    RSLF_TRY(copy_out(ctx, dst_vu, ctx->filtered, plane * 4));
+    RSLF_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return RSLF_OK;
+}
+
+extern "C" int rslf_cuda_downsample_epis(rslf_ctx* ctx, const float* in_epis, int V, int S, int U, int C,
+                                         float* out_epis, int* V2o, int* U2o)
+{
+    if (!ctx || !in_epis || !out_epis || (C != 1 && C != 3) || V < 1 || S < 1 || U < 1) return RSLF_ERR_ARG;
+    RSLF_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int V2 = cv_round_half(V), U2 = cv_round_half(U);
+    if (V2o) *V2o = V2;
+    if (U2o) *U2o = U2;
+    if (V2 < 1 || U2 < 1) return RSLF_ERR_ARG;
+    float *din = nullptr, *dout = nullptr;
+    const size_t nin = (size_t)V * S * U * C, nout = (size_t)V2 * S * U2 * C;
+    RSLF_TRY(dev_alloc(ctx, &din, nin));
+    int rc = dev_alloc(ctx, &dout, nout);
+    if (rc == RSLF_OK) {
+        cudaMemcpyAsync(din, in_epis, nin * 4, cudaMemcpyHostToDevice, ctx->stream);
+        rc = launch_downsample(ctx, din, V, S, U, C, dout, V2, U2);
+        if (rc == RSLF_OK) {
+            cudaMemcpyAsync(out_epis, dout, nout * 4, cudaMemcpyDeviceToHost, ctx->stream);
+            if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = RSLF_ERR_CUDA;
+        }
+    }
+    dev_free(&din); dev_free(&dout);
+    return rc;
+}
+
+extern "C" int rslf_cuda_set_bounds(rslf_ctx* ctx, const float* depth_up, const uint8_t* valid_up, int S, int Vu, int Uu,
+                                    int Vd, int Ud, float* dmin_map, float* dmax_map)
+{
+    if (!ctx || !depth_up || !valid_up || !dmin_map || !dmax_map) return RSLF_ERR_ARG;
+    RSLF_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t nu = (size_t)S * Vu * Uu, nd = (size_t)S * Vd * Ud;
+    float *d_dep = nullptr, *d_mn = nullptr, *d_mx = nullptr; uint8_t* d_val = nullptr; int *d_l = nullptr, *d_r = nullptr;
+    int rc = dev_alloc(ctx, &d_dep, nu);
+    if (rc == RSLF_OK) rc = dev_alloc(ctx, &d_val, nu);
+    if (rc == RSLF_OK) rc = dev_alloc(ctx, &d_l, nu);
+    if (rc == RSLF_OK) rc = dev_alloc(ctx, &d_r, nu);
+    if (rc == RSLF_OK) rc = dev_alloc(ctx, &d_mn, nd);
+    if (rc == RSLF_OK) rc = dev_alloc(ctx, &d_mx, nd);
+    if (rc == RSLF_OK) {
+        cudaMemcpyAsync(d_dep, depth_up, nu * 4, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(d_val, valid_up, nu, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(d_mn, dmin_map, nd * 4, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(d_mx, dmax_map, nd * 4, cudaMemcpyHostToDevice, ctx->stream);
+        const int rows = S * Vu;
+        nearest_valid_kernel<<<rslf_div_up((long long)rows * 32, 256), 256, 0, ctx->stream>>>(d_val, rows, Uu, d_l, d_r);
+        dim3 grid(rslf_div_up(Ud, 128), Vd, S);
+        set_bounds_kernel<<<grid, 128, 0, ctx->stream>>>(d_dep, d_l, d_r, S, Vu, Uu, Vd, Ud, d_mn, d_mx);
+        cudaMemcpyAsync(dmin_map, d_mn, nd * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaMemcpyAsync(dmax_map, d_mx, nd * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) rc = RSLF_ERR_CUDA;
+    }
+    dev_free(&d_dep); dev_free(&d_val); dev_free(&d_l); dev_free(&d_r); dev_free(&d_mn); dev_free(&d_mx);
+    return rc;
+}
+
+extern "C" int rslf_cuda_fuse_disp_maps(rslf_ctx* ctx, int levels, int S, const int* Vp, const int* Up,
+                                        const float* const* disp_p, const uint8_t* const* valid_p,
+                                        float* out_map_svu, uint8_t* out_valid_svu)
+{
+    if (!ctx || levels < 1 || levels > RSLF_MAX_LEVELS || !Vp || !Up || !disp_p || !valid_p) return RSLF_ERR_ARG;
+    RSLF_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    std::vector<float*> dd(levels, nullptr); std::vector<uint8_t*> dv(levels, nullptr);
+    const size_t px0 = (size_t)S * Vp[0] * Up[0];
+    float *fa = nullptr, *fb = nullptr, *om = nullptr; uint8_t *ma = nullptr, *mb = nullptr, *ov = nullptr;
+    int rc = RSLF_OK;
+    for (int p = 0; p < levels && rc == RSLF_OK; ++p) {
+        const size_t px = (size_t)S * Vp[p] * Up[p];
+        rc = dev_alloc(ctx, &dd[p], px);
+        if (rc == RSLF_OK) rc = dev_alloc(ctx, &dv[p], px);
+        if (rc == RSLF_OK) {
+            cudaMemcpyAsync(dd[p], disp_p[p], px * 4, cudaMemcpyHostToDevice, ctx->stream);
+            cudaMemcpyAsync(dv[p], valid_p[p], px, cudaMemcpyHostToDevice, ctx->stream);
+        }
+    }
+    if (rc == RSLF_OK) rc = dev_alloc(ctx, &fa, px0);
+    if (rc == RSLF_OK) rc = dev_alloc(ctx, &fb, px0);
+    if (rc == RSLF_OK) rc = dev_alloc(ctx, &ma, px0);
+    if (rc == RSLF_OK) rc = dev_alloc(ctx, &mb, px0);
+    if (rc == RSLF_OK) rc = dev_alloc(ctx, &om, px0);
+    if (rc == RSLF_OK) rc = dev_alloc(ctx, &ov, px0);
+    if (rc == RSLF_OK) {
+        /* temporarily borrow the ctx fuse buffers' slots */
+        float* sa = ctx->fuse_a; float* sb = ctx->fuse_b; uint8_t* sma = ctx->fuse_ma; uint8_t* smb = ctx->fuse_mb; int sS = ctx->S;
+        ctx->fuse_a = fa; ctx->fuse_b = fb; ctx->fuse_ma = ma; ctx->fuse_mb = mb; ctx->S = S;
+        rc = launch_fuse(ctx, levels, Vp, Up, dd.data(), dv.data(), om, ov);
+        ctx->fuse_a = sa; ctx->fuse_b = sb; ctx->fuse_ma = sma; ctx->fuse_mb = smb; ctx->S = sS;
+        if (rc == RSLF_OK) {
+            if (out_map_svu) cudaMemcpyAsync(out_map_svu, om, px0 * 4, cudaMemcpyDeviceToHost, ctx->stream);
+            if (out_valid_svu) cudaMemcpyAsync(out_valid_svu, ov, px0, cudaMemcpyDeviceToHost, ctx->stream);
+            if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = RSLF_ERR_CUDA;
+        }
+    }
+    for (int p = 0; p < levels; ++p) { dev_free(&dd[p]); dev_free(&dv[p]); }
+    dev_free(&fa); dev_free(&fb); dev_free(&ma); dev_free(&mb); dev_free(&om); dev_free(&ov);
+    return rc;
+}
+
+/* ------------------------------------------------------------------ measurement */
+extern "C" int rslf_cuda_measure_fp32_peak(rslf_ctx* ctx, double* gops_nofma, double* gflops_fma)
+{
+    if (!ctx) return RSLF_ERR_ARG;
+    RSLF_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    return measure_fp32_peak(ctx, gops_nofma, gflops_fma);
+}

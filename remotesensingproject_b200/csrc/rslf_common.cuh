@@ -1,0 +1,173 @@
+/*
+ * rslf_common.cuh — shared definitions of the sm_100a EPI depth library.
+ *
+ * Layouts (all dense, device memory):
+ *   EPI stacks  [V][S][U][C] float32  (the reference's Vec<Mat> epis: V Mats of S x U x C,
+ *                                      RSLightFields/src/rslf_io.cpp:194-227)
+ *   maps        [S][V][U]   float32 / uint8 (masks are 0 / 255)
+ * The whole library is compiled with -fmad=false: the reference rounds after
+ * every OpenCV operation, so no multiply-add may be contracted.
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/rslf_b200.h"
+
+#define RSLF_MAX_LEVELS 24
+
+struct rslf_level {
+    int V = 0, U = 0;
+    float* raw = nullptr;        /* un-normalised float stack (levels > 0, or float input)  */
+    float* epi = nullptr;        /* normalised stack [V][S][U][C]                             */
+    float* ce = nullptr;         /* edge confidence            [S][V][U]                      */
+    float* cd = nullptr;         /* disparity confidence       [S][V][U]                      */
+    float* depth = nullptr;      /* best depth                 [S][V][U]                      */
+    float* rbar = nullptr;       /* mean-shift radiance        [S][V][U][C]                   */
+    float* dmin = nullptr;       /* per-pixel bounds           [S][V][U]  (levels > 0 / edit) */
+    float* dmax = nullptr;
+    uint8_t* emask = nullptr;    /* edge-confidence mask       [S][V][U]                      */
+    uint8_t* remaining = nullptr;/* "still to compute" mask    [S][V][U]                      */
+    uint8_t* valid = nullptr;    /* validity mask for bounds / fuse [S][V][U]                 */
+    float slope = 1.f;
+    int nonneg = 1;              /* normalised stack has no negative value                    */
+    bool have_bounds = false;
+    size_t cap_px = 0;           /* allocated S*V*U                                           */
+};
+
+struct rslf_stage_clock {
+    std::vector<cudaEvent_t> pool;
+    size_t used = 0;
+    struct span { int stage; size_t a, b; };
+    std::vector<span> spans;
+};
+
+enum { ST_EDGE = 0, ST_DEPTH, ST_REDUCE, ST_MEDIAN, ST_PROP, ST_PYR, ST_COUNT };
+
+struct rslf_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int num_sm = 0;
+    size_t smem_optin = 0;
+    char err[512] = {0};
+
+    /* input */
+    int V = 0, S = 0, U = 0, C = 0, cv_depth = RSLF_DEPTH_32F;
+    float scale_factor = -1.f;
+    void* raw_in = nullptr;      /* level-0 raw stack as uploaded (u8 or f32), owned unless borrowed */
+    bool raw_borrowed = false;
+    size_t raw_cap = 0;
+    bool have_input = false;
+    int v0 = 0, V_total = 0;     /* row shard */
+
+    /* levels */
+    int n_levels = 0;
+    rslf_level lv[RSLF_MAX_LEVELS];
+
+    /* scratch */
+    int* items = nullptr;        /* compacted pixel list of a pass                            */
+    int* count = nullptr;        /* [0] = items in list; device scalar                        */
+    unsigned long long* total_px = nullptr;  /* accumulated computed pixels                   */
+    float* filtered = nullptr;   /* selective-median output plane [V][U]                      */
+    int* winner = nullptr;       /* propagation arbitration [S][V][U], INT_MAX when idle      */
+    int* arrive = nullptr;       /* per-item chunk arrival counters                           */
+    void* partials = nullptr;    /* per-(item, chunk) partial argmax records                  */
+    size_t partials_cap = 0;
+    int* nearest_l = nullptr;    /* bounds scratch [S][V][U]                                  */
+    int* nearest_r = nullptr;
+    float* minmax = nullptr;     /* [0]=max, [1]=min of a stack                               */
+    float* fuse_a = nullptr; float* fuse_b = nullptr;  /* fuse ping-pong maps [S][V][U]       */
+    uint8_t* fuse_ma = nullptr; uint8_t* fuse_mb = nullptr;
+    float* out_map = nullptr; uint8_t* out_valid = nullptr;
+    size_t scratch_px = 0;       /* S*V*U the scratch was sized for                           */
+    void* l2_flush = nullptr;
+    float* pile_depth_raw = nullptr;  /* 1D pile: unfiltered depth plane                      */
+
+    /* results state */
+    int last_kind = 0;           /* 1 = pile, 2 = depth2d, 3 = fine-to-coarse                 */
+    int pile_s_hat = 0;
+
+    /* timing */
+    rslf_timing timing;
+    int stage_timing = 1;
+    rslf_stage_clock clk;
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
+
+    /* NCCL (resolved lazily with dlopen; see rslf_comm.cuh) */
+    void* nccl_lib = nullptr;
+    void* nccl_comm = nullptr;
+    int rank = 0, world = 1;
+};
+
+#define RSLF_CUDA_TRY(ctx, call)                                                          \
+    do {                                                                                  \
+        cudaError_t _e = (call);                                                          \
+        if (_e != cudaSuccess) {                                                          \
+            snprintf((ctx)->err, sizeof((ctx)->err), "%s:%d: %s -> %s", __FILE__,         \
+                     __LINE__, #call, cudaGetErrorString(_e));                            \
+            return RSLF_ERR_CUDA;                                                         \
+        }                                                                                 \
+    } while (0)
+
+#define RSLF_TRY(call)                    \
+    do {                                  \
+        int _r = (call);                  \
+        if (_r != RSLF_OK) return _r;     \
+    } while (0)
+
+static inline int rslf_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+/*
+ * The reference compares float(sqrt(double sum of squares)) < eps
+ * (rslf_types.cpp:86-91).  sqrt and the float rounding are monotone, so the
+ * test equals  sum < T  for the smallest double T with float(sqrt(T)) >= eps.
+ * Found by bisection over the (ordered) bit patterns of positive doubles.
+ */
+static inline double rslf_sq_threshold(float eps) {
+    if (!(eps > 0.f)) return 0.0;          /* nothing is < eps */
+    uint64_t lo = 0, hi = 0x7ff0000000000000ULL;   /* f(0) true, f(inf) false */
+    while (hi - lo > 1) {
+        uint64_t mid = lo + (hi - lo) / 2;
+        double s; memcpy(&s, &mid, 8);
+        bool lt = (float)__builtin_sqrt(s) < eps;
+        if (lt) lo = mid; else hi = mid;
+    }
+    double T; memcpy(&T, &hi, 8);
+    return T;
+}
+
+/* device helpers ---------------------------------------------------------- */
+#ifdef __CUDACC__
+/* norm<float>(x) = float(abs(x) * 1.73205080757) (rslf_types.cpp:80-84) */
+__device__ __forceinline__ bool rslf_norm1_lt(float x, float eps) {
+    return (float)((double)fabsf(x) * 1.73205080757) < eps;
+}
+/* norm<Vec3f> < eps via the squared-sum threshold (see rslf_sq_threshold) */
+__device__ __forceinline__ bool rslf_norm3_lt(float x, float y, float z, double T) {
+    double s = (double)x * (double)x;
+    s = fma((double)y, (double)y, s);      /* the product of two floats is exact in double */
+    s = fma((double)z, (double)z, s);
+    return s < T;
+}
+template <int C>
+__device__ __forceinline__ bool rslf_norm_diff_lt(const float* a, const float* b, float eps, double T) {
+    if (C == 1) return rslf_norm1_lt(a[0] - b[0], eps);
+    return rslf_norm3_lt(a[0] - b[0], a[1] - b[1], a[2] - b[2], T);
+}
+/* cv::BORDER_REFLECT_101 */
+__device__ __forceinline__ int rslf_reflect101(int p, int n) {
+    if (n == 1) return 0;
+    while (p < 0 || p >= n) p = (p < 0) ? -p : 2 * n - 2 - p;
+    return p;
+}
+/* cv::BORDER_REFLECT */
+__device__ __forceinline__ int rslf_reflect(int p, int n) {
+    if (n == 1) return 0;
+    while (p < 0 || p >= n) p = (p < 0) ? -p - 1 : 2 * n - 1 - p;
+    return p;
+}
+#endif

@@ -1,0 +1,75 @@
+"""Pins the CPU oracle (oracle/rslf_oracle.cpp) against the cv2 replay of the
+reference's OpenCV call sequence (oracle/cv2_mirror.py -> tests/golden/*.npz).
+
+Masks and argmax indices must agree exactly; floats to 1e-6: cv2 4.13's
+multiply(a, a, scale) keeps a double intermediate where OpenCV 3.x (the
+reference's version) rounds per float operation, so the last ulp may differ.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+
+
+def _cases(golden_dir, pat):
+    return sorted(glob.glob(os.path.join(golden_dir, pat)))
+
+
+HERE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("path", _cases(HERE, "px_*.npz"), ids=os.path.basename)
+def test_edge_confidence_and_pixel_scores(path):
+    g = np.load(path)
+    epi = g["epi"]
+    s_hat = int(g["s_hat"])
+    ce, mask = oracle.edge_confidence(epi[None], s_hat)
+    np.testing.assert_array_equal(mask[0], g["mask"])
+    np.testing.assert_allclose(ce[0], g["ce"], rtol=1e-6, atol=1e-7)
+    for i, u in enumerate(g["us"]):
+        sc, rb, dv = oracle.pixel_scores(epi, s_hat, int(u), float(g["dmin"]), float(g["dmax"]), int(g["D"]))
+        np.testing.assert_array_equal(dv, g["dvals"][i])
+        np.testing.assert_allclose(sc, g["score"][i], rtol=0, atol=1e-6)
+        np.testing.assert_allclose(rb, g["rbar"][i], rtol=0, atol=1e-6)
+        # first maximum, like cv::minMaxLoc
+        assert int(np.argmax(sc)) == int(g["best"][i])
+        assert abs(float(sc.max()) - float(g["maxv"][i])) < 1e-6
+        assert abs(float(sc.astype(np.float64).mean()) - float(g["mean"][i])) < 1e-6
+
+
+@pytest.mark.parametrize("path", _cases(HERE, "down_*.npz"), ids=os.path.basename)
+def test_downsample(path):
+    g = np.load(path)
+    out = oracle.downsample(g["raw"])
+    assert out.shape == g["out"].shape
+    np.testing.assert_allclose(out, g["out"], rtol=5e-7, atol=0)
+
+
+def test_fuse(golden_dir):
+    g = np.load(os.path.join(golden_dir, "fuse_3lvl.npz"))
+    m, k = oracle.fuse([g["d0"], g["d1"], g["d2"]], [g["v0"], g["v1"], g["v2"]])
+    np.testing.assert_array_equal(k, g["out_valid"])
+    np.testing.assert_allclose(m, g["out_map"], rtol=0, atol=5e-6)
+
+
+def test_visiting_order_quirk():
+    # even S: line 0 is never a s_hat (core.hpp:981-990); odd S: every line once
+    assert oracle.visiting_order(6) == [3, 4, 2, 5, 1]
+    assert oracle.visiting_order(5) == [2, 3, 1, 4, 0]
+    assert sorted(oracle.visiting_order(9)) == list(range(9))
+
+
+def test_pyramid_dims_round_half_even():
+    # cvRound(n * 0.5): 135 -> 68, 75 -> 38, 45 -> 22, 33 -> 16
+    assert [oracle.half_size(n) for n in (135, 75, 45, 33, 17, 9)] == [68, 38, 22, 16, 8, 4]
+    assert oracle.pyramid_dims(600, 1200) == [(600, 1200), (300, 600), (150, 300), (75, 150), (38, 75), (19, 38)]
+    assert oracle.pyramid_dims(1080, 1920)[-1] == (17, 30)
+
+
+def test_constants():
+    p = oracle.default_params()
+    assert np.float32(p.shadow_level) == np.float32(0.05 * 1.73205080757)
+    assert np.float32(1.0 / float(np.float32(0.2) * np.float32(0.2))) == np.float32(24.999998)
