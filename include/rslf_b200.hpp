@@ -1,0 +1,411 @@
+/*
+ * rslf_b200.hpp — C++ host side of the B200-native EPI depth path.
+ *
+ * Header-only mirror of the reference's depth-computer / fine-to-coarse classes
+ * (RSLightFields/include/rslf_depth_computation.hpp: Depth1DComputer_pile :93-143,
+ * Depth2DComputer :166-229; rslf_fine_to_coarse.hpp: FineToCoarse :26-81;
+ * parameter block rslf_depth_computation_core.hpp:66-142) on top of the C ABI of
+ * rslf_b200.h.  Same class names, constructor arguments, run() / getters and
+ * result members, in namespace rslf_b200 so both can live in one program; a
+ * maintainer switches a call site by changing the namespace.
+ *
+ * cv::Mat: when <opencv2/core.hpp> is available the classes take and return
+ * cv::Mat / std::vector<cv::Mat> exactly like the reference.  This build image
+ * has no OpenCV C++ package, so otherwise a minimal layout-compatible stand-in
+ * (rows, cols, type, data, step, reference-counted storage) is used.
+ *
+ * Errors: the reference has no error codes of its own (only cv::Exception from
+ * OpenCV asserts); here every failing C-ABI call throws rslf_b200::Error carrying
+ * the code and the library's message.  There is no CPU fallback.
+ */
+#ifndef RSLF_B200_HPP
+#define RSLF_B200_HPP
+
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "rslf_b200.h"
+
+#if defined(__has_include)
+#if __has_include(<opencv2/core.hpp>) && !defined(RSLF_B200_NO_OPENCV)
+#include <opencv2/core.hpp>
+#define RSLF_B200_HAVE_OPENCV 1
+#endif
+#endif
+
+namespace rslf_b200
+{
+
+#ifdef RSLF_B200_HAVE_OPENCV
+using Mat = cv::Mat;
+using Vec3f = cv::Vec3f;
+#else
+/* ---- minimal cv::Mat stand-in (layout-compatible subset) ---- */
+#ifndef CV_8U
+#define CV_8U 0
+#define CV_32F 5
+#define CV_CN_SHIFT 3
+#define CV_MAKETYPE(depth, cn) (((depth) & 7) + (((cn) - 1) << CV_CN_SHIFT))
+#define CV_8UC1 CV_MAKETYPE(CV_8U, 1)
+#define CV_8UC3 CV_MAKETYPE(CV_8U, 3)
+#define CV_32FC1 CV_MAKETYPE(CV_32F, 1)
+#define CV_32FC3 CV_MAKETYPE(CV_32F, 3)
+#endif
+struct Vec3f { float val[3]; float& operator[](int i) { return val[i]; } const float& operator[](int i) const { return val[i]; } };
+
+class Mat
+{
+public:
+    int rows = 0, cols = 0;
+    unsigned char* data = nullptr;
+    size_t step = 0;                       /* bytes between rows */
+
+    Mat() {}
+    Mat(int a_rows, int a_cols, int a_type) { create(a_rows, a_cols, a_type); }
+    /* header over user memory (not owned), like cv::Mat(rows, cols, type, data, step) */
+    Mat(int a_rows, int a_cols, int a_type, void* a_data, size_t a_step = 0)
+        : rows(a_rows), cols(a_cols), data((unsigned char*)a_data), m_type(a_type)
+    {
+        step = a_step ? a_step : (size_t)a_cols * elemSize();
+    }
+    void create(int a_rows, int a_cols, int a_type)
+    {
+        rows = a_rows; cols = a_cols; m_type = a_type;
+        step = (size_t)cols * elemSize();
+        m_store = std::shared_ptr<unsigned char>(new unsigned char[step * (size_t)rows](), std::default_delete<unsigned char[]>());
+        data = m_store.get();
+    }
+    static Mat zeros(int a_rows, int a_cols, int a_type) { return Mat(a_rows, a_cols, a_type); }
+    int type() const { return m_type; }
+    int depth() const { return m_type & 7; }
+    int channels() const { return (m_type >> CV_CN_SHIFT) + 1; }
+    size_t elemSize1() const { return depth() == CV_8U ? 1 : 4; }
+    size_t elemSize() const { return elemSize1() * channels(); }
+    bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
+    bool isContinuous() const { return step == (size_t)cols * elemSize(); }
+    template <typename T> T* ptr(int r = 0) { return (T*)(data + (size_t)r * step); }
+    template <typename T> const T* ptr(int r = 0) const { return (const T*)(data + (size_t)r * step); }
+    template <typename T> T& at(int r, int c) { return ptr<T>(r)[c]; }
+    template <typename T> const T& at(int r, int c) const { return ptr<T>(r)[c]; }
+    Mat clone() const
+    {
+        Mat m(rows, cols, m_type);
+        for (int r = 0; r < rows; ++r) std::memcpy(m.data + (size_t)r * m.step, data + (size_t)r * step, (size_t)cols * elemSize());
+        return m;
+    }
+private:
+    int m_type = 0;
+    std::shared_ptr<unsigned char> m_store;
+};
+#endif /* RSLF_B200_HAVE_OPENCV */
+
+template <typename T> using Vec = std::vector<T>;
+
+class Error : public std::runtime_error
+{
+public:
+    Error(int a_code, const std::string& a_what) : std::runtime_error(a_what), code(a_code) {}
+    int code;
+};
+
+/* channel count of the template argument: float -> 1, Vec3f -> 3 */
+template <typename DataType> struct channels_of;
+template <> struct channels_of<float> { enum { value = 1 }; };
+template <> struct channels_of<Vec3f> { enum { value = 3 }; };
+
+/*
+ * rslf::Depth1DParameters<DataType> (core.hpp:66-142).  The interpolation class
+ * is always the linear one and the kernel class BandwidthKernel(h) — the only
+ * ones the reference instantiates (core.hpp:76-78) — so the two class pointers
+ * are replaced by the bandwidth h.
+ */
+template <typename DataType>
+struct Depth1DParameters
+{
+    Depth1DParameters()
+    {
+        rslf_params p;
+        rslf_params_default(&p);
+        par_edge_score_threshold = p.edge_score_threshold;
+        par_line_score_threshold = p.line_score_threshold;
+        par_disp_score_threshold = p.disp_score_threshold;
+        par_raw_score_threshold = p.raw_score_threshold;
+        par_mean_shift_max_iter = (float)p.mean_shift_max_iter;
+        par_edge_confidence_filter_size = p.edge_confidence_filter_size;
+        par_edge_confidence_opening_type = p.edge_confidence_opening_type;
+        par_edge_confidence_opening_size = p.edge_confidence_opening_size;
+        par_median_filter_size = p.median_filter_size;
+        par_median_filter_epsilon = p.median_filter_epsilon;
+        par_propagation_epsilon = p.propagation_epsilon;
+        par_slope_factor = p.slope_factor;
+        par_cut_shadows = p.cut_shadows != 0;
+        par_shadow_level = p.shadow_level;
+        par_kernel_bandwidth = p.kernel_h;
+    }
+    float par_edge_score_threshold;
+    float par_line_score_threshold;
+    float par_disp_score_threshold;
+    float par_raw_score_threshold;
+    float par_mean_shift_max_iter;        /* a float in the reference too (core.hpp:115) */
+    int par_edge_confidence_filter_size;
+    int par_edge_confidence_opening_type;
+    int par_edge_confidence_opening_size;
+    int par_median_filter_size;
+    float par_median_filter_epsilon;
+    float par_propagation_epsilon;
+    float par_slope_factor;
+    bool par_cut_shadows;
+    float par_shadow_level;
+    float par_kernel_bandwidth;           /* BandwidthKernel(h), rslf_kernels.hpp:43 */
+
+    static Depth1DParameters& get_default() { static Depth1DParameters s_default; return s_default; }
+
+    rslf_params to_abi() const
+    {
+        rslf_params p;
+        p.edge_score_threshold = par_edge_score_threshold; p.line_score_threshold = par_line_score_threshold;
+        p.disp_score_threshold = par_disp_score_threshold; p.raw_score_threshold = par_raw_score_threshold;
+        p.mean_shift_max_iter = (int)par_mean_shift_max_iter;
+        p.edge_confidence_filter_size = par_edge_confidence_filter_size;
+        p.edge_confidence_opening_type = par_edge_confidence_opening_type;
+        p.edge_confidence_opening_size = par_edge_confidence_opening_size;
+        p.median_filter_size = par_median_filter_size; p.median_filter_epsilon = par_median_filter_epsilon;
+        p.propagation_epsilon = par_propagation_epsilon; p.slope_factor = par_slope_factor;
+        p.cut_shadows = par_cut_shadows ? 1 : 0; p.shadow_level = par_shadow_level; p.kernel_h = par_kernel_bandwidth;
+        return p;
+    }
+};
+
+namespace detail
+{
+/* one rslf_ctx with RAII + error translation */
+class Device
+{
+public:
+    explicit Device(int a_device = 0) { check(rslf_cuda_create(a_device, &m_ctx), "rslf_cuda_create"); }
+    ~Device() { if (m_ctx) rslf_cuda_destroy(m_ctx); }
+    Device(const Device&) = delete;
+    Device& operator=(const Device&) = delete;
+    rslf_ctx* get() const { return m_ctx; }
+    void check(int a_rc, const char* a_what) const
+    {
+        if (a_rc == RSLF_OK) return;
+        std::string msg = std::string(a_what) + ": " + rslf_cuda_strerror(a_rc);
+        if (m_ctx) { msg += ": "; msg += rslf_cuda_last_error_text(m_ctx); }
+        throw Error(a_rc, msg);
+    }
+    /* the reference ctors' input handling (dc.hpp:425-477, 651-704): V Mats of S x U x C */
+    void upload(const Vec<Mat>& a_epis, float a_scale, int a_channels, int& V, int& S, int& U)
+    {
+        if (a_epis.empty() || a_epis[0].empty()) throw Error(RSLF_ERR_ARG, "empty EPI vector");
+        V = (int)a_epis.size(); S = a_epis[0].rows; U = a_epis[0].cols;
+        const int depth = a_epis[0].depth();
+        std::vector<const void*> ptrs(V);
+        for (int v = 0; v < V; ++v) {
+            const Mat& m = a_epis[v];
+            if (m.rows != S || m.cols != U || m.channels() != a_channels || m.depth() != depth || (size_t)m.step != (size_t)a_epis[0].step)
+                throw Error(RSLF_ERR_ARG, "EPIs must share size, type and step, and match the class's channel count");
+            ptrs[v] = m.data;
+        }
+        check(rslf_cuda_upload_epis(m_ctx, ptrs.data(), V, S, U, a_channels, depth, (size_t)a_epis[0].step, a_scale),
+              "rslf_cuda_upload_epis");
+    }
+private:
+    rslf_ctx* m_ctx = nullptr;
+};
+
+inline Vec<Mat> planes(int S, int V, int U, int type) { Vec<Mat> v(S); for (auto& m : v) m = Mat::zeros(V, U, type); return v; }
+/* dense [S][V][U] staging <-> S Mats */
+template <typename T>
+inline void scatter(const std::vector<T>& a_buf, Vec<Mat>& a_mats, int V, size_t a_row_elems)
+{
+    for (size_t s = 0; s < a_mats.size(); ++s)
+        for (int v = 0; v < V; ++v)
+            std::memcpy(a_mats[s].template ptr<T>(v), a_buf.data() + ((size_t)s * V + v) * a_row_elems, a_row_elems * sizeof(T));
+}
+} // namespace detail
+
+/* ---------------------------------------------------------------- Depth1DComputer_pile */
+template <typename DataType>
+class Depth1DComputer_pile
+{
+public:
+    Depth1DComputer_pile(const Vec<Mat>& epis, float dmin, float dmax, int dim_d, int s_hat = -1,
+                         float epi_scale_factor = -1,
+                         const Depth1DParameters<DataType>& parameters = Depth1DParameters<DataType>::get_default(),
+                         int device = 0)
+        : m_parameters(parameters), m_device(new detail::Device(device)), m_dim_d(dim_d), m_dmin(dmin), m_dmax(dmax)
+    {
+        m_device->upload(epis, epi_scale_factor, channels_of<DataType>::value, m_dim_v, m_dim_s, m_dim_u);
+        /* s_hat defaults to floor(S/2) (dc.hpp:489-498) */
+        m_s_hat = (s_hat < 0 || s_hat > m_dim_s - 1) ? (int)std::floor((0.0 + m_dim_s) / 2) : s_hat;
+    }
+    void run()
+    {
+        const int C = channels_of<DataType>::value;
+        rslf_params p = m_parameters.to_abi();
+        m_best_depth_v_u = Mat::zeros(m_dim_v, m_dim_u, CV_32FC1);
+        m_edge_confidence_v_u = Mat::zeros(m_dim_v, m_dim_u, CV_32FC1);
+        m_edge_confidence_mask_v_u = Mat::zeros(m_dim_v, m_dim_u, CV_8UC1);
+        m_disp_confidence_v_u = Mat::zeros(m_dim_v, m_dim_u, CV_32FC1);
+        m_rbar_v_u = Mat::zeros(m_dim_v, m_dim_u, CV_MAKETYPE(CV_32F, C));
+        m_device->check(rslf_cuda_depth1d_pile(m_device->get(), m_dmin, m_dmax, m_dim_d, m_s_hat, &p,
+                                               m_best_depth_v_u.template ptr<float>(), m_edge_confidence_v_u.template ptr<float>(),
+                                               m_edge_confidence_mask_v_u.template ptr<unsigned char>(),
+                                               m_disp_confidence_v_u.template ptr<float>(), m_rbar_v_u.template ptr<float>()),
+                        "rslf_cuda_depth1d_pile");
+    }
+    int get_s_hat() { return m_s_hat; }
+    rslf_timing get_timing() const { rslf_timing t; rslf_cuda_last_timing(m_device->get(), &t); return t; }
+
+    /* private in the reference (dc.hpp:124-140); exposed here because they are the results */
+    Mat m_edge_confidence_v_u, m_edge_confidence_mask_v_u, m_disp_confidence_v_u, m_rbar_v_u, m_best_depth_v_u;
+
+private:
+    const Depth1DParameters<DataType>& m_parameters;     /* held by reference, as in the reference (dc.hpp:142) */
+    std::unique_ptr<detail::Device> m_device;
+    int m_dim_d, m_dim_v = 0, m_dim_s = 0, m_dim_u = 0, m_s_hat = 0;
+    float m_dmin, m_dmax;
+};
+using Depth1DComputer_pile_1ch = Depth1DComputer_pile<float>;
+using Depth1DComputer_pile_3ch = Depth1DComputer_pile<Vec3f>;
+
+/* ---------------------------------------------------------------- Depth2DComputer */
+template <typename DataType>
+class Depth2DComputer
+{
+public:
+    Depth2DComputer(const Vec<Mat>& epis, float dmin, float dmax, int dim_d, float epi_scale_factor = -1,
+                    const Depth1DParameters<DataType>& parameters = Depth1DParameters<DataType>::get_default(),
+                    bool verbose = true, int device = 0)
+        : m_parameters(parameters), m_device(new detail::Device(device)), m_dim_d(dim_d), m_dmin(dmin), m_dmax(dmax),
+          m_verbose(verbose)
+    {
+        m_device->upload(epis, epi_scale_factor, channels_of<DataType>::value, m_dim_v, m_dim_s, m_dim_u);
+    }
+    void run()
+    {
+        const int C = channels_of<DataType>::value;
+        const int S = m_dim_s, V = m_dim_v, U = m_dim_u;
+        rslf_params p = m_parameters.to_abi();
+        const size_t px = (size_t)S * V * U;
+        std::vector<float> lo, hi;
+        if (!m_dmin_s_v_u.empty()) {
+            lo.resize(px); hi.resize(px);
+            for (int s = 0; s < S; ++s)
+                for (int v = 0; v < V; ++v) {
+                    std::memcpy(&lo[((size_t)s * V + v) * U], m_dmin_s_v_u[s].template ptr<float>(v), U * sizeof(float));
+                    std::memcpy(&hi[((size_t)s * V + v) * U], m_dmax_s_v_u[s].template ptr<float>(v), U * sizeof(float));
+                }
+        }
+        std::vector<float> depth(px), ce(px), cd(px), rbar(px * C);
+        std::vector<unsigned char> mask(px);
+        m_device->check(rslf_cuda_depth2d(m_device->get(), m_dmin, m_dmax, m_dim_d, &p, lo.empty() ? nullptr : lo.data(),
+                                          hi.empty() ? nullptr : hi.data(), depth.data(), ce.data(), mask.data(), cd.data(),
+                                          rbar.data()), "rslf_cuda_depth2d");
+        m_best_depth_s_v_u = detail::planes(S, V, U, CV_32FC1);
+        m_edge_confidence_s_v_u = detail::planes(S, V, U, CV_32FC1);
+        m_disp_confidence_s_v_u = detail::planes(S, V, U, CV_32FC1);
+        m_edge_confidence_mask_s_v_u = detail::planes(S, V, U, CV_8UC1);
+        m_rbar_s_v_u = detail::planes(S, V, U, CV_MAKETYPE(CV_32F, C));
+        detail::scatter(depth, m_best_depth_s_v_u, V, (size_t)U);
+        detail::scatter(ce, m_edge_confidence_s_v_u, V, (size_t)U);
+        detail::scatter(cd, m_disp_confidence_s_v_u, V, (size_t)U);
+        detail::scatter(mask, m_edge_confidence_mask_s_v_u, V, (size_t)U);
+        detail::scatter(rbar, m_rbar_s_v_u, V, (size_t)U * C);
+    }
+    const Vec<Mat>& get_depths_s_v_u() { return m_best_depth_s_v_u; }
+    /* C_e > threshold, or everything when accept_all is set (dc.hpp:893-915) */
+    Vec<Mat> get_valid_depths_mask_s_v_u()
+    {
+        rslf_params p = m_parameters.to_abi();
+        std::vector<unsigned char> m((size_t)m_dim_s * m_dim_v * m_dim_u);
+        m_device->check(rslf_cuda_depth2d_get_valid_mask(m_device->get(), m_accept_all ? 1 : 0, &p, m.data()),
+                        "rslf_cuda_depth2d_get_valid_mask");
+        Vec<Mat> out = detail::planes(m_dim_s, m_dim_v, m_dim_u, CV_8UC1);
+        detail::scatter(m, out, m_dim_v, (size_t)m_dim_u);
+        return out;
+    }
+    /* per-pixel bounds (dc.hpp:211-213): allocated on first use, filled with the global bounds */
+    Vec<Mat>& edit_dmin() { ensure_bounds(); return m_dmin_s_v_u; }
+    Vec<Mat>& edit_dmax() { ensure_bounds(); return m_dmax_s_v_u; }
+    void set_accept_all(bool b) { m_accept_all = b; }
+    rslf_timing get_timing() const { rslf_timing t; rslf_cuda_last_timing(m_device->get(), &t); return t; }
+
+    Vec<Mat> m_edge_confidence_s_v_u, m_edge_confidence_mask_s_v_u, m_disp_confidence_s_v_u, m_rbar_s_v_u, m_best_depth_s_v_u;
+
+private:
+    void ensure_bounds()
+    {
+        if (!m_dmin_s_v_u.empty()) return;
+        m_dmin_s_v_u = detail::planes(m_dim_s, m_dim_v, m_dim_u, CV_32FC1);
+        m_dmax_s_v_u = detail::planes(m_dim_s, m_dim_v, m_dim_u, CV_32FC1);
+        for (int s = 0; s < m_dim_s; ++s)
+            for (int v = 0; v < m_dim_v; ++v)
+                for (int u = 0; u < m_dim_u; ++u) {
+                    m_dmin_s_v_u[s].template at<float>(v, u) = m_dmin;
+                    m_dmax_s_v_u[s].template at<float>(v, u) = m_dmax;
+                }
+    }
+    const Depth1DParameters<DataType>& m_parameters;
+    std::unique_ptr<detail::Device> m_device;
+    int m_dim_d, m_dim_v = 0, m_dim_s = 0, m_dim_u = 0;
+    float m_dmin, m_dmax;
+    Vec<Mat> m_dmin_s_v_u, m_dmax_s_v_u;
+    bool m_accept_all = false;
+    bool m_verbose;
+};
+using Depth2DComputer_1ch = Depth2DComputer<float>;
+using Depth2DComputer_3ch = Depth2DComputer<Vec3f>;
+
+/* ---------------------------------------------------------------- FineToCoarse */
+template <typename DataType>
+class FineToCoarse
+{
+public:
+    FineToCoarse(const Vec<Mat>& a_epis, float a_d_min, float a_d_max, int a_dim_d, float a_epi_scale_factor = -1,
+                 const Depth1DParameters<DataType>& a_parameters = Depth1DParameters<DataType>::get_default(),
+                 int a_max_pyr_depth = -1, bool a_accept_all_last_scale = true, int a_device = 0)
+        : m_parameters(a_parameters), m_device(new detail::Device(a_device)), m_dim_d(a_dim_d), m_dmin(a_d_min),
+          m_dmax(a_d_max), m_max_pyr_depth(a_max_pyr_depth), m_accept_all_last_scale(a_accept_all_last_scale)
+    {
+        m_device->upload(a_epis, a_epi_scale_factor, channels_of<DataType>::value, m_dim_v, m_dim_s, m_dim_u);
+    }
+    void run()
+    {
+        rslf_params p = m_parameters.to_abi();
+        m_device->check(rslf_cuda_fine_to_coarse_run(m_device->get(), m_dmin, m_dmax, m_dim_d, &p, m_max_pyr_depth,
+                                                     m_accept_all_last_scale ? 1 : 0), "rslf_cuda_fine_to_coarse_run");
+    }
+    /* fused disparity maps and validity masks, one per view (ftc.hpp:301-322) */
+    void get_results(Vec<Mat>& a_out_map_s_v_u, Vec<Mat>& a_out_validity_s_v_u)
+    {
+        const size_t px = (size_t)m_dim_s * m_dim_v * m_dim_u;
+        std::vector<float> map(px);
+        std::vector<unsigned char> valid(px);
+        m_device->check(rslf_cuda_fine_to_coarse_get(m_device->get(), map.data(), valid.data()), "rslf_cuda_fine_to_coarse_get");
+        a_out_map_s_v_u = detail::planes(m_dim_s, m_dim_v, m_dim_u, CV_32FC1);
+        a_out_validity_s_v_u = detail::planes(m_dim_s, m_dim_v, m_dim_u, CV_8UC1);
+        detail::scatter(map, a_out_map_s_v_u, m_dim_v, (size_t)m_dim_u);
+        detail::scatter(valid, a_out_validity_s_v_u, m_dim_v, (size_t)m_dim_u);
+    }
+    rslf_timing get_timing() const { rslf_timing t; rslf_cuda_last_timing(m_device->get(), &t); return t; }
+
+private:
+    const Depth1DParameters<DataType>& m_parameters;
+    std::unique_ptr<detail::Device> m_device;
+    int m_dim_d, m_dim_v = 0, m_dim_s = 0, m_dim_u = 0;
+    float m_dmin, m_dmax;
+    int m_max_pyr_depth;
+    bool m_accept_all_last_scale;
+};
+using FineToCoarse_1ch = FineToCoarse<float>;
+using FineToCoarse_3ch = FineToCoarse<Vec3f>;
+
+} // namespace rslf_b200
+
+#endif /* RSLF_B200_HPP */

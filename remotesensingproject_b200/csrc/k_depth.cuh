@@ -99,15 +99,20 @@ template <> __device__ __forceinline__ void rad_load<4>(const float* p, float (&
     float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
 }
 
+#define DEPTH_UNR 4      /* views per unrolled block; the radiance rows are padded to a multiple of it */
+
+static __host__ __device__ inline int depth_padded_views(int S) { return (S + DEPTH_UNR - 1) / DEPTH_UNR * DEPTH_UNR; }
+
 template <int C, int H, bool NONNEG>
 __global__ void __launch_bounds__(32)
 depth_kernel(const depth_args a)
 {
     extern __shared__ float4 rad_raw[];
-    float* rad = reinterpret_cast<float*>(rad_raw);         /* [S][C][32*H] */
+    float* rad = reinterpret_cast<float*>(rad_raw);         /* [Spad][C][32*H]; rows >= S hold the sentinel */
     const int lane = threadIdx.x;
     const int S = a.S, U = a.U, D = a.D;
-    const int W = 32 * H;
+    const int Spad = depth_padded_views(S);
+    constexpr int W = 32 * H;
     const long long total = (long long)(*a.count) * a.chunks;
     const float inv = a.inv;
 
@@ -134,50 +139,71 @@ depth_kernel(const depth_args a)
             }
         }
         /* ---- radiances: I = (s_hat - s) * D * slope + u, linear interpolation (core.hpp:550-552,
-         *      interp.hpp:155-193); card_R = number of in-image views per hypothesis ---- */
+         *      interp.hpp:155-193); card_R = number of in-image views per hypothesis.
+         *      DEPTH_UNR views per step, all gathers of a step issued before the first use;
+         *      the loads use clamped indices so that they need no branch. ---- */
         float card[H];
 #pragma unroll
         for (int h = 0; h < H; ++h) card[h] = 0.f;
         const float uf = (float)u;
         __syncwarp();
-        for (int s = 0; s < S; ++s) {
-            const float k = (float)(a.s_hat - s);
-            const float* row = epi + (size_t)s * U * C;
-            float val[C][H];
+        for (int sb = 0; sb < Spad; sb += DEPTH_UNR) {
+            float e0[DEPTH_UNR][H][C], e1[DEPTH_UNR][H][C], tt[DEPTH_UNR][H];
+            bool ok[DEPTH_UNR][H];
 #pragma unroll
-            for (int h = 0; h < H; ++h) {
-                float I = k * Dv[h];
-                I = I * a.slope;
-                I = I + uf;
-                const float fl = floorf(I);
-                const int i0 = (int)fl;
-                const int i1 = i0 + ((I != fl) ? 1 : 0);            /* ceil */
-                if (!(i0 < 0 || i1 > U - 1) && (I == I)) {
-                    const float t = I - (float)i0;
-                    const float omt = 1.f - t;
+            for (int j = 0; j < DEPTH_UNR; ++j) {
+                const int s = sb + j;
+                const float k = (float)(a.s_hat - s);
+                const float* row = epi + (size_t)min(s, S - 1) * U * C;
+#pragma unroll
+                for (int h = 0; h < H; ++h) {
+                    float I = k * Dv[h];
+                    I = I * a.slope;
+                    I = I + uf;
+                    const float fl = floorf(I);
+                    const int i0 = (int)fl;
+                    const int i1 = i0 + ((I != fl) ? 1 : 0);            /* ceil */
+                    ok[j][h] = !(i0 < 0 || i1 > U - 1) && (I == I) && (s < S);
+                    tt[j][h] = I - (float)i0;
+                    const int c0 = min(max(i0, 0), U - 1), c1 = min(max(i1, 0), U - 1);
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
-                        float p = omt * __ldg(row + (size_t)i0 * C + c);
-                        float q = t * __ldg(row + (size_t)i1 * C + c);
-                        val[c][h] = p + q;
+                        e0[j][h][c] = __ldg(row + (size_t)c0 * C + c);
+                        e1[j][h][c] = __ldg(row + (size_t)c1 * C + c);
                     }
-                    card[h] += 1.0f;
-                } else {
-#pragma unroll
-                    for (int c = 0; c < C; ++c) val[c][h] = RSLF_RAD_SENTINEL;
                 }
             }
 #pragma unroll
-            for (int c = 0; c < C; ++c) rad_store<H>(rad + ((size_t)s * C + c) * W + lane * H, val[c]);
+            for (int j = 0; j < DEPTH_UNR; ++j) {
+                float val[C][H];
+#pragma unroll
+                for (int h = 0; h < H; ++h) {
+                    const float t = tt[j][h];
+                    const float omt = 1.f - t;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        const float p = omt * e0[j][h][c];
+                        const float q = t * e1[j][h][c];
+                        val[c][h] = ok[j][h] ? (p + q) : RSLF_RAD_SENTINEL;
+                    }
+                    card[h] += ok[j][h] ? 1.0f : 0.0f;
+                }
+#pragma unroll
+                for (int c = 0; c < C; ++c) rad_store<H>(rad + ((size_t)(sb + j) * C + c) * W + lane * H, val[c]);
+            }
         }
         __syncwarp();
-        /* ---- mean shift (core.hpp:577-610): r_bar <- row s_hat, then iterate ---- */
+        /* ---- mean shift (core.hpp:577-610): r_bar <- row s_hat, then iterate.  The loop runs over
+         *      the padded rows in blocks of DEPTH_UNR with the next block's LDS issued before the
+         *      current block's arithmetic; sentinel rows add K = 0 and r*K = +0, which leaves every
+         *      partial sum bit-identical. ---- */
         float rb[C][H];
 #pragma unroll
         for (int c = 0; c < C; ++c) rad_load<H>(rad + ((size_t)a.s_hat * C + c) * W + lane * H, rb[c]);
         float sK[H];
 #pragma unroll
         for (int h = 0; h < H; ++h) sK[h] = 0.f;
+        const float* rp = rad + lane * H;
         for (int it = 0; it < a.iters; ++it) {
             float sR[C][H];
 #pragma unroll
@@ -186,35 +212,50 @@ depth_kernel(const depth_args a)
 #pragma unroll
                 for (int c = 0; c < C; ++c) sR[c][h] = 0.f;
             }
-            const float* rp = rad + lane * H;
-#pragma unroll 2
-            for (int s = 0; s < S; ++s) {
-                float r[C][H];
+            float nx[DEPTH_UNR][C][H];
 #pragma unroll
-                for (int c = 0; c < C; ++c) rad_load<H>(rp + ((size_t)s * C + c) * W, r[c]);
+            for (int j = 0; j < DEPTH_UNR; ++j)
 #pragma unroll
-                for (int h = 0; h < H; ++h) {
-                    float b;
-                    if (C == 1) {
-                        const float x = r[0][h] - rb[0][h];              /* core.hpp:591 */
-                        b = (inv * x) * x;                               /* kern.cpp:21: multiply(src, src, scale) */
-                    } else {
-                        const float x0 = r[0][h] - rb[0][h];
-                        const float x1 = r[C > 1 ? 1 : 0][h] - rb[C > 1 ? 1 : 0][h];
-                        const float x2 = r[C > 2 ? 2 : 0][h] - rb[C > 2 ? 2 : 0][h];
-                        const float b0 = (inv * x0) * x0;                /* kern.cpp:43 */
-                        const float b1 = (inv * x1) * x1;
-                        const float b2 = (inv * x2) * x2;
-                        b = (b0 + b1) + b2;                              /* kern.cpp:47-49 */
+                for (int c = 0; c < C; ++c) rad_load<H>(rp + ((size_t)j * C + c) * W, nx[j][c]);
+            for (int sb = 0; sb < Spad; sb += DEPTH_UNR) {
+                float r[DEPTH_UNR][C][H];
+#pragma unroll
+                for (int j = 0; j < DEPTH_UNR; ++j)
+#pragma unroll
+                    for (int c = 0; c < C; ++c)
+#pragma unroll
+                        for (int h = 0; h < H; ++h) r[j][c][h] = nx[j][c][h];
+                const int sn = min(sb + DEPTH_UNR, Spad - DEPTH_UNR);       /* last block: harmless re-read */
+#pragma unroll
+                for (int j = 0; j < DEPTH_UNR; ++j)
+#pragma unroll
+                    for (int c = 0; c < C; ++c) rad_load<H>(rp + ((size_t)(sn + j) * C + c) * W, nx[j][c]);
+#pragma unroll
+                for (int j = 0; j < DEPTH_UNR; ++j) {
+#pragma unroll
+                    for (int h = 0; h < H; ++h) {
+                        float b;
+                        if (C == 1) {
+                            const float x = r[j][0][h] - rb[0][h];              /* core.hpp:591 */
+                            b = (inv * x) * x;                                  /* kern.cpp:21: multiply(src, src, scale) */
+                        } else {
+                            const float x0 = r[j][0][h] - rb[0][h];
+                            const float x1 = r[j][C > 1 ? 1 : 0][h] - rb[C > 1 ? 1 : 0][h];
+                            const float x2 = r[j][C > 2 ? 2 : 0][h] - rb[C > 2 ? 2 : 0][h];
+                            const float b0 = (inv * x0) * x0;                   /* kern.cpp:43 */
+                            const float b1 = (inv * x1) * x1;
+                            const float b2 = (inv * x2) * x2;
+                            b = (b0 + b1) + b2;                                 /* kern.cpp:47-49 */
+                        }
+                        const float kk = fmaxf(1.0f - b, 0.f);                  /* kern.cpp:23-25 / 51-53 */
+#pragma unroll
+                        for (int c = 0; c < C; ++c) {
+                            const float r0 = NONNEG ? r[j][c][h] : fmaxf(r[j][c][h], 0.f);   /* core.hpp:580 */
+                            const float p = r0 * kk;                            /* core.cpp:28 / 33-37 */
+                            sR[c][h] = sR[c][h] + p;                            /* core.hpp:602 */
+                        }
+                        sK[h] = sK[h] + kk;                                     /* core.hpp:603 */
                     }
-                    const float kk = fmaxf(1.0f - b, 0.f);               /* kern.cpp:23-25 / 51-53 */
-#pragma unroll
-                    for (int c = 0; c < C; ++c) {
-                        const float r0 = NONNEG ? r[c][h] : fmaxf(r[c][h], 0.f);   /* core.hpp:580 */
-                        const float p = r0 * kk;                         /* core.cpp:28 / 33-37 */
-                        sR[c][h] = sR[c][h] + p;                         /* core.hpp:602 */
-                    }
-                    sK[h] = sK[h] + kk;                                  /* core.hpp:603 */
                 }
             }
             /* r_bar = sum_rK / sum_K (x / 0 = 0 as in OpenCV 3), then max(., 0) (core.hpp:606-609) */
@@ -309,7 +350,7 @@ depth_kernel(const depth_args a)
 
 struct depth_plan { int H; int blocks_per_sm; size_t smem; int chunks; };
 
-static inline size_t depth_smem_bytes(int S, int C, int H) { return (size_t)S * C * 32 * H * sizeof(float); }
+static inline size_t depth_smem_bytes(int S, int C, int H) { return (size_t)depth_padded_views(S) * C * 32 * H * sizeof(float); }
 
 /* Chooses hypotheses per lane: the widest H that still leaves >= 8 resident warps per SM,
  * else the H with the most resident hypotheses.  RSLF_DEPTH_H overrides (experiments). */

@@ -76,7 +76,7 @@ static void free_level(rslf_level& L, bool keep_raw_borrowed_ptr = false)
     (void)keep_raw_borrowed_ptr;
     dev_free(&L.raw); dev_free(&L.epi); dev_free(&L.ce); dev_free(&L.cd); dev_free(&L.depth); dev_free(&L.rbar);
     dev_free(&L.dmin); dev_free(&L.dmax); dev_free(&L.emask); dev_free(&L.remaining); dev_free(&L.valid);
-    L.cap_px = 0; L.V = L.U = 0; L.have_bounds = false;
+    L.cap_px = 0; L.cap_stack = 0; L.V = L.U = 0; L.C = 0; L.have_bounds = false;
 }
 
 static void free_scratch(rslf_ctx* ctx)
@@ -95,14 +95,14 @@ static int ensure_scratch(rslf_ctx* ctx, bool need_2d, bool need_ftc)
 {
     const size_t plane = (size_t)ctx->V * ctx->U;
     const size_t px = plane * ctx->S;
-    if (ctx->scratch_px != px) {
+    if (ctx->scratch_px != px || ctx->scratch_plane != plane) {
         free_scratch(ctx);
         RSLF_TRY(dev_alloc(ctx, &ctx->items, plane));
         RSLF_TRY(dev_alloc(ctx, &ctx->filtered, plane));
         RSLF_TRY(dev_alloc(ctx, &ctx->arrive, plane));
         RSLF_TRY(dev_alloc(ctx, &ctx->pile_depth_raw, plane));
         RSLF_CUDA_TRY(ctx, cudaMemsetAsync(ctx->arrive, 0, plane * sizeof(int), ctx->stream));
-        ctx->scratch_px = px;
+        ctx->scratch_px = px; ctx->scratch_plane = plane;
     }
     if (need_2d && !ctx->winner) {
         RSLF_TRY(dev_alloc(ctx, &ctx->winner, px));
@@ -141,20 +141,23 @@ static int ensure_level(rslf_ctx* ctx, int p, int V, int U, bool full, bool with
     const size_t planes = full ? (size_t)ctx->S : 1;
     const size_t px = planes * V * U;
     const size_t stack = (size_t)V * ctx->S * U * ctx->C;
-    if (L.V != V || L.U != U || L.cap_px != px) {
-        float* raw = L.raw; float* epi = L.epi;            /* stacks survive a map re-allocation */
-        bool same_stack = (L.V == V && L.U == U);
+    if (L.V != V || L.U != U || L.cap_px != px || L.C != ctx->C) {
+        float* raw = L.raw; float* epi = L.epi; size_t cap_stack = L.cap_stack;   /* stacks survive a map re-allocation */
         L.raw = nullptr; L.epi = nullptr;
         free_level(L);
-        if (same_stack) { L.raw = raw; L.epi = epi; } else { if (raw) cudaFree(raw); if (epi) cudaFree(epi); }
-        L.V = V; L.U = U;
+        L.raw = raw; L.epi = epi; L.cap_stack = cap_stack;
+        L.V = V; L.U = U; L.C = ctx->C;
         RSLF_TRY(dev_alloc(ctx, &L.ce, px)); RSLF_TRY(dev_alloc(ctx, &L.cd, px));
         RSLF_TRY(dev_alloc(ctx, &L.depth, px)); RSLF_TRY(dev_alloc(ctx, &L.rbar, px * ctx->C));
         RSLF_TRY(dev_alloc(ctx, &L.emask, px)); RSLF_TRY(dev_alloc(ctx, &L.remaining, px));
         RSLF_TRY(dev_alloc(ctx, &L.valid, px));
         L.cap_px = px;
     }
-    if (!L.epi) RSLF_TRY(dev_alloc(ctx, &L.epi, stack));
+    if (L.cap_stack < stack) {
+        RSLF_TRY(dev_alloc(ctx, &L.epi, stack));
+        if (p > 0) RSLF_TRY(dev_alloc(ctx, &L.raw, stack));
+        L.cap_stack = stack;
+    }
     if (with_bounds && !L.dmin) {
         RSLF_TRY(dev_alloc(ctx, &L.dmin, px)); RSLF_TRY(dev_alloc(ctx, &L.dmax, px));
     }
@@ -780,7 +783,6 @@ extern "C" int rslf_cuda_fine_to_coarse_run(rslf_ctx* ctx, float dmin, float dma
     RSLF_TRY(ensure_scratch(ctx, true, true));
     for (int p = 0; p < levels; ++p) {
         RSLF_TRY(ensure_level(ctx, p, Vp[p], Up[p], true, true));
-        if (p > 0 && !ctx->lv[p].raw) RSLF_TRY(dev_alloc(ctx, &ctx->lv[p].raw, (size_t)Vp[p] * S * Up[p] * C));
     }
     ctx->n_levels = levels;
     RSLF_TRY(begin_run(ctx));

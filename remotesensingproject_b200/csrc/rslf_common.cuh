@@ -37,6 +37,8 @@ struct rslf_level {
     int nonneg = 1;              /* normalised stack has no negative value                    */
     bool have_bounds = false;
     size_t cap_px = 0;           /* allocated S*V*U                                           */
+    size_t cap_stack = 0;        /* allocated floats of epi (and raw, levels > 0)             */
+    int C = 0;                   /* channels the maps were allocated for                      */
 };
 
 struct rslf_stage_clock {
@@ -84,6 +86,7 @@ struct rslf_ctx {
     uint8_t* fuse_ma = nullptr; uint8_t* fuse_mb = nullptr;
     float* out_map = nullptr; uint8_t* out_valid = nullptr;
     size_t scratch_px = 0;       /* S*V*U the scratch was sized for                           */
+    size_t scratch_plane = 0;    /* V*U the scratch was sized for                             */
     void* l2_flush = nullptr;
     float* pile_depth_raw = nullptr;  /* 1D pile: unfiltered depth plane                      */
 

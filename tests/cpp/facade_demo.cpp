@@ -1,0 +1,79 @@
+/*
+ * facade_demo.cpp — the reference's demo call sequence
+ * (RSLightFields/tests/test_fine_to_coarse.cpp:56-63, test_depth_computation_2d.cpp:56-58,
+ * test_depth_computation_pile.cpp:49-51) through the C++ facade of include/rslf_b200.hpp.
+ * Reads a raw float32 [V][S][U][C] stack, runs the three computers and writes the
+ * result maps as raw files, which tests/test_cpp_facade.py compares with the oracle.
+ * usage: facade_demo in.bin V S U C D dmin dmax outprefix
+ */
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+
+#include "rslf_b200.hpp"
+
+using namespace rslf_b200;
+
+static void dump(const std::string& path, const Vec<Mat>& mats)
+{
+    FILE* f = fopen(path.c_str(), "wb");
+    for (const Mat& m : mats)
+        for (int r = 0; r < m.rows; ++r) fwrite(m.data + (size_t)r * m.step, m.elemSize(), m.cols, f);
+    fclose(f);
+}
+
+template <typename DataType>
+static int run_all(const Vec<Mat>& epis, int D, float dmin, float dmax, const std::string& out)
+{
+    Depth1DComputer_pile<DataType> pile(epis, dmin, dmax, D, -1, 1.0f);
+    pile.run();
+    dump(out + "_pile_depth.bin", Vec<Mat>{pile.m_best_depth_v_u});
+    dump(out + "_pile_mask.bin", Vec<Mat>{pile.m_edge_confidence_mask_v_u});
+
+    Depth2DComputer<DataType> d2(epis, dmin, dmax, D, 1.0f);
+    d2.run();
+    dump(out + "_2d_depth.bin", d2.get_depths_s_v_u());
+    dump(out + "_2d_valid.bin", d2.get_valid_depths_mask_s_v_u());
+    dump(out + "_2d_cd.bin", d2.m_disp_confidence_s_v_u);
+
+    FineToCoarse<DataType> ftc(epis, dmin, dmax, D, 1.0f);
+    ftc.run();
+    Vec<Mat> map, valid;
+    ftc.get_results(map, valid);
+    dump(out + "_ftc_map.bin", map);
+    dump(out + "_ftc_valid.bin", valid);
+    rslf_timing t = ftc.get_timing();
+    printf("fine-to-coarse: %d levels, %d passes, %.0f pixels, %.3f ms on device\n", t.levels, t.passes, t.computed_pixels, t.ms_total);
+
+    /* error behaviour: dim_d < 2 is rejected loudly */
+    try {
+        Depth2DComputer<DataType> bad(epis, dmin, dmax, 1, 1.0f);
+        bad.run();
+        printf("ERROR: dim_d = 1 was accepted\n");
+        return 1;
+    } catch (const Error& e) {
+        printf("expected failure: %s\n", e.what());
+    }
+    return 0;
+}
+
+int main(int argc, char** argv)
+{
+    if (argc < 10) { fprintf(stderr, "usage: %s in.bin V S U C D dmin dmax outprefix\n", argv[0]); return 2; }
+    const int V = atoi(argv[2]), S = atoi(argv[3]), U = atoi(argv[4]), C = atoi(argv[5]), D = atoi(argv[6]);
+    const float dmin = (float)atof(argv[7]), dmax = (float)atof(argv[8]);
+    Vec<Mat> epis(V);
+    FILE* f = fopen(argv[1], "rb");
+    if (!f) { perror("open"); return 2; }
+    for (int v = 0; v < V; ++v) {
+        epis[v] = Mat(S, U, CV_MAKETYPE(CV_32F, C));
+        if (fread(epis[v].data, sizeof(float), (size_t)S * U * C, f) != (size_t)S * U * C) { fprintf(stderr, "short read\n"); return 2; }
+    }
+    fclose(f);
+    try {
+        return C == 3 ? run_all<Vec3f>(epis, D, dmin, dmax, argv[9]) : run_all<float>(epis, D, dmin, dmax, argv[9]);
+    } catch (const Error& e) {
+        fprintf(stderr, "rslf_b200 error %d: %s\n", e.code, e.what());
+        return 1;
+    }
+}
