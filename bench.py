@@ -168,7 +168,7 @@ def main():
     import torch.distributed as dist
     from remotesensingproject_b200 import api
     from remotesensingproject_b200.synth import make_light_field
-    from remotesensingproject_b200.shard import row_shards
+    from remotesensingproject_b200.shard import shard_table
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -185,13 +185,13 @@ def main():
     # ---- synthetic light field, rendered on the device (rank-local rows when sharded) -------------------
     epis, _ = make_light_field(S, V, U, C, dmin=DMIN, dmax=DMAX, seed=cfg["seed"], value_range=cfg["rng"], device="cuda")
     if world > 1:
-        shards = row_shards(V, world)
-        v0, v1 = shards[rank]
+        starts = shard_table(V, U, world, pyramid=(cfg["mode"] == "ftc"))
+        v0, v1 = starts[rank], starts[rank + 1]
         uid = [api.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         ctx.comm_init(uid[0], rank, world)
         epis = epis[v0:v1].contiguous()
-        ctx.set_row_shard(v0, V)
+        ctx.set_row_shards(starts)
     torch.cuda.synchronize()
     Vloc = epis.shape[0]
 

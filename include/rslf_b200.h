@@ -224,15 +224,21 @@ int rslf_cuda_edge_confidence(rslf_ctx* ctx, int s, const rslf_params* params,
                               float* edge_conf_vu, uint8_t* edge_mask_vu);
 
 /* ---- multi-GPU (row sharding, one process per GPU) -----------------------
- * Rows are split in contiguous blocks; every rank uploads only its block plus
- * halo rows.  The only exchange on the path is the +-2-row halo of the
- * selective median (core.hpp:698-709), done with NCCL send/recv.
+ * The reference's only parallel axis is the image row v (OpenMP `parallel for`,
+ * core.hpp:743, :799, :1088).  Rows are split in contiguous blocks, rank r
+ * holding the global rows [row_starts[r], row_starts[r+1]); every rank uploads
+ * only its block and gets only its block of every result map.  Boundaries must
+ * be multiples of 2^(levels-1) so that each pyramid level splits at the same
+ * image position.  Exchanges on the path (NCCL over NVLink): the all-gather of
+ * the depth / mask / colour rows of line s_hat for the cross-row selective
+ * median of each pass (core.hpp:698-709), the raw rows a level's 7x7 blur
+ * reads beyond the block (ftc_core.cpp:37), the fused maps between fuse levels
+ * and the max of the input normalisation (dc.hpp:442-460).
  */
 int rslf_cuda_nccl_unique_id(void* id128 /* 128 bytes out */);
 int rslf_cuda_comm_init(rslf_ctx* ctx, const void* id128, int rank, int world);
-/* Declares which global rows [v0, v0+V) of a V_total-row light field the
- * uploaded stack holds (default: the whole field). */
-int rslf_cuda_set_row_shard(rslf_ctx* ctx, int v0, int V_total);
+/* row_starts: n_ranks + 1 entries, row_starts[0] = 0, row_starts[n_ranks] = total rows. */
+int rslf_cuda_set_row_shards(rslf_ctx* ctx, const int* row_starts, int n_ranks);
 
 /* ---- measurement helpers -------------------------------------------------- */
 /* Measured FP32 FADD/FMUL issue rate of this device in Gop/s (non-FMA, the

@@ -307,8 +307,11 @@ class Context:
         buf = (C.c_char * 128).from_buffer_copy(uid_bytes)
         self.check(lib().rslf_cuda_comm_init(self._h, buf, int(rank), int(world)), "rslf_cuda_comm_init")
 
-    def set_row_shard(self, v0, V_total):
-        self.check(lib().rslf_cuda_set_row_shard(self._h, int(v0), int(V_total)), "rslf_cuda_set_row_shard")
+    def set_row_shards(self, row_starts):
+        """row_starts: world + 1 global row boundaries (see remotesensingproject_b200.shard.row_shards)."""
+        n = len(row_starts) - 1
+        arr = (C.c_int * (n + 1))(*[int(x) for x in row_starts])
+        self.check(lib().rslf_cuda_set_row_shards(self._h, arr, n), "rslf_cuda_set_row_shards")
 
 
 def nccl_unique_id():

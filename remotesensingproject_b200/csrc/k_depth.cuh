@@ -19,10 +19,22 @@
  *     consecutive hypotheses.  Sums over views s run sequentially in ascending
  *     s inside a lane, exactly like cv::reduce over rows, so scores are
  *     bit-identical to the CPU path; no cross-lane arithmetic touches a score.
- *   - the warp's radiances r[s][c][d] live in shared memory ([s][c][32*H]
- *     floats, one LDS.32/64/128 per lane, conflict-free); out-of-image samples
- *     hold a large finite sentinel instead of NaN: K = max(1 - |x/h|^2, 0) is 0
- *     for it, as for NaN in the reference, and r*K contributes +0.
+ *   - EPI slicing: in view s the hypotheses of a warp item read one contiguous
+ *     segment of the EPI scanline (v, s).  The lanes issue one TMA bulk copy
+ *     per view (cp.async.bulk + mbarrier complete_tx; SASS UBLKCP / SYNCS) for
+ *     ALL views of the item at once, straight into the shared-memory row that
+ *     will hold that view's radiances; one mbarrier wait later every segment
+ *     is resident, so the HBM/L2 latency is paid once per item instead of once
+ *     per view.  Each row is then converted in place: the lanes read their two
+ *     neighbouring pixels, synchronise, and overwrite the row with the
+ *     interpolated radiances r[s][c][d] ([c][32*H] floats, conflict-free
+ *     LDS.32/64/128 in the mean shift).
+ *   - the first RV views can stay in REGISTERS instead (a first staging round
+ *     through the same rows): fewer shared-memory rows per warp, hence more
+ *     resident warps when S*C is large, and no LDS for those views.
+ *   - out-of-image samples hold a large finite sentinel instead of NaN:
+ *     K = max(1 - |x/h|^2, 0) is 0 for it, as for NaN in the reference, and
+ *     r*K contributes +0.
  *   - pixels with more hypotheses than one warp item holds are merged by the
  *     last-arriving warp (arrival counter per pixel), first maximum winning
  *     like cv::minMaxLoc.
@@ -43,6 +55,7 @@ struct __align__(16) rslf_partial {
 
 struct depth_args {
     const float* epi; int V, S, U, D; int s_hat; float slope; float inv; int iters;
+    int wpv_q16;                  /* pixels a chunk's hypotheses spread per view step, 16.16 fixed point (row sizing) */
     const int* items; const int* count;
     const float* dmin_map; const float* dmax_map; float dmin_c, dmax_c;
     float* ce; uint8_t* emask; float* cd; float* depth; float* rbar;   /* planes of line s_hat */
@@ -77,11 +90,6 @@ __global__ void compact_kernel(const uint8_t* __restrict__ emask, uint8_t* __res
     }
 }
 
-template <int H> struct rad_vec;
-template <> struct rad_vec<1> { typedef float type; };
-template <> struct rad_vec<2> { typedef float2 type; };
-template <> struct rad_vec<4> { typedef float4 type; };
-
 template <int H> __device__ __forceinline__ void rad_store(float* p, const float (&v)[H]);
 template <> __device__ __forceinline__ void rad_store<1>(float* p, const float (&v)[1]) { *p = v[0]; }
 template <> __device__ __forceinline__ void rad_store<2>(float* p, const float (&v)[2]) {
@@ -99,22 +107,161 @@ template <> __device__ __forceinline__ void rad_load<4>(const float* p, float (&
     float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
 }
 
-#define DEPTH_UNR 4      /* views per unrolled block; the radiance rows are padded to a multiple of it */
+#define DEPTH_UNR 4      /* views per unrolled block of the mean shift; rows are padded to a multiple of it */
+#define DEPTH_MAX_ROW_FLOATS 1024
 
 static __host__ __device__ inline int depth_padded_views(int S) { return (S + DEPTH_UNR - 1) / DEPTH_UNR * DEPTH_UNR; }
 
+/*
+ * Shared-memory rows.  Row r hosts, in staging round 0 (only if RV > 0), the scanline segment of view r
+ * (r < RV), and in round 1 the segment and then the radiances of view RV + r.  Its size is the larger of
+ * the radiance row (C * 32 * H floats) and the longest segment it may receive: a chunk's hypotheses spread
+ * over ceil(|s_hat - s| * wpv) + 3 pixels in view s (wpv in 16.16 fixed point so that host and device
+ * agree to the bit), plus 4 floats of alignment slack.
+ */
+static __host__ __device__ inline int depth_segment_floats(int s, int S, int s_hat, int wpv_q16, int C)
+{
+    if (s >= S) return 0;
+    long long k = s_hat > s ? s_hat - s : s - s_hat;
+    long long span = ((k * (long long)wpv_q16 + 65535) >> 16) + 3;
+    long long f = (span * C + 4 + 3) & ~3LL;
+    return (int)(f > DEPTH_MAX_ROW_FLOATS ? DEPTH_MAX_ROW_FLOATS : f);
+}
+static __host__ __device__ inline int depth_row_floats(int r, int S, int Spad, int RV, int s_hat, int wpv_q16, int C, int W)
+{
+    int f = C * W;
+    if (r < RV) { int g = depth_segment_floats(r, S, s_hat, wpv_q16, C); f = g > f ? g : f; }
+    if (RV + r < Spad) { int g = depth_segment_floats(RV + r, S, s_hat, wpv_q16, C); f = g > f ? g : f; }
+    return f;
+}
+static __host__ __device__ inline int depth_num_rows(int Spad, int RV) { return (Spad - RV) > RV ? (Spad - RV) : RV; }
+
+/* ---- mbarrier / TMA bulk-copy primitives (PTX; SASS: SYNCS.*, UBLKCP) ---- */
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    /* try_wait suspends the warp for a hardware-defined time slice; a copy that never lands (a protocol
+     * bug) traps instead of hanging the device */
+    unsigned done = 0;
+    for (int spin = 0; spin < (1 << 20); ++spin) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void tma_bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+/*
+ * Segment of scanline (v, s) that the chunk's hypotheses touch: pixels floor(min I) .. ceil(max I) with
+ * I = (s_hat - s) * D * slope + u at the chunk's first and last hypothesis (every float operation involved
+ * is monotone, so all other hypotheses fall in between), clipped to the image.  lo / hi are returned;
+ * lo > hi: nothing to stage (padding view, or the whole chunk leaves the image in this view).
+ */
+__device__ __forceinline__ void view_span(const depth_args& a, int s, float uf, float Dlo, float Dhi, int& lo_i, int& hi_i)
+{
+    const float k = (float)(a.s_hat - s);
+    float Ia = k * Dlo; Ia = Ia * a.slope; Ia = Ia + uf;
+    float Ib = k * Dhi; Ib = Ib * a.slope; Ib = Ib + uf;
+    const float lo = floorf(fminf(Ia, Ib)), hi = ceilf(fmaxf(Ia, Ib));
+    lo_i = 1; hi_i = 0;
+    if (s >= a.S || !(lo <= hi)) return;                     /* padding view or NaN */
+    lo_i = (int)fmaxf(lo, 0.f); hi_i = (int)fminf(hi, (float)(a.U - 1));
+}
+
+/* One view of the mean-shift sums for the lane's H hypotheses (core.hpp:591-603, kern.cpp:16-26 / 39-54,
+ * core.cpp:25-38): K = max(1 - |(r - r_bar)/h|^2, 0); sum_K += K; sum_rK += max(r, 0) * K. */
 template <int C, int H, bool NONNEG>
-__global__ void __launch_bounds__(32)
+__device__ __forceinline__ void ms_accumulate(const float (&r)[C][H], const float (&rb)[C][H], float inv,
+                                              float (&sR)[C][H], float (&sK)[H])
+{
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+        float b;
+        if (C == 1) {
+            const float x = r[0][h] - rb[0][h];
+            b = (inv * x) * x;                                  /* multiply(src, src, scale) */
+        } else {
+            const float x0 = r[0][h] - rb[0][h];
+            const float x1 = r[C > 1 ? 1 : 0][h] - rb[C > 1 ? 1 : 0][h];
+            const float x2 = r[C > 2 ? 2 : 0][h] - rb[C > 2 ? 2 : 0][h];
+            const float b0 = (inv * x0) * x0;
+            const float b1 = (inv * x1) * x1;
+            const float b2 = (inv * x2) * x2;
+            b = (b0 + b1) + b2;                                 /* reduce over channels: (c0 + c1) + c2 */
+        }
+        const float kk = fmaxf(1.0f - b, 0.f);
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const float r0 = NONNEG ? r[c][h] : fmaxf(r[c][h], 0.f);
+            const float p = r0 * kk;
+            sR[c][h] = sR[c][h] + p;
+        }
+        sK[h] = sK[h] + kk;
+    }
+}
+
+/* Register budget.  The register file is split per SM sub-partition (512 registers per lane each) and
+ * the one-warp blocks are spread over the four sub-partitions, so k resident warps per sub-partition
+ * may use 512 / k registers: 255 (k = 2), 168 (3), 128 (4), 96 (5), 80 (6), 64 (8). */
+#define DEPTH_REG_ESTIMATE(C, H, RV) ((RV) * (C) * (H) + 48 + 36 * (H))
+template <int C, int H, int RV> struct depth_min_blocks {
+    enum { est = DEPTH_REG_ESTIMATE(C, H, RV), wps = 512 / est, value = 4 * (wps > 8 ? 8 : (wps < 1 ? 1 : wps)) };
+};
+
+template <int C, int H, bool NONNEG, int RV>
+__global__ void __launch_bounds__(32, depth_min_blocks<C, H, RV>::value)
 depth_kernel(const depth_args a)
 {
-    extern __shared__ float4 rad_raw[];
-    float* rad = reinterpret_cast<float*>(rad_raw);         /* [Spad][C][32*H]; rows >= S hold the sentinel */
+    extern __shared__ float4 smem_raw[];
     const int lane = threadIdx.x;
     const int S = a.S, U = a.U, D = a.D;
-    const int Spad = depth_padded_views(S);
+    const int Spad = max(depth_padded_views(S), RV);
+    const int nrows = depth_num_rows(Spad, RV);
+    const int nblk = (Spad - RV) / DEPTH_UNR;               /* blocks of DEPTH_UNR shared-memory views */
     constexpr int W = 32 * H;
+    /* [mbarrier, 16 B][row offsets: nrows + 1 ints, padded to 16 B][rows] */
+    int* row_off = reinterpret_cast<int*>(smem_raw) + 4;
+    float* rows = reinterpret_cast<float*>(smem_raw) + 4 + ((nrows + 1 + 3) & ~3);
+    const unsigned bar = smem_u32(smem_raw);
     const long long total = (long long)(*a.count) * a.chunks;
     const float inv = a.inv;
+
+    /* prologue: mbarrier and the row offset table (exclusive prefix sum of the row sizes) */
+    if (lane == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    {
+        int carry = 0;
+        for (int base = 0; base < nrows; base += 32) {
+            const int r = base + lane;
+            int f = (r < nrows) ? depth_row_floats(r, S, Spad, RV, a.s_hat, a.wpv_q16, C, W) : 0;
+            int incl = f;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, off);
+                if (lane >= off) incl += t;
+            }
+            if (r < nrows) row_off[r] = carry + incl - f;
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) row_off[nrows] = carry;
+    }
+    __syncwarp();
+    unsigned phase = 0;                                     /* mbarrier phase parity */
 
     for (long long w = blockIdx.x; w < total; w += gridDim.x) {
         const int item = (int)(w / a.chunks);
@@ -123,11 +270,10 @@ depth_kernel(const depth_args a)
         const int v = pix / U, u = pix - v * U;
         const float dmin = a.dmin_map ? a.dmin_map[pix] : a.dmin_c;
         const float dmax = a.dmax_map ? a.dmax_map[pix] : a.dmax_c;
-        const float* epi = a.epi + (size_t)v * S * (size_t)U * C;
         const int dbase = chunk * W + lane * H;
-
+        const float uf = (float)u;
         /* D[d] = dmin + d * (dmax - dmin) / (dim_d - 1)   (core.hpp:547-548) */
-        float Dv[H];
+        float Dv[H], Dlo, Dhi;
         {
             const float range = dmax - dmin;
             const float den = (float)(D - 1);
@@ -137,24 +283,72 @@ depth_kernel(const depth_args a)
                 t = t / den;
                 Dv[h] = dmin + t;
             }
+            /* first and last real hypothesis of the chunk: they bound every lane's EPI line */
+            float t = (float)(chunk * W) * range; t = t / den; Dlo = dmin + t;
+            t = (float)(min(chunk * W + W, D) - 1) * range; t = t / den; Dhi = dmin + t;
         }
-        /* ---- radiances: I = (s_hat - s) * D * slope + u, linear interpolation (core.hpp:550-552,
-         *      interp.hpp:155-193); card_R = number of in-image views per hypothesis.
-         *      DEPTH_UNR views per step, all gathers of a step issued before the first use;
-         *      the loads use clamped indices so that they need no branch. ---- */
-        float card[H];
+        const long long row0 = (long long)v * S * U;           /* pixel index of (v, s = 0, u = 0) */
+        float card[H], rb[C][H];
 #pragma unroll
-        for (int h = 0; h < H; ++h) card[h] = 0.f;
-        const float uf = (float)u;
-        __syncwarp();
-        for (int sb = 0; sb < Spad; sb += DEPTH_UNR) {
-            float e0[DEPTH_UNR][H][C], e1[DEPTH_UNR][H][C], tt[DEPTH_UNR][H];
-            bool ok[DEPTH_UNR][H];
+        for (int h = 0; h < H; ++h) {
+            card[h] = 0.f;
 #pragma unroll
-            for (int j = 0; j < DEPTH_UNR; ++j) {
-                const int s = sb + j;
+            for (int c = 0; c < C; ++c) rb[c][h] = 0.f;
+        }
+        float rr[RV > 0 ? RV : 1][C][H];
+
+        /* ---- radiances (interp.hpp:155-193) and card_R.  Round 0 (RV > 0): views [0, RV) -> registers;
+         *      round 1: views [RV, Spad) -> shared-memory rows.  Per round: the lanes issue one TMA bulk
+         *      copy per view into that view's row, wait once, then convert the rows in place. ---- */
+#pragma unroll 1
+        for (int round = (RV > 0 ? 0 : 1); round < 2; ++round) {
+            const int vbase = round ? RV : 0;
+            const int nviews = round ? (Spad - RV) : RV;
+            __syncwarp();
+            {
+                unsigned bytes = 0;
+                for (int r = lane; r < nviews; r += 32) {
+                    int lo, hi;
+                    view_span(a, vbase + r, uf, Dlo, Dhi, lo, hi);
+                    if (lo <= hi) {
+                        const long long a0 = (row0 + (long long)(vbase + r) * U + lo) * C, a1 = (row0 + (long long)(vbase + r) * U + hi + 1) * C;
+                        const long long n = ((a1 - (a0 & ~3LL)) + 3) & ~3LL;
+                        bytes += 4u * (unsigned)min(n, (long long)(row_off[r + 1] - row_off[r]));
+                    }
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, off);
+                if (lane == 0) mbar_arrive_expect_tx(bar, bytes);
+                __syncwarp();
+                for (int r = lane; r < nviews; r += 32) {
+                    int lo, hi;
+                    view_span(a, vbase + r, uf, Dlo, Dhi, lo, hi);
+                    if (lo <= hi) {
+                        const long long a0 = (row0 + (long long)(vbase + r) * U + lo) * C, a1 = (row0 + (long long)(vbase + r) * U + hi + 1) * C;
+                        const long long a0a = a0 & ~3LL;
+                        const long long n = ((a1 - a0a) + 3) & ~3LL;
+                        const unsigned nb = 4u * (unsigned)min(n, (long long)(row_off[r + 1] - row_off[r]));
+                        tma_bulk_g2s(smem_u32(rows + row_off[r]), a.epi + a0a, nb, bar);
+                    }
+                }
+            }
+            mbar_wait(bar, phase);
+            phase ^= 1u;
+            /* in-place conversion, one view per step */
+#pragma unroll 2
+            for (int r = 0; r < nviews; ++r) {
+                const int s = vbase + r;
+                float* row = rows + row_off[r];
+                const int cap = row_off[r + 1] - row_off[r];
+                int lo, hi;
+                view_span(a, s, uf, Dlo, Dhi, lo, hi);
+                /* float offset of the row's pixel 0 inside the staged segment: the segment starts at the
+                 * 16-byte aligned float index below (row0 + s*U + lo) * C */
+                const int mis = ((int)((row0 + (long long)s * U + lo) & 3LL) * C) & 3;
+                const int rel = mis - lo * C;
+                const int nfl = (lo <= hi) ? min(((hi + 1 - lo) * C + mis + 3) & ~3, cap) : 0;
                 const float k = (float)(a.s_hat - s);
-                const float* row = epi + (size_t)min(s, S - 1) * U * C;
+                float val[C][H];
 #pragma unroll
                 for (int h = 0; h < H; ++h) {
                     float I = k * Dv[h];
@@ -163,47 +357,49 @@ depth_kernel(const depth_args a)
                     const float fl = floorf(I);
                     const int i0 = (int)fl;
                     const int i1 = i0 + ((I != fl) ? 1 : 0);            /* ceil */
-                    ok[j][h] = !(i0 < 0 || i1 > U - 1) && (I == I) && (s < S);
-                    tt[j][h] = I - (float)i0;
-                    const int c0 = min(max(i0, 0), U - 1), c1 = min(max(i1, 0), U - 1);
-#pragma unroll
-                    for (int c = 0; c < C; ++c) {
-                        e0[j][h][c] = __ldg(row + (size_t)c0 * C + c);
-                        e1[j][h][c] = __ldg(row + (size_t)c1 * C + c);
-                    }
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < DEPTH_UNR; ++j) {
-                float val[C][H];
-#pragma unroll
-                for (int h = 0; h < H; ++h) {
-                    const float t = tt[j][h];
+                    const bool ok = !(i0 < 0 || i1 > U - 1) && (I == I) && (s < S) && (dbase + h < D);
+                    const float t = I - (float)i0;
                     const float omt = 1.f - t;
+                    const int p0 = rel + i0 * C, p1 = rel + i1 * C;
+                    float e0[C], e1[C];
+                    if (ok && (p0 < 0 || p1 + C > nfl)) {               /* not staged: segment longer than the row */
+                        const float* g = a.epi + (row0 + (long long)s * U) * C;
+#pragma unroll
+                        for (int c = 0; c < C; ++c) { e0[c] = __ldg(g + (size_t)i0 * C + c); e1[c] = __ldg(g + (size_t)i1 * C + c); }
+                    } else {
+                        const int q0 = ok ? p0 : 0, q1 = ok ? p1 : 0;
+#pragma unroll
+                        for (int c = 0; c < C; ++c) { e0[c] = row[q0 + c]; e1[c] = row[q1 + c]; }
+                    }
 #pragma unroll
                     for (int c = 0; c < C; ++c) {
-                        const float p = omt * e0[j][h][c];
-                        const float q = t * e1[j][h][c];
-                        val[c][h] = ok[j][h] ? (p + q) : RSLF_RAD_SENTINEL;
+                        const float p = omt * e0[c];
+                        const float q = t * e1[c];
+                        val[c][h] = ok ? (p + q) : RSLF_RAD_SENTINEL;
+                        if (s == a.s_hat) rb[c][h] = val[c][h];         /* r_bar <- row s_hat (core.hpp:577) */
                     }
-                    card[h] += ok[j][h] ? 1.0f : 0.0f;
+                    card[h] += ok ? 1.0f : 0.0f;
                 }
+                __syncwarp();                                           /* every lane has read the segment */
 #pragma unroll
-                for (int c = 0; c < C; ++c) rad_store<H>(rad + ((size_t)(sb + j) * C + c) * W + lane * H, val[c]);
+                for (int c = 0; c < C; ++c) rad_store<H>(row + c * W + lane * H, val[c]);
+            }
+            __syncwarp();
+            if (RV > 0 && round == 0) {
+#pragma unroll
+                for (int j = 0; j < RV; ++j)
+#pragma unroll
+                    for (int c = 0; c < C; ++c) rad_load<H>(rows + row_off[j] + c * W + lane * H, rr[j][c]);
             }
         }
-        __syncwarp();
-        /* ---- mean shift (core.hpp:577-610): r_bar <- row s_hat, then iterate.  The loop runs over
-         *      the padded rows in blocks of DEPTH_UNR with the next block's LDS issued before the
-         *      current block's arithmetic; sentinel rows add K = 0 and r*K = +0, which leaves every
-         *      partial sum bit-identical. ---- */
-        float rb[C][H];
-#pragma unroll
-        for (int c = 0; c < C; ++c) rad_load<H>(rad + ((size_t)a.s_hat * C + c) * W + lane * H, rb[c]);
+        /* ---- mean shift (core.hpp:577-610).  Shared-memory rows are consumed in blocks of DEPTH_UNR
+         *      views with two register buffers in ping-pong: the LDS of the next block are in flight
+         *      while the current one is accumulated.  Sentinel rows add K = 0 and r*K = +0, which
+         *      leaves every partial sum bit-identical. ---- */
         float sK[H];
 #pragma unroll
         for (int h = 0; h < H; ++h) sK[h] = 0.f;
-        const float* rp = rad + lane * H;
+        const float* const rp = rows + lane * H;
         for (int it = 0; it < a.iters; ++it) {
             float sR[C][H];
 #pragma unroll
@@ -212,51 +408,30 @@ depth_kernel(const depth_args a)
 #pragma unroll
                 for (int c = 0; c < C; ++c) sR[c][h] = 0.f;
             }
-            float nx[DEPTH_UNR][C][H];
-#pragma unroll
-            for (int j = 0; j < DEPTH_UNR; ++j)
-#pragma unroll
-                for (int c = 0; c < C; ++c) rad_load<H>(rp + ((size_t)j * C + c) * W, nx[j][c]);
-            for (int sb = 0; sb < Spad; sb += DEPTH_UNR) {
-                float r[DEPTH_UNR][C][H];
+            float ba[DEPTH_UNR][C][H], bb[DEPTH_UNR][C][H];
+            auto load_block = [&](int bi, float (&dst)[DEPTH_UNR][C][H]) {
+                const int4 o = *reinterpret_cast<const int4*>(row_off + bi * DEPTH_UNR);
+                const int oo[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
                 for (int j = 0; j < DEPTH_UNR; ++j)
 #pragma unroll
-                    for (int c = 0; c < C; ++c)
+                    for (int c = 0; c < C; ++c) rad_load<H>(rp + oo[j] + c * W, dst[j][c]);
+            };
+            if (nblk > 0) load_block(0, ba);
 #pragma unroll
-                        for (int h = 0; h < H; ++h) r[j][c][h] = nx[j][c][h];
-                const int sn = min(sb + DEPTH_UNR, Spad - DEPTH_UNR);       /* last block: harmless re-read */
+            for (int j = 0; j < RV; ++j) ms_accumulate<C, H, NONNEG>(rr[j], rb, inv, sR, sK);
+            int bi = 0;
+            for (; bi + 2 <= nblk; bi += 2) {
+                load_block(bi + 1, bb);
 #pragma unroll
-                for (int j = 0; j < DEPTH_UNR; ++j)
+                for (int j = 0; j < DEPTH_UNR; ++j) ms_accumulate<C, H, NONNEG>(ba[j], rb, inv, sR, sK);
+                load_block(min(bi + 2, nblk - 1), ba);                   /* last: harmless re-read */
 #pragma unroll
-                    for (int c = 0; c < C; ++c) rad_load<H>(rp + ((size_t)(sn + j) * C + c) * W, nx[j][c]);
+                for (int j = 0; j < DEPTH_UNR; ++j) ms_accumulate<C, H, NONNEG>(bb[j], rb, inv, sR, sK);
+            }
+            if (bi < nblk) {
 #pragma unroll
-                for (int j = 0; j < DEPTH_UNR; ++j) {
-#pragma unroll
-                    for (int h = 0; h < H; ++h) {
-                        float b;
-                        if (C == 1) {
-                            const float x = r[j][0][h] - rb[0][h];              /* core.hpp:591 */
-                            b = (inv * x) * x;                                  /* kern.cpp:21: multiply(src, src, scale) */
-                        } else {
-                            const float x0 = r[j][0][h] - rb[0][h];
-                            const float x1 = r[j][C > 1 ? 1 : 0][h] - rb[C > 1 ? 1 : 0][h];
-                            const float x2 = r[j][C > 2 ? 2 : 0][h] - rb[C > 2 ? 2 : 0][h];
-                            const float b0 = (inv * x0) * x0;                   /* kern.cpp:43 */
-                            const float b1 = (inv * x1) * x1;
-                            const float b2 = (inv * x2) * x2;
-                            b = (b0 + b1) + b2;                                 /* kern.cpp:47-49 */
-                        }
-                        const float kk = fmaxf(1.0f - b, 0.f);                  /* kern.cpp:23-25 / 51-53 */
-#pragma unroll
-                        for (int c = 0; c < C; ++c) {
-                            const float r0 = NONNEG ? r[j][c][h] : fmaxf(r[j][c][h], 0.f);   /* core.hpp:580 */
-                            const float p = r0 * kk;                            /* core.cpp:28 / 33-37 */
-                            sR[c][h] = sR[c][h] + p;                            /* core.hpp:602 */
-                        }
-                        sK[h] = sK[h] + kk;                                     /* core.hpp:603 */
-                    }
-                }
+                for (int j = 0; j < DEPTH_UNR; ++j) ms_accumulate<C, H, NONNEG>(ba[j], rb, inv, sR, sK);
             }
             /* r_bar = sum_rK / sum_K (x / 0 = 0 as in OpenCV 3), then max(., 0) (core.hpp:606-609) */
 #pragma unroll
@@ -348,53 +523,86 @@ depth_kernel(const depth_args a)
     }
 }
 
-struct depth_plan { int H; int blocks_per_sm; size_t smem; int chunks; };
+struct depth_plan { int H; int RV; int blocks_per_sm; size_t smem; int chunks; int wpv_q16; };
 
-static inline size_t depth_smem_bytes(int S, int C, int H) { return (size_t)depth_padded_views(S) * C * 32 * H * sizeof(float); }
-
-/* Chooses hypotheses per lane: the widest H that still leaves >= 8 resident warps per SM,
- * else the H with the most resident hypotheses.  RSLF_DEPTH_H overrides (experiments). */
-static depth_plan plan_depth(const rslf_ctx* ctx, int S, int C, int D)
+/* pixels a chunk of 32*H hypotheses spreads per view step, 16.16 fixed point, rounded up */
+static inline int depth_wpv_q16(int D, int H, float dmin, float dmax, float slope)
 {
-    const size_t budget = 200 * 1024;     /* leave some of the 228 KB to L1 for the EPI gathers */
-    int bestH = 1; long bestScore = -1; int bestW = 1;
-    const char* env = getenv("RSLF_DEPTH_H");
-    int forced = env ? atoi(env) : 0;
-    for (int H = 4; H >= 1; H >>= 1) {
-        if (forced && H != forced) continue;
-        size_t sm = depth_smem_bytes(S, C, H);
-        if (sm > ctx->smem_optin) continue;
-        if (!forced && H > 1 && 32 * (H / 2) >= D) continue;        /* would leave lanes idle */
-        int w = (int)(budget / (sm + 1024));
-        if (w < 1) w = 1;
-        if (w > 32) w = 32;
-        long score = (w >= 8) ? (1000000L * H) : (long)w * H;
-        if (score > bestScore) { bestScore = score; bestH = H; bestW = w; }
-    }
-    depth_plan p;
-    p.H = bestH; p.blocks_per_sm = bestW; p.smem = depth_smem_bytes(S, C, bestH);
-    p.chunks = rslf_div_up(D, 32 * bestH);
-    return p;
+    double per_view = std::fabs((double)dmax - (double)dmin) * std::fabs((double)slope) * (32.0 * H - 1.0) / (double)(D - 1);
+    if (!(per_view < 1024.0)) per_view = 1024.0;
+    return (int)std::ceil(per_view * 65536.0);
 }
 
-template <int C, int H, bool NONNEG>
+static inline size_t depth_smem_bytes(int S, int C, int H, int RV, int s_hat, int wpv_q16)
+{
+    int spad = depth_padded_views(S);
+    if (spad < RV) spad = RV;
+    const int nrows = depth_num_rows(spad, RV);
+    size_t fl = 4 + ((nrows + 1 + 3) & ~3);
+    for (int r = 0; r < nrows; ++r) fl += depth_row_floats(r, S, spad, RV, s_hat, wpv_q16, C, 32 * H);
+    return fl * sizeof(float);
+}
+
+/* (H, RV) variants that are instantiated */
+static const int k_depth_variants[][2] = {{1, 0}, {1, 16}, {1, 32}, {2, 0}, {2, 16}, {4, 0}};
+
+/* resident warps per SM allowed by the register file (see depth_min_blocks) */
+static inline int depth_reg_warps(int C, int H, int RV)
+{
+    int wps = 512 / DEPTH_REG_ESTIMATE(C, H, RV);
+    return 4 * (wps > 8 ? 8 : (wps < 1 ? 1 : wps));
+}
+
+/*
+ * Chooses hypotheses per lane (H) and register-resident views (RV): the variant with the most
+ * resident warps per SM (shared memory and register file both counted), preferring wider lanes
+ * and register views on ties.  RSLF_DEPTH_H / RSLF_DEPTH_RV force a variant (experiments, tests).
+ */
+static depth_plan plan_depth(const rslf_ctx* ctx, int S, int C, int D, int s_hat, float dmin, float dmax, float slope)
+{
+    const size_t budget = 224 * 1024;     /* the gathers go through TMA, L1 needs no share */
+    const char* eh = getenv("RSLF_DEPTH_H");
+    const char* er = getenv("RSLF_DEPTH_RV");
+    const int fH = eh ? atoi(eh) : 0, fRV = er ? atoi(er) : -1;
+    depth_plan best; best.H = 1; best.RV = 0; best.blocks_per_sm = 1;
+    best.wpv_q16 = depth_wpv_q16(D, 1, dmin, dmax, slope);
+    best.smem = depth_smem_bytes(S, C, 1, 0, s_hat, best.wpv_q16);
+    double bestScore = -1;
+    for (auto& var : k_depth_variants) {
+        const int H = var[0], RV = var[1];
+        if (fH && H != fH) continue;
+        if (fRV >= 0 && RV != fRV) continue;
+        if (!fH && H > 1 && 32 * (H / 2) >= D) continue;            /* would leave lanes idle */
+        if (fRV < 0 && 2 * RV > depth_padded_views(S)) continue;    /* register views must be a minority */
+        const int wpv = depth_wpv_q16(D, H, dmin, dmax, slope);
+        const size_t sm = depth_smem_bytes(S, C, H, RV, s_hat, wpv);
+        if (sm > ctx->smem_optin) continue;
+        int w_smem = (int)(budget / (sm + 1024));
+        int w_regs = depth_reg_warps(C, H, RV);
+        int w = std::min(std::min(w_smem, w_regs), 32);
+        if (w < 1) w = 1;
+        /* resident hypotheses-in-flight saturate around 16 warps; register views save the LDS issue slots */
+        double score = std::min(w, 16) * (H == 1 ? 1.0 : (H == 2 ? 1.06 : 1.08)) * (1.0 + 0.002 * std::min(RV, S));
+        if (score > bestScore) { bestScore = score; best.H = H; best.RV = RV; best.blocks_per_sm = w; best.smem = sm; best.wpv_q16 = wpv; }
+    }
+    best.chunks = rslf_div_up(D, 32 * best.H);
+    return best;
+}
+
+template <int C, int H, bool NONNEG, int RV>
 static int launch_depth_t(rslf_ctx* ctx, const depth_args& a, const depth_plan& p)
 {
-    auto kern = depth_kernel<C, H, NONNEG>;
-    /* shared-memory carve-out: what the resident warps need, the rest stays L1 for the EPI gathers */
-    static int configured_carve = -1;
-    int carve = (int)((p.blocks_per_sm * (p.smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
-    if (carve > 100) carve = 100;
-    if (configured_carve != carve) {
+    auto kern = depth_kernel<C, H, NONNEG, RV>;
+    static bool configured = false;
+    if (!configured) {
         RSLF_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
-        RSLF_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
-        configured_carve = carve;
+        RSLF_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        configured = true;
     }
     int occ = 0;
     RSLF_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32, p.smem));
     if (occ < 1) occ = 1;
-    int bps = occ < p.blocks_per_sm ? occ : p.blocks_per_sm;
-    kern<<<ctx->num_sm * bps, 32, p.smem, ctx->stream>>>(a);
+    kern<<<ctx->num_sm * occ, 32, p.smem, ctx->stream>>>(a);
     RSLF_CUDA_TRY(ctx, cudaGetLastError());
     ctx->timing.kernel_launches += 1;
     ctx->timing.depth_launches += 1;
@@ -403,12 +611,14 @@ static int launch_depth_t(rslf_ctx* ctx, const depth_args& a, const depth_plan& 
 
 static int launch_depth(rslf_ctx* ctx, int C, bool nonneg, const depth_args& a, const depth_plan& p)
 {
-#define RSLF_DEPTH_CASE(CC, HH)                                                      \
-    if (C == CC && p.H == HH)                                                        \
-        return nonneg ? launch_depth_t<CC, HH, true>(ctx, a, p) : launch_depth_t<CC, HH, false>(ctx, a, p);
-    RSLF_DEPTH_CASE(1, 1) RSLF_DEPTH_CASE(1, 2) RSLF_DEPTH_CASE(1, 4)
-    RSLF_DEPTH_CASE(3, 1) RSLF_DEPTH_CASE(3, 2) RSLF_DEPTH_CASE(3, 4)
+#define RSLF_DEPTH_CASE(CC, HH, RR)                                                          \
+    if (C == CC && p.H == HH && p.RV == RR)                                                  \
+        return nonneg ? launch_depth_t<CC, HH, true, RR>(ctx, a, p) : launch_depth_t<CC, HH, false, RR>(ctx, a, p);
+    RSLF_DEPTH_CASE(1, 1, 0) RSLF_DEPTH_CASE(1, 1, 16) RSLF_DEPTH_CASE(1, 1, 32)
+    RSLF_DEPTH_CASE(1, 2, 0) RSLF_DEPTH_CASE(1, 2, 16) RSLF_DEPTH_CASE(1, 4, 0)
+    RSLF_DEPTH_CASE(3, 1, 0) RSLF_DEPTH_CASE(3, 1, 16) RSLF_DEPTH_CASE(3, 1, 32)
+    RSLF_DEPTH_CASE(3, 2, 0) RSLF_DEPTH_CASE(3, 2, 16) RSLF_DEPTH_CASE(3, 4, 0)
 #undef RSLF_DEPTH_CASE
-    snprintf(ctx->err, sizeof(ctx->err), "unsupported channel count %d", C);
+    snprintf(ctx->err, sizeof(ctx->err), "no depth kernel variant for C=%d H=%d RV=%d", C, p.H, p.RV);
     return RSLF_ERR_UNSUPPORTED;
 }

@@ -8,26 +8,47 @@
  * epsilon (norm) of the centre pixel's; unmasked outputs are 0.
  *
  * One thread per pixel; the window values sit in registers (fully unrolled) and
- * the rank-n/2 element is found by counting, which needs no data-dependent
- * indexing.  Colours are addressed through (colour, row_stride) so that a
- * row-sharded run can pass the gathered colour plane of line s_hat.
+ * are sorted by a fixed compare-exchange network (Batcher), so no data-dependent
+ * indexing is needed.  Colours are addressed through (colour, row_stride), and the rows
+ * to filter through (v_begin, v_count), so that a row-sharded run filters its own rows
+ * out of the gathered planes of line s_hat.
  */
 #pragma once
 #include "rslf_common.cuh"
 #include <math_constants.h>
 
+/* compare-exchange on registers */
+__device__ __forceinline__ void med_cswap(float& a, float& b) { const float lo = fminf(a, b), hi = fmaxf(a, b); a = lo; b = hi; }
+
+/* Batcher's odd-even merge sort as a fixed compare-exchange network for any N (Knuth 5.2.2 M);
+ * every index is a compile-time constant after unrolling, so the array stays in registers. */
+template <int N>
+__device__ __forceinline__ void sort_network(float (&a)[N])
+{
+#pragma unroll
+    for (int p = 1; p < N; p <<= 1)
+#pragma unroll
+        for (int k = p; k >= 1; k >>= 1)
+#pragma unroll
+            for (int j = k % p; j + k < N; j += 2 * k)
+#pragma unroll
+                for (int i = 0; i < k; ++i)
+                    if (i + j + k < N && (i + j) / (2 * p) == (i + j + k) / (2 * p)) med_cswap(a[i + j], a[i + j + k]);
+}
+
 template <int C, int WIDTH>
 __global__ void __launch_bounds__(128)
 selective_median_kernel(const float* __restrict__ src, const uint8_t* __restrict__ mask,
                         const float* __restrict__ colour, size_t colour_row_stride,
-                        int V, int U, float eps, double eps_T, float* __restrict__ dst)
+                        int V, int U, int v_begin, float eps, double eps_T, float* __restrict__ dst)
 {
     constexpr int N = (2 * WIDTH + 1) * (2 * WIDTH + 1);
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
-    const int v = blockIdx.y;
+    const int v = blockIdx.y + v_begin;            /* row in the (possibly gathered) planes */
     if (u >= U) return;
     const size_t o = (size_t)v * U + u;
-    if (!mask[o]) { dst[o] = 0.f; return; }
+    const size_t od = (size_t)blockIdx.y * U + u;     /* dst holds this rank's rows only */
+    if (!mask[o]) { dst[od] = 0.f; return; }
     float pc[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) pc[c] = __ldg(colour + (size_t)v * colour_row_stride + (size_t)u * C + c);
@@ -48,33 +69,28 @@ selective_median_kernel(const float* __restrict__ src, const uint8_t* __restrict
             val[(dk + WIDTH) * (2 * WIDTH + 1) + (dl + WIDTH)] = x;
         }
     }
-    /* rank n/2 among the n selected values (the rejected ones are +inf and sort last).
-     * A depth of +inf itself cannot be told from a rejected slot; depths are finite. */
+    /* element of rank n/2 among the n selected values (std::nth_element at n/2, core.hpp:712-713): sort the
+     * window, the rejected slots are +inf and end up last.  Depths are finite, so +inf is unambiguous. */
+    sort_network<N>(val);
     const int rank = n / 2;
-    float out = val[WIDTH * (2 * WIDTH + 1) + WIDTH];
+    float out = val[0];
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-        int less = 0, eq = 0;
-#pragma unroll
-        for (int j = 0; j < N; ++j) {
-            less += (val[j] < val[i]) ? 1 : 0;
-            eq += (val[j] == val[i]) ? 1 : 0;
-        }
-        if (less <= rank && rank < less + eq) out = val[i];
-    }
-    dst[o] = out;
+    for (int i = 1; i <= N / 2; ++i) out = (rank == i) ? val[i] : out;
+    dst[od] = out;
 }
 
 static int launch_selective_median(rslf_ctx* ctx, const float* src, const uint8_t* mask, const float* colour,
-                                   size_t colour_row_stride, int V, int U, int C, int size, float eps, float* dst)
+                                   size_t colour_row_stride, int V, int U, int C, int size, float eps, float* dst,
+                                   int v_begin = 0, int v_count = -1)
 {
     const int width = (size - 1) / 2;
-    dim3 grid(rslf_div_up(U, 128), V);
+    if (v_count < 0) v_count = V;
+    dim3 grid(rslf_div_up(U, 128), v_count);
     const double T = rslf_sq_threshold(eps);
 #define RSLF_MED_CASE(CC, WW)                                                                             \
     if (C == CC && width == WW) {                                                                         \
         selective_median_kernel<CC, WW><<<grid, 128, 0, ctx->stream>>>(src, mask, colour, colour_row_stride, \
-                                                                       V, U, eps, T, dst);                \
+                                                                       V, U, v_begin, eps, T, dst);       \
         RSLF_CUDA_TRY(ctx, cudaGetLastError());                                                           \
         ctx->timing.kernel_launches += 1;                                                                 \
         return RSLF_OK;                                                                                   \

@@ -41,32 +41,53 @@ propagate_kernel(const prop_args a)
     const size_t o = (size_t)v * a.U + u;
     if (!a.emask_p[o]) return;
     const float cur = a.filtered[o];
-    float rb[C];
-#pragma unroll
-    for (int c = 0; c < C; ++c) rb[c] = a.rbar_p[o * C + c];
-    const float cdv = (PHASE == 1) ? a.cd_p[o] : 0.f;
     const size_t plane = (size_t)a.V * a.U;
     const int s_begin = blockIdx.z * PROP_SG;
-    const int s_end = min(a.S, s_begin + PROP_SG);
-    for (int s = s_begin; s < s_end; ++s) {
+    /* targets of the PROP_SG views of this thread; the mask bytes are fetched together */
+    size_t tgt[PROP_SG];
+    uint8_t rem[PROP_SG];
+#pragma unroll
+    for (int j = 0; j < PROP_SG; ++j) {
+        const int s = s_begin + j;
         float t = cur * (float)(a.s_hat - s);
         t = t * a.slope;
         const int q = u + (int)roundf(t);
-        if (q < 0 || q >= a.U) continue;
-        const size_t tgt = (size_t)s * plane + (size_t)v * a.U + q;
-        if (!a.remaining[tgt]) continue;
-        const float* e = a.epi + (((size_t)v * a.S + s) * (size_t)a.U + q) * C;
-        float ec[C];
+        const bool in = (s < a.S) && (q >= 0) && (q < a.U);
+        tgt[j] = (size_t)min(s, a.S - 1) * plane + (size_t)v * a.U + min(max(q, 0), a.U - 1);
+        rem[j] = in ? a.remaining[tgt[j]] : (uint8_t)0;
+    }
+    bool any = false;
 #pragma unroll
-        for (int c = 0; c < C; ++c) ec[c] = __ldg(e + c);
-        if (!rslf_norm_diff_lt<C>(ec, rb, a.eps, a.eps_T)) continue;
-        if (PHASE == 0) {
-            atomicMin(a.winner + tgt, u);
-        } else if (a.winner[tgt] == u) {
-            a.depth[tgt] = cur;
-            a.cd[tgt] = cdv;
-            a.remaining[tgt] = 0;
-            a.winner[tgt] = 0x7fffffff;
+    for (int j = 0; j < PROP_SG; ++j) any |= (rem[j] != 0);
+    if (!any) return;
+    if (PHASE == 0) {
+        float rb[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) rb[c] = a.rbar_p[o * C + c];
+#pragma unroll
+        for (int j = 0; j < PROP_SG; ++j) {
+            if (!rem[j]) continue;
+            /* colour of the target pixel: E_v(s, q); tgt = (s*V + v)*U + q  ->  epi index ((v*S + s)*U + q)*C */
+            const int s = s_begin + j;
+            const size_t q = tgt[j] - ((size_t)s * plane + (size_t)v * a.U);
+            const float* e = a.epi + (((size_t)v * a.S + s) * (size_t)a.U + q) * C;
+            float ec[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) ec[c] = __ldg(e + c);
+            if (rslf_norm_diff_lt<C>(ec, rb, a.eps, a.eps_T)) atomicMin(a.winner + tgt[j], u);
+        }
+    } else {
+        /* the arbitration entry equals u only if this source passed every test in phase 0 and is the lowest */
+        const float cdv = a.cd_p[o];
+#pragma unroll
+        for (int j = 0; j < PROP_SG; ++j) {
+            if (!rem[j]) continue;
+            if (a.winner[tgt[j]] == u) {
+                a.depth[tgt[j]] = cur;
+                a.cd[tgt[j]] = cdv;
+                a.remaining[tgt[j]] = 0;
+                a.winner[tgt[j]] = 0x7fffffff;
+            }
         }
     }
 }

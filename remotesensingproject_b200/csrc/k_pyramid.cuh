@@ -72,14 +72,17 @@ __global__ void normalise_u8_kernel(const uint8_t* __restrict__ in, size_t n, fl
 
 template <int C>
 __global__ void __launch_bounds__(DS_THREADS)
-downsample_kernel(const float* __restrict__ in, int V, int S, int U, float* __restrict__ out, int V2, int U2)
+downsample_kernel(const float* __restrict__ in, int V, int S, int U, float* __restrict__ out, int V2, int U2,
+                  int ov_begin, int ov_count)
 {
     constexpr int IW = 2 * DS_TU + 6, IH = 2 * DS_TV + 6, BW = 2 * DS_TU;
     __shared__ float tin[IH][IW * C];
     __shared__ float hb[IH][BW * C];
     const float k0 = 9.f / 32.f, k1 = 7.f / 32.f, k2 = 3.5f / 32.f, k3 = 1.f / 32.f;
     const int s = blockIdx.z;
-    const int ou0 = blockIdx.x * DS_TU, ov0 = blockIdx.y * DS_TV;
+    /* `in` holds all V rows of the level; this launch writes the ov_count output rows from ov_begin on
+     * into `out` (local row 0 = output row ov_begin), so a row-sharded rank produces only its rows */
+    const int ou0 = blockIdx.x * DS_TU, ov0 = ov_begin + blockIdx.y * DS_TV;
     const int iu0 = 2 * ou0 - 3, iv0 = 2 * ov0 - 3;
     for (int i = threadIdx.x; i < IH * IW * C; i += DS_THREADS) {
         int r = i / (IW * C), rem = i - r * (IW * C);
@@ -106,7 +109,7 @@ downsample_kernel(const float* __restrict__ in, int V, int S, int U, float* __re
         int r = i / (DS_TU * C), rem = i - r * (DS_TU * C);
         int p = rem / C, c = rem - p * C;
         const int ov = ov0 + r, ou = ou0 + p;
-        if (ov >= V2 || ou >= U2) continue;
+        if (ov >= V2 || ov >= ov_begin + ov_count || ou >= U2) continue;
         /* source rows / columns of the 2x2 mean, clamped at odd edges */
         const int r0 = min(2 * ov, V - 1) - iv0, r1 = min(2 * ov + 1, V - 1) - iv0;
         const int c0 = min(2 * ou, U - 1) - 2 * ou0, c1 = min(2 * ou + 1, U - 1) - 2 * ou0;
@@ -125,7 +128,7 @@ downsample_kernel(const float* __restrict__ in, int V, int S, int U, float* __re
             }
         }
         const float sum = ((bl[0][0] + bl[0][1]) + bl[1][0]) + bl[1][1];
-        out[(((size_t)ov * S + s) * (size_t)U2 + ou) * C + c] = sum * 0.25f;
+        out[(((size_t)(ov - ov_begin) * S + s) * (size_t)U2 + ou) * C + c] = sum * 0.25f;
     }
 }
 
@@ -182,17 +185,21 @@ __global__ void nearest_valid_kernel(const uint8_t* __restrict__ valid, int rows
 /* bounds of level p+1 (down) from depth / nearest-valid tables of level p (up) */
 __global__ void set_bounds_kernel(const float* __restrict__ depth_up, const int* __restrict__ left,
                                   const int* __restrict__ right, int S, int Vu, int Uu, int Vd, int Ud,
-                                  float* __restrict__ dmin_map, float* __restrict__ dmax_map)
+                                  float* __restrict__ dmin_map, float* __restrict__ dmax_map,
+                                  int Vu_tot, int vu0, int vd0)
 {
+    /* Vu / Vd: rows held locally (first global rows vu0 / vd0); Vu_tot: global rows of the upper level */
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
     const int v = blockIdx.y, s = blockIdx.z;
     if (u >= Ud) return;
-    const int v_up = min(2 * v, Vu - 1);
+    const int v_up_g = min(2 * (v + vd0), Vu_tot - 1);
+    const int v_up = v_up_g - vu0;
     const int u_up = min(2 * u, Uu - 1);
     float mn = 0.f, mx = 0.f; int n = 0;
     for (int line = 0; line < 2; ++line) {
         const int vv = v_up + line;
-        if (line == 1 && !(vv < Vu)) break;
+        if (line == 1 && !(v_up_g + 1 < Vu_tot)) break;
+        if (vv < 0 || vv >= Vu) continue;          /* cannot happen with aligned shards */
         const size_t ro = ((size_t)s * Vu + vv) * (size_t)Uu;
         const int jl = (u_up - 1 >= 1) ? left[ro + u_up - 1] : -1;
         const int jr = (u_up + 1 <= Uu - 1) ? right[ro + u_up + 1] : Uu;
@@ -218,12 +225,16 @@ __global__ void set_bounds_kernel(const float* __restrict__ depth_up, const int*
  */
 __global__ void fuse_level_kernel(const float* __restrict__ map_down, const uint8_t* __restrict__ mask_down,
                                   int Vs, int Us, const float* __restrict__ disp, const uint8_t* __restrict__ valid,
-                                  int Vd, int Ud, float* __restrict__ map_out, uint8_t* __restrict__ mask_out)
+                                  int Vd, int Ud, float* __restrict__ map_out, uint8_t* __restrict__ mask_out,
+                                  int y0, int Vd_loc)
 {
+    /* map_down / mask_down: the whole coarser level; disp / valid / outputs: the Vd_loc local rows from
+     * global row y0 on (Vd = global rows of the finer level) */
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y, s = blockIdx.z;
+    const int yl = blockIdx.y, s = blockIdx.z;
+    const int y = yl + y0;
     if (x >= Ud) return;
-    const size_t o = ((size_t)s * Vd + y) * (size_t)Ud + x;
+    const size_t o = ((size_t)s * Vd_loc + yl) * (size_t)Ud + x;
     const double sx = (double)Us / Ud, sy = (double)Vs / Vd;
     const uint8_t* mk = mask_down + (size_t)s * Vs * Us;
     const int ny = min((int)floor(y * sy), Vs - 1), nx = min((int)floor(x * sx), Us - 1);
@@ -251,10 +262,11 @@ __global__ void fuse_level_kernel(const float* __restrict__ map_down, const uint
 __device__ __forceinline__ void sort2(float& a, float& b) { float lo = fminf(a, b), hi = fmaxf(a, b); a = lo; b = hi; }
 
 /* cv::medianBlur(float32, 3): 3x3 median, BORDER_REPLICATE */
-__global__ void median3x3_kernel(const float* __restrict__ src, int V, int U, float* __restrict__ dst)
+__global__ void median3x3_kernel(const float* __restrict__ src, int V, int U, float* __restrict__ dst, int v0, int V_loc)
 {
+    /* src: all V rows; dst: the V_loc local rows from global row v0 on */
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
-    const int v = blockIdx.y, s = blockIdx.z;
+    const int v = blockIdx.y + v0, s = blockIdx.z;
     if (u >= U) return;
     const float* p = src + (size_t)s * V * U;
     float w[9]; int n = 0;
@@ -273,5 +285,5 @@ __global__ void median3x3_kernel(const float* __restrict__ src, int V, int U, fl
     sort2(w[3], w[6]); sort2(w[1], w[4]); sort2(w[2], w[5]);
     sort2(w[4], w[7]); sort2(w[4], w[2]); sort2(w[6], w[4]);
     sort2(w[4], w[2]);
-    dst[((size_t)s * V + v) * (size_t)U + u] = w[4];
+    dst[((size_t)s * V_loc + (v - v0)) * (size_t)U + u] = w[4];
 }

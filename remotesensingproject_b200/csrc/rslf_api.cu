@@ -87,6 +87,9 @@ static void free_scratch(rslf_ctx* ctx)
     dev_free(&ctx->nearest_l); dev_free(&ctx->nearest_r);
     dev_free(&ctx->fuse_a); dev_free(&ctx->fuse_b); dev_free(&ctx->fuse_ma); dev_free(&ctx->fuse_mb);
     dev_free(&ctx->out_map); dev_free(&ctx->out_valid); dev_free(&ctx->pile_depth_raw);
+    dev_free(&ctx->g_depth); dev_free(&ctx->g_colour); dev_free(&ctx->g_mask); ctx->g_plane_cap = 0;
+    dev_free(&ctx->g_raw); ctx->g_raw_cap = 0;
+    dev_free(&ctx->g_map); dev_free(&ctx->g_map2); dev_free(&ctx->g_mk); dev_free(&ctx->g_mk2); ctx->g_map_cap = 0;
     ctx->scratch_px = 0;
 }
 
@@ -140,7 +143,7 @@ static int ensure_level(rslf_ctx* ctx, int p, int V, int U, bool full, bool with
     rslf_level& L = ctx->lv[p];
     const size_t planes = full ? (size_t)ctx->S : 1;
     const size_t px = planes * V * U;
-    const size_t stack = (size_t)V * ctx->S * U * ctx->C;
+    const size_t stack = (size_t)V * ctx->S * U * ctx->C + 64;     /* + slack: TMA segments end on 16-byte boundaries */
     if (L.V != V || L.U != U || L.cap_px != px || L.C != ctx->C) {
         float* raw = L.raw; float* epi = L.epi; size_t cap_stack = L.cap_stack;   /* stacks survive a map re-allocation */
         L.raw = nullptr; L.epi = nullptr;
@@ -438,6 +441,35 @@ extern "C" int rslf_cuda_upload_images(rslf_ctx* ctx, const void* const* img_ptr
     return RSLF_OK;
 }
 
+/* gathered planes of one line (row-sharded runs) */
+static int ensure_gather_planes(rslf_ctx* ctx, size_t plane_tot)
+{
+    if (ctx->g_plane_cap >= plane_tot) return RSLF_OK;
+    RSLF_TRY(dev_alloc(ctx, &ctx->g_depth, plane_tot));
+    RSLF_TRY(dev_alloc(ctx, &ctx->g_colour, plane_tot * ctx->C));
+    RSLF_TRY(dev_alloc(ctx, &ctx->g_mask, plane_tot));
+    ctx->g_plane_cap = plane_tot;
+    return RSLF_OK;
+}
+
+/* Global view of a row-sharded [S][Vloc][U] map: the map itself on one GPU, else gathered into slot 0 / 1. */
+static int global_svu_f32(rslf_ctx* ctx, const float* local, int S, int U, const shard_tab& t, int slot, const float** out)
+{
+    if (ctx->world <= 1) { *out = local; return RSLF_OK; }
+    float* dst = slot ? ctx->g_map2 : ctx->g_map;
+    RSLF_TRY(comm_gather_svu(ctx, local, 4, S, U, t, dst));
+    *out = dst;
+    return RSLF_OK;
+}
+static int global_svu_u8(rslf_ctx* ctx, const uint8_t* local, int S, int U, const shard_tab& t, int slot, const uint8_t** out)
+{
+    if (ctx->world <= 1) { *out = local; return RSLF_OK; }
+    uint8_t* dst = slot ? ctx->g_mk2 : ctx->g_mk;
+    RSLF_TRY(comm_gather_svu(ctx, local, 1, S, U, t, dst));
+    *out = dst;
+    return RSLF_OK;
+}
+
 /* ------------------------------------------------------------------ one s_hat pass */
 struct pass_io {
     int level; int s_hat; int D; float dmin, dmax; bool use_bound_maps;
@@ -461,7 +493,7 @@ static int run_depth_pass(rslf_ctx* ctx, const rslf_params& P, const pass_io& io
         RSLF_CUDA_TRY(ctx, cudaGetLastError());
         ctx->timing.kernel_launches += 1;
     }
-    depth_plan plan = plan_depth(ctx, S, C, io.D);
+    depth_plan plan = plan_depth(ctx, S, C, io.D, io.s_hat, io.dmin, io.dmax, P.slope_factor);
     if (plan.chunks > 1) RSLF_TRY(ensure_partials(ctx, plane * plan.chunks));
     depth_args a;
     a.epi = L.epi; a.V = V; a.S = S; a.U = U; a.D = io.D; a.s_hat = io.s_hat; a.slope = P.slope_factor;
@@ -474,6 +506,7 @@ static int run_depth_pass(rslf_ctx* ctx, const rslf_params& P, const pass_io& io
     a.depth = io.pile ? ctx->pile_depth_raw : L.depth + po;
     a.rbar = L.rbar + po * C;
     a.raw_thr = P.raw_score_threshold;
+    a.wpv_q16 = plan.wpv_q16;
     a.chunks = plan.chunks; a.partials = (rslf_partial*)ctx->partials; a.arrive = ctx->arrive;
     {
         stage_scope sc(ctx, ST_DEPTH);
@@ -481,9 +514,19 @@ static int run_depth_pass(rslf_ctx* ctx, const rslf_params& P, const pass_io& io
     }
     {
         stage_scope sc(ctx, ST_MEDIAN);
-        /* colours of line s_hat: row v starts at epi + (v*S + s_hat)*U*C */
-        RSLF_TRY(launch_selective_median(ctx, a.depth, L.emask + po, L.epi + (size_t)io.s_hat * U * C, (size_t)S * U * C,
-                                         V, U, C, P.median_filter_size, P.median_filter_epsilon, ctx->filtered));
+        if (ctx->world > 1) {
+            /* the only cross-row step of a pass (core.hpp:698-709): every rank needs the depth, mask and colour
+             * rows of line s_hat next to its block -> all-gather them, then filter the local rows */
+            const shard_tab t = level_shards(ctx, io.level, L.Vtot);
+            RSLF_TRY(ensure_gather_planes(ctx, (size_t)L.Vtot * U));
+            RSLF_TRY(comm_gather_median_planes(ctx, a.depth, L.emask + po, L.epi + (size_t)io.s_hat * U * C, (size_t)S * U * C, U, C, t));
+            RSLF_TRY(launch_selective_median(ctx, ctx->g_depth, ctx->g_mask, ctx->g_colour, (size_t)U * C, L.Vtot, U, C,
+                                             P.median_filter_size, P.median_filter_epsilon, ctx->filtered, L.v0, V));
+        } else {
+            /* colours of line s_hat: row v starts at epi + (v*S + s_hat)*U*C */
+            RSLF_TRY(launch_selective_median(ctx, a.depth, L.emask + po, L.epi + (size_t)io.s_hat * U * C, (size_t)S * U * C,
+                                             V, U, C, P.median_filter_size, P.median_filter_epsilon, ctx->filtered));
+        }
     }
     return RSLF_OK;
 }
@@ -572,6 +615,8 @@ static int copy_out(rslf_ctx* ctx, void* host, const void* dev, size_t bytes)
     return RSLF_OK;
 }
 
+static int prepare_shards(rslf_ctx* ctx, int levels);
+
 /* ------------------------------------------------------------------ Depth1DComputer_pile */
 extern "C" int rslf_cuda_depth1d_pile_run(rslf_ctx* ctx, float dmin, float dmax, int dim_d, int s_hat,
                                           const rslf_params* params)
@@ -582,9 +627,11 @@ extern "C" int rslf_cuda_depth1d_pile_run(rslf_ctx* ctx, float dmin, float dmax,
     const int V = ctx->V, U = ctx->U, S = ctx->S, C = ctx->C;
     if (s_hat < 0 || s_hat > S - 1) s_hat = (int)std::floor((0.0 + S) / 2);      /* dc.hpp:489-498 */
     RSLF_TRY(ensure_scratch(ctx, false, false));
+    RSLF_TRY(prepare_shards(ctx, 1));
     RSLF_TRY(ensure_level(ctx, 0, V, U, false, false));
     ctx->n_levels = 1;
     rslf_level& L = ctx->lv[0];
+    L.v0 = ctx->v0; L.Vtot = ctx->V_total;
     L.slope = P.slope_factor;
     RSLF_TRY(normalise_level(ctx, 0, ctx->raw_in, ctx->cv_depth));
     const size_t plane = (size_t)V * U;
@@ -653,9 +700,11 @@ extern "C" int rslf_cuda_depth2d_run(rslf_ctx* ctx, float dmin, float dmax, int 
     const int V = ctx->V, U = ctx->U, S = ctx->S;
     RSLF_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     RSLF_TRY(ensure_scratch(ctx, true, false));
+    RSLF_TRY(prepare_shards(ctx, 1));
     RSLF_TRY(ensure_level(ctx, 0, V, U, true, dmin_svu != nullptr));
     ctx->n_levels = 1;
     rslf_level& L = ctx->lv[0];
+    L.v0 = ctx->v0; L.Vtot = ctx->V_total;
     const size_t px = (size_t)S * V * U;
     if (dmin_svu) {
         RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(L.dmin, dmin_svu, px * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -722,39 +771,72 @@ extern "C" int rslf_cuda_depth2d_get_valid_mask(rslf_ctx* ctx, int accept_all, c
 /* ------------------------------------------------------------------ FineToCoarse */
 static inline int cv_round_half(int n) { return (int)std::nearbyint(n * 0.5); }   /* cvRound: half to even */
 
-static int launch_downsample(rslf_ctx* ctx, const float* in, int V, int S, int U, int C, float* out, int V2, int U2)
+static int launch_downsample(rslf_ctx* ctx, const float* in, int V, int S, int U, int C, float* out, int V2, int U2,
+                             int ov_begin = 0, int ov_count = -1)
 {
-    dim3 grid(rslf_div_up(U2, DS_TU), rslf_div_up(V2, DS_TV), S);
-    if (C == 1) downsample_kernel<1><<<grid, DS_THREADS, 0, ctx->stream>>>(in, V, S, U, out, V2, U2);
-    else downsample_kernel<3><<<grid, DS_THREADS, 0, ctx->stream>>>(in, V, S, U, out, V2, U2);
+    if (ov_count < 0) ov_count = V2;
+    dim3 grid(rslf_div_up(U2, DS_TU), rslf_div_up(ov_count, DS_TV), S);
+    if (C == 1) downsample_kernel<1><<<grid, DS_THREADS, 0, ctx->stream>>>(in, V, S, U, out, V2, U2, ov_begin, ov_count);
+    else downsample_kernel<3><<<grid, DS_THREADS, 0, ctx->stream>>>(in, V, S, U, out, V2, U2, ov_begin, ov_count);
     RSLF_CUDA_TRY(ctx, cudaGetLastError());
     ctx->timing.kernel_launches += 1;
     return RSLF_OK;
 }
 
-static int launch_fuse(rslf_ctx* ctx, int levels, const int* Vp, const int* Up, const float* const* disp,
+/* fuse_disp_maps (ftc_core.cpp:69-135).  Vp: GLOBAL rows per level; disp / valid / outputs hold the local rows
+ * described by tabs[p] (one rank: everything). */
+static int launch_fuse(rslf_ctx* ctx, int levels, const int* Vp, const int* Up, const shard_tab* tabs, const float* const* disp,
                        const uint8_t* const* valid, float* out_map, uint8_t* out_valid)
 {
-    const int S = ctx->S;
-    const float* map_down = disp[levels - 1];
-    const uint8_t* mask_down = valid[levels - 1];
+    const int S = ctx->S, r = ctx->rank;
+    const float* map_down = nullptr; const uint8_t* mask_down = nullptr;
+    RSLF_TRY(global_svu_f32(ctx, disp[levels - 1], S, Up[levels - 1], tabs[levels - 1], 0, &map_down));
+    RSLF_TRY(global_svu_u8(ctx, valid[levels - 1], S, Up[levels - 1], tabs[levels - 1], 0, &mask_down));
     float* fa = ctx->fuse_a; float* fb = ctx->fuse_b; uint8_t* ma = ctx->fuse_ma; uint8_t* mb = ctx->fuse_mb;
     for (int p = levels - 1; p > 0; --p) {
         const int Vn = Vp[p - 1], Un = Up[p - 1];
-        dim3 grid(rslf_div_up(Un, 128), Vn, S);
+        const int y0 = tabs[p - 1].b[r], Vn_loc = tabs[p - 1].b[r + 1] - y0;
+        dim3 grid(rslf_div_up(Un, 128), Vn_loc, S);
         uint8_t* mout = (p == 1) ? out_valid : ma;
-        fuse_level_kernel<<<grid, 128, 0, ctx->stream>>>(map_down, mask_down, Vp[p], Up[p], disp[p - 1], valid[p - 1], Vn, Un, fa, mout);
+        fuse_level_kernel<<<grid, 128, 0, ctx->stream>>>(map_down, mask_down, Vp[p], Up[p], disp[p - 1], valid[p - 1], Vn, Un, fa, mout, y0, Vn_loc);
         RSLF_CUDA_TRY(ctx, cudaGetLastError());
         ctx->timing.kernel_launches += 1;
-        map_down = fa; mask_down = mout;
+        /* the next (finer) level interpolates across rank borders, the final median reads +-1 row */
+        RSLF_TRY(global_svu_f32(ctx, fa, S, Un, tabs[p - 1], p & 1, &map_down));
+        if (p > 1) RSLF_TRY(global_svu_u8(ctx, mout, S, Un, tabs[p - 1], p & 1, &mask_down));
         std::swap(fa, fb); std::swap(ma, mb);
     }
-    const size_t px = (size_t)S * Vp[0] * Up[0];
-    if (levels == 1) RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(out_valid, mask_down, px, cudaMemcpyDeviceToDevice, ctx->stream));
-    dim3 grid(rslf_div_up(Up[0], 128), Vp[0], S);
-    median3x3_kernel<<<grid, 128, 0, ctx->stream>>>(map_down, Vp[0], Up[0], out_map);
+    const int v0 = tabs[0].b[r], V_loc = tabs[0].b[r + 1] - v0;
+    const size_t px = (size_t)S * V_loc * Up[0];
+    if (levels == 1) RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(out_valid, valid[0], px, cudaMemcpyDeviceToDevice, ctx->stream));
+    dim3 grid(rslf_div_up(Up[0], 128), V_loc, S);
+    median3x3_kernel<<<grid, 128, 0, ctx->stream>>>(map_down, Vp[0], Up[0], out_map, v0, V_loc);
     RSLF_CUDA_TRY(ctx, cudaGetLastError());
     ctx->timing.kernel_launches += 1;
+    return RSLF_OK;
+}
+
+static shard_tab single_tab(int V) { shard_tab t; t.n = 1; t.b[0] = 0; t.b[1] = V; return t; }
+
+/* Row-shard bookkeeping of a run: sets the level-0 table for a single rank, checks a multi-rank one. */
+static int prepare_shards(rslf_ctx* ctx, int levels)
+{
+    if (ctx->world <= 1) {
+        ctx->row_starts[0] = 0; ctx->row_starts[1] = ctx->V; ctx->v0 = 0; ctx->V_total = ctx->V; ctx->rank = 0;
+        return RSLF_OK;
+    }
+    if (!ctx->have_shards) { snprintf(ctx->err, sizeof(ctx->err), "multi-rank run without rslf_cuda_set_row_shards"); return RSLF_ERR_STATE; }
+    if (ctx->row_starts[ctx->rank + 1] - ctx->row_starts[ctx->rank] != ctx->V) {
+        snprintf(ctx->err, sizeof(ctx->err), "uploaded %d rows but the shard table gives this rank %d", ctx->V,
+                 ctx->row_starts[ctx->rank + 1] - ctx->row_starts[ctx->rank]);
+        return RSLF_ERR_ARG;
+    }
+    const int align = 1 << (levels - 1);
+    for (int r = 1; r < ctx->world; ++r)
+        if (ctx->row_starts[r] % align) {
+            snprintf(ctx->err, sizeof(ctx->err), "shard boundary %d is not a multiple of %d (2^(levels-1))", ctx->row_starts[r], align);
+            return RSLF_ERR_ARG;
+        }
     return RSLF_OK;
 }
 
@@ -763,12 +845,12 @@ extern "C" int rslf_cuda_fine_to_coarse_run(rslf_ctx* ctx, float dmin, float dma
 {
     RSLF_TRY(check_params(ctx, params, dim_d));
     RSLF_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    const int S = ctx->S, C = ctx->C;
-    /* pyramid sizes: while (V > 10 && U > 10 && depth < max) (ftc.hpp:130), dsize = cvRound(n * 0.5) */
+    const int S = ctx->S, C = ctx->C, r = ctx->world > 1 ? ctx->rank : 0;
+    /* pyramid sizes from the GLOBAL field: while (V > 10 && U > 10 && depth < max) (ftc.hpp:130), dsize = cvRound(n * 0.5) */
     int Vp[RSLF_MAX_LEVELS], Up[RSLF_MAX_LEVELS];
     int levels = 0;
     {
-        int V = ctx->V, U = ctx->U;
+        int V = (ctx->world > 1 && ctx->have_shards) ? ctx->V_total : ctx->V, U = ctx->U;
         int maxd = (max_pyr_depth < 1) ? RSLF_MAX_LEVELS : std::min(max_pyr_depth, RSLF_MAX_LEVELS);
         while (V > 10 && U > 10 && levels < maxd) {
             Vp[levels] = V; Up[levels] = U; ++levels;
@@ -780,16 +862,39 @@ extern "C" int rslf_cuda_fine_to_coarse_run(rslf_ctx* ctx, float dmin, float dma
         snprintf(ctx->err, sizeof(ctx->err), "8-bit pyramids (OpenCV integer blur) are not implemented; convert to float32 or use max_pyr_depth=1");
         return RSLF_ERR_UNSUPPORTED;
     }
+    RSLF_TRY(prepare_shards(ctx, levels));
+    shard_tab tabs[RSLF_MAX_LEVELS];
+    int Vl[RSLF_MAX_LEVELS];                                  /* local rows per level */
+    for (int p = 0; p < levels; ++p) {
+        tabs[p] = level_shards(ctx, p, Vp[p]);
+        Vl[p] = tabs[p].b[r + 1] - tabs[p].b[r];
+        for (int q = 0; q < ctx->world; ++q)
+            if (tabs[p].b[q + 1] - tabs[p].b[q] < 1) {
+                snprintf(ctx->err, sizeof(ctx->err), "rank %d would hold no row of pyramid level %d; use fewer ranks", q, p);
+                return RSLF_ERR_ARG;
+            }
+    }
     RSLF_TRY(ensure_scratch(ctx, true, true));
     for (int p = 0; p < levels; ++p) {
-        RSLF_TRY(ensure_level(ctx, p, Vp[p], Up[p], true, true));
+        RSLF_TRY(ensure_level(ctx, p, Vl[p], Up[p], true, true));
+        ctx->lv[p].v0 = tabs[p].b[r]; ctx->lv[p].Vtot = Vp[p];
+    }
+    if (ctx->world > 1) {
+        const size_t gpx = (size_t)S * Vp[0] * Up[0];
+        if (ctx->g_map_cap < gpx) {
+            RSLF_TRY(dev_alloc(ctx, &ctx->g_map, gpx)); RSLF_TRY(dev_alloc(ctx, &ctx->g_map2, gpx));
+            RSLF_TRY(dev_alloc(ctx, &ctx->g_mk, gpx)); RSLF_TRY(dev_alloc(ctx, &ctx->g_mk2, gpx));
+            ctx->g_map_cap = gpx;
+        }
+        const size_t graw = (size_t)Vp[0] * S * Up[0] * C + 64;
+        if (levels > 1 && ctx->g_raw_cap < graw) { RSLF_TRY(dev_alloc(ctx, &ctx->g_raw, graw)); ctx->g_raw_cap = graw; }
     }
     ctx->n_levels = levels;
     RSLF_TRY(begin_run(ctx));
     const rslf_params& P0 = *params;
     for (int p = 0; p < levels; ++p) {
         rslf_level& L = ctx->lv[p];
-        const size_t px = (size_t)S * Vp[p] * Up[p];
+        const size_t px = (size_t)S * Vl[p] * Up[p];
         const void* raw = (p == 0) ? ctx->raw_in : (const void*)L.raw;
         RSLF_TRY(normalise_level(ctx, p, raw, p == 0 ? ctx->cv_depth : RSLF_DEPTH_32F));
         rslf_params P = P0;
@@ -809,15 +914,23 @@ extern "C" int rslf_cuda_fine_to_coarse_run(rslf_ctx* ctx, float dmin, float dma
             ctx->timing.kernel_launches += 1;
             if (p + 1 < levels) {
                 rslf_level& N = ctx->lv[p + 1];
-                RSLF_TRY(launch_downsample(ctx, (const float*)raw, Vp[p], S, Up[p], C, N.raw, Vp[p + 1], Up[p + 1]));
-                const size_t npx = (size_t)S * Vp[p + 1] * Up[p + 1];
+                /* next level's raw stack (ftc.hpp:146): the 7x7 blur reads 3 rows beyond the rank's block, so a
+                 * sharded run first gathers the level's raw rows */
+                const float* ds_in = (const float*)raw;
+                if (ctx->world > 1) {
+                    RSLF_TRY(comm_gather_rows(ctx, raw, (size_t)S * Up[p] * C * sizeof(float), tabs[p], ctx->g_raw));
+                    ds_in = ctx->g_raw;
+                }
+                RSLF_TRY(launch_downsample(ctx, ds_in, Vp[p], S, Up[p], C, N.raw, Vp[p + 1], Up[p + 1], tabs[p + 1].b[r], Vl[p + 1]));
+                const size_t npx = (size_t)S * Vl[p + 1] * Up[p + 1];
                 fill_f32_kernel<<<stream_grid(ctx, npx), 256, 0, ctx->stream>>>(N.dmin, npx, dmin);
                 fill_f32_kernel<<<stream_grid(ctx, npx), 256, 0, ctx->stream>>>(N.dmax, npx, dmax);
-                const int rows = S * Vp[p];
+                /* bounds of level p+1 from level p (ftc.hpp:201-294): rows 2v, 2v+1 are local (aligned shards) */
+                const int rows = S * Vl[p];
                 nearest_valid_kernel<<<rslf_div_up((long long)rows * 32, 256), 256, 0, ctx->stream>>>(L.valid, rows, Up[p], ctx->nearest_l, ctx->nearest_r);
-                dim3 grid(rslf_div_up(Up[p + 1], 128), Vp[p + 1], S);
-                set_bounds_kernel<<<grid, 128, 0, ctx->stream>>>(L.depth, ctx->nearest_l, ctx->nearest_r, S, Vp[p], Up[p],
-                                                                 Vp[p + 1], Up[p + 1], N.dmin, N.dmax);
+                dim3 grid(rslf_div_up(Up[p + 1], 128), Vl[p + 1], S);
+                set_bounds_kernel<<<grid, 128, 0, ctx->stream>>>(L.depth, ctx->nearest_l, ctx->nearest_r, S, Vl[p], Up[p],
+                                                                 Vl[p + 1], Up[p + 1], N.dmin, N.dmax, Vp[p], tabs[p].b[r], tabs[p + 1].b[r]);
                 ctx->timing.kernel_launches += 4;
             }
             RSLF_CUDA_TRY(ctx, cudaGetLastError());
@@ -828,7 +941,7 @@ extern "C" int rslf_cuda_fine_to_coarse_run(rslf_ctx* ctx, float dmin, float dma
         stage_scope sc(ctx, ST_PYR);
         const float* dp[RSLF_MAX_LEVELS]; const uint8_t* vp[RSLF_MAX_LEVELS];
         for (int p = 0; p < levels; ++p) { dp[p] = ctx->lv[p].depth; vp[p] = ctx->lv[p].valid; }
-        RSLF_TRY(launch_fuse(ctx, levels, Vp, Up, dp, vp, ctx->out_map, ctx->out_valid));
+        RSLF_TRY(launch_fuse(ctx, levels, Vp, Up, tabs, dp, vp, ctx->out_map, ctx->out_valid));
     }
     ctx->last_kind = 3;
     return end_run(ctx, dim_d);
@@ -967,7 +1080,7 @@ extern "C" int rslf_cuda_set_bounds(rslf_ctx* ctx, const float* depth_up, const 
         const int rows = S * Vu;
         nearest_valid_kernel<<<rslf_div_up((long long)rows * 32, 256), 256, 0, ctx->stream>>>(d_val, rows, Uu, d_l, d_r);
         dim3 grid(rslf_div_up(Ud, 128), Vd, S);
-        set_bounds_kernel<<<grid, 128, 0, ctx->stream>>>(d_dep, d_l, d_r, S, Vu, Uu, Vd, Ud, d_mn, d_mx);
+        set_bounds_kernel<<<grid, 128, 0, ctx->stream>>>(d_dep, d_l, d_r, S, Vu, Uu, Vd, Ud, d_mn, d_mx, Vu, 0, 0);
         cudaMemcpyAsync(dmin_map, d_mn, nd * 4, cudaMemcpyDeviceToHost, ctx->stream);
         cudaMemcpyAsync(dmax_map, d_mx, nd * 4, cudaMemcpyDeviceToHost, ctx->stream);
         if (cudaStreamSynchronize(ctx->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) rc = RSLF_ERR_CUDA;
@@ -1005,7 +1118,14 @@ extern "C" int rslf_cuda_fuse_disp_maps(rslf_ctx* ctx, int levels, int S, const 
         /* temporarily borrow the ctx fuse buffers' slots */
         float* sa = ctx->fuse_a; float* sb = ctx->fuse_b; uint8_t* sma = ctx->fuse_ma; uint8_t* smb = ctx->fuse_mb; int sS = ctx->S;
         ctx->fuse_a = fa; ctx->fuse_b = fb; ctx->fuse_ma = ma; ctx->fuse_mb = mb; ctx->S = S;
-        rc = launch_fuse(ctx, levels, Vp, Up, dd.data(), dv.data(), om, ov);
+        {
+            /* host maps are whole: a single-rank table, whatever the ctx's communicator */
+            std::vector<shard_tab> tabs(levels);
+            for (int p = 0; p < levels; ++p) tabs[p] = single_tab(Vp[p]);
+            int sw = ctx->world, sr = ctx->rank; ctx->world = 1; ctx->rank = 0;
+            rc = launch_fuse(ctx, levels, Vp, Up, tabs.data(), dd.data(), dv.data(), om, ov);
+            ctx->world = sw; ctx->rank = sr;
+        }
         ctx->fuse_a = sa; ctx->fuse_b = sb; ctx->fuse_ma = sma; ctx->fuse_mb = smb; ctx->S = sS;
         if (rc == RSLF_OK) {
             if (out_map_svu) cudaMemcpyAsync(out_map_svu, om, px0 * 4, cudaMemcpyDeviceToHost, ctx->stream);

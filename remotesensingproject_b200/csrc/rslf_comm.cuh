@@ -9,6 +9,7 @@
  */
 #pragma once
 #include <dlfcn.h>
+#include <algorithm>
 #include "rslf_common.cuh"
 
 typedef struct { char internal[128]; } rslf_nccl_uid;
@@ -96,6 +97,120 @@ static int comm_allgather_bytes(rslf_ctx* ctx, const void* send, void* recv, siz
     return RSLF_OK;
 }
 
+/* ---- row shards -------------------------------------------------------------
+ * Rank r holds the global rows [b[r], b[r+1]) of a level.  Level-0 boundaries are multiples of
+ * 2^(levels-1), so level p splits at b0[r] >> p and bound propagation (rows 2v, 2v+1 -> v) is local.
+ */
+struct shard_tab { int n; int b[65]; };
+
+static shard_tab level_shards(const rslf_ctx* ctx, int p, int Vtot_p)
+{
+    shard_tab t; t.n = ctx->world;
+    for (int r = 0; r <= ctx->world; ++r) {
+        int v = ctx->row_starts[r] >> p;
+        t.b[r] = v < Vtot_p ? v : Vtot_p;
+    }
+    t.b[0] = 0; t.b[ctx->world] = Vtot_p;
+    return t;
+}
+static int shard_max_rows(const shard_tab& t) { int m = 0; for (int r = 0; r < t.n; ++r) m = std::max(m, t.b[r + 1] - t.b[r]); return m; }
+static bool shard_equal(const shard_tab& t) { for (int r = 0; r < t.n; ++r) if (t.b[r + 1] - t.b[r] != t.b[1] - t.b[0]) return false; return true; }
+
+static int comm_ensure_stage(rslf_ctx* ctx, size_t blockbytes)
+{
+    if (ctx->g_stage_cap >= blockbytes) return RSLF_OK;
+    if (ctx->g_send) cudaFree(ctx->g_send);
+    if (ctx->g_recv) cudaFree(ctx->g_recv);
+    ctx->g_send = ctx->g_recv = nullptr; ctx->g_stage_cap = 0;
+    if (cudaMalloc(&ctx->g_send, blockbytes) != cudaSuccess || cudaMalloc(&ctx->g_recv, blockbytes * ctx->world) != cudaSuccess) {
+        snprintf(ctx->err, sizeof(ctx->err), "cudaMalloc(gather staging %zu x %d)", blockbytes, ctx->world);
+        return RSLF_ERR_NOMEM;
+    }
+    ctx->g_stage_cap = blockbytes;
+    return RSLF_OK;
+}
+
+/* all ranks' rows of a row-major [V][row_bytes] array -> global [Vtot][row_bytes] on every rank */
+static int comm_gather_rows(rslf_ctx* ctx, const void* local, size_t row_bytes, const shard_tab& t, void* global)
+{
+    const int r0 = ctx->rank;
+    const size_t mine = (size_t)(t.b[r0 + 1] - t.b[r0]) * row_bytes;
+    if (shard_equal(t)) {
+        RSLF_NCCL_TRY(ctx, g_nccl.AllGather(local, global, mine, RSLF_NCCL_UINT8, ctx->nccl_comm, ctx->stream));
+        return RSLF_OK;
+    }
+    const size_t blockbytes = (size_t)shard_max_rows(t) * row_bytes;
+    RSLF_TRY(comm_ensure_stage(ctx, blockbytes));
+    RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->g_send, local, mine, cudaMemcpyDeviceToDevice, ctx->stream));
+    RSLF_NCCL_TRY(ctx, g_nccl.AllGather(ctx->g_send, ctx->g_recv, blockbytes, RSLF_NCCL_UINT8, ctx->nccl_comm, ctx->stream));
+    for (int r = 0; r < t.n; ++r) {
+        const size_t n = (size_t)(t.b[r + 1] - t.b[r]) * row_bytes;
+        if (n) RSLF_CUDA_TRY(ctx, cudaMemcpyAsync((char*)global + (size_t)t.b[r] * row_bytes, (char*)ctx->g_recv + r * blockbytes, n,
+                                                  cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    return RSLF_OK;
+}
+
+/* all ranks' rows of a [S][Vloc][U] map -> global [S][Vtot][U] on every rank */
+static int comm_gather_svu(rslf_ctx* ctx, const void* local, size_t elem, int S, int U, const shard_tab& t, void* global)
+{
+    const int r0 = ctx->rank, Vtot = t.b[t.n];
+    const size_t maxrows = shard_max_rows(t), blockbytes = (size_t)S * maxrows * U * elem;
+    RSLF_TRY(comm_ensure_stage(ctx, blockbytes));
+    const size_t wloc = (size_t)(t.b[r0 + 1] - t.b[r0]) * U * elem;
+    if (wloc) RSLF_CUDA_TRY(ctx, cudaMemcpy2DAsync(ctx->g_send, maxrows * U * elem, local, wloc, wloc, S, cudaMemcpyDeviceToDevice, ctx->stream));
+    RSLF_NCCL_TRY(ctx, g_nccl.AllGather(ctx->g_send, ctx->g_recv, blockbytes, RSLF_NCCL_UINT8, ctx->nccl_comm, ctx->stream));
+    for (int r = 0; r < t.n; ++r) {
+        const size_t wr = (size_t)(t.b[r + 1] - t.b[r]) * U * elem;
+        if (wr) RSLF_CUDA_TRY(ctx, cudaMemcpy2DAsync((char*)global + (size_t)t.b[r] * U * elem, (size_t)Vtot * U * elem,
+                                                     (char*)ctx->g_recv + r * blockbytes, maxrows * U * elem, wr, S,
+                                                     cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    return RSLF_OK;
+}
+
+/* per-pass exchange for the selective median: depth, colour and mask rows of line s_hat of every rank */
+__global__ void unpack_median_kernel(const char* __restrict__ recv, size_t blockbytes, size_t off_colour, size_t off_mask,
+                                     shard_tab t, int U, int C, float* __restrict__ g_depth, float* __restrict__ g_colour,
+                                     uint8_t* __restrict__ g_mask)
+{
+    const int k = blockIdx.y;                   /* global row */
+    int r = 0;
+    while (r + 1 < t.n && k >= t.b[r + 1]) ++r;
+    const int lv = k - t.b[r];
+    const char* blk = recv + (size_t)r * blockbytes;
+    const float* d = reinterpret_cast<const float*>(blk) + (size_t)lv * U;
+    const float* c = reinterpret_cast<const float*>(blk + off_colour) + (size_t)lv * U * C;
+    const uint8_t* m = reinterpret_cast<const uint8_t*>(blk + off_mask) + (size_t)lv * U;
+    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < U; u += gridDim.x * blockDim.x) {
+        g_depth[(size_t)k * U + u] = d[u];
+        g_mask[(size_t)k * U + u] = m[u];
+        for (int cc = 0; cc < C; ++cc) g_colour[((size_t)k * U + u) * C + cc] = c[(size_t)u * C + cc];
+    }
+}
+
+static int comm_gather_median_planes(rslf_ctx* ctx, const float* depth_plane, const uint8_t* mask_plane, const float* colour0,
+                                     size_t colour_row_stride_floats, int U, int C, const shard_tab& t)
+{
+    const int r0 = ctx->rank, Vloc = t.b[r0 + 1] - t.b[r0], Vtot = t.b[t.n];
+    const size_t maxrows = shard_max_rows(t);
+    const size_t off_colour = maxrows * U * 4, off_mask = off_colour + maxrows * U * C * 4;
+    const size_t blockbytes = (off_mask + maxrows * U + 15) & ~(size_t)15;
+    RSLF_TRY(comm_ensure_stage(ctx, blockbytes));
+    char* send = (char*)ctx->g_send;
+    RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(send, depth_plane, (size_t)Vloc * U * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    RSLF_CUDA_TRY(ctx, cudaMemcpy2DAsync(send + off_colour, (size_t)U * C * 4, colour0, colour_row_stride_floats * 4, (size_t)U * C * 4, Vloc,
+                                         cudaMemcpyDeviceToDevice, ctx->stream));
+    RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(send + off_mask, mask_plane, (size_t)Vloc * U, cudaMemcpyDeviceToDevice, ctx->stream));
+    RSLF_NCCL_TRY(ctx, g_nccl.AllGather(ctx->g_send, ctx->g_recv, blockbytes, RSLF_NCCL_UINT8, ctx->nccl_comm, ctx->stream));
+    dim3 grid(std::max(1, std::min(8, (U + 127) / 128)), Vtot);
+    unpack_median_kernel<<<grid, 128, 0, ctx->stream>>>((const char*)ctx->g_recv, blockbytes, off_colour, off_mask, t, U, C,
+                                                        ctx->g_depth, ctx->g_colour, ctx->g_mask);
+    RSLF_CUDA_TRY(ctx, cudaGetLastError());
+    ctx->timing.kernel_launches += 1;
+    return RSLF_OK;
+}
+
 extern "C" int rslf_cuda_nccl_unique_id(void* id128)
 {
     if (!id128) return RSLF_ERR_ARG;
@@ -119,9 +234,15 @@ extern "C" int rslf_cuda_comm_init(rslf_ctx* ctx, const void* id128, int rank, i
     return RSLF_OK;
 }
 
-extern "C" int rslf_cuda_set_row_shard(rslf_ctx* ctx, int v0, int V_total)
+extern "C" int rslf_cuda_set_row_shards(rslf_ctx* ctx, const int* row_starts, int n_ranks)
 {
-    if (!ctx || v0 < 0 || V_total < 1) return RSLF_ERR_ARG;
-    ctx->v0 = v0; ctx->V_total = V_total;
+    if (!ctx || !row_starts || n_ranks < 1 || n_ranks > 64) return RSLF_ERR_ARG;
+    if (n_ranks != ctx->world) { snprintf(ctx->err, sizeof(ctx->err), "shard table has %d ranks, communicator %d", n_ranks, ctx->world); return RSLF_ERR_ARG; }
+    for (int r = 0; r < n_ranks; ++r)
+        if (row_starts[r] < 0 || row_starts[r + 1] <= row_starts[r]) { snprintf(ctx->err, sizeof(ctx->err), "shard table must be strictly increasing"); return RSLF_ERR_ARG; }
+    if (row_starts[0] != 0) return RSLF_ERR_ARG;
+    for (int r = 0; r <= n_ranks; ++r) ctx->row_starts[r] = row_starts[r];
+    ctx->v0 = row_starts[ctx->rank]; ctx->V_total = row_starts[n_ranks];
+    ctx->have_shards = true;
     return RSLF_OK;
 }

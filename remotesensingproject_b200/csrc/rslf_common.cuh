@@ -21,7 +21,8 @@
 #define RSLF_MAX_LEVELS 24
 
 struct rslf_level {
-    int V = 0, U = 0;
+    int V = 0, U = 0;            /* rows held by this rank, columns                           */
+    int v0 = 0, Vtot = 0;        /* first global row of this rank, global rows of the level   */
     float* raw = nullptr;        /* un-normalised float stack (levels > 0, or float input)  */
     float* epi = nullptr;        /* normalised stack [V][S][U][C]                             */
     float* ce = nullptr;         /* edge confidence            [S][V][U]                      */
@@ -64,7 +65,9 @@ struct rslf_ctx {
     bool raw_borrowed = false;
     size_t raw_cap = 0;
     bool have_input = false;
-    int v0 = 0, V_total = 0;     /* row shard */
+    int v0 = 0, V_total = 0;     /* row shard: first global row, global rows (level 0)        */
+    int row_starts[65] = {0};    /* level-0 shard table, world + 1 entries                    */
+    bool have_shards = false;
 
     /* levels */
     int n_levels = 0;
@@ -88,6 +91,12 @@ struct rslf_ctx {
     size_t scratch_px = 0;       /* S*V*U the scratch was sized for                           */
     size_t scratch_plane = 0;    /* V*U the scratch was sized for                             */
     void* l2_flush = nullptr;
+    /* row-sharded runs: gathered planes of line s_hat for the cross-row median, staging */
+    float* g_depth = nullptr; float* g_colour = nullptr; uint8_t* g_mask = nullptr;
+    void* g_send = nullptr; void* g_recv = nullptr; size_t g_stage_cap = 0; size_t g_plane_cap = 0;
+    float* g_raw = nullptr; size_t g_raw_cap = 0;        /* gathered raw stack of a level (downsample halo) */
+    float* g_map = nullptr; float* g_map2 = nullptr; uint8_t* g_mk = nullptr; uint8_t* g_mk2 = nullptr;
+    size_t g_map_cap = 0;        /* gathered fuse maps (two slots), S*Vtot*U each */
     float* pile_depth_raw = nullptr;  /* 1D pile: unfiltered depth plane                      */
 
     /* results state */

@@ -27,3 +27,16 @@ def row_shards(V, world, align=1):
         b1 = blocks * (r + 1) // world
         out.append((min(V, b0 * align), min(V, b1 * align)))
     return out
+
+
+def shard_table(V, U, world, max_pyr_depth=-1, pyramid=True):
+    """Row boundaries [b0 .. b_world] for `world` ranks, aligned to 2^(levels-1) rows when the
+    fine-to-coarse pyramid runs; raises if a rank would be left without rows at the coarsest level."""
+    levels = len(pyramid_levels(V, U, max_pyr_depth)) if pyramid else 1
+    align = 1 << max(0, levels - 1)
+    sh = row_shards(V, world, align)
+    starts = [a for a, _ in sh] + [V]
+    for a, b in zip(starts[:-1], starts[1:]):
+        if (b >> (levels - 1)) - (a >> (levels - 1)) < 1 and b != V or b <= a:
+            raise ValueError("%d rows cannot be split over %d ranks with %d pyramid levels" % (V, world, levels))
+    return starts

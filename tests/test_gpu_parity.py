@@ -60,22 +60,33 @@ def test_edge_confidence_golden(gpu_ctx, golden_dir):
 
 # --------------------------------------------------------------------------- Depth1DComputer_pile
 PILE_CASES = [
-    # S, V, U, C, D, forced H (0 = planner's choice)
-    (9, 8, 64, 3, 16, 0),      # H=1, one chunk
-    (8, 8, 64, 1, 40, 0),      # H=2, even S
-    (7, 6, 50, 3, 100, 0),     # H=4
-    (7, 6, 50, 1, 300, 0),     # H=4, three chunks (last-arriver merge)
-    (5, 6, 40, 3, 70, 1),      # H=1 forced, three chunks, D not a multiple of 32
-    (6, 5, 33, 3, 64, 2),      # H=2 forced
+    # S, V, U, C, D, forced H (0 = planner's choice), forced register-resident views (-1 = planner's choice)
+    (9, 8, 64, 3, 16, 0, -1),
+    (8, 8, 64, 1, 40, 0, -1),      # even S
+    (7, 6, 50, 3, 100, 0, -1),
+    (7, 6, 50, 1, 300, 0, -1),     # several chunks of hypotheses (last-arriver merge)
+    (5, 6, 40, 3, 70, 1, 0),       # H=1, three chunks, D not a multiple of 32, all views in shared memory
+    (6, 5, 33, 3, 64, 2, 0),
+    (7, 5, 33, 3, 130, 4, 0),
+    (21, 5, 40, 3, 40, 1, 16),     # 16 views in registers, 5 (+3 padding) in shared memory
+    (37, 4, 40, 3, 40, 1, 32),
+    (50, 4, 40, 3, 33, 1, 48),
+    (19, 4, 40, 3, 70, 2, 16),
+    (9, 4, 40, 3, 20, 1, 16),      # fewer views than register slots
+    (20, 4, 40, 1, 40, 1, 16),
+    (33, 4, 40, 1, 70, 2, 16),
+    (51, 3, 40, 1, 40, 1, 48),
 ]
 
 
-@pytest.mark.parametrize("S,V,U,C,D,H", PILE_CASES)
-def test_depth1d_pile(gpu_ctx, monkeypatch, S, V, U, C, D, H):
+@pytest.mark.parametrize("S,V,U,C,D,H,RV", PILE_CASES)
+def test_depth1d_pile(gpu_ctx, monkeypatch, S, V, U, C, D, H, RV):
+    monkeypatch.delenv("RSLF_DEPTH_H", raising=False)
+    monkeypatch.delenv("RSLF_DEPTH_RV", raising=False)
     if H:
         monkeypatch.setenv("RSLF_DEPTH_H", str(H))
-    else:
-        monkeypatch.delenv("RSLF_DEPTH_H", raising=False)
+    if RV >= 0:
+        monkeypatch.setenv("RSLF_DEPTH_RV", str(RV))
     epis = lf(S, V, U, C, seed=100 + S + D)
     comp = api.Depth1DComputer_pile(epis, -1.0, 2.0, D, epi_scale_factor=1.0, ctx=gpu_ctx).run()
     ref = oracle.depth1d_pile(oracle.normalise(epis, 1.0), -1.0, 2.0, D)
