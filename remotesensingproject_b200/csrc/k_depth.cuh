@@ -232,12 +232,14 @@ depth_kernel(const depth_args a)
     const int nrows = depth_num_rows(Spad, RV);
     const int nblk = (Spad - RV) / DEPTH_UNR;               /* blocks of DEPTH_UNR shared-memory views */
     constexpr int W = 32 * H;
-    /* [mbarrier, 16 B][row offsets: nrows + 1 ints, padded to 16 B][rows] */
+    /* [mbarrier, 16 B][row offsets: nrows + 1 ints, padded to 16 B][per-row staging records: nrows int4][rows] */
     int* row_off = reinterpret_cast<int*>(smem_raw) + 4;
-    float* rows = reinterpret_cast<float*>(smem_raw) + 4 + ((nrows + 1 + 3) & ~3);
+    int4* meta = reinterpret_cast<int4*>(row_off + ((nrows + 1 + 3) & ~3));
+    float* rows = reinterpret_cast<float*>(meta + nrows);
     const unsigned bar = smem_u32(smem_raw);
     const long long total = (long long)(*a.count) * a.chunks;
     const float inv = a.inv;
+    const float Um1f = (float)(U - 1);
 
     /* prologue: mbarrier and the row offset table (exclusive prefix sum of the row sizes) */
     if (lane == 0) {
@@ -288,10 +290,11 @@ depth_kernel(const depth_args a)
             t = (float)(min(chunk * W + W, D) - 1) * range; t = t / den; Dhi = dmin + t;
         }
         const long long row0 = (long long)v * S * U;           /* pixel index of (v, s = 0, u = 0) */
-        float card[H], rb[C][H];
+        int cardi[H];
+        float rb[C][H];
 #pragma unroll
         for (int h = 0; h < H; ++h) {
-            card[h] = 0.f;
+            cardi[h] = 0;
 #pragma unroll
             for (int c = 0; c < C; ++c) rb[c][h] = 0.f;
         }
@@ -306,85 +309,94 @@ depth_kernel(const depth_args a)
             const int nviews = round ? (Spad - RV) : RV;
             __syncwarp();
             {
+                /* staging record of row r: x = float offset of the scanline's pixel 0 inside the staged
+                 * segment, y = floats staged (multiple of 4), z = row offset, w = 1 if the segment was cut */
                 unsigned bytes = 0;
                 for (int r = lane; r < nviews; r += 32) {
                     int lo, hi;
                     view_span(a, vbase + r, uf, Dlo, Dhi, lo, hi);
+                    int4 m; m.x = 0; m.y = 0; m.z = row_off[r]; m.w = 0;
                     if (lo <= hi) {
-                        const long long a0 = (row0 + (long long)(vbase + r) * U + lo) * C, a1 = (row0 + (long long)(vbase + r) * U + hi + 1) * C;
-                        const long long n = ((a1 - (a0 & ~3LL)) + 3) & ~3LL;
-                        bytes += 4u * (unsigned)min(n, (long long)(row_off[r + 1] - row_off[r]));
+                        const int mis = ((int)((row0 + (long long)(vbase + r) * U + lo) & 3LL) * C) & 3;
+                        const int want = ((hi + 1 - lo) * C + mis + 3) & ~3;
+                        const int cap = row_off[r + 1] - m.z;
+                        m.x = mis - lo * C; m.y = min(want, cap); m.w = want > cap;
+                        bytes += 4u * (unsigned)m.y;
                     }
+                    meta[r] = m;
                 }
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, off);
                 if (lane == 0) mbar_arrive_expect_tx(bar, bytes);
                 __syncwarp();
                 for (int r = lane; r < nviews; r += 32) {
-                    int lo, hi;
-                    view_span(a, vbase + r, uf, Dlo, Dhi, lo, hi);
-                    if (lo <= hi) {
-                        const long long a0 = (row0 + (long long)(vbase + r) * U + lo) * C, a1 = (row0 + (long long)(vbase + r) * U + hi + 1) * C;
-                        const long long a0a = a0 & ~3LL;
-                        const long long n = ((a1 - a0a) + 3) & ~3LL;
-                        const unsigned nb = 4u * (unsigned)min(n, (long long)(row_off[r + 1] - row_off[r]));
-                        tma_bulk_g2s(smem_u32(rows + row_off[r]), a.epi + a0a, nb, bar);
-                    }
+                    const int4 m = meta[r];
+                    /* segment start in the stack: (row0 + s*U) * C - m.x floats, 16-byte aligned by construction */
+                    if (m.y > 0)
+                        tma_bulk_g2s(smem_u32(rows + m.z), a.epi + ((row0 + (long long)(vbase + r) * U) * C - m.x), 4u * (unsigned)m.y, bar);
                 }
             }
             mbar_wait(bar, phase);
             phase ^= 1u;
-            /* in-place conversion, one view per step */
-#pragma unroll 2
-            for (int r = 0; r < nviews; ++r) {
-                const int s = vbase + r;
-                float* row = rows + row_off[r];
-                const int cap = row_off[r + 1] - row_off[r];
-                int lo, hi;
-                view_span(a, s, uf, Dlo, Dhi, lo, hi);
-                /* float offset of the row's pixel 0 inside the staged segment: the segment starts at the
-                 * 16-byte aligned float index below (row0 + s*U + lo) * C */
-                const int mis = ((int)((row0 + (long long)s * U + lo) & 3LL) * C) & 3;
-                const int rel = mis - lo * C;
-                const int nfl = (lo <= hi) ? min(((hi + 1 - lo) * C + mis + 3) & ~3, cap) : 0;
-                const float k = (float)(a.s_hat - s);
-                float val[C][H];
+            /* in-place conversion, DEPTH_UNR views per step (all segment reads of the step, one warp
+             * synchronisation, then the radiance stores): I = (s_hat - s) * D * slope + u (core.hpp:550-552);
+             * floor / ceil neighbours, in-image test and linear interpolation (interp.hpp:171-185).
+             * Views >= S (padding) and out-of-image samples become the sentinel. */
+#pragma unroll 1
+            for (int rb0 = 0; rb0 < nviews; rb0 += DEPTH_UNR) {
+                float val[DEPTH_UNR][C][H];
+                int roff[DEPTH_UNR];
 #pragma unroll
-                for (int h = 0; h < H; ++h) {
-                    float I = k * Dv[h];
-                    I = I * a.slope;
-                    I = I + uf;
-                    const float fl = floorf(I);
-                    const int i0 = (int)fl;
-                    const int i1 = i0 + ((I != fl) ? 1 : 0);            /* ceil */
-                    const bool ok = !(i0 < 0 || i1 > U - 1) && (I == I) && (s < S) && (dbase + h < D);
-                    const float t = I - (float)i0;
-                    const float omt = 1.f - t;
-                    const int p0 = rel + i0 * C, p1 = rel + i1 * C;
-                    float e0[C], e1[C];
-                    if (ok && (p0 < 0 || p1 + C > nfl)) {               /* not staged: segment longer than the row */
-                        const float* g = a.epi + (row0 + (long long)s * U) * C;
+                for (int j = 0; j < DEPTH_UNR; ++j) {
+                    const int s = vbase + rb0 + j;
+                    const int4 m = meta[rb0 + j];
+                    roff[j] = m.z;
+                    const float* row = rows + m.z;
+                    const float k = (float)(a.s_hat - s);
 #pragma unroll
-                        for (int c = 0; c < C; ++c) { e0[c] = __ldg(g + (size_t)i0 * C + c); e1[c] = __ldg(g + (size_t)i1 * C + c); }
-                    } else {
-                        const int q0 = ok ? p0 : 0, q1 = ok ? p1 : 0;
+                    for (int h = 0; h < H; ++h) {
+                        float I = k * Dv[h];
+                        I = I * a.slope;
+                        I = I + uf;
+                        const float fl = floorf(I);
+                        const int i0 = (int)fl;
+                        const int ne = (I != fl) ? 1 : 0;                   /* ceil(I) = floor(I) + ne */
+                        /* i0 >= 0 and i1 <= U-1  <=>  0 <= I <= U-1 (NaN fails both); padding never counts */
+                        const bool ok = (I >= 0.f) && (I <= Um1f) && (dbase + h < D) && (s < S);
+                        const float t = I - fl;                             /* = I - float(i0) */
+                        const float omt = 1.f - t;
+                        const int p0 = m.x + i0 * C, p1 = p0 + ne * C;
+                        float e0[C], e1[C];
+                        if (m.w && ok && (p0 < 0 || p1 + C > m.y)) {         /* cut segment (user-edited bounds only) */
+                            const float* g = a.epi + (row0 + (long long)s * U) * C;
 #pragma unroll
-                        for (int c = 0; c < C; ++c) { e0[c] = row[q0 + c]; e1[c] = row[q1 + c]; }
+                            for (int c = 0; c < C; ++c) { e0[c] = __ldg(g + (size_t)i0 * C + c); e1[c] = __ldg(g + (size_t)(i0 + ne) * C + c); }
+                        } else {
+                            const int q0 = ok ? p0 : 0, q1 = ok ? p1 : 0;
+#pragma unroll
+                            for (int c = 0; c < C; ++c) { e0[c] = row[q0 + c]; e1[c] = row[q1 + c]; }
+                        }
+#pragma unroll
+                        for (int c = 0; c < C; ++c) {
+                            const float p = omt * e0[c];
+                            const float q = t * e1[c];
+                            val[j][c][h] = ok ? (p + q) : RSLF_RAD_SENTINEL;
+                        }
+                        cardi[h] += ok ? 1 : 0;
                     }
-#pragma unroll
-                    for (int c = 0; c < C; ++c) {
-                        const float p = omt * e0[c];
-                        const float q = t * e1[c];
-                        val[c][h] = ok ? (p + q) : RSLF_RAD_SENTINEL;
-                        if (s == a.s_hat) rb[c][h] = val[c][h];         /* r_bar <- row s_hat (core.hpp:577) */
-                    }
-                    card[h] += ok ? 1.0f : 0.0f;
                 }
-                __syncwarp();                                           /* every lane has read the segment */
+                __syncwarp();                                               /* every lane has read the segments */
 #pragma unroll
-                for (int c = 0; c < C; ++c) rad_store<H>(row + c * W + lane * H, val[c]);
+                for (int j = 0; j < DEPTH_UNR; ++j)
+#pragma unroll
+                    for (int c = 0; c < C; ++c) rad_store<H>(rows + roff[j] + c * W + lane * H, val[j][c]);
             }
             __syncwarp();
+            /* r_bar <- radiances of view s_hat (core.hpp:577) */
+            if (a.s_hat >= vbase && a.s_hat < vbase + nviews) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) rad_load<H>(rows + row_off[a.s_hat - vbase] + c * W + lane * H, rb[c]);
+            }
             if (RV > 0 && round == 0) {
 #pragma unroll
                 for (int j = 0; j < RV; ++j)
@@ -392,6 +404,9 @@ depth_kernel(const depth_args a)
                     for (int c = 0; c < C; ++c) rad_load<H>(rows + row_off[j] + c * W + lane * H, rr[j][c]);
             }
         }
+        float card[H];
+#pragma unroll
+        for (int h = 0; h < H; ++h) card[h] = (float)cardi[h];
         /* ---- mean shift (core.hpp:577-610).  Shared-memory rows are consumed in blocks of DEPTH_UNR
          *      views with two register buffers in ping-pong: the LDS of the next block are in flight
          *      while the current one is accumulated.  Sentinel rows add K = 0 and r*K = +0, which
@@ -538,7 +553,7 @@ static inline size_t depth_smem_bytes(int S, int C, int H, int RV, int s_hat, in
     int spad = depth_padded_views(S);
     if (spad < RV) spad = RV;
     const int nrows = depth_num_rows(spad, RV);
-    size_t fl = 4 + ((nrows + 1 + 3) & ~3);
+    size_t fl = 4 + ((nrows + 1 + 3) & ~3) + 4 * (size_t)nrows;       /* mbarrier, row offsets, staging records */
     for (int r = 0; r < nrows; ++r) fl += depth_row_floats(r, S, spad, RV, s_hat, wpv_q16, C, 32 * H);
     return fl * sizeof(float);
 }
@@ -582,7 +597,7 @@ static depth_plan plan_depth(const rslf_ctx* ctx, int S, int C, int D, int s_hat
         int w = std::min(std::min(w_smem, w_regs), 32);
         if (w < 1) w = 1;
         /* resident hypotheses-in-flight saturate around 16 warps; register views save the LDS issue slots */
-        double score = std::min(w, 16) * (H == 1 ? 1.0 : (H == 2 ? 1.06 : 1.08)) * (1.0 + 0.002 * std::min(RV, S));
+        double score = std::min(w, 12) * (H == 1 ? 1.0 : (H == 2 ? 1.12 : 1.25)) * (1.0 + 0.002 * std::min(RV, S));
         if (score > bestScore) { bestScore = score; best.H = H; best.RV = RV; best.blocks_per_sm = w; best.smem = sm; best.wpv_q16 = wpv; }
     }
     best.chunks = rslf_div_up(D, 32 * best.H);
