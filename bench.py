@@ -152,7 +152,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default=os.environ.get("RSLF_BENCH_CONFIG", "c2"), choices=sorted(CONFIGS))
+    ap.add_argument("--config", default=os.environ.get("RSLF_BENCH_CONFIG", "c3"), choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()

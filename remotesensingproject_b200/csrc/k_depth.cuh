@@ -213,6 +213,71 @@ __device__ __forceinline__ void ms_accumulate(const float (&r)[C][H], const floa
     }
 }
 
+
+/*
+ * In-place conversion of the staged rows of one round, DEPTH_UNR views per step (all segment reads of
+ * the step, one warp synchronisation, then the radiance stores): I = (s_hat - s) * D * slope + u
+ * (core.hpp:550-552); floor / ceil neighbours, in-image test and linear interpolation
+ * (interp.hpp:171-185).  Views >= S (padding) and out-of-image samples become the sentinel.
+ * ufl = u as float, NaN for lanes whose hypothesis index is >= D (they then fail every test).
+ */
+template <int C, int H, bool FALLBACK>
+__device__ __forceinline__ void convert_rows(const depth_args& a, const int4* meta, float* rows, int vbase, int nviews,
+                                             int lane, long long row0, const float (&ufl)[H], float Um1f,
+                                             const float (&Dv)[H], int (&cardi)[H])
+{
+    constexpr int W = 32 * H;
+#pragma unroll 1
+    for (int rb0 = 0; rb0 < nviews; rb0 += DEPTH_UNR) {
+        float val[DEPTH_UNR][C][H];
+        int roff[DEPTH_UNR];
+#pragma unroll
+        for (int j = 0; j < DEPTH_UNR; ++j) {
+            const int s = vbase + rb0 + j;
+            const int4 m = meta[rb0 + j];
+            roff[j] = m.z;
+            const float* row = rows + m.z;
+            const float k = (float)(a.s_hat - s);
+#pragma unroll
+            for (int h = 0; h < H; ++h) {
+                float I = k * Dv[h];
+                I = I * a.slope;
+                I = I + ufl[h];
+                const float fl = floorf(I);
+                const int i0 = (int)fl;
+                const int ne = (I != fl) ? 1 : 0;                   /* ceil(I) = floor(I) + ne */
+                /* i0 >= 0 and i1 <= U-1  <=>  0 <= I <= U-1 (NaN fails both) */
+                const bool ok = (I >= 0.f) && (I <= Um1f) && (s < a.S);
+                const float t = I - fl;                             /* = I - float(i0) */
+                const float omt = 1.f - t;
+                const int p0 = m.x + i0 * C, p1 = p0 + ne * C;
+                float e0[C], e1[C];
+                if (FALLBACK && m.w && ok && (p0 < 0 || p1 + C > m.y)) {
+                    const float* g = a.epi + (row0 + (long long)s * a.U) * C;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) { e0[c] = __ldg(g + (size_t)i0 * C + c); e1[c] = __ldg(g + (size_t)(i0 + ne) * C + c); }
+                } else {
+                    const int q0 = ok ? p0 : 0, q1 = ok ? p1 : 0;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) { e0[c] = row[q0 + c]; e1[c] = row[q1 + c]; }
+                }
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const float p = omt * e0[c];
+                    const float q = t * e1[c];
+                    val[j][c][h] = ok ? (p + q) : RSLF_RAD_SENTINEL;
+                }
+                cardi[h] += ok ? 1 : 0;
+            }
+        }
+        __syncwarp();                                               /* every lane has read the segments */
+#pragma unroll
+        for (int j = 0; j < DEPTH_UNR; ++j)
+#pragma unroll
+            for (int c = 0; c < C; ++c) rad_store<H>(rows + roff[j] + c * W + lane * H, val[j][c]);
+    }
+}
+
 /* Register budget.  The register file is split per SM sub-partition (512 registers per lane each) and
  * the one-warp blocks are spread over the four sub-partitions, so k resident warps per sub-partition
  * may use 512 / k registers: 255 (k = 2), 168 (3), 128 (4), 96 (5), 80 (6), 64 (8). */
@@ -274,6 +339,9 @@ depth_kernel(const depth_args a)
         const float dmax = a.dmax_map ? a.dmax_map[pix] : a.dmax_c;
         const int dbase = chunk * W + lane * H;
         const float uf = (float)u;
+        float ufl[H];                                          /* u, or NaN for padding hypotheses (d >= D) */
+#pragma unroll
+        for (int h = 0; h < H; ++h) ufl[h] = (dbase + h < D) ? uf : __int_as_float(0x7fc00000);
         /* D[d] = dmin + d * (dmax - dmin) / (dim_d - 1)   (core.hpp:547-548) */
         float Dv[H], Dlo, Dhi;
         {
@@ -307,11 +375,12 @@ depth_kernel(const depth_args a)
         for (int round = (RV > 0 ? 0 : 1); round < 2; ++round) {
             const int vbase = round ? RV : 0;
             const int nviews = round ? (Spad - RV) : RV;
+            bool any_cut = false;
             __syncwarp();
             {
                 /* staging record of row r: x = float offset of the scanline's pixel 0 inside the staged
                  * segment, y = floats staged (multiple of 4), z = row offset, w = 1 if the segment was cut */
-                unsigned bytes = 0;
+                unsigned bytes = 0, cut = 0;
                 for (int r = lane; r < nviews; r += 32) {
                     int lo, hi;
                     view_span(a, vbase + r, uf, Dlo, Dhi, lo, hi);
@@ -321,14 +390,14 @@ depth_kernel(const depth_args a)
                         const int want = ((hi + 1 - lo) * C + mis + 3) & ~3;
                         const int cap = row_off[r + 1] - m.z;
                         m.x = mis - lo * C; m.y = min(want, cap); m.w = want > cap;
-                        bytes += 4u * (unsigned)m.y;
+                        bytes += 4u * (unsigned)m.y; cut |= (unsigned)m.w;
                     }
                     meta[r] = m;
                 }
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, off);
                 if (lane == 0) mbar_arrive_expect_tx(bar, bytes);
-                __syncwarp();
+                any_cut = __any_sync(0xffffffffu, cut != 0);
                 for (int r = lane; r < nviews; r += 32) {
                     const int4 m = meta[r];
                     /* segment start in the stack: (row0 + s*U) * C - m.x floats, 16-byte aligned by construction */
@@ -338,59 +407,10 @@ depth_kernel(const depth_args a)
             }
             mbar_wait(bar, phase);
             phase ^= 1u;
-            /* in-place conversion, DEPTH_UNR views per step (all segment reads of the step, one warp
-             * synchronisation, then the radiance stores): I = (s_hat - s) * D * slope + u (core.hpp:550-552);
-             * floor / ceil neighbours, in-image test and linear interpolation (interp.hpp:171-185).
-             * Views >= S (padding) and out-of-image samples become the sentinel. */
-#pragma unroll 1
-            for (int rb0 = 0; rb0 < nviews; rb0 += DEPTH_UNR) {
-                float val[DEPTH_UNR][C][H];
-                int roff[DEPTH_UNR];
-#pragma unroll
-                for (int j = 0; j < DEPTH_UNR; ++j) {
-                    const int s = vbase + rb0 + j;
-                    const int4 m = meta[rb0 + j];
-                    roff[j] = m.z;
-                    const float* row = rows + m.z;
-                    const float k = (float)(a.s_hat - s);
-#pragma unroll
-                    for (int h = 0; h < H; ++h) {
-                        float I = k * Dv[h];
-                        I = I * a.slope;
-                        I = I + uf;
-                        const float fl = floorf(I);
-                        const int i0 = (int)fl;
-                        const int ne = (I != fl) ? 1 : 0;                   /* ceil(I) = floor(I) + ne */
-                        /* i0 >= 0 and i1 <= U-1  <=>  0 <= I <= U-1 (NaN fails both); padding never counts */
-                        const bool ok = (I >= 0.f) && (I <= Um1f) && (dbase + h < D) && (s < S);
-                        const float t = I - fl;                             /* = I - float(i0) */
-                        const float omt = 1.f - t;
-                        const int p0 = m.x + i0 * C, p1 = p0 + ne * C;
-                        float e0[C], e1[C];
-                        if (m.w && ok && (p0 < 0 || p1 + C > m.y)) {         /* cut segment (user-edited bounds only) */
-                            const float* g = a.epi + (row0 + (long long)s * U) * C;
-#pragma unroll
-                            for (int c = 0; c < C; ++c) { e0[c] = __ldg(g + (size_t)i0 * C + c); e1[c] = __ldg(g + (size_t)(i0 + ne) * C + c); }
-                        } else {
-                            const int q0 = ok ? p0 : 0, q1 = ok ? p1 : 0;
-#pragma unroll
-                            for (int c = 0; c < C; ++c) { e0[c] = row[q0 + c]; e1[c] = row[q1 + c]; }
-                        }
-#pragma unroll
-                        for (int c = 0; c < C; ++c) {
-                            const float p = omt * e0[c];
-                            const float q = t * e1[c];
-                            val[j][c][h] = ok ? (p + q) : RSLF_RAD_SENTINEL;
-                        }
-                        cardi[h] += ok ? 1 : 0;
-                    }
-                }
-                __syncwarp();                                               /* every lane has read the segments */
-#pragma unroll
-                for (int j = 0; j < DEPTH_UNR; ++j)
-#pragma unroll
-                    for (int c = 0; c < C; ++c) rad_store<H>(rows + roff[j] + c * W + lane * H, val[j][c]);
-            }
+            /* in-place conversion of the rows; the variant with the global-memory fallback is only needed when a
+             * segment was cut to its row (user-edited bounds wider than the global range) */
+            if (any_cut) convert_rows<C, H, true>(a, meta, rows, vbase, nviews, lane, row0, ufl, Um1f, Dv, cardi);
+            else convert_rows<C, H, false>(a, meta, rows, vbase, nviews, lane, row0, ufl, Um1f, Dv, cardi);
             __syncwarp();
             /* r_bar <- radiances of view s_hat (core.hpp:577) */
             if (a.s_hat >= vbase && a.s_hat < vbase + nviews) {
@@ -569,9 +589,12 @@ static inline int depth_reg_warps(int C, int H, int RV)
 }
 
 /*
- * Chooses hypotheses per lane (H) and register-resident views (RV): the variant with the most
- * resident warps per SM (shared memory and register file both counted), preferring wider lanes
- * and register views on ties.  RSLF_DEPTH_H / RSLF_DEPTH_RV force a variant (experiments, tests).
+ * Chooses hypotheses per lane (H) and register-resident views (RV).  Measured on B200 (profiles/):
+ * beyond 8 resident warps per SM (2 per scheduler) more residency buys nothing, while every
+ * register-resident view saves its LDS and shrinks the warp's shared memory; wide lanes (H = 2, 4) pay
+ * off only for gray stacks, whose rows are small.  So: RGB -> H = 1 and the largest RV that still leaves
+ * >= 8 warps; gray -> the widest H that D fills, RV = 0.  Among equals, more resident warps win.
+ * RSLF_DEPTH_H / RSLF_DEPTH_RV force a variant (experiments, tests).
  */
 static depth_plan plan_depth(const rslf_ctx* ctx, int S, int C, int D, int s_hat, float dmin, float dmax, float slope)
 {
@@ -588,7 +611,9 @@ static depth_plan plan_depth(const rslf_ctx* ctx, int S, int C, int D, int s_hat
         if (fH && H != fH) continue;
         if (fRV >= 0 && RV != fRV) continue;
         if (!fH && H > 1 && 32 * (H / 2) >= D) continue;            /* would leave lanes idle */
-        if (fRV < 0 && 2 * RV > depth_padded_views(S)) continue;    /* register views must be a minority */
+        if (fRV < 0 && RV > 0 && RV > depth_padded_views(S) - DEPTH_UNR) continue;
+        if (!fH && fRV < 0 && C == 3 && H != 1) continue;
+        if (!fH && fRV < 0 && C == 1 && RV != 0) continue;
         const int wpv = depth_wpv_q16(D, H, dmin, dmax, slope);
         const size_t sm = depth_smem_bytes(S, C, H, RV, s_hat, wpv);
         if (sm > ctx->smem_optin) continue;
@@ -596,8 +621,7 @@ static depth_plan plan_depth(const rslf_ctx* ctx, int S, int C, int D, int s_hat
         int w_regs = depth_reg_warps(C, H, RV);
         int w = std::min(std::min(w_smem, w_regs), 32);
         if (w < 1) w = 1;
-        /* resident hypotheses-in-flight saturate around 16 warps; register views save the LDS issue slots */
-        double score = std::min(w, 12) * (H == 1 ? 1.0 : (H == 2 ? 1.12 : 1.25)) * (1.0 + 0.002 * std::min(RV, S));
+        double score = 1000.0 * std::min(w, 8) + 10.0 * RV + 100.0 * H + 0.1 * w;
         if (score > bestScore) { bestScore = score; best.H = H; best.RV = RV; best.blocks_per_sm = w; best.smem = sm; best.wpv_q16 = wpv; }
     }
     best.chunks = rslf_div_up(D, 32 * best.H);

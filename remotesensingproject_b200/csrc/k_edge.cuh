@@ -28,7 +28,8 @@ template <int C>
 __global__ void __launch_bounds__(EDGE_THREADS)
 edge_confidence_kernel(const float* __restrict__ epi, int V, int S, int U, int s_first, int s_count,
                        int fs, int cut_shadows, float shadow_level, double shadow_T, float thr,
-                       float* __restrict__ ce_out, uint8_t* __restrict__ mask_out)
+                       float* __restrict__ ce_out, uint8_t* __restrict__ mask_out,
+                       float dark_eps, double dark_T, int* __restrict__ rowdark)
 {
     extern __shared__ float seg[];                 /* (EDGE_TILE + fs - 1) * C floats */
     const int centre = (fs - 1) / 2;
@@ -46,12 +47,13 @@ edge_confidence_kernel(const float* __restrict__ epi, int V, int S, int U, int s
     }
     __syncthreads();
     const size_t out_row = ((size_t)si * V + v) * (size_t)U;
+    int ndark = 0;
 #pragma unroll
     for (int k = 0; k < EDGE_PPT; ++k) {
         /* pixel index inside the tile: consecutive threads take consecutive pixels (coalesced stores) */
         const int p = k * EDGE_THREADS + threadIdx.x;
         const int u = u0 + p;
-        if (u >= U) break;
+        if (u >= U) continue;
         float x[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) x[c] = seg[(p + centre) * C + c];
@@ -73,13 +75,27 @@ edge_confidence_kernel(const float* __restrict__ epi, int V, int S, int U, int s
         }
         ce_out[out_row + u] = acc;
         mask_out[out_row + u] = (acc > thr) ? 255 : 0;
+        if (rowdark && acc > thr) {
+            /* confident pixels darker than the propagation epsilon: the only ones a source without r_bar
+             * (a pixel that was itself propagated) can still paint (see k_propagate.cuh) */
+            bool dk;
+            if (C == 1) dk = rslf_norm1_lt(x[0], dark_eps);
+            else dk = rslf_norm3_lt(x[0], x[C > 1 ? 1 : 0], x[C > 2 ? 2 : 0], dark_T);
+            ndark += dk ? 1 : 0;
+        }
+    }
+    if (rowdark) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) ndark += __shfl_xor_sync(0xffffffffu, ndark, off);
+        if ((threadIdx.x & 31) == 0 && ndark) atomicAdd(rowdark + (size_t)si * V + v, ndark);
     }
 }
 
 /* Launch for lines [s_first, s_first + s_count) of every row; output planes are
  * [s_count][V][U] starting at ce_out / mask_out. */
 static int launch_edge_confidence(rslf_ctx* ctx, const float* epi, int V, int S, int U, int C, int s_first,
-                                  int s_count, const rslf_params& P, float* ce_out, uint8_t* mask_out)
+                                  int s_count, const rslf_params& P, float* ce_out, uint8_t* mask_out,
+                                  int* rowdark = nullptr)
 {
     int fs = P.edge_confidence_filter_size;
     if (fs < 1 || fs > EDGE_MAX_FS) {
@@ -93,12 +109,15 @@ static int launch_edge_confidence(rslf_ctx* ctx, const float* epi, int V, int S,
     dim3 grid((unsigned)((size_t)V * s_count), rslf_div_up(U, EDGE_TILE));
     size_t smem = (size_t)(EDGE_TILE + fs - 1) * C * sizeof(float);
     double T = rslf_sq_threshold(P.shadow_level);
+    const double dT = rslf_sq_threshold(P.propagation_epsilon);
     if (C == 1)
         edge_confidence_kernel<1><<<grid, EDGE_THREADS, smem, ctx->stream>>>(
-            epi, V, S, U, s_first, s_count, fs, P.cut_shadows, P.shadow_level, T, P.edge_score_threshold, ce_out, mask_out);
+            epi, V, S, U, s_first, s_count, fs, P.cut_shadows, P.shadow_level, T, P.edge_score_threshold, ce_out, mask_out,
+            P.propagation_epsilon, dT, rowdark);
     else
         edge_confidence_kernel<3><<<grid, EDGE_THREADS, smem, ctx->stream>>>(
-            epi, V, S, U, s_first, s_count, fs, P.cut_shadows, P.shadow_level, T, P.edge_score_threshold, ce_out, mask_out);
+            epi, V, S, U, s_first, s_count, fs, P.cut_shadows, P.shadow_level, T, P.edge_score_threshold, ce_out, mask_out,
+            P.propagation_epsilon, dT, rowdark);
     RSLF_CUDA_TRY(ctx, cudaGetLastError());
     ctx->timing.kernel_launches += 1;
     return RSLF_OK;

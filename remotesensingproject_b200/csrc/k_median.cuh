@@ -40,7 +40,8 @@ template <int C, int WIDTH>
 __global__ void __launch_bounds__(128)
 selective_median_kernel(const float* __restrict__ src, const uint8_t* __restrict__ mask,
                         const float* __restrict__ colour, size_t colour_row_stride,
-                        int V, int U, int v_begin, float eps, double eps_T, float* __restrict__ dst)
+                        int V, int U, int v_begin, float eps, double eps_T, float* __restrict__ dst,
+                        const uint8_t* __restrict__ fresh, const int* __restrict__ rowdark_v)
 {
     constexpr int N = (2 * WIDTH + 1) * (2 * WIDTH + 1);
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
@@ -49,6 +50,10 @@ selective_median_kernel(const float* __restrict__ src, const uint8_t* __restrict
     const size_t o = (size_t)v * U + u;
     const size_t od = (size_t)blockIdx.y * U + u;     /* dst holds this rank's rows only */
     if (!mask[o]) { dst[od] = 0.f; return; }
+    /* the filtered value is only ever read by the propagation: needed for the pixels computed in this pass
+     * (fresh: still flagged in the line's remaining mask) and, in rows that still hold dark targets, for the
+     * pixels painted earlier (see k_propagate.cuh).  fresh == nullptr: filter every masked pixel. */
+    if (fresh && !fresh[od] && rowdark_v[blockIdx.y] <= 0) { dst[od] = 0.f; return; }
     float pc[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) pc[c] = __ldg(colour + (size_t)v * colour_row_stride + (size_t)u * C + c);
@@ -81,7 +86,8 @@ selective_median_kernel(const float* __restrict__ src, const uint8_t* __restrict
 
 static int launch_selective_median(rslf_ctx* ctx, const float* src, const uint8_t* mask, const float* colour,
                                    size_t colour_row_stride, int V, int U, int C, int size, float eps, float* dst,
-                                   int v_begin = 0, int v_count = -1)
+                                   int v_begin = 0, int v_count = -1, const uint8_t* fresh = nullptr,
+                                   const int* rowdark_v = nullptr)
 {
     const int width = (size - 1) / 2;
     if (v_count < 0) v_count = V;
@@ -90,7 +96,7 @@ static int launch_selective_median(rslf_ctx* ctx, const float* src, const uint8_
 #define RSLF_MED_CASE(CC, WW)                                                                             \
     if (C == CC && width == WW) {                                                                         \
         selective_median_kernel<CC, WW><<<grid, 128, 0, ctx->stream>>>(src, mask, colour, colour_row_stride, \
-                                                                       V, U, v_begin, eps, T, dst);       \
+                                                                       V, U, v_begin, eps, T, dst, fresh, rowdark_v); \
         RSLF_CUDA_TRY(ctx, cudaGetLastError());                                                           \
         ctx->timing.kernel_launches += 1;                                                                 \
         return RSLF_OK;                                                                                   \

@@ -14,7 +14,13 @@
  * arbitration buffer, pass 2 lets exactly the winner commit and re-arms the
  * buffer.  Rows are independent (the reference's OpenMP axis, :1088).
  *
- * One thread per (source pixel, group of PROP_SG views).
+ * Sources come in two kinds.  (1) Pixels computed in this pass: they are the compacted work list of the
+ * pass (sparse after the first pass) and carry their mean-shift radiance r_bar; one thread per (list
+ * entry, view).  (2) Pixels of the line that were painted by an earlier pass: their r_bar is the zero it was
+ * initialised with (dc.hpp:744), so they can only paint targets whose own colour norm is below eps, i.e.
+ * confident-but-dark pixels; per (s, v) row the edge-confidence kernel counted those (rowdark), and a block
+ * of the dense kernel returns at once when its rows hold none.  A pixel computed in this pass whose r_bar
+ * happens to be exactly zero is handled by both kinds; the arbitration makes that idempotent.
  */
 #pragma once
 #include "rslf_common.cuh"
@@ -29,80 +35,101 @@ struct prop_args {
     const float* rbar_p;         /* plane s_hat, [V][U][C] */
     const float* cd_p;           /* plane s_hat */
     float* depth; float* cd; uint8_t* remaining; int* winner;   /* [S][V][U] */
+    const int* items; const int* count;                         /* work list of the pass */
+    int* rowdark;                                                /* [S][V] confident-and-dark pixels still unpainted (upper bound) */
 };
 
+/* one (source, view) pair; PHASE 0: arbitration, PHASE 1: commit */
+template <int C, int PHASE>
+__device__ __forceinline__ void propagate_one(const prop_args& a, int v, int u, int s, float cur, const float (&rb)[C], float cdv)
+{
+    float t = cur * (float)(a.s_hat - s);
+    t = t * a.slope;
+    const int q = u + (int)roundf(t);
+    if (q < 0 || q >= a.U) return;
+    const size_t tgt = ((size_t)s * a.V + v) * (size_t)a.U + q;
+    if (!a.remaining[tgt]) return;
+    if (PHASE == 0) {
+        const float* e = a.epi + (((size_t)v * a.S + s) * (size_t)a.U + q) * C;
+        float ec[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) ec[c] = __ldg(e + c);
+        if (rslf_norm_diff_lt<C>(ec, rb, a.eps, a.eps_T)) atomicMin(a.winner + tgt, u);
+    } else if (a.winner[tgt] == u) {
+        /* the arbitration entry equals u only if this source passed every test in phase 0 and is the lowest */
+        a.depth[tgt] = cur;
+        a.cd[tgt] = cdv;
+        a.remaining[tgt] = 0;
+        a.winner[tgt] = 0x7fffffff;
+        if (a.rowdark) {
+            const float* e = a.epi + (((size_t)v * a.S + s) * (size_t)a.U + q) * C;
+            float ec[C], z[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) { ec[c] = __ldg(e + c); z[c] = 0.f; }
+            if (rslf_norm_diff_lt<C>(ec, z, a.eps, a.eps_T)) atomicSub(a.rowdark + (size_t)s * a.V + v, 1);
+        }
+    }
+}
+
+/* kind (1): the pass's work list x views */
 template <int C, int PHASE>
 __global__ void __launch_bounds__(PROP_THREADS)
-propagate_kernel(const prop_args a)
+propagate_list_kernel(const prop_args a)
 {
-    const int u = blockIdx.x * PROP_THREADS + threadIdx.x;
-    const int v = blockIdx.y;
-    if (u >= a.U) return;
-    const size_t o = (size_t)v * a.U + u;
-    if (!a.emask_p[o]) return;
-    const float cur = a.filtered[o];
-    const size_t plane = (size_t)a.V * a.U;
-    const int s_begin = blockIdx.z * PROP_SG;
-    /* targets of the PROP_SG views of this thread; the mask bytes are fetched together */
-    size_t tgt[PROP_SG];
-    uint8_t rem[PROP_SG];
-#pragma unroll
-    for (int j = 0; j < PROP_SG; ++j) {
-        const int s = s_begin + j;
-        float t = cur * (float)(a.s_hat - s);
-        t = t * a.slope;
-        const int q = u + (int)roundf(t);
-        const bool in = (s < a.S) && (q >= 0) && (q < a.U);
-        tgt[j] = (size_t)min(s, a.S - 1) * plane + (size_t)v * a.U + min(max(q, 0), a.U - 1);
-        rem[j] = in ? a.remaining[tgt[j]] : (uint8_t)0;
-    }
-    bool any = false;
-#pragma unroll
-    for (int j = 0; j < PROP_SG; ++j) any |= (rem[j] != 0);
-    if (!any) return;
-    if (PHASE == 0) {
+    const int n = *a.count;
+    const long long total = (long long)n * a.S;
+    for (long long i = (long long)blockIdx.x * PROP_THREADS + threadIdx.x; i < total; i += (long long)gridDim.x * PROP_THREADS) {
+        const int it = (int)(i / a.S), s = (int)(i - (long long)it * a.S);
+        const int pix = a.items[it];
+        if (!a.emask_p[pix]) continue;                      /* score <= threshold: dropped by the depth kernel */
+        const int v = pix / a.U, u = pix - v * a.U;
         float rb[C];
 #pragma unroll
-        for (int c = 0; c < C; ++c) rb[c] = a.rbar_p[o * C + c];
+        for (int c = 0; c < C; ++c) rb[c] = a.rbar_p[(size_t)pix * C + c];
+        propagate_one<C, PHASE>(a, v, u, s, a.filtered[pix], rb, PHASE ? a.cd_p[pix] : 0.f);
+    }
+}
+
+/* kind (2): pixels painted earlier (r_bar == 0); block = (row v, group of PROP_SG views), threads over u */
+template <int C, int PHASE>
+__global__ void __launch_bounds__(PROP_THREADS)
+propagate_dark_kernel(const prop_args a)
+{
+    const int v = blockIdx.x;
+    const int s_begin = blockIdx.y * PROP_SG, s_end = min(a.S, s_begin + PROP_SG);
+    unsigned live = 0;                                      /* views of the group that still hold a dark target */
+    for (int s = s_begin; s < s_end; ++s) live |= (a.rowdark[(size_t)s * a.V + v] > 0) ? (1u << (s - s_begin)) : 0u;
+    if (!live) return;
+    for (int u = threadIdx.x; u < a.U; u += PROP_THREADS) {
+        const size_t o = (size_t)v * a.U + u;
+        if (!a.emask_p[o]) continue;
+        float rb[C]; bool zero = true;
 #pragma unroll
-        for (int j = 0; j < PROP_SG; ++j) {
-            if (!rem[j]) continue;
-            /* colour of the target pixel: E_v(s, q); tgt = (s*V + v)*U + q  ->  epi index ((v*S + s)*U + q)*C */
-            const int s = s_begin + j;
-            const size_t q = tgt[j] - ((size_t)s * plane + (size_t)v * a.U);
-            const float* e = a.epi + (((size_t)v * a.S + s) * (size_t)a.U + q) * C;
-            float ec[C];
-#pragma unroll
-            for (int c = 0; c < C; ++c) ec[c] = __ldg(e + c);
-            if (rslf_norm_diff_lt<C>(ec, rb, a.eps, a.eps_T)) atomicMin(a.winner + tgt[j], u);
-        }
-    } else {
-        /* the arbitration entry equals u only if this source passed every test in phase 0 and is the lowest */
-        const float cdv = a.cd_p[o];
-#pragma unroll
-        for (int j = 0; j < PROP_SG; ++j) {
-            if (!rem[j]) continue;
-            if (a.winner[tgt[j]] == u) {
-                a.depth[tgt[j]] = cur;
-                a.cd[tgt[j]] = cdv;
-                a.remaining[tgt[j]] = 0;
-                a.winner[tgt[j]] = 0x7fffffff;
-            }
-        }
+        for (int c = 0; c < C; ++c) { rb[c] = a.rbar_p[o * C + c]; zero = zero && (rb[c] == 0.f); }
+        if (!zero) continue;
+        const float cur = a.filtered[o];
+        const float cdv = PHASE ? a.cd_p[o] : 0.f;
+        for (int s = s_begin; s < s_end; ++s)
+            if (live & (1u << (s - s_begin))) propagate_one<C, PHASE>(a, v, u, s, cur, rb, cdv);
     }
 }
 
 static int launch_propagate(rslf_ctx* ctx, int C, const prop_args& a)
 {
-    dim3 grid(rslf_div_up(a.U, PROP_THREADS), a.V, rslf_div_up(a.S, PROP_SG));
+    const int lb = ctx->num_sm * 16;
+    dim3 gd(a.V, rslf_div_up(a.S, PROP_SG));
     if (C == 1) {
-        propagate_kernel<1, 0><<<grid, PROP_THREADS, 0, ctx->stream>>>(a);
-        propagate_kernel<1, 1><<<grid, PROP_THREADS, 0, ctx->stream>>>(a);
+        propagate_list_kernel<1, 0><<<lb, PROP_THREADS, 0, ctx->stream>>>(a);
+        propagate_dark_kernel<1, 0><<<gd, PROP_THREADS, 0, ctx->stream>>>(a);
+        propagate_list_kernel<1, 1><<<lb, PROP_THREADS, 0, ctx->stream>>>(a);
+        propagate_dark_kernel<1, 1><<<gd, PROP_THREADS, 0, ctx->stream>>>(a);
     } else {
-        propagate_kernel<3, 0><<<grid, PROP_THREADS, 0, ctx->stream>>>(a);
-        propagate_kernel<3, 1><<<grid, PROP_THREADS, 0, ctx->stream>>>(a);
+        propagate_list_kernel<3, 0><<<lb, PROP_THREADS, 0, ctx->stream>>>(a);
+        propagate_dark_kernel<3, 0><<<gd, PROP_THREADS, 0, ctx->stream>>>(a);
+        propagate_list_kernel<3, 1><<<lb, PROP_THREADS, 0, ctx->stream>>>(a);
+        propagate_dark_kernel<3, 1><<<gd, PROP_THREADS, 0, ctx->stream>>>(a);
     }
     RSLF_CUDA_TRY(ctx, cudaGetLastError());
-    ctx->timing.kernel_launches += 2;
+    ctx->timing.kernel_launches += 4;
     return RSLF_OK;
 }

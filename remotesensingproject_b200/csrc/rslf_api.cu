@@ -75,7 +75,7 @@ static void free_level(rslf_level& L, bool keep_raw_borrowed_ptr = false)
 {
     (void)keep_raw_borrowed_ptr;
     dev_free(&L.raw); dev_free(&L.epi); dev_free(&L.ce); dev_free(&L.cd); dev_free(&L.depth); dev_free(&L.rbar);
-    dev_free(&L.dmin); dev_free(&L.dmax); dev_free(&L.emask); dev_free(&L.remaining); dev_free(&L.valid);
+    dev_free(&L.dmin); dev_free(&L.dmax); dev_free(&L.emask); dev_free(&L.remaining); dev_free(&L.valid); dev_free(&L.rowdark);
     L.cap_px = 0; L.cap_stack = 0; L.V = L.U = 0; L.C = 0; L.have_bounds = false;
 }
 
@@ -154,6 +154,7 @@ static int ensure_level(rslf_ctx* ctx, int p, int V, int U, bool full, bool with
         RSLF_TRY(dev_alloc(ctx, &L.depth, px)); RSLF_TRY(dev_alloc(ctx, &L.rbar, px * ctx->C));
         RSLF_TRY(dev_alloc(ctx, &L.emask, px)); RSLF_TRY(dev_alloc(ctx, &L.remaining, px));
         RSLF_TRY(dev_alloc(ctx, &L.valid, px));
+        RSLF_TRY(dev_alloc(ctx, &L.rowdark, (planes + 1) * (size_t)V));
         L.cap_px = px;
     }
     if (L.cap_stack < stack) {
@@ -470,6 +471,15 @@ static int global_svu_u8(rslf_ctx* ctx, const uint8_t* local, int S, int U, cons
     return RSLF_OK;
 }
 
+__global__ void row_sum_kernel(const int* __restrict__ rowdark, int S, int V, int* __restrict__ out)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    int t = 0;
+    for (int s = 0; s < S; ++s) t += rowdark[(size_t)s * V + v];
+    out[v] = t;
+}
+
 /* ------------------------------------------------------------------ one s_hat pass */
 struct pass_io {
     int level; int s_hat; int D; float dmin, dmax; bool use_bound_maps;
@@ -521,11 +531,13 @@ static int run_depth_pass(rslf_ctx* ctx, const rslf_params& P, const pass_io& io
             RSLF_TRY(ensure_gather_planes(ctx, (size_t)L.Vtot * U));
             RSLF_TRY(comm_gather_median_planes(ctx, a.depth, L.emask + po, L.epi + (size_t)io.s_hat * U * C, (size_t)S * U * C, U, C, t));
             RSLF_TRY(launch_selective_median(ctx, ctx->g_depth, ctx->g_mask, ctx->g_colour, (size_t)U * C, L.Vtot, U, C,
-                                             P.median_filter_size, P.median_filter_epsilon, ctx->filtered, L.v0, V));
+                                             P.median_filter_size, P.median_filter_epsilon, ctx->filtered, L.v0, V,
+                                             io.pile ? nullptr : L.remaining + po, io.pile ? nullptr : L.rowdark + (size_t)S * V));
         } else {
             /* colours of line s_hat: row v starts at epi + (v*S + s_hat)*U*C */
             RSLF_TRY(launch_selective_median(ctx, a.depth, L.emask + po, L.epi + (size_t)io.s_hat * U * C, (size_t)S * U * C,
-                                             V, U, C, P.median_filter_size, P.median_filter_epsilon, ctx->filtered));
+                                             V, U, C, P.median_filter_size, P.median_filter_epsilon, ctx->filtered, 0, -1,
+                                             io.pile ? nullptr : L.remaining + po, io.pile ? nullptr : L.rowdark + (size_t)S * V));
         }
     }
     return RSLF_OK;
@@ -554,9 +566,14 @@ static int run_depth2d_level(rslf_ctx* ctx, int p, const rslf_params& P, float d
     RSLF_CUDA_TRY(ctx, cudaMemsetAsync(L.depth, 0, px * sizeof(float), ctx->stream));
     RSLF_CUDA_TRY(ctx, cudaMemsetAsync(L.cd, 0, px * sizeof(float), ctx->stream));
     RSLF_CUDA_TRY(ctx, cudaMemsetAsync(L.rbar, 0, px * C * sizeof(float), ctx->stream));
+    RSLF_CUDA_TRY(ctx, cudaMemsetAsync(L.rowdark, 0, ((size_t)S + 1) * V * sizeof(int), ctx->stream));
     {
         stage_scope sc(ctx, ST_EDGE);
-        RSLF_TRY(launch_edge_confidence(ctx, L.epi, V, S, U, C, 0, S, P, L.ce, L.emask));
+        RSLF_TRY(launch_edge_confidence(ctx, L.epi, V, S, U, C, 0, S, P, L.ce, L.emask, L.rowdark));
+        /* rows that hold a dark target in any view: rowdark[S][v] = sum over s (an upper bound for the whole level) */
+        row_sum_kernel<<<rslf_div_up(V, 256), 256, 0, ctx->stream>>>(L.rowdark, S, V, L.rowdark + (size_t)S * V);
+        RSLF_CUDA_TRY(ctx, cudaGetLastError());
+        ctx->timing.kernel_launches += 1;
     }
     RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(L.remaining, L.emask, px, cudaMemcpyDeviceToDevice, ctx->stream));   /* core.hpp:958-963 */
     std::vector<int> order = visiting_order(S);
@@ -574,6 +591,7 @@ static int run_depth2d_level(rslf_ctx* ctx, int p, const rslf_params& P, float d
             a.emask_p = L.emask + (size_t)s_hat * plane; a.filtered = ctx->filtered;
             a.rbar_p = L.rbar + (size_t)s_hat * plane * C; a.cd_p = L.cd + (size_t)s_hat * plane;
             a.depth = L.depth; a.cd = L.cd; a.remaining = L.remaining; a.winner = ctx->winner;
+            a.items = ctx->items; a.count = ctx->count + io.count_slot; a.rowdark = L.rowdark;
             RSLF_TRY(launch_propagate(ctx, C, a));
         }
         ++pass;

@@ -34,6 +34,7 @@ struct rslf_level {
     uint8_t* emask = nullptr;    /* edge-confidence mask       [S][V][U]                      */
     uint8_t* remaining = nullptr;/* "still to compute" mask    [S][V][U]                      */
     uint8_t* valid = nullptr;    /* validity mask for bounds / fuse [S][V][U]                 */
+    int* rowdark = nullptr;      /* [S][V] confident-and-dark pixels not yet painted, then [V] row sums */
     float slope = 1.f;
     int nonneg = 1;              /* normalised stack has no negative value                    */
     bool have_bounds = false;

@@ -175,6 +175,23 @@ def test_depth2d_per_pixel_bounds(gpu_ctx):
     np.testing.assert_array_equal(comp.m_edge_confidence_mask_s_v_u, ref["edge_mask"])
 
 
+def test_depth2d_bounds_wider_than_global_range(gpu_ctx):
+    """edit_dmin / edit_dmax maps far wider than the constructor's range: the staged scanline segments are
+    cut to their rows and the kernel's global-memory fallback has to give the same radiances."""
+    S, V, U, C, D = 9, 4, 200, 3, 40
+    epis = lf(S, V, U, C, seed=78, dmin=-3.0, dmax=3.0)
+    comp = api.Depth2DComputer(epis, 0.0, 0.25, D, epi_scale_factor=1.0, ctx=gpu_ctx)
+    comp.edit_dmin()[:] = np.float32(-20.0)
+    comp.edit_dmax()[:] = np.float32(20.0)
+    comp.run()
+    lo = np.full((S, V, U), -20.0, np.float32)
+    hi = np.full((S, V, U), 20.0, np.float32)
+    ref = oracle.depth2d(oracle.normalise(epis, 1.0), 0.0, 0.25, D, dmin_svu=lo, dmax_svu=hi)
+    np.testing.assert_array_equal(comp.m_best_depth_s_v_u, ref["best_depth"])
+    np.testing.assert_array_equal(comp.m_disp_confidence_s_v_u, ref["disp_conf"])
+    np.testing.assert_array_equal(comp.m_rbar_s_v_u, ref["rbar"])
+
+
 # --------------------------------------------------------------------------- FineToCoarse
 @pytest.mark.parametrize("S,V,U,C,D,scale", [(5, 44, 60, 3, 16, 1.0), (4, 27, 90, 1, 24, -1.0)])
 def test_fine_to_coarse(gpu_ctx, S, V, U, C, D, scale):
