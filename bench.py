@@ -123,6 +123,7 @@ def reference_arm(args, cfg, name):
     if rank != 0:
         return
     import oracle
+    oracle.set_num_threads(os.cpu_count() or 1)      # torchrun exports OMP_NUM_THREADS=1; the arm uses every host core
     cores = oracle.num_threads()
     rows = cpu_rows(cfg, budget_s=max(3.0, 60.0 / max(1, args.steps + args.warmup)))
     epis = cpu_sample(cfg, rows)
@@ -138,7 +139,7 @@ def reference_arm(args, cfg, name):
         rows, name, cfg["S"], cfg["U"], cfg["D"], cfg["mode"])
     line = {"impl": "reference", "metric": "EPI samples/sec (pixel x disparity x view)", "value": v, "unit": "samples/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_t / args.steps * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": name + ": " + cfg["desc"], "sample": sample},
             "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -228,16 +229,16 @@ def main():
     sampler.stop_flag.set()
     sampler.join()
     stats = torch.tensor([wall, acc["samples"], acc["ms_total"], acc["ms_depth"], acc["kernel_launches"],
-                          acc["depth_launches"]], dtype=torch.float64, device="cuda")
+                          acc["depth_launches"], acc["computed_pixels"]], dtype=torch.float64, device="cuda")
     if world > 1:
         mx = stats.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = stats.clone()
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         wall, samples = float(mx[0]), float(sm[1])
-        launches = float(sm[4])
+        launches, pixels = float(sm[4]), float(sm[6])
     else:
-        samples, launches = acc["samples"], acc["kernel_launches"]
+        samples, launches, pixels = acc["samples"], acc["kernel_launches"], acc["computed_pixels"]
     value = samples / wall
 
     # ---- e2e: pinned host stack in, result maps out, through the mirror classes -----------------------------
@@ -306,8 +307,9 @@ def main():
             "hbm_peak_gbs": peaks.get("hbm_gbs"), "hbm_peak_kind": peak_kind,
         }
         cpu = None
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:          # the CPU baseline is timed at N = 1 only
             import oracle
+            oracle.set_num_threads(os.cpu_count() or 1)
             rows = cpu_rows(cfg, budget_s=15.0)
             ce = cpu_sample(cfg, rows)
             cs, ct = run_cpu(cfg, ce)
@@ -317,12 +319,12 @@ def main():
         line = {
             "metric": "EPI samples/sec (pixel x disparity x view)", "value": value, "unit": "samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3,
-            "higher_is_better": True, "scaling": "strong" if world > 1 else "weak", "vs_baseline": None,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": name + ": " + cfg["desc"], "S": S, "V": V, "U": U, "C": C, "D": D,
                        "dmin": DMIN, "dmax": DMAX, "sharding": "rows x%d" % world,
                        "l2": "256 MB memset between steps (L2 flush)",
-                       "samples_per_step": samples / args.steps, "pixels_per_step": acc["computed_pixels"] / args.steps,
+                       "samples_per_step": samples / args.steps, "pixels_per_step": pixels / args.steps,
                        "ms_per_disparity_result_device": acc["ms_total"] / args.steps},
             "stages_ms_per_step": {k: acc[k] / args.steps for k in ("ms_edge", "ms_depth", "ms_reduce", "ms_median",
                                                                      "ms_propagate", "ms_pyramid")},

@@ -36,12 +36,19 @@ __device__ __forceinline__ void sort_network(float (&a)[N])
                     if (i + j + k < N && (i + j) / (2 * p) == (i + j + k) / (2 * p)) med_cswap(a[i + j], a[i + j + k]);
 }
 
-template <int C, int WIDTH>
+/* rows of the neighbouring ranks (row-sharded runs): the two rows above / below this rank's block of the
+ * depth, mask and colour planes of line s_hat; nullptr where the block touches the image border */
+struct median_halo {
+    const float* top_depth; const float* top_colour; const uint8_t* top_mask;     /* rows v = -2, -1 */
+    const float* bot_depth; const float* bot_colour; const uint8_t* bot_mask;     /* rows v = V, V + 1 */
+};
+
+template <int C, int WIDTH, bool HALO>
 __global__ void __launch_bounds__(128)
 selective_median_kernel(const float* __restrict__ src, const uint8_t* __restrict__ mask,
                         const float* __restrict__ colour, size_t colour_row_stride,
                         int V, int U, int v_begin, float eps, double eps_T, float* __restrict__ dst,
-                        const uint8_t* __restrict__ fresh, const int* __restrict__ rowdark_v)
+                        const uint8_t* __restrict__ fresh, const int* __restrict__ rowdark_v, const median_halo halo)
 {
     constexpr int N = (2 * WIDTH + 1) * (2 * WIDTH + 1);
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
@@ -61,15 +68,27 @@ selective_median_kernel(const float* __restrict__ src, const uint8_t* __restrict
     int n = 0;
 #pragma unroll
     for (int dk = -WIDTH; dk <= WIDTH; ++dk) {
+        const int k = v + dk;
+        /* the window row: inside the block, in a neighbour's halo rows, or outside the image */
+        const float* srow = nullptr; const uint8_t* mrow = nullptr; const float* crow = nullptr;
+        if (k >= 0 && k < V) {
+            srow = src + (size_t)k * U; mrow = mask + (size_t)k * U; crow = colour + (size_t)k * colour_row_stride;
+        } else if (HALO && k < 0 && k >= -2 && halo.top_depth) {
+            srow = halo.top_depth + (size_t)(k + 2) * U; mrow = halo.top_mask + (size_t)(k + 2) * U;
+            crow = halo.top_colour + (size_t)(k + 2) * U * C;
+        } else if (HALO && k >= V && k < V + 2 && halo.bot_depth) {
+            srow = halo.bot_depth + (size_t)(k - V) * U; mrow = halo.bot_mask + (size_t)(k - V) * U;
+            crow = halo.bot_colour + (size_t)(k - V) * U * C;
+        }
 #pragma unroll
         for (int dl = -WIDTH; dl <= WIDTH; ++dl) {
-            const int k = v + dk, l = u + dl;
+            const int l = u + dl;
             float x = CUDART_INF_F;
-            if (k >= 0 && k < V && l >= 0 && l < U && mask[(size_t)k * U + l]) {
+            if (srow && l >= 0 && l < U && mrow[l]) {
                 float q[C];
 #pragma unroll
-                for (int c = 0; c < C; ++c) q[c] = __ldg(colour + (size_t)k * colour_row_stride + (size_t)l * C + c);
-                if (rslf_norm_diff_lt<C>(pc, q, eps, eps_T)) { x = src[(size_t)k * U + l]; ++n; }
+                for (int c = 0; c < C; ++c) q[c] = __ldg(crow + (size_t)l * C + c);
+                if (rslf_norm_diff_lt<C>(pc, q, eps, eps_T)) { x = srow[l]; ++n; }
             }
             val[(dk + WIDTH) * (2 * WIDTH + 1) + (dl + WIDTH)] = x;
         }
@@ -87,19 +106,23 @@ selective_median_kernel(const float* __restrict__ src, const uint8_t* __restrict
 static int launch_selective_median(rslf_ctx* ctx, const float* src, const uint8_t* mask, const float* colour,
                                    size_t colour_row_stride, int V, int U, int C, int size, float eps, float* dst,
                                    int v_begin = 0, int v_count = -1, const uint8_t* fresh = nullptr,
-                                   const int* rowdark_v = nullptr)
+                                   const int* rowdark_v = nullptr, const median_halo* halo = nullptr)
 {
     const int width = (size - 1) / 2;
     if (v_count < 0) v_count = V;
     dim3 grid(rslf_div_up(U, 128), v_count);
     const double T = rslf_sq_threshold(eps);
-#define RSLF_MED_CASE(CC, WW)                                                                             \
-    if (C == CC && width == WW) {                                                                         \
-        selective_median_kernel<CC, WW><<<grid, 128, 0, ctx->stream>>>(src, mask, colour, colour_row_stride, \
-                                                                       V, U, v_begin, eps, T, dst, fresh, rowdark_v); \
-        RSLF_CUDA_TRY(ctx, cudaGetLastError());                                                           \
-        ctx->timing.kernel_launches += 1;                                                                 \
-        return RSLF_OK;                                                                                   \
+    median_halo h; memset(&h, 0, sizeof(h));
+    if (halo) h = *halo;
+#define RSLF_MED_CASE(CC, WW)                                                                              \
+    if (C == CC && width == WW) {                                                                          \
+        if (halo) selective_median_kernel<CC, WW, true><<<grid, 128, 0, ctx->stream>>>(                    \
+            src, mask, colour, colour_row_stride, V, U, v_begin, eps, T, dst, fresh, rowdark_v, h);        \
+        else selective_median_kernel<CC, WW, false><<<grid, 128, 0, ctx->stream>>>(                        \
+            src, mask, colour, colour_row_stride, V, U, v_begin, eps, T, dst, fresh, rowdark_v, h);        \
+        RSLF_CUDA_TRY(ctx, cudaGetLastError());                                                            \
+        ctx->timing.kernel_launches += 1;                                                                  \
+        return RSLF_OK;                                                                                    \
     }
     RSLF_MED_CASE(1, 0) RSLF_MED_CASE(1, 1) RSLF_MED_CASE(1, 2) RSLF_MED_CASE(1, 3)
     RSLF_MED_CASE(3, 0) RSLF_MED_CASE(3, 1) RSLF_MED_CASE(3, 2) RSLF_MED_CASE(3, 3)

@@ -525,14 +525,28 @@ static int run_depth_pass(rslf_ctx* ctx, const rslf_params& P, const pass_io& io
     {
         stage_scope sc(ctx, ST_MEDIAN);
         if (ctx->world > 1) {
-            /* the only cross-row step of a pass (core.hpp:698-709): every rank needs the depth, mask and colour
-             * rows of line s_hat next to its block -> all-gather them, then filter the local rows */
+            /* the only cross-row step of a pass (core.hpp:698-709): the window reaches (size-1)/2 rows into the
+             * neighbouring ranks' blocks */
             const shard_tab t = level_shards(ctx, io.level, L.Vtot);
-            RSLF_TRY(ensure_gather_planes(ctx, (size_t)L.Vtot * U));
-            RSLF_TRY(comm_gather_median_planes(ctx, a.depth, L.emask + po, L.epi + (size_t)io.s_hat * U * C, (size_t)S * U * C, U, C, t));
-            RSLF_TRY(launch_selective_median(ctx, ctx->g_depth, ctx->g_mask, ctx->g_colour, (size_t)U * C, L.Vtot, U, C,
-                                             P.median_filter_size, P.median_filter_epsilon, ctx->filtered, L.v0, V,
-                                             io.pile ? nullptr : L.remaining + po, io.pile ? nullptr : L.rowdark + (size_t)S * V));
+            int min_rows = L.Vtot;
+            for (int q = 0; q < t.n; ++q) min_rows = std::min(min_rows, t.b[q + 1] - t.b[q]);
+            const float* colour0 = L.epi + (size_t)io.s_hat * U * C;
+            const uint8_t* fresh = io.pile ? nullptr : L.remaining + po;
+            const int* rdv = io.pile ? nullptr : L.rowdark + (size_t)S * V;
+            const char* force_full = getenv("RSLF_MEDIAN_GATHER");     /* "full": test hook for the fallback below */
+            if ((P.median_filter_size - 1) / 2 <= 2 && min_rows >= 2 && !(force_full && force_full[0] == 'f')) {
+                /* halo exchange: 2 + 2 rows per rank in one small all-gather, read in place by the median */
+                median_halo halo;
+                RSLF_TRY(comm_exchange_median_halo(ctx, a.depth, L.emask + po, colour0, (size_t)S * U * C, U, C, t, &halo));
+                RSLF_TRY(launch_selective_median(ctx, a.depth, L.emask + po, colour0, (size_t)S * U * C, V, U, C,
+                                                 P.median_filter_size, P.median_filter_epsilon, ctx->filtered, 0, -1, fresh, rdv, &halo));
+            } else {
+                /* thin blocks (coarse levels) or wide windows: gather the whole planes of line s_hat */
+                RSLF_TRY(ensure_gather_planes(ctx, (size_t)L.Vtot * U));
+                RSLF_TRY(comm_gather_median_planes(ctx, a.depth, L.emask + po, colour0, (size_t)S * U * C, U, C, t));
+                RSLF_TRY(launch_selective_median(ctx, ctx->g_depth, ctx->g_mask, ctx->g_colour, (size_t)U * C, L.Vtot, U, C,
+                                                 P.median_filter_size, P.median_filter_epsilon, ctx->filtered, L.v0, V, fresh, rdv));
+            }
         } else {
             /* colours of line s_hat: row v starts at epi + (v*S + s_hat)*U*C */
             RSLF_TRY(launch_selective_median(ctx, a.depth, L.emask + po, L.epi + (size_t)io.s_hat * U * C, (size_t)S * U * C,

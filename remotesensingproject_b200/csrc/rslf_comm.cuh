@@ -211,6 +211,55 @@ static int comm_gather_median_planes(rslf_ctx* ctx, const float* depth_plane, co
     return RSLF_OK;
 }
 
+/* per-pass halo exchange for the selective median when every rank holds >= 2 rows: each rank contributes
+ * its first two and last two rows of the depth / colour / mask planes of line s_hat (4 rows), one small
+ * all-gather, and the median kernel reads its neighbours' rows straight out of the receive buffer */
+__global__ void pack_median_halo_kernel(const float* __restrict__ depth, const uint8_t* __restrict__ mask,
+                                        const float* __restrict__ colour0, size_t colour_row_stride, int Vloc, int U, int C,
+                                        char* __restrict__ send, size_t off_colour, size_t off_mask)
+{
+    const int j = blockIdx.y;                                  /* 0,1: first rows; 2,3: last rows */
+    const int v = (j < 2) ? j : Vloc - 4 + j;
+    float* d = reinterpret_cast<float*>(send) + (size_t)j * U;
+    float* c = reinterpret_cast<float*>(send + off_colour) + (size_t)j * U * C;
+    uint8_t* m = reinterpret_cast<uint8_t*>(send + off_mask) + (size_t)j * U;
+    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < U; u += gridDim.x * blockDim.x) {
+        d[u] = depth[(size_t)v * U + u];
+        m[u] = mask[(size_t)v * U + u];
+        for (int cc = 0; cc < C; ++cc) c[(size_t)u * C + cc] = colour0[(size_t)v * colour_row_stride + (size_t)u * C + cc];
+    }
+}
+
+static int comm_exchange_median_halo(rslf_ctx* ctx, const float* depth_plane, const uint8_t* mask_plane, const float* colour0,
+                                     size_t colour_row_stride_floats, int U, int C, const shard_tab& t, median_halo* out)
+{
+    const int r0 = ctx->rank, Vloc = t.b[r0 + 1] - t.b[r0];
+    const size_t off_colour = (size_t)4 * U * 4, off_mask = off_colour + (size_t)4 * U * C * 4;
+    const size_t blockbytes = (off_mask + (size_t)4 * U + 15) & ~(size_t)15;
+    RSLF_TRY(comm_ensure_stage(ctx, blockbytes));
+    dim3 grid(std::max(1, std::min(8, (U + 127) / 128)), 4);
+    pack_median_halo_kernel<<<grid, 128, 0, ctx->stream>>>(depth_plane, mask_plane, colour0, colour_row_stride_floats, Vloc, U, C,
+                                                           (char*)ctx->g_send, off_colour, off_mask);
+    RSLF_CUDA_TRY(ctx, cudaGetLastError());
+    ctx->timing.kernel_launches += 1;
+    RSLF_NCCL_TRY(ctx, g_nccl.AllGather(ctx->g_send, ctx->g_recv, blockbytes, RSLF_NCCL_UINT8, ctx->nccl_comm, ctx->stream));
+    memset(out, 0, sizeof(*out));
+    const char* recv = (const char*)ctx->g_recv;
+    if (r0 > 0) {                                              /* rows 2, 3 of the rank above = its last two rows */
+        const char* b = recv + (size_t)(r0 - 1) * blockbytes;
+        out->top_depth = reinterpret_cast<const float*>(b) + (size_t)2 * U;
+        out->top_colour = reinterpret_cast<const float*>(b + off_colour) + (size_t)2 * U * C;
+        out->top_mask = reinterpret_cast<const uint8_t*>(b + off_mask) + (size_t)2 * U;
+    }
+    if (r0 + 1 < t.n) {                                        /* rows 0, 1 of the rank below = its first two rows */
+        const char* b = recv + (size_t)(r0 + 1) * blockbytes;
+        out->bot_depth = reinterpret_cast<const float*>(b);
+        out->bot_colour = reinterpret_cast<const float*>(b + off_colour);
+        out->bot_mask = reinterpret_cast<const uint8_t*>(b + off_mask);
+    }
+    return RSLF_OK;
+}
+
 extern "C" int rslf_cuda_nccl_unique_id(void* id128)
 {
     if (!id128) return RSLF_ERR_ARG;

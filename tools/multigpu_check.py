@@ -22,8 +22,12 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     failures = 0
     cases = [dict(S=7, V=96, U=80, C=3, D=24, mode="ftc", scale=1.0), dict(S=6, V=128, U=70, C=1, D=40, mode="ftc", scale=-1.0),
-             dict(S=5, V=50, U=64, C=3, D=16, mode="depth2d", scale=1.0)]
+             dict(S=5, V=50, U=64, C=3, D=16, mode="depth2d", scale=1.0),
+             dict(S=5, V=64, U=72, C=3, D=16, mode="ftc", scale=1.0, gather="full")]
     for i, c in enumerate(cases):
+        os.environ.pop("RSLF_MEDIAN_GATHER", None)
+        if c.get("gather"):
+            os.environ["RSLF_MEDIAN_GATHER"] = c["gather"]      # whole-plane all-gather instead of the halo exchange
         epis, _ = make_light_field_np(c["S"], c["V"], c["U"], c["C"], dmin=-1.0, dmax=2.0, seed=300 + i, layers=5)
         if c["scale"] < 0:
             epis = (epis * 200.0 + 5.0).astype(np.float32)
