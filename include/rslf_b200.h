@@ -244,6 +244,8 @@ int rslf_cuda_set_row_shards(rslf_ctx* ctx, const int* row_starts, int n_ranks);
 /* Measured FP32 FADD/FMUL issue rate of this device in Gop/s (non-FMA, the
  * instruction mix of the mean-shift kernel); used as roofline denominator. */
 int rslf_cuda_measure_fp32_peak(rslf_ctx* ctx, double* gops_nofma, double* gflops_fma);
+/* The same separately rounded multiply / add mix issued as packed FP32x2 instructions (FFMA2 / FADD2). */
+int rslf_cuda_measure_fp32x2_peak(rslf_ctx* ctx, double* gops_nofma_packed);
 /* Writes >126 MB on the device so the next timed step starts with a cold L2. */
 int rslf_cuda_flush_l2(rslf_ctx* ctx);
 int rslf_cuda_sync(rslf_ctx* ctx);

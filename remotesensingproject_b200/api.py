@@ -303,6 +303,11 @@ class Context:
         self.check(lib().rslf_cuda_measure_fp32_peak(self._h, C.byref(a), C.byref(b)), "rslf_cuda_measure_fp32_peak")
         return a.value, b.value
 
+    def measure_fp32x2_peak(self):
+        a = C.c_double()
+        self.check(lib().rslf_cuda_measure_fp32x2_peak(self._h, C.byref(a)), "rslf_cuda_measure_fp32x2_peak")
+        return a.value
+
     def comm_init(self, uid_bytes, rank, world):
         buf = (C.c_char * 128).from_buffer_copy(uid_bytes)
         self.check(lib().rslf_cuda_comm_init(self._h, buf, int(rank), int(world)), "rslf_cuda_comm_init")

@@ -55,6 +55,7 @@ struct __align__(16) rslf_partial {
 
 struct depth_args {
     const float* epi; int V, S, U, D; int s_hat; float slope; float inv; int iters;
+    float negzero;                /* -0.0f, opaque to the compiler: addend of the packed multiplies */
     int wpv_q16;                  /* pixels a chunk's hypotheses spread per view step, 16.16 fixed point (row sizing) */
     const int* items; const int* count;
     const float* dmin_map; const float* dmax_map; float dmin_c, dmax_c;
@@ -214,6 +215,122 @@ __device__ __forceinline__ void ms_accumulate(const float (&r)[C][H], const floa
 }
 
 
+/* ---- packed FP32x2 arithmetic (Blackwell FFMA2 / FADD2) ------------------------------------------------
+ * sm_100a issues two separately rounded FP32 operations per lane with one instruction; a micro-benchmark
+ * whose second operands are loop constants (served by the operand-reuse cache) reaches 73.9 T multiply /
+ * add operations per second against 36.2 T with scalar instructions (k_peak.cuh).  In the mean shift the
+ * operands are fresh register pairs, a packed instruction then reads 4 - 6 registers and the register
+ * file's two banks make it issue over 2 - 3 cycles: measured on B200 the packed variant is bit-identical
+ * to the scalar one and NOT faster (C3: 1347 ms against 1321 ms in the depth kernel), so it is compiled
+ * out by default (RSLF_PACKED_FP32=1 re-enables it; tests pass either way).  Each half of a packed
+ * operation is an ordinary round-to-nearest-even operation.
+ * CAUTION: ptxas 12.9 contracts a packed multiply that feeds a packed add into one FFMA2 even with
+ * --fmad=false and explicit .rn (seen in SASS), which would change the rounding.  The multiply is therefore
+ * written as fma(a, b, nz) with nz = -0.0 read from the kernel arguments: ptxas cannot know the value, so
+ * it stays a genuine FFMA2 that nothing can be contracted with, and a * b + (-0) rounds exactly like
+ * a * b (including the sign of a zero product).
+ */
+#ifndef RSLF_PACKED_FP32
+#define RSLF_PACKED_FP32 0      /* measured: no faster than scalar in this kernel, see below */
+#endif
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b, f32x2 nz) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(nz));
+    return r;
+}
+
+/*
+ * Two consecutive views (va: view s, vb: view s + 1) of the mean-shift sums, same arithmetic and the same
+ * accumulation order as two calls of ms_accumulate, issued as packed operations:
+ *   H even   : pairs of neighbouring hypotheses, every operation packed;
+ *   C=3, H=1 : (c0, c1) of one view form a pair, c2 of the two views form a pair;
+ *   C=1, H=1 : the two views form a pair (the two accumulations stay scalar and ordered).
+ */
+template <int C, int H, bool NONNEG>
+__device__ __forceinline__ void ms_accumulate_pair(const float (&va)[C][H], const float (&vb)[C][H], const float (&rb)[C][H],
+                                                   float inv, f32x2 NZ, float (&sR)[C][H], float (&sK)[H])
+{
+#if RSLF_PACKED_FP32
+    const f32x2 INV = pk2(inv, inv), ONE = pk2(1.0f, 1.0f);
+    if (H % 2 == 0) {
+#pragma unroll
+        for (int view = 0; view < 2; ++view) {
+            const float (&r)[C][H] = view ? vb : va;
+#pragma unroll
+            for (int hp = 0; hp < H / 2; ++hp) {
+                const int h0 = 2 * hp, h1 = (2 * hp + 1) % H;
+                f32x2 R[C], B[C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    R[c] = pk2(r[c][h0], r[c][h1]);
+                    const f32x2 X = sub2(R[c], pk2(rb[c][h0], rb[c][h1]));
+                    B[c] = mul2(mul2(INV, X, NZ), X, NZ);
+                }
+                f32x2 Bs = B[0];
+                if (C == 3) Bs = add2(add2(B[0], B[C > 1 ? 1 : 0]), B[C > 2 ? 2 : 0]);
+                float k0, k1;
+                upk2(sub2(ONE, Bs), k0, k1);
+                k0 = fmaxf(k0, 0.f); k1 = fmaxf(k1, 0.f);
+                const f32x2 K = pk2(k0, k1);
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    f32x2 R0 = R[c];
+                    if (!NONNEG) R0 = pk2(fmaxf(r[c][h0], 0.f), fmaxf(r[c][h1], 0.f));
+                    const f32x2 A = add2(pk2(sR[c][h0], sR[c][h1]), mul2(R0, K, NZ));
+                    upk2(A, sR[c][h0], sR[c][h1]);
+                }
+                upk2(add2(pk2(sK[h0], sK[h1]), K), sK[h0], sK[h1]);
+            }
+        }
+    } else if (C == 3) {
+        constexpr int c1 = C > 1 ? 1 : 0, c2 = C > 2 ? 2 : 0;
+        const f32x2 RB01 = pk2(rb[0][0], rb[c1][0]), RB2 = pk2(rb[c2][0], rb[c2][0]);
+        const f32x2 R01a = pk2(va[0][0], va[c1][0]), R01b = pk2(vb[0][0], vb[c1][0]), R2 = pk2(va[c2][0], vb[c2][0]);
+        const f32x2 X01a = sub2(R01a, RB01), X01b = sub2(R01b, RB01), X2 = sub2(R2, RB2);
+        const f32x2 B01a = mul2(mul2(INV, X01a, NZ), X01a, NZ), B01b = mul2(mul2(INV, X01b, NZ), X01b, NZ), B2 = mul2(mul2(INV, X2, NZ), X2, NZ);
+        float b0a, b1a, b0b, b1b;
+        upk2(B01a, b0a, b1a); upk2(B01b, b0b, b1b);
+        const float sa = b0a + b1a, sb = b0b + b1b;                  /* (c0 + c1), then + c2 */
+        float ka, kb;
+        upk2(sub2(ONE, add2(pk2(sa, sb), B2)), ka, kb);
+        ka = fmaxf(ka, 0.f); kb = fmaxf(kb, 0.f);
+        f32x2 Q01a = R01a, Q01b = R01b, Q2 = R2;
+        if (!NONNEG) {
+            Q01a = pk2(fmaxf(va[0][0], 0.f), fmaxf(va[c1][0], 0.f)); Q01b = pk2(fmaxf(vb[0][0], 0.f), fmaxf(vb[c1][0], 0.f));
+            Q2 = pk2(fmaxf(va[c2][0], 0.f), fmaxf(vb[c2][0], 0.f));
+        }
+        f32x2 A01 = pk2(sR[0][0], sR[c1][0]);
+        A01 = add2(A01, mul2(Q01a, pk2(ka, ka), NZ));                    /* view s first, then view s + 1 */
+        A01 = add2(A01, mul2(Q01b, pk2(kb, kb), NZ));
+        upk2(A01, sR[0][0], sR[c1][0]);
+        float p2a, p2b;
+        upk2(mul2(Q2, pk2(ka, kb), NZ), p2a, p2b);
+        sR[c2][0] = sR[c2][0] + p2a; sR[c2][0] = sR[c2][0] + p2b;
+        sK[0] = sK[0] + ka; sK[0] = sK[0] + kb;
+    } else {
+        const f32x2 R = pk2(va[0][0], vb[0][0]);
+        const f32x2 X = sub2(R, pk2(rb[0][0], rb[0][0]));
+        float ka, kb;
+        upk2(sub2(ONE, mul2(mul2(INV, X, NZ), X, NZ)), ka, kb);
+        ka = fmaxf(ka, 0.f); kb = fmaxf(kb, 0.f);
+        f32x2 Q = R;
+        if (!NONNEG) Q = pk2(fmaxf(va[0][0], 0.f), fmaxf(vb[0][0], 0.f));
+        float pa, pb;
+        upk2(mul2(Q, pk2(ka, kb), NZ), pa, pb);
+        sR[0][0] = sR[0][0] + pa; sR[0][0] = sR[0][0] + pb;
+        sK[0] = sK[0] + ka; sK[0] = sK[0] + kb;
+    }
+#else
+    ms_accumulate<C, H, NONNEG>(va, rb, inv, sR, sK);
+    ms_accumulate<C, H, NONNEG>(vb, rb, inv, sR, sK);
+#endif
+}
+
 /*
  * In-place conversion of the staged rows of one round, DEPTH_UNR views per step (all segment reads of
  * the step, one warp synchronisation, then the radiance stores): I = (s_hat - s) * D * slope + u
@@ -304,6 +421,7 @@ depth_kernel(const depth_args a)
     const unsigned bar = smem_u32(smem_raw);
     const long long total = (long long)(*a.count) * a.chunks;
     const float inv = a.inv;
+    const f32x2 NZ = pk2(a.negzero, a.negzero);          /* -0.0 the compiler cannot see (see mul2) */
     const float Um1f = (float)(U - 1);
 
     /* prologue: mbarrier and the row offset table (exclusive prefix sum of the row sizes) */
@@ -454,19 +572,19 @@ depth_kernel(const depth_args a)
             };
             if (nblk > 0) load_block(0, ba);
 #pragma unroll
-            for (int j = 0; j < RV; ++j) ms_accumulate<C, H, NONNEG>(rr[j], rb, inv, sR, sK);
+            for (int j = 0; j < RV; j += 2) ms_accumulate_pair<C, H, NONNEG>(rr[j], rr[RV > 1 ? j + 1 : 0], rb, inv, NZ, sR, sK);
             int bi = 0;
             for (; bi + 2 <= nblk; bi += 2) {
                 load_block(bi + 1, bb);
 #pragma unroll
-                for (int j = 0; j < DEPTH_UNR; ++j) ms_accumulate<C, H, NONNEG>(ba[j], rb, inv, sR, sK);
+                for (int j = 0; j < DEPTH_UNR; j += 2) ms_accumulate_pair<C, H, NONNEG>(ba[j], ba[j + 1], rb, inv, NZ, sR, sK);
                 load_block(min(bi + 2, nblk - 1), ba);                   /* last: harmless re-read */
 #pragma unroll
-                for (int j = 0; j < DEPTH_UNR; ++j) ms_accumulate<C, H, NONNEG>(bb[j], rb, inv, sR, sK);
+                for (int j = 0; j < DEPTH_UNR; j += 2) ms_accumulate_pair<C, H, NONNEG>(bb[j], bb[j + 1], rb, inv, NZ, sR, sK);
             }
             if (bi < nblk) {
 #pragma unroll
-                for (int j = 0; j < DEPTH_UNR; ++j) ms_accumulate<C, H, NONNEG>(ba[j], rb, inv, sR, sK);
+                for (int j = 0; j < DEPTH_UNR; j += 2) ms_accumulate_pair<C, H, NONNEG>(ba[j], ba[j + 1], rb, inv, NZ, sR, sK);
             }
             /* r_bar = sum_rK / sum_K (x / 0 = 0 as in OpenCV 3), then max(., 0) (core.hpp:606-609) */
 #pragma unroll

@@ -507,7 +507,7 @@ static int run_depth_pass(rslf_ctx* ctx, const rslf_params& P, const pass_io& io
     if (plan.chunks > 1) RSLF_TRY(ensure_partials(ctx, plane * plan.chunks));
     depth_args a;
     a.epi = L.epi; a.V = V; a.S = S; a.U = U; a.D = io.D; a.s_hat = io.s_hat; a.slope = P.slope_factor;
-    a.inv = kernel_inv(P, C); a.iters = P.mean_shift_max_iter;
+    a.inv = kernel_inv(P, C); a.iters = P.mean_shift_max_iter; a.negzero = -0.0f;
     a.items = ctx->items; a.count = count;
     a.dmin_map = io.use_bound_maps ? L.dmin + po : nullptr;
     a.dmax_map = io.use_bound_maps ? L.dmax + po : nullptr;
@@ -1176,4 +1176,12 @@ extern "C" int rslf_cuda_measure_fp32_peak(rslf_ctx* ctx, double* gops_nofma, do
     if (!ctx) return RSLF_ERR_ARG;
     RSLF_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     return measure_fp32_peak(ctx, gops_nofma, gflops_fma);
+}
+
+/* Gop/s of separately rounded FP32 multiplies / adds issued as packed f32x2 instructions (FFMA2 / FADD2). */
+extern "C" int rslf_cuda_measure_fp32x2_peak(rslf_ctx* ctx, double* gops_nofma_packed)
+{
+    if (!ctx) return RSLF_ERR_ARG;
+    RSLF_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    return measure_fp32x2_peak(ctx, gops_nofma_packed);
 }

@@ -36,6 +36,7 @@ def main():
     out = {}
     if "peak" in which:
         out["fp32_peak_gops_nofma,gflops_fma"] = ctx.measure_fp32_peak()
+        out["fp32x2_peak_gops_nofma"] = ctx.measure_fp32x2_peak()
         print(out, flush=True)
     p = api.default_params()
     if any(w.startswith("c1") for w in which):
