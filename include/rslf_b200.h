@@ -202,6 +202,10 @@ int rslf_cuda_fine_to_coarse_get_level(rslf_ctx* ctx, int level,
  * in: dense [V][S][U][C]; out: dense [V2][S][U2][C], V2 = cvRound(V/2). */
 int rslf_cuda_downsample_epis(rslf_ctx* ctx, const float* in_epis, int V, int S,
                               int U, int C, float* out_epis, int* V2, int* U2);
+/* The same for CV_8U stacks, which stay 8-bit between pyramid levels: OpenCV's integer Gaussian
+ * ([8,28,56,72,56,28,8]/256 twice, (acc + 2^15) >> 16) and integer half-size resize, bit-exact to cv2. */
+int rslf_cuda_downsample_epis_u8(rslf_ctx* ctx, const uint8_t* in_epis, int V, int S,
+                                 int U, int C, uint8_t* out_epis, int* V2, int* U2);
 /* rslf::fuse_disp_maps (src/rslf_fine_to_coarse_core.cpp:69-135).  disp_p[p] and
  * valid_p[p] are dense [S][V_p][U_p] host maps, finest first. */
 int rslf_cuda_fuse_disp_maps(rslf_ctx* ctx, int levels, int S, const int* Vp,

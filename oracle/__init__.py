@@ -175,6 +175,12 @@ def half_size(n):
 
 
 def downsample(raw):
+    raw = np.ascontiguousarray(raw)
+    if raw.dtype == np.uint8:
+        V, S, U, Cc = raw.shape
+        out = np.zeros((half_size(V), S, half_size(U), Cc), np.uint8)
+        lib().orc_downsample_u8(_b(raw), V, S, U, Cc, _b(out))
+        return out
     raw = _c32(raw)
     V, S, U, Cc = raw.shape
     out = np.zeros((half_size(V), S, half_size(U), Cc), np.float32)

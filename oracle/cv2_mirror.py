@@ -203,6 +203,12 @@ def generate(outdir):
     m, k = fuse(disp_p, valid_p)
     np.savez_compressed(os.path.join(outdir, "fuse_3lvl.npz"), d0=disp_p[0], d1=disp_p[1], d2=disp_p[2],
                         v0=valid_p[0], v1=valid_p[1], v2=valid_p[2], out_map=m, out_valid=k)
+    # 8-bit stacks take OpenCV's integer blur / resize paths (own generator so the fixtures above keep their stream)
+    rng8 = np.random.default_rng(777)
+    for name, (V, S, U, C) in {"down_u8_c3_odd": (23, 2, 37, 3), "down_u8_c1_135": (27, 2, 135, 1),
+                               "down_u8_c1_even": (24, 2, 30, 1)}.items():
+        raw = rng8.integers(0, 256, (V, S, U, C), dtype=np.uint8)
+        np.savez_compressed(os.path.join(outdir, name + ".npz"), raw=raw, out=downsample(raw))
     print("wrote fixtures to", outdir)
 
 

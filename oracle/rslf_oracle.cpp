@@ -478,6 +478,58 @@ void downsample(const float* in, const Dims& g, float* out, int V2, int U2) {
 }
 
 /*
+ * downsample_EPIs (ftc_core.cpp:14-60) for 8-bit stacks, which stay 8-bit between pyramid levels
+ * (ftc.hpp:142-147 normalises each level from the un-normalised stack).  OpenCV's CV_8U paths, bit-exact
+ * against cv2 (oracle/cv2_mirror.py, tests/golden/down_u8_*.npz): GaussianBlur 7x7 sigma 0 = integer kernel
+ * [8,28,56,72,56,28,8] (sum 256) along rows, then along columns, result (acc + 2^15) >> 16, BORDER_REFLECT;
+ * resize fx=fy=0.5 = (a+b+c+d+2) >> 2, and where an odd dimension leaves only one source row / column the
+ * exact mean of the available pixels rounded half to even.
+ */
+void downsample_u8(const uint8_t* in, const Dims& g, uint8_t* out, int V2, int U2) {
+    const int V = g.V, S = g.S, U = g.U, C = g.C;
+    static const int K[7] = {8, 28, 56, 72, 56, 28, 8};
+    Dims go{V2, S, U2, C};
+#pragma omp parallel
+    {
+        std::vector<int32_t> hbuf((size_t)V * U * C);
+        std::vector<uint8_t> blur((size_t)V * U * C);
+#pragma omp for schedule(dynamic, 1)
+        for (int s = 0; s < S; ++s) {
+            for (int v = 0; v < V; ++v)
+                for (int u = 0; u < U; ++u)
+                    for (int c = 0; c < C; ++c) {
+                        int32_t acc = 0;
+                        for (int j = 0; j < 7; ++j) acc += K[j] * (int32_t)in[epi_off(g, v, s, reflect(u + j - 3, U)) + c];
+                        hbuf[((size_t)v * U + u) * C + c] = acc;
+                    }
+            for (int v = 0; v < V; ++v)
+                for (int u = 0; u < U; ++u)
+                    for (int c = 0; c < C; ++c) {
+                        int32_t acc = 0;
+                        for (int j = 0; j < 7; ++j) acc += K[j] * hbuf[((size_t)reflect(v + j - 3, V) * U + u) * C + c];
+                        blur[((size_t)v * U + u) * C + c] = (uint8_t)((acc + 32768) >> 16);
+                    }
+            for (int v = 0; v < V2; ++v) {
+                const int nr = (2 * v + 1 < V) ? 2 : 1;
+                for (int u = 0; u < U2; ++u) {
+                    const int nc = (2 * u + 1 < U) ? 2 : 1;
+                    for (int c = 0; c < C; ++c) {
+                        int sum = 0;
+                        for (int a = 0; a < nr; ++a)
+                            for (int b = 0; b < nc; ++b) sum += blur[((size_t)(2 * v + a) * U + (2 * u + b)) * C + c];
+                        int n = nr * nc, r;
+                        if (n == 4) r = (sum + 2) >> 2;
+                        else if (n == 2) r = (sum + ((sum >> 1) & 1)) >> 1;      /* half to even */
+                        else r = sum;
+                        out[epi_off(go, v, s, u) + c] = (uint8_t)r;
+                    }
+                }
+            }
+        }
+    }
+}
+
+/*
  * FineToCoarse::run bound propagation (ftc.hpp:201-294) from level p (up) to
  * level p+1 (down).  Left scan tests indices u_up-1 .. 1 (index 0 never),
  * right scan u_up+1 .. U_up-1.
@@ -749,6 +801,11 @@ void orc_downsample(const float* in, int V, int S, int U, int C, float* out) {
     downsample(in, g, out, cv_round(V * 0.5), cv_round(U * 0.5));
 }
 
+void orc_downsample_u8(const uint8_t* in, int V, int S, int U, int C, uint8_t* out) {
+    Dims g{V, S, U, C};
+    downsample_u8(in, g, out, cv_round(V * 0.5), cv_round(U * 0.5));
+}
+
 void orc_set_bounds(const float* depth_up, const uint8_t* valid_up, int S, int Vu, int Uu, int Vd, int Ud,
                     float* dmin_map, float* dmax_map) {
     set_bounds(depth_up, valid_up, S, Vu, Uu, Vd, Ud, dmin_map, dmax_map);
@@ -775,8 +832,7 @@ int orc_pyramid_dims(int V, int U, int max_pyr_depth, int* Vp, int* Up) {
 
 /*
  * FineToCoarse ctor + run + get_results (ftc.hpp:103-322) for a float32 or 8U
- * level-0 stack `raw` ([V][S][U][C]).  8U stacks are only supported single
- * level here (the 8-bit pyramid uses OpenCV's integer blur).
+ * level-0 stack `raw` ([V][S][U][C]); 8-bit stacks stay 8-bit between levels.
  * level_out (optional): per level p, pointers to caller-allocated
  * [depth, ce, cd, dmin, dmax] float maps and [emask] — see python wrapper.
  * Returns total pixels evaluated; samples_out = sum over levels computed*D*S.
@@ -789,10 +845,11 @@ double orc_fine_to_coarse(const void* raw, int cv_depth, int V, int S, int U, in
     int Vp[32], Up[32];
     int levels = orc_pyramid_dims(V, U, max_pyr_depth, Vp, Up);
     if (levels == 0) return 0;
-    if (cv_depth != RSLF_DEPTH_32F && levels > 1) return -1;
+    if (cv_depth != RSLF_DEPTH_32F && cv_depth != RSLF_DEPTH_8U) return -1;
     std::vector<std::vector<float>> depth(levels), ce(levels), cd(levels), dmn(levels), dmx(levels);
     std::vector<std::vector<uint8_t>> emask(levels), valid(levels);
     std::vector<float> raw_cur, raw_next, norm, rbar;
+    std::vector<uint8_t> raw8_cur, raw8_next;
     size_t n0 = (size_t)V * S * U * C;
     const void* cur_raw = raw;
     double total = 0;
@@ -800,7 +857,7 @@ double orc_fine_to_coarse(const void* raw, int cv_depth, int V, int S, int U, in
         Dims g{Vp[p], S, Up[p], C};
         size_t n = (size_t)S * Vp[p] * Up[p];
         norm.resize((size_t)Vp[p] * S * Up[p] * C);
-        normalise(cur_raw, p == 0 ? cv_depth : RSLF_DEPTH_32F, norm.size(), scale_factor, norm.data());
+        normalise(cur_raw, cv_depth, norm.size(), scale_factor, norm.data());
         rslf_params P = *Pp;
         P.slope_factor = (float)((0.0 + Up[p]) / Up[0]);          /* ftc.hpp:139 */
         depth[p].assign(n, 0.f); ce[p].assign(n, 0.f); cd[p].assign(n, 0.f); emask[p].assign(n, 0);
@@ -818,15 +875,20 @@ double orc_fine_to_coarse(const void* raw, int cv_depth, int V, int S, int U, in
             valid[p][i] = accept_all ? (ce[p][i] > -1.f ? 255 : 0) : (ce[p][i] > P.edge_score_threshold ? 255 : 0);
         if (p + 1 < levels) {
             /* next level's raw stack (ftc.hpp:146) and bounds (ftc.hpp:201-294) */
-            raw_next.resize((size_t)Vp[p + 1] * S * Up[p + 1] * C);
-            downsample((const float*)cur_raw, g, raw_next.data(), Vp[p + 1], Up[p + 1]);
+            if (cv_depth == RSLF_DEPTH_8U) {
+                raw8_next.resize((size_t)Vp[p + 1] * S * Up[p + 1] * C);
+                downsample_u8((const uint8_t*)cur_raw, g, raw8_next.data(), Vp[p + 1], Up[p + 1]);
+            } else {
+                raw_next.resize((size_t)Vp[p + 1] * S * Up[p + 1] * C);
+                downsample((const float*)cur_raw, g, raw_next.data(), Vp[p + 1], Up[p + 1]);
+            }
             size_t nn = (size_t)S * Vp[p + 1] * Up[p + 1];
             dmn[p + 1].assign(nn, dmin); dmx[p + 1].assign(nn, dmax);
             /* bounds use level p's validity with m_accept_all as set: only the last level accepts all */
             set_bounds(depth[p].data(), valid[p].data(), S, Vp[p], Up[p], Vp[p + 1], Up[p + 1], dmn[p + 1].data(),
                        dmx[p + 1].data());
-            raw_cur.swap(raw_next);
-            cur_raw = raw_cur.data();
+            if (cv_depth == RSLF_DEPTH_8U) { raw8_cur.swap(raw8_next); cur_raw = raw8_cur.data(); }
+            else { raw_cur.swap(raw_next); cur_raw = raw_cur.data(); }
         }
     }
     (void)n0;

@@ -247,10 +247,16 @@ class Context:
         return dst
 
     def downsample_epis(self, raw):
-        raw = np.ascontiguousarray(raw, np.float32)
+        raw = np.ascontiguousarray(raw)
         V, S, U, Cc = raw.shape
         v2 = C.c_int()
         u2 = C.c_int()
+        if raw.dtype == np.uint8:
+            out = np.empty((int(np.rint(V * 0.5)), S, int(np.rint(U * 0.5)), Cc), np.uint8)
+            self.check(lib().rslf_cuda_downsample_epis_u8(self._h, _bp(raw), V, S, U, Cc, _bp(out), C.byref(v2),
+                                                          C.byref(u2)), "rslf_cuda_downsample_epis_u8")
+            return out
+        raw = np.ascontiguousarray(raw, np.float32)
         out = np.empty((int(np.rint(V * 0.5)), S, int(np.rint(U * 0.5)), Cc), np.float32)
         self.check(lib().rslf_cuda_downsample_epis(self._h, _fp(raw), V, S, U, Cc, _fp(out), C.byref(v2), C.byref(u2)),
                    "rslf_cuda_downsample_epis")

@@ -27,8 +27,9 @@
  *     is resident, so the HBM/L2 latency is paid once per item instead of once
  *     per view.  Each row is then converted in place: the lanes read their two
  *     neighbouring pixels, synchronise, and overwrite the row with the
- *     interpolated radiances r[s][c][d] ([c][32*H] floats, conflict-free
- *     LDS.32/64/128 in the mean shift).
+ *     interpolated radiances, four views at a time, transposed to
+ *     [c][h][lane][view] so that one LDS.128 of a lane fetches a channel of
+ *     four consecutive views in the mean shift (conflict-free).
  *   - the first RV views can stay in REGISTERS instead (a first staging round
  *     through the same rows): fewer shared-memory rows per warp, hence more
  *     resident warps when S*C is large, and no LDS for those views.
@@ -91,23 +92,6 @@ __global__ void compact_kernel(const uint8_t* __restrict__ emask, uint8_t* __res
     }
 }
 
-template <int H> __device__ __forceinline__ void rad_store(float* p, const float (&v)[H]);
-template <> __device__ __forceinline__ void rad_store<1>(float* p, const float (&v)[1]) { *p = v[0]; }
-template <> __device__ __forceinline__ void rad_store<2>(float* p, const float (&v)[2]) {
-    *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]);
-}
-template <> __device__ __forceinline__ void rad_store<4>(float* p, const float (&v)[4]) {
-    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-}
-template <int H> __device__ __forceinline__ void rad_load(const float* p, float (&v)[H]);
-template <> __device__ __forceinline__ void rad_load<1>(const float* p, float (&v)[1]) { v[0] = *p; }
-template <> __device__ __forceinline__ void rad_load<2>(const float* p, float (&v)[2]) {
-    float2 t = *reinterpret_cast<const float2*>(p); v[0] = t.x; v[1] = t.y;
-}
-template <> __device__ __forceinline__ void rad_load<4>(const float* p, float (&v)[4]) {
-    float4 t = *reinterpret_cast<const float4*>(p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-}
-
 #define DEPTH_UNR 4      /* views per unrolled block of the mean shift; rows are padded to a multiple of it */
 #define DEPTH_MAX_ROW_FLOATS 1024
 
@@ -128,11 +112,19 @@ static __host__ __device__ inline int depth_segment_floats(int s, int S, int s_h
     long long f = (span * C + 4 + 3) & ~3LL;
     return (int)(f > DEPTH_MAX_ROW_FLOATS ? DEPTH_MAX_ROW_FLOATS : f);
 }
-static __host__ __device__ inline int depth_row_floats(int r, int S, int Spad, int RV, int s_hat, int wpv_q16, int C, int W)
+/* Shared memory is organised in blocks of DEPTH_UNR rows.  Block b hosts the views DEPTH_UNR*b .. +3 of
+ * staging round 0 (if below RV) and the views RV + DEPTH_UNR*b .. +3 of round 1.  While staged, view j of the
+ * block owns the sub-area [j * pitch, (j + 1) * pitch) with pitch = max(C * 32 * H, longest segment of the
+ * block); after the conversion the block's first DEPTH_UNR * C * 32 * H floats hold the radiances transposed
+ * as [c][h][lane][view j], so that ONE LDS.128 of a lane fetches a channel of all four views. */
+static __host__ __device__ inline int depth_block_pitch(int b, int S, int Spad, int RV, int s_hat, int wpv_q16, int C, int W)
 {
     int f = C * W;
-    if (r < RV) { int g = depth_segment_floats(r, S, s_hat, wpv_q16, C); f = g > f ? g : f; }
-    if (RV + r < Spad) { int g = depth_segment_floats(RV + r, S, s_hat, wpv_q16, C); f = g > f ? g : f; }
+    for (int j = 0; j < DEPTH_UNR; ++j) {
+        const int r = b * DEPTH_UNR + j;
+        if (r < RV) { int g = depth_segment_floats(r, S, s_hat, wpv_q16, C); f = g > f ? g : f; }
+        if (RV + r < Spad) { int g = depth_segment_floats(RV + r, S, s_hat, wpv_q16, C); f = g > f ? g : f; }
+    }
     return f;
 }
 static __host__ __device__ inline int depth_num_rows(int Spad, int RV) { return (Spad - RV) > RV ? (Spad - RV) : RV; }
@@ -339,20 +331,17 @@ __device__ __forceinline__ void ms_accumulate_pair(const float (&va)[C][H], cons
  * ufl = u as float, NaN for lanes whose hypothesis index is >= D (they then fail every test).
  */
 template <int C, int H, bool FALLBACK>
-__device__ __forceinline__ void convert_rows(const depth_args& a, const int4* meta, float* rows, int vbase, int nviews,
+__device__ __forceinline__ void convert_rows(const depth_args& a, const int4* meta, const int* blk_off, float* rows, int vbase, int nviews,
                                              int lane, long long row0, const float (&ufl)[H], float Um1f,
                                              const float (&Dv)[H], int (&cardi)[H])
 {
-    constexpr int W = 32 * H;
 #pragma unroll 1
     for (int rb0 = 0; rb0 < nviews; rb0 += DEPTH_UNR) {
         float val[DEPTH_UNR][C][H];
-        int roff[DEPTH_UNR];
 #pragma unroll
         for (int j = 0; j < DEPTH_UNR; ++j) {
             const int s = vbase + rb0 + j;
             const int4 m = meta[rb0 + j];
-            roff[j] = m.z;
             const float* row = rows + m.z;
             const float k = (float)(a.s_hat - s);
 #pragma unroll
@@ -388,10 +377,14 @@ __device__ __forceinline__ void convert_rows(const depth_args& a, const int4* me
             }
         }
         __syncwarp();                                               /* every lane has read the segments */
+        /* radiances of the block, transposed: [c][h][lane][view j] */
+        float* blk = rows + blk_off[rb0 / DEPTH_UNR];
 #pragma unroll
-        for (int j = 0; j < DEPTH_UNR; ++j)
+        for (int c = 0; c < C; ++c)
 #pragma unroll
-            for (int c = 0; c < C; ++c) rad_store<H>(rows + roff[j] + c * W + lane * H, val[j][c]);
+            for (int h = 0; h < H; ++h)
+                *reinterpret_cast<float4*>(blk + ((c * H + h) * 32 + lane) * DEPTH_UNR) =
+                    make_float4(val[0][c][h], val[1][c][h], val[2][c][h], val[3][c][h]);
     }
 }
 
@@ -414,9 +407,10 @@ depth_kernel(const depth_args a)
     const int nrows = depth_num_rows(Spad, RV);
     const int nblk = (Spad - RV) / DEPTH_UNR;               /* blocks of DEPTH_UNR shared-memory views */
     constexpr int W = 32 * H;
-    /* [mbarrier, 16 B][row offsets: nrows + 1 ints, padded to 16 B][per-row staging records: nrows int4][rows] */
-    int* row_off = reinterpret_cast<int*>(smem_raw) + 4;
-    int4* meta = reinterpret_cast<int4*>(row_off + ((nrows + 1 + 3) & ~3));
+    /* [mbarrier, 16 B][block offsets: nblocks + 1 ints, padded to 16 B][per-row staging records: nrows int4][blocks] */
+    const int nblocks = nrows / DEPTH_UNR;
+    int* blk_off = reinterpret_cast<int*>(smem_raw) + 4;
+    int4* meta = reinterpret_cast<int4*>(blk_off + ((nblocks + 1 + 3) & ~3));
     float* rows = reinterpret_cast<float*>(meta + nrows);
     const unsigned bar = smem_u32(smem_raw);
     const long long total = (long long)(*a.count) * a.chunks;
@@ -424,26 +418,26 @@ depth_kernel(const depth_args a)
     const f32x2 NZ = pk2(a.negzero, a.negzero);          /* -0.0 the compiler cannot see (see mul2) */
     const float Um1f = (float)(U - 1);
 
-    /* prologue: mbarrier and the row offset table (exclusive prefix sum of the row sizes) */
+    /* prologue: mbarrier and the block offset table (exclusive prefix sum of the block sizes) */
     if (lane == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     {
         int carry = 0;
-        for (int base = 0; base < nrows; base += 32) {
-            const int r = base + lane;
-            int f = (r < nrows) ? depth_row_floats(r, S, Spad, RV, a.s_hat, a.wpv_q16, C, W) : 0;
+        for (int base = 0; base < nblocks; base += 32) {
+            const int b = base + lane;
+            int f = (b < nblocks) ? DEPTH_UNR * depth_block_pitch(b, S, Spad, RV, a.s_hat, a.wpv_q16, C, W) : 0;
             int incl = f;
 #pragma unroll
             for (int off = 1; off < 32; off <<= 1) {
                 const int t = __shfl_up_sync(0xffffffffu, incl, off);
                 if (lane >= off) incl += t;
             }
-            if (r < nrows) row_off[r] = carry + incl - f;
+            if (b < nblocks) blk_off[b] = carry + incl - f;
             carry += __shfl_sync(0xffffffffu, incl, 31);
         }
-        if (lane == 0) row_off[nrows] = carry;
+        if (lane == 0) blk_off[nblocks] = carry;
     }
     __syncwarp();
     unsigned phase = 0;                                     /* mbarrier phase parity */
@@ -502,11 +496,12 @@ depth_kernel(const depth_args a)
                 for (int r = lane; r < nviews; r += 32) {
                     int lo, hi;
                     view_span(a, vbase + r, uf, Dlo, Dhi, lo, hi);
-                    int4 m; m.x = 0; m.y = 0; m.z = row_off[r]; m.w = 0;
+                    const int bo = blk_off[r / DEPTH_UNR], pitch = (blk_off[r / DEPTH_UNR + 1] - bo) / DEPTH_UNR;
+                    int4 m; m.x = 0; m.y = 0; m.z = bo + (r % DEPTH_UNR) * pitch; m.w = 0;
                     if (lo <= hi) {
                         const int mis = ((int)((row0 + (long long)(vbase + r) * U + lo) & 3LL) * C) & 3;
                         const int want = ((hi + 1 - lo) * C + mis + 3) & ~3;
-                        const int cap = row_off[r + 1] - m.z;
+                        const int cap = pitch;
                         m.x = mis - lo * C; m.y = min(want, cap); m.w = want > cap;
                         bytes += 4u * (unsigned)m.y; cut |= (unsigned)m.w;
                     }
@@ -527,19 +522,28 @@ depth_kernel(const depth_args a)
             phase ^= 1u;
             /* in-place conversion of the rows; the variant with the global-memory fallback is only needed when a
              * segment was cut to its row (user-edited bounds wider than the global range) */
-            if (any_cut) convert_rows<C, H, true>(a, meta, rows, vbase, nviews, lane, row0, ufl, Um1f, Dv, cardi);
-            else convert_rows<C, H, false>(a, meta, rows, vbase, nviews, lane, row0, ufl, Um1f, Dv, cardi);
+            if (any_cut) convert_rows<C, H, true>(a, meta, blk_off, rows, vbase, nviews, lane, row0, ufl, Um1f, Dv, cardi);
+            else convert_rows<C, H, false>(a, meta, blk_off, rows, vbase, nviews, lane, row0, ufl, Um1f, Dv, cardi);
             __syncwarp();
             /* r_bar <- radiances of view s_hat (core.hpp:577) */
             if (a.s_hat >= vbase && a.s_hat < vbase + nviews) {
 #pragma unroll
-                for (int c = 0; c < C; ++c) rad_load<H>(rows + row_off[a.s_hat - vbase] + c * W + lane * H, rb[c]);
+                for (int c = 0; c < C; ++c)
+#pragma unroll
+                    for (int h = 0; h < H; ++h)
+                        rb[c][h] = rows[blk_off[(a.s_hat - vbase) / DEPTH_UNR] + ((c * H + h) * 32 + lane) * DEPTH_UNR + (a.s_hat - vbase) % DEPTH_UNR];
             }
             if (RV > 0 && round == 0) {
 #pragma unroll
-                for (int j = 0; j < RV; ++j)
+                for (int b = 0; b < RV / DEPTH_UNR; ++b)
 #pragma unroll
-                    for (int c = 0; c < C; ++c) rad_load<H>(rows + row_off[j] + c * W + lane * H, rr[j][c]);
+                    for (int c = 0; c < C; ++c)
+#pragma unroll
+                        for (int h = 0; h < H; ++h) {
+                            const float4 t = *reinterpret_cast<const float4*>(rows + blk_off[b] + ((c * H + h) * 32 + lane) * DEPTH_UNR);
+                            rr[b * DEPTH_UNR + 0][c][h] = t.x; rr[b * DEPTH_UNR + 1][c][h] = t.y;
+                            rr[b * DEPTH_UNR + 2][c][h] = t.z; rr[b * DEPTH_UNR + 3][c][h] = t.w;
+                        }
             }
         }
         float card[H];
@@ -552,7 +556,6 @@ depth_kernel(const depth_args a)
         float sK[H];
 #pragma unroll
         for (int h = 0; h < H; ++h) sK[h] = 0.f;
-        const float* const rp = rows + lane * H;
         for (int it = 0; it < a.iters; ++it) {
             float sR[C][H];
 #pragma unroll
@@ -563,12 +566,14 @@ depth_kernel(const depth_args a)
             }
             float ba[DEPTH_UNR][C][H], bb[DEPTH_UNR][C][H];
             auto load_block = [&](int bi, float (&dst)[DEPTH_UNR][C][H]) {
-                const int4 o = *reinterpret_cast<const int4*>(row_off + bi * DEPTH_UNR);
-                const int oo[4] = {o.x, o.y, o.z, o.w};
+                const float* blk = rows + blk_off[bi] + lane * DEPTH_UNR;
 #pragma unroll
-                for (int j = 0; j < DEPTH_UNR; ++j)
+                for (int c = 0; c < C; ++c)
 #pragma unroll
-                    for (int c = 0; c < C; ++c) rad_load<H>(rp + oo[j] + c * W, dst[j][c]);
+                    for (int h = 0; h < H; ++h) {
+                        const float4 t = *reinterpret_cast<const float4*>(blk + (c * H + h) * 32 * DEPTH_UNR);
+                        dst[0][c][h] = t.x; dst[1][c][h] = t.y; dst[2][c][h] = t.z; dst[3][c][h] = t.w;
+                    }
             };
             if (nblk > 0) load_block(0, ba);
 #pragma unroll
@@ -690,9 +695,9 @@ static inline size_t depth_smem_bytes(int S, int C, int H, int RV, int s_hat, in
 {
     int spad = depth_padded_views(S);
     if (spad < RV) spad = RV;
-    const int nrows = depth_num_rows(spad, RV);
-    size_t fl = 4 + ((nrows + 1 + 3) & ~3) + 4 * (size_t)nrows;       /* mbarrier, row offsets, staging records */
-    for (int r = 0; r < nrows; ++r) fl += depth_row_floats(r, S, spad, RV, s_hat, wpv_q16, C, 32 * H);
+    const int nrows = depth_num_rows(spad, RV), nblocks = nrows / DEPTH_UNR;
+    size_t fl = 4 + ((nblocks + 1 + 3) & ~3) + 4 * (size_t)nrows;       /* mbarrier, block offsets, staging records */
+    for (int b = 0; b < nblocks; ++b) fl += (size_t)DEPTH_UNR * depth_block_pitch(b, S, spad, RV, s_hat, wpv_q16, C, 32 * H);
     return fl * sizeof(float);
 }
 

@@ -132,6 +132,66 @@ downsample_kernel(const float* __restrict__ in, int V, int S, int U, float* __re
     }
 }
 
+/* ---- downsample_EPIs, 8-bit stacks (they stay 8-bit between levels, ftc.hpp:142-147) ----------------
+ * OpenCV's CV_8U paths, bit-exact against cv2 (tests/golden/down_u8_*.npz): integer kernel
+ * [8,28,56,72,56,28,8] (sum 256) along rows then columns, (acc + 2^15) >> 16, BORDER_REFLECT; half-size
+ * resize = (a+b+c+d+2) >> 2, or the half-to-even rounded mean where an odd dimension leaves a single
+ * source row / column.  Same tiling as the float kernel.
+ */
+template <int C>
+__global__ void __launch_bounds__(DS_THREADS)
+downsample_u8_kernel(const uint8_t* __restrict__ in, int V, int S, int U, uint8_t* __restrict__ out, int V2, int U2,
+                     int ov_begin, int ov_count)
+{
+    constexpr int IW = 2 * DS_TU + 6, IH = 2 * DS_TV + 6, BW = 2 * DS_TU;
+    __shared__ uint8_t tin[IH][IW * C];
+    __shared__ int hb[IH][BW * C];
+    const int K[7] = {8, 28, 56, 72, 56, 28, 8};
+    const int s = blockIdx.z;
+    const int ou0 = blockIdx.x * DS_TU, ov0 = ov_begin + blockIdx.y * DS_TV;
+    const int iu0 = 2 * ou0 - 3, iv0 = 2 * ov0 - 3;
+    for (int i = threadIdx.x; i < IH * IW * C; i += DS_THREADS) {
+        int r = i / (IW * C), rem = i - r * (IW * C);
+        int p = rem / C, c = rem - p * C;
+        int vv = rslf_reflect(min(iv0 + r, V - 1 + 3), V);
+        int uu = rslf_reflect(min(iu0 + p, U - 1 + 3), U);
+        tin[r][rem] = in[(((size_t)vv * S + s) * (size_t)U + uu) * C + c];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < IH * BW * C; i += DS_THREADS) {
+        int r = i / (BW * C), rem = i - r * (BW * C);
+        int p = rem / C, c = rem - p * C;
+        int acc = 0;
+#pragma unroll
+        for (int j = 0; j < 7; ++j) acc += K[j] * (int)tin[r][(p + j) * C + c];
+        hb[r][rem] = acc;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < DS_TV * DS_TU * C; i += DS_THREADS) {
+        int r = i / (DS_TU * C), rem = i - r * (DS_TU * C);
+        int p = rem / C, c = rem - p * C;
+        const int ov = ov0 + r, ou = ou0 + p;
+        if (ov >= V2 || ov >= ov_begin + ov_count || ou >= U2) continue;
+        const int nr = (2 * ov + 1 < V) ? 2 : 1, nc = (2 * ou + 1 < U) ? 2 : 1;
+        int sum = 0;
+        for (int a = 0; a < nr; ++a) {
+            const int rr = 2 * ov + a - iv0;
+            for (int b = 0; b < nc; ++b) {
+                const int cc = (2 * ou + b - 2 * ou0) * C + c;
+                int acc = 0;
+#pragma unroll
+                for (int j = 0; j < 7; ++j) acc += K[j] * hb[rr + j - 3][cc];
+                sum += (acc + 32768) >> 16;
+            }
+        }
+        const int n = nr * nc;
+        int res = sum;
+        if (n == 4) res = (sum + 2) >> 2;
+        else if (n == 2) res = (sum + ((sum >> 1) & 1)) >> 1;          /* half to even */
+        out[(((size_t)(ov - ov_begin) * S + s) * (size_t)U2 + ou) * C + c] = (uint8_t)res;
+    }
+}
+
 /* ---- validity mask ---- */
 __global__ void valid_mask_kernel(const float* __restrict__ ce, size_t n, float thr, int accept_all,
                                   uint8_t* __restrict__ valid)

@@ -815,6 +815,18 @@ static int launch_downsample(rslf_ctx* ctx, const float* in, int V, int S, int U
     return RSLF_OK;
 }
 
+static int launch_downsample_u8(rslf_ctx* ctx, const uint8_t* in, int V, int S, int U, int C, uint8_t* out, int V2, int U2,
+                                int ov_begin = 0, int ov_count = -1)
+{
+    if (ov_count < 0) ov_count = V2;
+    dim3 grid(rslf_div_up(U2, DS_TU), rslf_div_up(ov_count, DS_TV), S);
+    if (C == 1) downsample_u8_kernel<1><<<grid, DS_THREADS, 0, ctx->stream>>>(in, V, S, U, out, V2, U2, ov_begin, ov_count);
+    else downsample_u8_kernel<3><<<grid, DS_THREADS, 0, ctx->stream>>>(in, V, S, U, out, V2, U2, ov_begin, ov_count);
+    RSLF_CUDA_TRY(ctx, cudaGetLastError());
+    ctx->timing.kernel_launches += 1;
+    return RSLF_OK;
+}
+
 /* fuse_disp_maps (ftc_core.cpp:69-135).  Vp: GLOBAL rows per level; disp / valid / outputs hold the local rows
  * described by tabs[p] (one rank: everything). */
 static int launch_fuse(rslf_ctx* ctx, int levels, const int* Vp, const int* Up, const shard_tab* tabs, const float* const* disp,
@@ -890,10 +902,6 @@ extern "C" int rslf_cuda_fine_to_coarse_run(rslf_ctx* ctx, float dmin, float dma
         }
     }
     if (levels == 0) { snprintf(ctx->err, sizeof(ctx->err), "light field smaller than the minimum pyramid size"); return RSLF_ERR_ARG; }
-    if (ctx->cv_depth != RSLF_DEPTH_32F && levels > 1) {
-        snprintf(ctx->err, sizeof(ctx->err), "8-bit pyramids (OpenCV integer blur) are not implemented; convert to float32 or use max_pyr_depth=1");
-        return RSLF_ERR_UNSUPPORTED;
-    }
     RSLF_TRY(prepare_shards(ctx, levels));
     shard_tab tabs[RSLF_MAX_LEVELS];
     int Vl[RSLF_MAX_LEVELS];                                  /* local rows per level */
@@ -928,7 +936,8 @@ extern "C" int rslf_cuda_fine_to_coarse_run(rslf_ctx* ctx, float dmin, float dma
         rslf_level& L = ctx->lv[p];
         const size_t px = (size_t)S * Vl[p] * Up[p];
         const void* raw = (p == 0) ? ctx->raw_in : (const void*)L.raw;
-        RSLF_TRY(normalise_level(ctx, p, raw, p == 0 ? ctx->cv_depth : RSLF_DEPTH_32F));
+        /* 8-bit stacks stay 8-bit between levels (OpenCV's integer blur / resize), float stacks stay float */
+        RSLF_TRY(normalise_level(ctx, p, raw, ctx->cv_depth));
         rslf_params P = P0;
         P.slope_factor = (float)((0.0 + Up[p]) / Up[0]);                        /* ftc.hpp:139 */
         L.slope = P.slope_factor;
@@ -948,12 +957,17 @@ extern "C" int rslf_cuda_fine_to_coarse_run(rslf_ctx* ctx, float dmin, float dma
                 rslf_level& N = ctx->lv[p + 1];
                 /* next level's raw stack (ftc.hpp:146): the 7x7 blur reads 3 rows beyond the rank's block, so a
                  * sharded run first gathers the level's raw rows */
-                const float* ds_in = (const float*)raw;
+                const size_t esz = (ctx->cv_depth == RSLF_DEPTH_8U) ? 1 : sizeof(float);
+                const void* ds_in = raw;
                 if (ctx->world > 1) {
-                    RSLF_TRY(comm_gather_rows(ctx, raw, (size_t)S * Up[p] * C * sizeof(float), tabs[p], ctx->g_raw));
+                    RSLF_TRY(comm_gather_rows(ctx, raw, (size_t)S * Up[p] * C * esz, tabs[p], ctx->g_raw));
                     ds_in = ctx->g_raw;
                 }
-                RSLF_TRY(launch_downsample(ctx, ds_in, Vp[p], S, Up[p], C, N.raw, Vp[p + 1], Up[p + 1], tabs[p + 1].b[r], Vl[p + 1]));
+                if (ctx->cv_depth == RSLF_DEPTH_8U)
+                    RSLF_TRY(launch_downsample_u8(ctx, (const uint8_t*)ds_in, Vp[p], S, Up[p], C, (uint8_t*)N.raw, Vp[p + 1], Up[p + 1],
+                                                  tabs[p + 1].b[r], Vl[p + 1]));
+                else
+                    RSLF_TRY(launch_downsample(ctx, (const float*)ds_in, Vp[p], S, Up[p], C, N.raw, Vp[p + 1], Up[p + 1], tabs[p + 1].b[r], Vl[p + 1]));
                 const size_t npx = (size_t)S * Vl[p + 1] * Up[p + 1];
                 fill_f32_kernel<<<stream_grid(ctx, npx), 256, 0, ctx->stream>>>(N.dmin, npx, dmin);
                 fill_f32_kernel<<<stream_grid(ctx, npx), 256, 0, ctx->stream>>>(N.dmax, npx, dmax);
@@ -1084,6 +1098,31 @@ extern "C" int rslf_cuda_downsample_epis(rslf_ctx* ctx, const float* in_epis, in
         rc = launch_downsample(ctx, din, V, S, U, C, dout, V2, U2);
         if (rc == RSLF_OK) {
             cudaMemcpyAsync(out_epis, dout, nout * 4, cudaMemcpyDeviceToHost, ctx->stream);
+            if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = RSLF_ERR_CUDA;
+        }
+    }
+    dev_free(&din); dev_free(&dout);
+    return rc;
+}
+
+extern "C" int rslf_cuda_downsample_epis_u8(rslf_ctx* ctx, const uint8_t* in_epis, int V, int S, int U, int C,
+                                            uint8_t* out_epis, int* V2o, int* U2o)
+{
+    if (!ctx || !in_epis || !out_epis || (C != 1 && C != 3) || V < 1 || S < 1 || U < 1) return RSLF_ERR_ARG;
+    RSLF_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int V2 = cv_round_half(V), U2 = cv_round_half(U);
+    if (V2o) *V2o = V2;
+    if (U2o) *U2o = U2;
+    if (V2 < 1 || U2 < 1) return RSLF_ERR_ARG;
+    uint8_t *din = nullptr, *dout = nullptr;
+    const size_t nin = (size_t)V * S * U * C, nout = (size_t)V2 * S * U2 * C;
+    RSLF_TRY(dev_alloc(ctx, &din, nin));
+    int rc = dev_alloc(ctx, &dout, nout);
+    if (rc == RSLF_OK) {
+        cudaMemcpyAsync(din, in_epis, nin, cudaMemcpyHostToDevice, ctx->stream);
+        rc = launch_downsample_u8(ctx, din, V, S, U, C, dout, V2, U2);
+        if (rc == RSLF_OK) {
+            cudaMemcpyAsync(out_epis, dout, nout, cudaMemcpyDeviceToHost, ctx->stream);
             if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = RSLF_ERR_CUDA;
         }
     }

@@ -23,7 +23,7 @@
 struct rslf_level {
     int V = 0, U = 0;            /* rows held by this rank, columns                           */
     int v0 = 0, Vtot = 0;        /* first global row of this rank, global rows of the level   */
-    float* raw = nullptr;        /* un-normalised float stack (levels > 0, or float input)  */
+    float* raw = nullptr;        /* un-normalised stack of levels > 0 (float32, or uint8 for 8-bit input: raw8 aliases it) */
     float* epi = nullptr;        /* normalised stack [V][S][U][C]                             */
     float* ce = nullptr;         /* edge confidence            [S][V][U]                      */
     float* cd = nullptr;         /* disparity confidence       [S][V][U]                      */

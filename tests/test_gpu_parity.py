@@ -248,6 +248,33 @@ def test_downsample_golden_and_oracle(gpu_ctx, golden_dir):
     np.testing.assert_array_equal(gpu_ctx.downsample_epis(raw), oracle.downsample(raw))
 
 
+def test_downsample_uint8_golden_and_oracle(gpu_ctx, golden_dir):
+    """8-bit stacks: OpenCV's integer blur / resize paths, bit-exact against the cv2 fixtures."""
+    for name in ("down_u8_c3_odd", "down_u8_c1_135", "down_u8_c1_even"):
+        g = np.load(os.path.join(golden_dir, name + ".npz"))
+        out = gpu_ctx.downsample_epis(g["raw"])
+        assert out.dtype == np.uint8
+        np.testing.assert_array_equal(out, g["out"])
+        np.testing.assert_array_equal(out, oracle.downsample(g["raw"]))
+    rng = np.random.default_rng(2)
+    raw = rng.integers(0, 256, (75, 2, 131, 3), dtype=np.uint8)
+    np.testing.assert_array_equal(gpu_ctx.downsample_epis(raw), oracle.downsample(raw))
+
+
+def test_fine_to_coarse_uint8_pyramid(gpu_ctx):
+    """CV_8U input through the whole pyramid (levels stay 8-bit, each normalised by 1/255)."""
+    epis = lf(5, 46, 70, 3, seed=61)
+    u8 = np.clip(np.rint(epis * 255.0), 0, 255).astype(np.uint8)
+    ftc = api.FineToCoarse(u8, -1.0, 2.0, 16, ctx=gpu_ctx).run()
+    out_map, out_valid = ftc.get_results()
+    ref = oracle.fine_to_coarse(u8, -1.0, 2.0, 16)
+    assert len(ftc.get_levels()) == len(ref["dims"]) >= 3
+    for lg, lr in zip(ftc.get_levels(), ref["levels"]):
+        assert_maps_equal(lg, lr, ["edge_mask", "edge_conf", "dmin", "dmax", "best_depth", "disp_conf"])
+    np.testing.assert_array_equal(out_valid, ref["valid"])
+    np.testing.assert_array_equal(out_map, ref["map"])
+
+
 def test_set_bounds(gpu_ctx):
     rng = np.random.default_rng(12)
     S, Vu, Uu = 3, 23, 77

@@ -40,12 +40,20 @@ def test_edge_confidence_and_pixel_scores(path):
         assert abs(float(sc.astype(np.float64).mean()) - float(g["mean"][i])) < 1e-6
 
 
-@pytest.mark.parametrize("path", _cases(HERE, "down_*.npz"), ids=os.path.basename)
+@pytest.mark.parametrize("path", [p for p in _cases(HERE, "down_*.npz") if "_u8_" not in p], ids=os.path.basename)
 def test_downsample(path):
     g = np.load(path)
     out = oracle.downsample(g["raw"])
     assert out.shape == g["out"].shape
     np.testing.assert_allclose(out, g["out"], rtol=5e-7, atol=0)
+
+
+@pytest.mark.parametrize("path", _cases(HERE, "down_u8_*.npz"), ids=os.path.basename)
+def test_downsample_uint8_is_bit_exact(path):
+    g = np.load(path)
+    out = oracle.downsample(g["raw"])
+    assert out.dtype == np.uint8
+    np.testing.assert_array_equal(out, g["out"])
 
 
 def test_fuse(golden_dir):
