@@ -15,8 +15,8 @@
  * buffer.  Rows are independent (the reference's OpenMP axis, :1088).
  *
  * Sources come in two kinds.  (1) Pixels computed in this pass: they are the compacted work list of the
- * pass (sparse after the first pass) and carry their mean-shift radiance r_bar; one thread per (list
- * entry, view).  (2) Pixels of the line that were painted by an earlier pass: their r_bar is the zero it was
+ * pass (sparse after the first pass) and carry their mean-shift radiance r_bar; one warp per list entry,
+ * lanes over the views.  (2) Pixels of the line that were painted by an earlier pass: their r_bar is the zero it was
  * initialised with (dc.hpp:744), so they can only paint targets whose own colour norm is below eps, i.e.
  * confident-but-dark pixels; per (s, v) row the edge-confidence kernel counted those (rowdark), and a block
  * of the dense kernel returns at once when its rows hold none.  A pixel computed in this pass whose r_bar
@@ -71,22 +71,24 @@ __device__ __forceinline__ void propagate_one(const prop_args& a, int v, int u, 
     }
 }
 
-/* kind (1): the pass's work list x views */
+/* kind (1): the pass's work list; one warp per list entry (its source data is loaded once), lanes over views */
 template <int C, int PHASE>
 __global__ void __launch_bounds__(PROP_THREADS)
 propagate_list_kernel(const prop_args a)
 {
     const int n = *a.count;
-    const long long total = (long long)n * a.S;
-    for (long long i = (long long)blockIdx.x * PROP_THREADS + threadIdx.x; i < total; i += (long long)gridDim.x * PROP_THREADS) {
-        const int it = (int)(i / a.S), s = (int)(i - (long long)it * a.S);
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * PROP_THREADS) >> 5;
+    for (int it = (blockIdx.x * PROP_THREADS + threadIdx.x) >> 5; it < n; it += warps) {
         const int pix = a.items[it];
         if (!a.emask_p[pix]) continue;                      /* score <= threshold: dropped by the depth kernel */
         const int v = pix / a.U, u = pix - v * a.U;
         float rb[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) rb[c] = a.rbar_p[(size_t)pix * C + c];
-        propagate_one<C, PHASE>(a, v, u, s, a.filtered[pix], rb, PHASE ? a.cd_p[pix] : 0.f);
+        const float cur = a.filtered[pix];
+        const float cdv = PHASE ? a.cd_p[pix] : 0.f;
+        for (int s = lane; s < a.S; s += 32) propagate_one<C, PHASE>(a, v, u, s, cur, rb, cdv);
     }
 }
 
