@@ -344,3 +344,19 @@ def test_upload_images_builds_epis(gpu_ctx):
     ce_b, m_b = gpu_ctx.edge_confidence(2, p)
     np.testing.assert_array_equal(ce_a, ce_b)
     np.testing.assert_array_equal(m_a, m_b)
+
+
+def test_row_sharded_run_equals_single_gpu():
+    """Two ranks on two GPUs (torchrun + NCCL): every output block is bit-identical to the one-GPU result.
+    Skipped on boxes with a single GPU (the driver's -m gpu run); tools/multigpu_check.py is the same check."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tools", "multigpu_check.py")],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "multi-GPU parity OK" in r.stdout
