@@ -231,13 +231,15 @@ int rslf_cuda_edge_confidence(rslf_ctx* ctx, int s, const rslf_params* params,
  * The reference's only parallel axis is the image row v (OpenMP `parallel for`,
  * core.hpp:743, :799, :1088).  Rows are split in contiguous blocks, rank r
  * holding the global rows [row_starts[r], row_starts[r+1]); every rank uploads
- * only its block and gets only its block of every result map.  Boundaries must
- * be multiples of 2^(levels-1) so that each pyramid level splits at the same
- * image position.  Exchanges on the path (NCCL over NVLink): the all-gather of
- * the depth / mask / colour rows of line s_hat for the cross-row selective
- * median of each pass (core.hpp:698-709), the raw rows a level's 7x7 blur
- * reads beyond the block (ftc_core.cpp:37), the fused maps between fuse levels
- * and the max of the input normalisation (dc.hpp:442-460).
+ * only its block and gets only its block of every result map.  Pyramid level p
+ * is sharded while every boundary is a multiple of 2^p and every rank keeps
+ * >= 2 rows; coarser levels are computed whole by every rank.  Exchanges on the
+ * path: the two rows next to each block of the depth / mask / colour planes of
+ * line s_hat for the cross-row selective median of each pass (core.hpp:698-709)
+ * — peer-to-peer stores over NVLink (CUDA IPC), NCCL all-gather as fallback —,
+ * the raw rows a level's 7x7 blur reads beyond the block (ftc_core.cpp:37),
+ * the fused maps between fuse levels and the max of the input normalisation
+ * (dc.hpp:442-460), all NCCL.
  */
 int rslf_cuda_nccl_unique_id(void* id128 /* 128 bytes out */);
 int rslf_cuda_comm_init(rslf_ctx* ctx, const void* id128, int rank, int world);

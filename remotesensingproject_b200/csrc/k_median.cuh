@@ -41,6 +41,9 @@ __device__ __forceinline__ void sort_network(float (&a)[N])
 struct median_halo {
     const float* top_depth; const float* top_colour; const uint8_t* top_mask;     /* rows v = -2, -1 */
     const float* bot_depth; const float* bot_colour; const uint8_t* bot_mask;     /* rows v = V, V + 1 */
+    /* peer-to-peer exchange: the neighbours store the rows into this rank's buffer and then raise these
+     * flags to `seq`; the kernel waits for them before it touches a halo row (nullptr: NCCL path, no wait) */
+    const volatile unsigned* flag_top; const volatile unsigned* flag_bot; unsigned seq;
 };
 
 template <int C, int WIDTH, bool HALO>
@@ -53,6 +56,17 @@ selective_median_kernel(const float* __restrict__ src, const uint8_t* __restrict
     constexpr int N = (2 * WIDTH + 1) * (2 * WIDTH + 1);
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
     const int v = blockIdx.y + v_begin;            /* row in the (possibly gathered) planes */
+    if (HALO && (halo.flag_top || halo.flag_bot)) {
+        /* blocks whose window reaches a neighbour's rows wait until those rows have landed (bounded spin) */
+        const bool need_top = halo.flag_top && v < WIDTH, need_bot = halo.flag_bot && v >= V - WIDTH;
+        if ((need_top || need_bot) && threadIdx.x == 0) {
+            int spin = 0;
+            while ((need_top && (int)(*halo.flag_top - halo.seq) < 0) || (need_bot && (int)(*halo.flag_bot - halo.seq) < 0))
+                if (++spin > (1 << 26)) __trap();
+            __threadfence_system();
+        }
+        __syncthreads();
+    }
     if (u >= U) return;
     const size_t o = (size_t)v * U + u;
     const size_t od = (size_t)blockIdx.y * U + u;     /* dst holds this rank's rows only */

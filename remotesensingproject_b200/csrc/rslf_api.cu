@@ -94,9 +94,11 @@ static void free_scratch(rslf_ctx* ctx)
 }
 
 /* scratch shared by all levels, sized for level 0 */
-static int ensure_scratch(rslf_ctx* ctx, bool need_2d, bool need_ftc)
+static int ensure_scratch(rslf_ctx* ctx, bool need_2d, bool need_ftc, size_t plane_override = 0)
 {
-    const size_t plane = (size_t)ctx->V * ctx->U;
+    /* the largest V x U plane any level of the run holds on this rank (a replicated coarse level may exceed
+     * the rank's share of level 0) */
+    const size_t plane = plane_override ? plane_override : (size_t)ctx->V * ctx->U;
     const size_t px = plane * ctx->S;
     if (ctx->scratch_px != px || ctx->scratch_plane != plane) {
         free_scratch(ctx);
@@ -206,10 +208,10 @@ static int normalise_level(rslf_ctx* ctx, int p, const void* raw, int cv_depth)
         RSLF_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         float sf = ctx->scale_factor;
         if (sf < 0.f) {
-            if (ctx->world > 1) RSLF_TRY(comm_allreduce_max(ctx, ctx->minmax, 1, &mm[0]));
+            if (ctx->world > 1 && !L.replicated) RSLF_TRY(comm_allreduce_max(ctx, ctx->minmax, 1, &mm[0]));
             sf = mm[0];
         }
-        if (ctx->world > 1) { /* a shard may hold no negative value while another does: agree */
+        if (ctx->world > 1 && !L.replicated) { /* a shard may hold no negative value while another does: agree */
             float neg = (mm[1] < 0.f) ? 1.f : 0.f, out = neg;
             RSLF_TRY(comm_allreduce_max_host(ctx, neg, &out));
             if (out > 0.f) mm[1] = -1.f;
@@ -268,7 +270,7 @@ extern "C" int rslf_cuda_create(int device, rslf_ctx** out)
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return RSLF_ERR_CUDA; }
     cudaEventCreate(&ctx->ev_a); cudaEventCreate(&ctx->ev_b);
     if (cudaMalloc((void**)&ctx->count, RSLF_COUNT_SLOTS * sizeof(int)) != cudaSuccess ||
-        cudaMalloc((void**)&ctx->total_px, sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMalloc((void**)&ctx->total_px, 2 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaMalloc((void**)&ctx->minmax, 4 * sizeof(float)) != cudaSuccess) {
         rslf_cuda_destroy(ctx); return RSLF_ERR_CUDA;
     }
@@ -499,7 +501,7 @@ static int run_depth_pass(rslf_ctx* ctx, const rslf_params& P, const pass_io& io
     {
         stage_scope sc(ctx, ST_REDUCE);
         compact_kernel<<<stream_grid(ctx, plane), 256, 0, ctx->stream>>>(
-            L.emask + po, io.pile ? nullptr : L.remaining + po, (int)plane, ctx->items, count, ctx->total_px);
+            L.emask + po, io.pile ? nullptr : L.remaining + po, (int)plane, ctx->items, count, ctx->total_px + (L.replicated ? 1 : 0));
         RSLF_CUDA_TRY(ctx, cudaGetLastError());
         ctx->timing.kernel_launches += 1;
     }
@@ -524,7 +526,7 @@ static int run_depth_pass(rslf_ctx* ctx, const rslf_params& P, const pass_io& io
     }
     {
         stage_scope sc(ctx, ST_MEDIAN);
-        if (ctx->world > 1) {
+        if (ctx->world > 1 && !L.replicated) {
             /* the only cross-row step of a pass (core.hpp:698-709): the window reaches (size-1)/2 rows into the
              * neighbouring ranks' blocks */
             const shard_tab t = level_shards(ctx, io.level, L.Vtot);
@@ -537,7 +539,11 @@ static int run_depth_pass(rslf_ctx* ctx, const rslf_params& P, const pass_io& io
             if ((P.median_filter_size - 1) / 2 <= 2 && min_rows >= 2 && !(force_full && force_full[0] == 'f')) {
                 /* halo exchange: 2 + 2 rows per rank in one small all-gather, read in place by the median */
                 median_halo halo;
-                RSLF_TRY(comm_exchange_median_halo(ctx, a.depth, L.emask + po, colour0, (size_t)S * U * C, U, C, t, &halo));
+                /* peer-to-peer stores over NVLink when CUDA IPC between the ranks works, else one small all-gather */
+                if (comm_p2p_setup(ctx, ctx->U, C) == RSLF_OK)
+                    RSLF_TRY(comm_p2p_exchange_median_halo(ctx, a.depth, L.emask + po, colour0, (size_t)S * U * C, U, C, t, &halo));
+                else
+                    RSLF_TRY(comm_exchange_median_halo(ctx, a.depth, L.emask + po, colour0, (size_t)S * U * C, U, C, t, &halo));
                 RSLF_TRY(launch_selective_median(ctx, a.depth, L.emask + po, colour0, (size_t)S * U * C, V, U, C,
                                                  P.median_filter_size, P.median_filter_epsilon, ctx->filtered, 0, -1, fresh, rdv, &halo));
             } else {
@@ -622,7 +628,7 @@ static int begin_run(rslf_ctx* ctx)
     ctx->timing.ms_h2d = h2d;
     clk_reset(ctx);
     RSLF_CUDA_TRY(ctx, cudaMemsetAsync(ctx->count, 0, RSLF_COUNT_SLOTS * sizeof(int), ctx->stream));
-    RSLF_CUDA_TRY(ctx, cudaMemsetAsync(ctx->total_px, 0, sizeof(unsigned long long), ctx->stream));
+    RSLF_CUDA_TRY(ctx, cudaMemsetAsync(ctx->total_px, 0, 2 * sizeof(unsigned long long), ctx->stream));
     RSLF_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
     return RSLF_OK;
 }
@@ -630,11 +636,13 @@ static int begin_run(rslf_ctx* ctx)
 static int end_run(rslf_ctx* ctx, int D)
 {
     RSLF_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_b, ctx->stream));
-    unsigned long long total = 0;
-    RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(&total, ctx->total_px, sizeof(total), cudaMemcpyDeviceToHost, ctx->stream));
+    unsigned long long both[2] = {0, 0};
+    RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(both, ctx->total_px, sizeof(both), cudaMemcpyDeviceToHost, ctx->stream));
     RSLF_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     RSLF_CUDA_TRY(ctx, cudaEventElapsedTime(&ctx->timing.ms_total, ctx->ev_a, ctx->ev_b));
     if (ctx->stage_timing) clk_resolve(ctx);
+    /* levels that every rank computes whole are counted once (by rank 0), so that the sum over ranks is the job's work */
+    const unsigned long long total = both[0] + ((ctx->world <= 1 || ctx->rank == 0) ? both[1] : 0ULL);
     ctx->timing.computed_pixels = (double)total;
     ctx->timing.samples = (double)total * D * ctx->S;
     return RSLF_OK;
@@ -663,7 +671,7 @@ extern "C" int rslf_cuda_depth1d_pile_run(rslf_ctx* ctx, float dmin, float dmax,
     RSLF_TRY(ensure_level(ctx, 0, V, U, false, false));
     ctx->n_levels = 1;
     rslf_level& L = ctx->lv[0];
-    L.v0 = ctx->v0; L.Vtot = ctx->V_total;
+    L.v0 = ctx->v0; L.Vtot = ctx->V_total; L.replicated = false;
     L.slope = P.slope_factor;
     RSLF_TRY(normalise_level(ctx, 0, ctx->raw_in, ctx->cv_depth));
     const size_t plane = (size_t)V * U;
@@ -736,7 +744,7 @@ extern "C" int rslf_cuda_depth2d_run(rslf_ctx* ctx, float dmin, float dmax, int 
     RSLF_TRY(ensure_level(ctx, 0, V, U, true, dmin_svu != nullptr));
     ctx->n_levels = 1;
     rslf_level& L = ctx->lv[0];
-    L.v0 = ctx->v0; L.Vtot = ctx->V_total;
+    L.v0 = ctx->v0; L.Vtot = ctx->V_total; L.replicated = false;
     const size_t px = (size_t)S * V * U;
     if (dmin_svu) {
         RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(L.dmin, dmin_svu, px * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -827,32 +835,41 @@ static int launch_downsample_u8(rslf_ctx* ctx, const uint8_t* in, int V, int S, 
     return RSLF_OK;
 }
 
-/* fuse_disp_maps (ftc_core.cpp:69-135).  Vp: GLOBAL rows per level; disp / valid / outputs hold the local rows
- * described by tabs[p] (one rank: everything). */
-static int launch_fuse(rslf_ctx* ctx, int levels, const int* Vp, const int* Up, const shard_tab* tabs, const float* const* disp,
-                       const uint8_t* const* valid, float* out_map, uint8_t* out_valid)
+/* fuse_disp_maps (ftc_core.cpp:69-135).  Vp: GLOBAL rows per level; disp / valid / outputs of a sharded level hold
+ * the rank's rows (tabs[p]); a replicated level (rep[p]) is whole on every rank. */
+static int launch_fuse(rslf_ctx* ctx, int levels, const int* Vp, const int* Up, const shard_tab* tabs, const bool* rep,
+                       const float* const* disp, const uint8_t* const* valid, float* out_map, uint8_t* out_valid)
 {
     const int S = ctx->S, r = ctx->rank;
-    const float* map_down = nullptr; const uint8_t* mask_down = nullptr;
-    RSLF_TRY(global_svu_f32(ctx, disp[levels - 1], S, Up[levels - 1], tabs[levels - 1], 0, &map_down));
-    RSLF_TRY(global_svu_u8(ctx, valid[levels - 1], S, Up[levels - 1], tabs[levels - 1], 0, &mask_down));
+    auto whole = [&](int p) { return ctx->world <= 1 || rep[p]; };
+    const float* map_down = disp[levels - 1]; const uint8_t* mask_down = valid[levels - 1];
+    if (!whole(levels - 1)) {
+        RSLF_TRY(global_svu_f32(ctx, disp[levels - 1], S, Up[levels - 1], tabs[levels - 1], 0, &map_down));
+        RSLF_TRY(global_svu_u8(ctx, valid[levels - 1], S, Up[levels - 1], tabs[levels - 1], 0, &mask_down));
+    }
     float* fa = ctx->fuse_a; float* fb = ctx->fuse_b; uint8_t* ma = ctx->fuse_ma; uint8_t* mb = ctx->fuse_mb;
     for (int p = levels - 1; p > 0; --p) {
         const int Vn = Vp[p - 1], Un = Up[p - 1];
-        const int y0 = tabs[p - 1].b[r], Vn_loc = tabs[p - 1].b[r + 1] - y0;
+        const int y0 = whole(p - 1) ? 0 : tabs[p - 1].b[r], Vn_loc = whole(p - 1) ? Vn : tabs[p - 1].b[r + 1] - y0;
         dim3 grid(rslf_div_up(Un, 128), Vn_loc, S);
         uint8_t* mout = (p == 1) ? out_valid : ma;
         fuse_level_kernel<<<grid, 128, 0, ctx->stream>>>(map_down, mask_down, Vp[p], Up[p], disp[p - 1], valid[p - 1], Vn, Un, fa, mout, y0, Vn_loc);
         RSLF_CUDA_TRY(ctx, cudaGetLastError());
         ctx->timing.kernel_launches += 1;
         /* the next (finer) level interpolates across rank borders, the final median reads +-1 row */
-        RSLF_TRY(global_svu_f32(ctx, fa, S, Un, tabs[p - 1], p & 1, &map_down));
-        if (p > 1) RSLF_TRY(global_svu_u8(ctx, mout, S, Un, tabs[p - 1], p & 1, &mask_down));
+        map_down = fa; mask_down = mout;
+        if (!whole(p - 1)) {
+            RSLF_TRY(global_svu_f32(ctx, fa, S, Un, tabs[p - 1], p & 1, &map_down));
+            if (p > 1) RSLF_TRY(global_svu_u8(ctx, mout, S, Un, tabs[p - 1], p & 1, &mask_down));
+        }
         std::swap(fa, fb); std::swap(ma, mb);
     }
-    const int v0 = tabs[0].b[r], V_loc = tabs[0].b[r + 1] - v0;
+    const int v0 = whole(0) ? 0 : tabs[0].b[r], V_loc = whole(0) ? Vp[0] : tabs[0].b[r + 1] - v0;
     const size_t px = (size_t)S * V_loc * Up[0];
-    if (levels == 1) RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(out_valid, valid[0], px, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (levels == 1) {
+        RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(out_valid, valid[0], px, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (!whole(0)) RSLF_TRY(global_svu_f32(ctx, disp[0], S, Up[0], tabs[0], 0, &map_down));
+    }
     dim3 grid(rslf_div_up(Up[0], 128), V_loc, S);
     median3x3_kernel<<<grid, 128, 0, ctx->stream>>>(map_down, Vp[0], Up[0], out_map, v0, V_loc);
     RSLF_CUDA_TRY(ctx, cudaGetLastError());
@@ -875,12 +892,7 @@ static int prepare_shards(rslf_ctx* ctx, int levels)
                  ctx->row_starts[ctx->rank + 1] - ctx->row_starts[ctx->rank]);
         return RSLF_ERR_ARG;
     }
-    const int align = 1 << (levels - 1);
-    for (int r = 1; r < ctx->world; ++r)
-        if (ctx->row_starts[r] % align) {
-            snprintf(ctx->err, sizeof(ctx->err), "shard boundary %d is not a multiple of %d (2^(levels-1))", ctx->row_starts[r], align);
-            return RSLF_ERR_ARG;
-        }
+    (void)levels;
     return RSLF_OK;
 }
 
@@ -903,21 +915,41 @@ extern "C" int rslf_cuda_fine_to_coarse_run(rslf_ctx* ctx, float dmin, float dma
     }
     if (levels == 0) { snprintf(ctx->err, sizeof(ctx->err), "light field smaller than the minimum pyramid size"); return RSLF_ERR_ARG; }
     RSLF_TRY(prepare_shards(ctx, levels));
+    /* Multi-rank runs shard the fine levels by rows and REPLICATE the coarse ones: level p can be sharded while
+     * every boundary is a multiple of 2^p (so that levels split at the same image position and the bound
+     * propagation rows 2v, 2v+1 -> v stay local) and every rank keeps >= 2 rows; the remaining levels are a
+     * few thousand pixels and are computed whole by every rank (identical results), which avoids both thin
+     * blocks and coarse alignment of the level-0 shards (load balance). */
     shard_tab tabs[RSLF_MAX_LEVELS];
-    int Vl[RSLF_MAX_LEVELS];                                  /* local rows per level */
-    for (int p = 0; p < levels; ++p) {
-        tabs[p] = level_shards(ctx, p, Vp[p]);
-        Vl[p] = tabs[p].b[r + 1] - tabs[p].b[r];
-        for (int q = 0; q < ctx->world; ++q)
-            if (tabs[p].b[q + 1] - tabs[p].b[q] < 1) {
-                snprintf(ctx->err, sizeof(ctx->err), "rank %d would hold no row of pyramid level %d; use fewer ranks", q, p);
-                return RSLF_ERR_ARG;
-            }
+    bool rep[RSLF_MAX_LEVELS];
+    int Vl[RSLF_MAX_LEVELS];                                  /* rows of the level held by this rank */
+    int sharded_levels = levels;
+    if (ctx->world > 1) {
+        sharded_levels = 1;
+        while (sharded_levels < levels) {
+            bool ok = true;
+            for (int q = 1; q < ctx->world; ++q) ok = ok && (ctx->row_starts[q] % (1 << sharded_levels) == 0);
+            const shard_tab t = level_shards(ctx, sharded_levels, Vp[sharded_levels]);
+            for (int q = 0; q < ctx->world; ++q) ok = ok && (t.b[q + 1] - t.b[q] >= 2);
+            if (!ok) break;
+            ++sharded_levels;
+        }
     }
-    RSLF_TRY(ensure_scratch(ctx, true, true));
+    size_t max_plane = 0;
+    for (int p = 0; p < levels; ++p) {
+        rep[p] = (ctx->world > 1 && p >= sharded_levels);
+        tabs[p] = rep[p] ? single_tab(Vp[p]) : level_shards(ctx, p, Vp[p]);
+        Vl[p] = rep[p] ? Vp[p] : tabs[p].b[r + 1] - tabs[p].b[r];
+        if (Vl[p] < 1) { snprintf(ctx->err, sizeof(ctx->err), "rank %d would hold no row of pyramid level %d; use fewer ranks", r, p); return RSLF_ERR_ARG; }
+        max_plane = std::max(max_plane, (size_t)Vl[p] * Up[p]);
+    }
+    /* the first replicated level derives its bounds from the gathered maps of the last sharded level */
+    if (ctx->world > 1 && sharded_levels < levels)
+        max_plane = std::max(max_plane, (size_t)Vp[sharded_levels - 1] * Up[sharded_levels - 1]);
+    RSLF_TRY(ensure_scratch(ctx, true, true, max_plane));
     for (int p = 0; p < levels; ++p) {
         RSLF_TRY(ensure_level(ctx, p, Vl[p], Up[p], true, true));
-        ctx->lv[p].v0 = tabs[p].b[r]; ctx->lv[p].Vtot = Vp[p];
+        ctx->lv[p].v0 = rep[p] ? 0 : tabs[p].b[r]; ctx->lv[p].Vtot = Vp[p]; ctx->lv[p].replicated = rep[p];
     }
     if (ctx->world > 1) {
         const size_t gpx = (size_t)S * Vp[0] * Up[0];
@@ -955,28 +987,37 @@ extern "C" int rslf_cuda_fine_to_coarse_run(rslf_ctx* ctx, float dmin, float dma
             ctx->timing.kernel_launches += 1;
             if (p + 1 < levels) {
                 rslf_level& N = ctx->lv[p + 1];
+                const bool sh = (ctx->world > 1 && !rep[p]);             /* level p is sharded */
                 /* next level's raw stack (ftc.hpp:146): the 7x7 blur reads 3 rows beyond the rank's block, so a
-                 * sharded run first gathers the level's raw rows */
+                 * sharded level first gathers its raw rows */
                 const size_t esz = (ctx->cv_depth == RSLF_DEPTH_8U) ? 1 : sizeof(float);
                 const void* ds_in = raw;
-                if (ctx->world > 1) {
+                if (sh) {
                     RSLF_TRY(comm_gather_rows(ctx, raw, (size_t)S * Up[p] * C * esz, tabs[p], ctx->g_raw));
                     ds_in = ctx->g_raw;
                 }
+                const int ov0 = rep[p + 1] ? 0 : tabs[p + 1].b[r];
                 if (ctx->cv_depth == RSLF_DEPTH_8U)
-                    RSLF_TRY(launch_downsample_u8(ctx, (const uint8_t*)ds_in, Vp[p], S, Up[p], C, (uint8_t*)N.raw, Vp[p + 1], Up[p + 1],
-                                                  tabs[p + 1].b[r], Vl[p + 1]));
+                    RSLF_TRY(launch_downsample_u8(ctx, (const uint8_t*)ds_in, Vp[p], S, Up[p], C, (uint8_t*)N.raw, Vp[p + 1], Up[p + 1], ov0, Vl[p + 1]));
                 else
-                    RSLF_TRY(launch_downsample(ctx, (const float*)ds_in, Vp[p], S, Up[p], C, N.raw, Vp[p + 1], Up[p + 1], tabs[p + 1].b[r], Vl[p + 1]));
+                    RSLF_TRY(launch_downsample(ctx, (const float*)ds_in, Vp[p], S, Up[p], C, N.raw, Vp[p + 1], Up[p + 1], ov0, Vl[p + 1]));
                 const size_t npx = (size_t)S * Vl[p + 1] * Up[p + 1];
                 fill_f32_kernel<<<stream_grid(ctx, npx), 256, 0, ctx->stream>>>(N.dmin, npx, dmin);
                 fill_f32_kernel<<<stream_grid(ctx, npx), 256, 0, ctx->stream>>>(N.dmax, npx, dmax);
-                /* bounds of level p+1 from level p (ftc.hpp:201-294): rows 2v, 2v+1 are local (aligned shards) */
-                const int rows = S * Vl[p];
-                nearest_valid_kernel<<<rslf_div_up((long long)rows * 32, 256), 256, 0, ctx->stream>>>(L.valid, rows, Up[p], ctx->nearest_l, ctx->nearest_r);
+                /* bounds of level p+1 from level p (ftc.hpp:201-294): rows 2v, 2v+1 are local when both levels are
+                 * sharded (aligned blocks); the first replicated level reads the gathered maps of level p */
+                const float* b_depth = L.depth; const uint8_t* b_valid = L.valid;
+                int b_rows = Vl[p], b_v0 = sh ? tabs[p].b[r] : 0;
+                if (sh && rep[p + 1]) {
+                    RSLF_TRY(global_svu_f32(ctx, L.depth, S, Up[p], tabs[p], 0, &b_depth));
+                    RSLF_TRY(global_svu_u8(ctx, L.valid, S, Up[p], tabs[p], 0, &b_valid));
+                    b_rows = Vp[p]; b_v0 = 0;
+                }
+                const int rows = S * b_rows;
+                nearest_valid_kernel<<<rslf_div_up((long long)rows * 32, 256), 256, 0, ctx->stream>>>(b_valid, rows, Up[p], ctx->nearest_l, ctx->nearest_r);
                 dim3 grid(rslf_div_up(Up[p + 1], 128), Vl[p + 1], S);
-                set_bounds_kernel<<<grid, 128, 0, ctx->stream>>>(L.depth, ctx->nearest_l, ctx->nearest_r, S, Vl[p], Up[p],
-                                                                 Vl[p + 1], Up[p + 1], N.dmin, N.dmax, Vp[p], tabs[p].b[r], tabs[p + 1].b[r]);
+                set_bounds_kernel<<<grid, 128, 0, ctx->stream>>>(b_depth, ctx->nearest_l, ctx->nearest_r, S, b_rows, Up[p],
+                                                                 Vl[p + 1], Up[p + 1], N.dmin, N.dmax, Vp[p], b_v0, ov0);
                 ctx->timing.kernel_launches += 4;
             }
             RSLF_CUDA_TRY(ctx, cudaGetLastError());
@@ -987,7 +1028,7 @@ extern "C" int rslf_cuda_fine_to_coarse_run(rslf_ctx* ctx, float dmin, float dma
         stage_scope sc(ctx, ST_PYR);
         const float* dp[RSLF_MAX_LEVELS]; const uint8_t* vp[RSLF_MAX_LEVELS];
         for (int p = 0; p < levels; ++p) { dp[p] = ctx->lv[p].depth; vp[p] = ctx->lv[p].valid; }
-        RSLF_TRY(launch_fuse(ctx, levels, Vp, Up, tabs, dp, vp, ctx->out_map, ctx->out_valid));
+        RSLF_TRY(launch_fuse(ctx, levels, Vp, Up, tabs, rep, dp, vp, ctx->out_map, ctx->out_valid));
     }
     ctx->last_kind = 3;
     return end_run(ctx, dim_d);
@@ -1194,7 +1235,8 @@ extern "C" int rslf_cuda_fuse_disp_maps(rslf_ctx* ctx, int levels, int S, const 
             std::vector<shard_tab> tabs(levels);
             for (int p = 0; p < levels; ++p) tabs[p] = single_tab(Vp[p]);
             int sw = ctx->world, sr = ctx->rank; ctx->world = 1; ctx->rank = 0;
-            rc = launch_fuse(ctx, levels, Vp, Up, tabs.data(), dd.data(), dv.data(), om, ov);
+            bool norep[RSLF_MAX_LEVELS] = {false};
+            rc = launch_fuse(ctx, levels, Vp, Up, tabs.data(), norep, dd.data(), dv.data(), om, ov);
             ctx->world = sw; ctx->rank = sr;
         }
         ctx->fuse_a = sa; ctx->fuse_b = sb; ctx->fuse_ma = sma; ctx->fuse_mb = smb; ctx->S = sS;

@@ -10,6 +10,7 @@
 #pragma once
 #include <dlfcn.h>
 #include <algorithm>
+#include <vector>
 #include "rslf_common.cuh"
 
 typedef struct { char internal[128]; } rslf_nccl_uid;
@@ -65,6 +66,12 @@ static int nccl_load(char* err, size_t errlen)
 
 static void comm_destroy(rslf_ctx* ctx)
 {
+    if (ctx->p2p_up) cudaIpcCloseMemHandle(ctx->p2p_up);
+    if (ctx->p2p_dn) cudaIpcCloseMemHandle(ctx->p2p_dn);
+    ctx->p2p_up = ctx->p2p_dn = nullptr;
+    if (ctx->p2p_buf) cudaFree(ctx->p2p_buf);
+    if (ctx->p2p_done) cudaFree(ctx->p2p_done);
+    ctx->p2p_buf = nullptr; ctx->p2p_done = nullptr; ctx->p2p_state = 0;
     if (ctx->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->nccl_comm);
     ctx->nccl_comm = nullptr;
 }
@@ -256,6 +263,141 @@ static int comm_exchange_median_halo(rslf_ctx* ctx, const float* depth_plane, co
         out->bot_depth = reinterpret_cast<const float*>(b);
         out->bot_colour = reinterpret_cast<const float*>(b + off_colour);
         out->bot_mask = reinterpret_cast<const uint8_t*>(b + off_mask);
+    }
+    return RSLF_OK;
+}
+
+/* ---- peer-to-peer halo exchange (NVLink, CUDA IPC) ----------------------------------------------------
+ * The per-pass median exchange is latency-bound (4 rows per rank).  Instead of a collective, every rank
+ * stores its two first / two last rows of line s_hat straight into its neighbours' receive buffers with
+ * ordinary global stores over NVLink and raises a sequence flag there; the neighbour's median kernel waits
+ * for the flag.  No rank ever waits inside a producer, so there is no circular wait; two buffer slots
+ * alternate because a rank can be at most one pass ahead of its neighbour (its next push comes after its
+ * own median, which waited for the neighbour's push of the same pass).
+ * Receive buffer of a rank: [slot 0 | slot 1] x [from above | from below] x area, then 4 flags.
+ */
+static size_t p2p_area_bytes(int U, int C) { return (((size_t)2 * U * 4 + (size_t)2 * U * C * 4 + (size_t)2 * U) + 255) & ~(size_t)255; }
+
+static int comm_p2p_setup(rslf_ctx* ctx, int U, int C)
+{
+    if (ctx->p2p_state != 0 && ctx->p2p_area >= p2p_area_bytes(U, C)) return ctx->p2p_state > 0 ? RSLF_OK : RSLF_ERR_UNSUPPORTED;
+    if (ctx->p2p_state < 0) return RSLF_ERR_UNSUPPORTED;
+    const char* mode = getenv("RSLF_HALO");
+    if (mode && mode[0] == 'n') { ctx->p2p_state = -1; return RSLF_ERR_UNSUPPORTED; }
+    ctx->p2p_state = -1;
+    /* all ranks must agree on using P2P: any failure below is reduced over the ranks before anyone commits */
+    const size_t area = p2p_area_bytes(U, C), total = 4 * area + 256;
+    float ok = 1.f;
+    if (ctx->p2p_buf) { cudaFree(ctx->p2p_buf); ctx->p2p_buf = nullptr; }
+    if (cudaMalloc((void**)&ctx->p2p_buf, total) != cudaSuccess) ok = 0.f;
+    if (!ctx->p2p_done && cudaMalloc((void**)&ctx->p2p_done, sizeof(int)) != cudaSuccess) ok = 0.f;
+    cudaIpcMemHandle_t mine; memset(&mine, 0, sizeof(mine));
+    if (ok > 0.f) {
+        cudaMemsetAsync(ctx->p2p_buf, 0, total, ctx->stream);
+        cudaMemsetAsync(ctx->p2p_done, 0, sizeof(int), ctx->stream);
+        if (cudaIpcGetMemHandle(&mine, ctx->p2p_buf) != cudaSuccess) ok = 0.f;
+    }
+    cudaGetLastError();
+    /* exchange the handles with one all-gather (through device staging) */
+    const size_t hs = sizeof(cudaIpcMemHandle_t);
+    std::vector<cudaIpcMemHandle_t> all(ctx->world);
+    {
+        RSLF_TRY(comm_ensure_stage(ctx, 256));
+        RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->g_send, &mine, hs, cudaMemcpyHostToDevice, ctx->stream));
+        RSLF_NCCL_TRY(ctx, g_nccl.AllGather(ctx->g_send, ctx->g_recv, hs, RSLF_NCCL_UINT8, ctx->nccl_comm, ctx->stream));
+        RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(all.data(), ctx->g_recv, hs * ctx->world, cudaMemcpyDeviceToHost, ctx->stream));
+        RSLF_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    char *up = nullptr, *dn = nullptr;
+    if (ok > 0.f && ctx->rank > 0 && cudaIpcOpenMemHandle((void**)&up, all[ctx->rank - 1], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) ok = 0.f;
+    if (ok > 0.f && ctx->rank + 1 < ctx->world && cudaIpcOpenMemHandle((void**)&dn, all[ctx->rank + 1], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) ok = 0.f;
+    cudaGetLastError();
+    float bad = (ok > 0.f) ? 0.f : 1.f, anybad = bad;
+    RSLF_TRY(comm_allreduce_max_host(ctx, bad, &anybad));
+    if (anybad > 0.f) {
+        if (up) cudaIpcCloseMemHandle(up);
+        if (dn) cudaIpcCloseMemHandle(dn);
+        return RSLF_ERR_UNSUPPORTED;                        /* every rank falls back to the NCCL halo exchange */
+    }
+    if (ctx->p2p_up) cudaIpcCloseMemHandle(ctx->p2p_up);
+    if (ctx->p2p_dn) cudaIpcCloseMemHandle(ctx->p2p_dn);
+    ctx->p2p_up = up; ctx->p2p_dn = dn; ctx->p2p_area = area; ctx->p2p_seq = 0; ctx->p2p_state = 1;
+    return RSLF_OK;
+}
+
+struct p2p_push_args {
+    const float* depth; const uint8_t* mask; const float* colour0; size_t colour_row_stride; int Vloc, U, C;
+    char* up_area; char* dn_area;                   /* where my first rows go (neighbour above: its "from below" area) / my last rows */
+    unsigned* up_flag; unsigned* dn_flag; unsigned seq; int* done; int nblocks;
+};
+
+__global__ void p2p_push_halo_kernel(const p2p_push_args a)
+{
+    const int j = blockIdx.y;                                  /* 0,1: first rows -> rank above; 2,3: last rows -> rank below */
+    char* dst = (j < 2) ? a.up_area : a.dn_area;
+    if (dst) {
+        const int v = (j < 2) ? j : a.Vloc - 4 + j, jj = j & 1;
+        float* d = reinterpret_cast<float*>(dst) + (size_t)jj * a.U;
+        float* c = reinterpret_cast<float*>(dst + (size_t)2 * a.U * 4) + (size_t)jj * a.U * a.C;
+        uint8_t* m = reinterpret_cast<uint8_t*>(dst + (size_t)2 * a.U * 4 + (size_t)2 * a.U * a.C * 4) + (size_t)jj * a.U;
+        for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < a.U; u += gridDim.x * blockDim.x) {
+            d[u] = a.depth[(size_t)v * a.U + u];
+            m[u] = a.mask[(size_t)v * a.U + u];
+            for (int cc = 0; cc < a.C; ++cc) c[(size_t)u * a.C + cc] = a.colour0[(size_t)v * a.colour_row_stride + (size_t)u * a.C + cc];
+        }
+    }
+    /* the last block to finish raises the neighbours' flags, after every store of the grid is visible system-wide */
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int old = atomicAdd(a.done, 1);
+        if (old == a.nblocks - 1) {
+            *a.done = 0;
+            __threadfence_system();
+            if (a.up_flag) *reinterpret_cast<volatile unsigned*>(a.up_flag) = a.seq;
+            if (a.dn_flag) *reinterpret_cast<volatile unsigned*>(a.dn_flag) = a.seq;
+        }
+    }
+}
+
+/* layout helpers of a receive buffer: area(slot, side) with side 0 = from above, 1 = from below; flags after the areas */
+static inline size_t p2p_area_off(const rslf_ctx* ctx, int slot, int side) { return ((size_t)slot * 2 + side) * ctx->p2p_area; }
+static inline size_t p2p_flag_off(const rslf_ctx* ctx, int slot, int side) { return 4 * ctx->p2p_area + ((size_t)slot * 2 + side) * sizeof(unsigned); }
+
+static int comm_p2p_exchange_median_halo(rslf_ctx* ctx, const float* depth_plane, const uint8_t* mask_plane, const float* colour0,
+                                         size_t colour_row_stride_floats, int U, int C, const shard_tab& t, median_halo* out)
+{
+    const int r0 = ctx->rank, Vloc = t.b[r0 + 1] - t.b[r0];
+    const unsigned seq = ++ctx->p2p_seq;
+    const int slot = (int)(seq & 1u);
+    p2p_push_args a;
+    a.depth = depth_plane; a.mask = mask_plane; a.colour0 = colour0; a.colour_row_stride = colour_row_stride_floats;
+    a.Vloc = Vloc; a.U = U; a.C = C; a.seq = seq; a.done = ctx->p2p_done;
+    /* my first rows are the rows BELOW the block of the rank above: its side 1; my last rows: side 0 of the rank below */
+    a.up_area = ctx->p2p_up ? ctx->p2p_up + p2p_area_off(ctx, slot, 1) : nullptr;
+    a.dn_area = ctx->p2p_dn ? ctx->p2p_dn + p2p_area_off(ctx, slot, 0) : nullptr;
+    a.up_flag = ctx->p2p_up ? reinterpret_cast<unsigned*>(ctx->p2p_up + p2p_flag_off(ctx, slot, 1)) : nullptr;
+    a.dn_flag = ctx->p2p_dn ? reinterpret_cast<unsigned*>(ctx->p2p_dn + p2p_flag_off(ctx, slot, 0)) : nullptr;
+    dim3 grid(std::max(1, std::min(8, (U + 127) / 128)), 4);
+    a.nblocks = (int)(grid.x * grid.y);
+    p2p_push_halo_kernel<<<grid, 128, 0, ctx->stream>>>(a);
+    RSLF_CUDA_TRY(ctx, cudaGetLastError());
+    ctx->timing.kernel_launches += 1;
+    memset(out, 0, sizeof(*out));
+    out->seq = seq;
+    if (r0 > 0) {
+        const char* b = ctx->p2p_buf + p2p_area_off(ctx, slot, 0);
+        out->top_depth = reinterpret_cast<const float*>(b);
+        out->top_colour = reinterpret_cast<const float*>(b + (size_t)2 * U * 4);
+        out->top_mask = reinterpret_cast<const uint8_t*>(b + (size_t)2 * U * 4 + (size_t)2 * U * C * 4);
+        out->flag_top = reinterpret_cast<const volatile unsigned*>(ctx->p2p_buf + p2p_flag_off(ctx, slot, 0));
+    }
+    if (r0 + 1 < t.n) {
+        const char* b = ctx->p2p_buf + p2p_area_off(ctx, slot, 1);
+        out->bot_depth = reinterpret_cast<const float*>(b);
+        out->bot_colour = reinterpret_cast<const float*>(b + (size_t)2 * U * 4);
+        out->bot_mask = reinterpret_cast<const uint8_t*>(b + (size_t)2 * U * 4 + (size_t)2 * U * C * 4);
+        out->flag_bot = reinterpret_cast<const volatile unsigned*>(ctx->p2p_buf + p2p_flag_off(ctx, slot, 1));
     }
     return RSLF_OK;
 }

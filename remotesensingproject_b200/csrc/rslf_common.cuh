@@ -23,6 +23,7 @@
 struct rslf_level {
     int V = 0, U = 0;            /* rows held by this rank, columns                           */
     int v0 = 0, Vtot = 0;        /* first global row of this rank, global rows of the level   */
+    bool replicated = false;     /* multi-rank run: this (coarse) level is computed whole by every rank */
     float* raw = nullptr;        /* un-normalised stack of levels > 0 (float32, or uint8 for 8-bit input: raw8 aliases it) */
     float* epi = nullptr;        /* normalised stack [V][S][U][C]                             */
     float* ce = nullptr;         /* edge confidence            [S][V][U]                      */
@@ -77,7 +78,7 @@ struct rslf_ctx {
     /* scratch */
     int* items = nullptr;        /* compacted pixel list of a pass                            */
     int* count = nullptr;        /* [0] = items in list; device scalar                        */
-    unsigned long long* total_px = nullptr;  /* accumulated computed pixels                   */
+    unsigned long long* total_px = nullptr;  /* [0] computed pixels of sharded levels, [1] of replicated levels */
     float* filtered = nullptr;   /* selective-median output plane [V][U]                      */
     int* winner = nullptr;       /* propagation arbitration [S][V][U], INT_MAX when idle      */
     int* arrive = nullptr;       /* per-item chunk arrival counters                           */
@@ -110,6 +111,11 @@ struct rslf_ctx {
     rslf_stage_clock clk;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
 
+    /* peer-to-peer halo exchange over NVLink (CUDA IPC): local receive buffer, the neighbours' buffers */
+    char* p2p_buf = nullptr; char* p2p_up = nullptr; char* p2p_dn = nullptr;
+    size_t p2p_area = 0;         /* bytes of one halo area (2 rows of depth, colour, mask) */
+    unsigned p2p_seq = 0; int p2p_state = 0;   /* 0 = not set up, 1 = ready, -1 = unavailable */
+    int* p2p_done = nullptr;     /* block completion counter of the push kernel */
     /* NCCL (resolved lazily with dlopen; see rslf_comm.cuh) */
     void* nccl_lib = nullptr;
     void* nccl_comm = nullptr;

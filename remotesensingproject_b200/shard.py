@@ -29,14 +29,20 @@ def row_shards(V, world, align=1):
     return out
 
 
-def shard_table(V, U, world, max_pyr_depth=-1, pyramid=True):
-    """Row boundaries [b0 .. b_world] for `world` ranks, aligned to 2^(levels-1) rows when the
-    fine-to-coarse pyramid runs; raises if a rank would be left without rows at the coarsest level."""
+def shard_table(V, U, world, max_pyr_depth=-1, pyramid=True, min_rows=16):
+    """Row boundaries [b0 .. b_world] for `world` ranks.
+
+    With the fine-to-coarse pyramid the library shards level p by rows as long as every boundary is a multiple
+    of 2^p and replicates the remaining (coarse, tiny) levels on every rank.  The boundaries are therefore
+    aligned to 2^k with k as large as possible while a rank keeps about `min_rows` rows at level k: fine enough
+    for balanced blocks, coarse enough that only a few thousand pixels are computed redundantly."""
     levels = len(pyramid_levels(V, U, max_pyr_depth)) if pyramid else 1
-    align = 1 << max(0, levels - 1)
+    k = 0
+    while k + 1 < levels and (V // world) >> (k + 1) >= min_rows:
+        k += 1
+    align = 1 << k
     sh = row_shards(V, world, align)
     starts = [a for a, _ in sh] + [V]
-    for a, b in zip(starts[:-1], starts[1:]):
-        if (b >> (levels - 1)) - (a >> (levels - 1)) < 1 and b != V or b <= a:
-            raise ValueError("%d rows cannot be split over %d ranks with %d pyramid levels" % (V, world, levels))
+    if any(b <= a for a, b in zip(starts[:-1], starts[1:])):
+        raise ValueError("%d rows cannot be split over %d ranks" % (V, world))
     return starts

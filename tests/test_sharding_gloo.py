@@ -21,19 +21,22 @@ from remotesensingproject_b200.shard import pyramid_levels, row_shards, shard_ta
 
 
 def test_shard_tables():
-    # C3: 7 levels -> boundaries multiples of 64, every rank keeps >= 1 row at the coarsest level
+    # C3 on 8 ranks: boundaries multiples of 8 (levels 0-3 are sharded, 4-6 replicated), blocks balanced within 8 rows
     starts = shard_table(1080, 1920, 8)
-    assert starts[0] == 0 and starts[-1] == 1080 and all(b % 64 == 0 for b in starts[1:-1])
+    assert starts[0] == 0 and starts[-1] == 1080 and all(b % 8 == 0 for b in starts[1:-1])
+    rows = [b - a for a, b in zip(starts[:-1], starts[1:])]
+    assert max(rows) - min(rows) <= 8
     levels = len(pyramid_levels(1080, 1920))
     assert levels == 7
-    for p in range(levels):
+    for p in range(4):                      # every sharded level keeps >= 2 rows per rank
         b = [s >> p for s in starts[:-1]] + [pyramid_levels(1080, 1920)[p][0]]
-        assert all(y > x for x, y in zip(b[:-1], b[1:]))
+        assert all(y - x >= 2 for x, y in zip(b[:-1], b[1:]))
+    assert shard_table(1080, 1920, 2) == [0, 544, 1080]
     assert pyramid_levels(600, 1200) == [(600, 1200), (300, 600), (150, 300), (75, 150), (38, 75), (19, 38)]
     assert row_shards(10, 3) == [(0, 3), (3, 6), (6, 10)]
     assert shard_table(540, 960, 4, pyramid=False) == [0, 135, 270, 405, 540]
     with pytest.raises(ValueError):
-        shard_table(24, 60, 16)           # 2 levels: 12 blocks of 2 rows cannot feed 16 ranks
+        shard_table(12, 60, 16)           # fewer rows than ranks
 
 
 def _free_port():

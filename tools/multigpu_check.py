@@ -23,14 +23,23 @@ def main():
     failures = 0
     cases = [dict(S=7, V=96, U=80, C=3, D=24, mode="ftc", scale=1.0), dict(S=6, V=128, U=70, C=1, D=40, mode="ftc", scale=-1.0),
              dict(S=5, V=50, U=64, C=3, D=16, mode="depth2d", scale=1.0),
-             dict(S=5, V=64, U=72, C=3, D=16, mode="ftc", scale=1.0, gather="full")]
+             dict(S=5, V=64, U=72, C=3, D=16, mode="ftc", scale=1.0, gather="full"),
+             dict(S=6, V=80, U=90, C=3, D=20, mode="ftc", scale=1.0, halo="nccl"),
+             # boundary 50 is a multiple of 2 only: levels 0-1 sharded, levels 2-3 replicated on every rank
+             dict(S=5, V=100, U=90, C=3, D=16, mode="ftc", scale=-1.0),
+             dict(S=4, V=100, U=90, C=1, D=24, mode="ftc", scale=1.0, u8=True)]
     for i, c in enumerate(cases):
         os.environ.pop("RSLF_MEDIAN_GATHER", None)
+        os.environ.pop("RSLF_HALO", None)
+        if c.get("halo"):
+            os.environ["RSLF_HALO"] = c["halo"]                 # "nccl": small all-gather instead of peer-to-peer stores
         if c.get("gather"):
             os.environ["RSLF_MEDIAN_GATHER"] = c["gather"]      # whole-plane all-gather instead of the halo exchange
         epis, _ = make_light_field_np(c["S"], c["V"], c["U"], c["C"], dmin=-1.0, dmax=2.0, seed=300 + i, layers=5)
         if c["scale"] < 0:
             epis = (epis * 200.0 + 5.0).astype(np.float32)
+        if c.get("u8"):
+            epis = np.clip(np.rint(epis * 255.0), 0, 255).astype(np.uint8)
         p = api.default_params()
         # single-GPU result (every rank computes it on its own device)
         ctx1 = api.Context(local)
