@@ -156,6 +156,7 @@ def main():
     ap.add_argument("--config", default=os.environ.get("RSLF_BENCH_CONFIG", "c3"), choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--even-rows", action="store_true", help="multi-GPU: equal row counts instead of work-balanced blocks")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200" and args.config != "tiny":
         args.warmup = 3
@@ -169,7 +170,7 @@ def main():
     import torch.distributed as dist
     from remotesensingproject_b200 import api
     from remotesensingproject_b200.synth import make_light_field
-    from remotesensingproject_b200.shard import shard_table
+    from remotesensingproject_b200.shard import row_work_estimate, shard_table
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -183,18 +184,29 @@ def main():
     S, V, U, C, D = cfg["S"], cfg["V"], cfg["U"], cfg["C"], cfg["D"]
     p = api.default_params()
 
-    # ---- synthetic light field, rendered on the device (rank-local rows when sharded) -------------------
-    epis, _ = make_light_field(S, V, U, C, dmin=DMIN, dmax=DMAX, seed=cfg["seed"], value_range=cfg["rng"], device="cuda")
+    # ---- synthetic light field, rendered on the device; every rank keeps the whole field so that it can re-cut its block ----
+    full, _ = make_light_field(S, V, U, C, dmin=DMIN, dmax=DMAX, seed=cfg["seed"], value_range=cfg["rng"], device="cuda")
+    epis, starts, shard_policy = full, [0, V], "one block"
     if world > 1:
-        starts = shard_table(V, U, world, pyramid=(cfg["mode"] == "ftc"))
-        v0, v1 = starts[rank], starts[rank + 1]
         uid = [api.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         ctx.comm_init(uid[0], rank, world)
-        epis = epis[v0:v1].contiguous()
+
+    def cut_blocks(weights, policy):
+        """Row blocks for all ranks (decided by rank 0), then this rank's block of the stack."""
+        nonlocal epis, starts, shard_policy
+        box = [shard_table(V, U, world, pyramid=(cfg["mode"] == "ftc"), weights=weights) if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        starts, shard_policy = box[0], policy
+        epis = full[starts[rank]:starts[rank + 1]].contiguous()
+        ctx.set_epis_device(epis, cfg["scale"])
         ctx.set_row_shards(starts)
+
+    if world > 1:
+        # first cut: blocks balanced by the number of edge-confident pixels per row (static estimate)
+        cut_blocks(None if args.even_rows else (row_work_estimate(full, cfg["scale"]) if rank == 0 else None),
+                   "equal rows" if args.even_rows else "balanced by edge-confident pixels per row")
     torch.cuda.synchronize()
-    Vloc = epis.shape[0]
 
     def run_once():
         if cfg["mode"] == "ftc":
@@ -210,10 +222,22 @@ def main():
             dist.barrier()
 
     # ---- value: stack resident in HBM ---------------------------------------------------------------------
-    ctx.set_epis_device(epis, cfg["scale"])
-    for _ in range(args.warmup):
+    if world == 1:
+        ctx.set_epis_device(epis, cfg["scale"])
+    for w in range(args.warmup):
         ctx.flush_l2()
         run_once()
+        if w == 0 and world > 1 and not args.even_rows:
+            # The ranks advance in lock-step (per-pass halo exchange), so the heaviest block sets the pace.  Re-cut
+            # the blocks once from the work actually measured in this first warm-up step: pixels evaluated per row
+            # (rslf_cuda_get_row_work).  Results do not depend on the cut; the remaining warm-up steps and every
+            # timed step run on the final blocks.
+            mine = torch.zeros(V, dtype=torch.float64, device="cuda")
+            mine[starts[rank]:starts[rank + 1]] = torch.from_numpy(ctx.row_work().astype(np.float64)).cuda()
+            dist.all_reduce(mine)
+            cut_blocks((mine + 1.0).cpu().tolist() if rank == 0 else None,
+                       "balanced by the per-row work measured in the first warm-up step")
+    Vloc = epis.shape[0]
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
@@ -230,11 +254,17 @@ def main():
     sampler.join()
     stats = torch.tensor([wall, acc["samples"], acc["ms_total"], acc["ms_depth"], acc["kernel_launches"],
                           acc["depth_launches"], acc["computed_pixels"]], dtype=torch.float64, device="cuda")
+    per_rank = None
     if world > 1:
         mx = stats.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = stats.clone()
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        allr = [torch.zeros_like(stats) for _ in range(world)]
+        dist.all_gather(allr, stats)
+        per_rank = {"rows": [starts[i + 1] - starts[i] for i in range(world)],
+                    "ms_depth_per_step": [float(t[3]) / args.steps for t in allr],
+                    "pixels_per_step": [float(t[6]) / args.steps for t in allr]}
         wall, samples = float(mx[0]), float(sm[1])
         launches, pixels = float(sm[4]), float(sm[6])
     else:
@@ -322,7 +352,7 @@ def main():
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": name + ": " + cfg["desc"], "S": S, "V": V, "U": U, "C": C, "D": D,
-                       "dmin": DMIN, "dmax": DMAX, "sharding": "rows x%d" % world,
+                       "dmin": DMIN, "dmax": DMAX, "sharding": "rows x%d, %s" % (world, shard_policy), "per_rank": per_rank,
                        "l2": "256 MB memset between steps (L2 flush)",
                        "samples_per_step": samples / args.steps, "pixels_per_step": pixels / args.steps,
                        "ms_per_disparity_result_device": acc["ms_total"] / args.steps},

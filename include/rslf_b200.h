@@ -246,6 +246,10 @@ int rslf_cuda_comm_init(rslf_ctx* ctx, const void* id128, int rank, int world);
 /* row_starts: n_ranks + 1 entries, row_starts[0] = 0, row_starts[n_ranks] = total rows. */
 int rslf_cuda_set_row_shards(rslf_ctx* ctx, const int* row_starts, int n_ranks);
 
+/* Pixels evaluated per image row of this rank's block during the last run (every pass and level, coarse
+ * levels mapped back to level-0 rows): the work profile for balancing the row blocks of the next run. */
+int rslf_cuda_get_row_work(rslf_ctx* ctx, unsigned* rows_out /* V entries */);
+
 /* ---- measurement helpers -------------------------------------------------- */
 /* Measured FP32 FADD/FMUL issue rate of this device in Gop/s (non-FMA, the
  * instruction mix of the mean-shift kernel); used as roofline denominator. */

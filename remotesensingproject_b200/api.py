@@ -314,6 +314,13 @@ class Context:
         self.check(lib().rslf_cuda_measure_fp32x2_peak(self._h, C.byref(a)), "rslf_cuda_measure_fp32x2_peak")
         return a.value
 
+    def row_work(self):
+        """Pixels evaluated per local image row in the last run (numpy uint32 [V])."""
+        V = self.dims[0]
+        out = np.zeros(V, np.uint32)
+        self.check(lib().rslf_cuda_get_row_work(self._h, out.ctypes.data_as(C.POINTER(C.c_uint))), "rslf_cuda_get_row_work")
+        return out
+
     def comm_init(self, uid_bytes, rank, world):
         buf = (C.c_char * 128).from_buffer_copy(uid_bytes)
         self.check(lib().rslf_cuda_comm_init(self._h, buf, int(rank), int(world)), "rslf_cuda_comm_init")

@@ -65,15 +65,25 @@ struct depth_args {
     int chunks; rslf_partial* partials; int* arrive;
 };
 
-/* remaining &= emask (in place) and list the survivors; remaining == nullptr: list emask. */
+/* remaining &= emask (in place) and list the survivors; remaining == nullptr: list emask.
+ * rowwork (optional): per level-0 row of this rank, the number of pixels evaluated so far in the run — row v
+ * of this level counts for level-0 row ((v + v0) << shift) - v0_base (load balancing of row-sharded runs). */
 __global__ void compact_kernel(const uint8_t* __restrict__ emask, uint8_t* __restrict__ remaining, int n,
                                int* __restrict__ items, int* __restrict__ count,
-                               unsigned long long* __restrict__ total)
+                               unsigned long long* __restrict__ total,
+                               unsigned* __restrict__ rowwork, int U, int v0, int shift, int v0_base, int rows_base,
+                               int V, int border_lo, int border_hi, int select)
 {
+    /* select 0: every row; 1: only the border rows (v < border_lo or v >= V - border_hi); 2: only the others */
     const int lane = threadIdx.x & 31;
     for (int base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < n; base += gridDim.x * blockDim.x) {
         int i = base + lane;
         uint8_t m = 0;
+        if (i < n && select) {
+            const int v = i / U;
+            const bool border = (v < border_lo) || (v >= V - border_hi);
+            if (border != (select == 1)) i = n;                  /* not this launch's row */
+        }
         if (i < n) {
             m = emask[i];
             if (remaining) { m &= remaining[i]; remaining[i] = m; }
@@ -88,6 +98,11 @@ __global__ void compact_kernel(const uint8_t* __restrict__ emask, uint8_t* __res
             }
             pos = __shfl_sync(0xffffffffu, pos, 0);
             if (m) items[pos + __popc(bal & ((1u << lane) - 1u))] = i;
+            if (rowwork && m) {
+                int r = (((i / U) + v0) << shift) - v0_base;
+                r = min(max(r, 0), rows_base - 1);
+                atomicAdd(rowwork + r, 1u);
+            }
         }
     }
 }

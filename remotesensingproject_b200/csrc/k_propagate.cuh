@@ -36,6 +36,7 @@ struct prop_args {
     const float* cd_p;           /* plane s_hat */
     float* depth; float* cd; uint8_t* remaining; int* winner;   /* [S][V][U] */
     const int* items; const int* count;                         /* work list of the pass */
+    const int* items2; const int* count2;                       /* second part of the list (row-sharded runs), or nullptr */
     int* rowdark;                                                /* [S][V] confident-and-dark pixels still unpainted (upper bound) */
 };
 
@@ -71,34 +72,33 @@ __device__ __forceinline__ void propagate_one(const prop_args& a, int v, int u, 
     }
 }
 
-/* kind (1): the pass's work list; one warp per list entry (its source data is loaded once), lanes over views */
+/* One launch per phase: the first list_blocks blocks walk the pass's work list (kind 1: one warp per list
+ * entry, whose source data is loaded once, lanes over views), the remaining blocks are (row v, group of PROP_SG
+ * views) pairs for the pixels painted earlier (kind 2: r_bar == 0), threads over u. */
 template <int C, int PHASE>
 __global__ void __launch_bounds__(PROP_THREADS)
-propagate_list_kernel(const prop_args a)
+propagate_kernel(const prop_args a, int list_blocks)
 {
-    const int n = *a.count;
-    const int lane = threadIdx.x & 31;
-    const int warps = (gridDim.x * PROP_THREADS) >> 5;
-    for (int it = (blockIdx.x * PROP_THREADS + threadIdx.x) >> 5; it < n; it += warps) {
-        const int pix = a.items[it];
-        if (!a.emask_p[pix]) continue;                      /* score <= threshold: dropped by the depth kernel */
-        const int v = pix / a.U, u = pix - v * a.U;
-        float rb[C];
+    if ((int)blockIdx.x < list_blocks) {
+        const int n1 = *a.count, n = n1 + (a.count2 ? *a.count2 : 0);
+        const int lane = threadIdx.x & 31;
+        const int warps = (list_blocks * PROP_THREADS) >> 5;
+        for (int it = (blockIdx.x * PROP_THREADS + threadIdx.x) >> 5; it < n; it += warps) {
+            const int pix = (it < n1) ? a.items[it] : a.items2[it - n1];
+            if (!a.emask_p[pix]) continue;                  /* score <= threshold: dropped by the depth kernel */
+            const int v = pix / a.U, u = pix - v * a.U;
+            float rb[C];
 #pragma unroll
-        for (int c = 0; c < C; ++c) rb[c] = a.rbar_p[(size_t)pix * C + c];
-        const float cur = a.filtered[pix];
-        const float cdv = PHASE ? a.cd_p[pix] : 0.f;
-        for (int s = lane; s < a.S; s += 32) propagate_one<C, PHASE>(a, v, u, s, cur, rb, cdv);
+            for (int c = 0; c < C; ++c) rb[c] = a.rbar_p[(size_t)pix * C + c];
+            const float cur = a.filtered[pix];
+            const float cdv = PHASE ? a.cd_p[pix] : 0.f;
+            for (int s = lane; s < a.S; s += 32) propagate_one<C, PHASE>(a, v, u, s, cur, rb, cdv);
+        }
+        return;
     }
-}
-
-/* kind (2): pixels painted earlier (r_bar == 0); block = (row v, group of PROP_SG views), threads over u */
-template <int C, int PHASE>
-__global__ void __launch_bounds__(PROP_THREADS)
-propagate_dark_kernel(const prop_args a)
-{
-    const int v = blockIdx.x;
-    const int s_begin = blockIdx.y * PROP_SG, s_end = min(a.S, s_begin + PROP_SG);
+    const int idx = (int)blockIdx.x - list_blocks;
+    const int v = idx % a.V;
+    const int s_begin = (idx / a.V) * PROP_SG, s_end = min(a.S, s_begin + PROP_SG);
     unsigned live = 0;                                      /* views of the group that still hold a dark target */
     for (int s = s_begin; s < s_end; ++s) live |= (a.rowdark[(size_t)s * a.V + v] > 0) ? (1u << (s - s_begin)) : 0u;
     if (!live) return;
@@ -119,19 +119,15 @@ propagate_dark_kernel(const prop_args a)
 static int launch_propagate(rslf_ctx* ctx, int C, const prop_args& a)
 {
     const int lb = ctx->num_sm * 16;
-    dim3 gd(a.V, rslf_div_up(a.S, PROP_SG));
+    const int grid = lb + a.V * rslf_div_up(a.S, PROP_SG);
     if (C == 1) {
-        propagate_list_kernel<1, 0><<<lb, PROP_THREADS, 0, ctx->stream>>>(a);
-        propagate_dark_kernel<1, 0><<<gd, PROP_THREADS, 0, ctx->stream>>>(a);
-        propagate_list_kernel<1, 1><<<lb, PROP_THREADS, 0, ctx->stream>>>(a);
-        propagate_dark_kernel<1, 1><<<gd, PROP_THREADS, 0, ctx->stream>>>(a);
+        propagate_kernel<1, 0><<<grid, PROP_THREADS, 0, ctx->stream>>>(a, lb);
+        propagate_kernel<1, 1><<<grid, PROP_THREADS, 0, ctx->stream>>>(a, lb);
     } else {
-        propagate_list_kernel<3, 0><<<lb, PROP_THREADS, 0, ctx->stream>>>(a);
-        propagate_dark_kernel<3, 0><<<gd, PROP_THREADS, 0, ctx->stream>>>(a);
-        propagate_list_kernel<3, 1><<<lb, PROP_THREADS, 0, ctx->stream>>>(a);
-        propagate_dark_kernel<3, 1><<<gd, PROP_THREADS, 0, ctx->stream>>>(a);
+        propagate_kernel<3, 0><<<grid, PROP_THREADS, 0, ctx->stream>>>(a, lb);
+        propagate_kernel<3, 1><<<grid, PROP_THREADS, 0, ctx->stream>>>(a, lb);
     }
     RSLF_CUDA_TRY(ctx, cudaGetLastError());
-    ctx->timing.kernel_launches += 4;
+    ctx->timing.kernel_launches += 2;
     return RSLF_OK;
 }

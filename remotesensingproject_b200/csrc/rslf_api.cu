@@ -102,7 +102,7 @@ static int ensure_scratch(rslf_ctx* ctx, bool need_2d, bool need_ftc, size_t pla
     const size_t px = plane * ctx->S;
     if (ctx->scratch_px != px || ctx->scratch_plane != plane) {
         free_scratch(ctx);
-        RSLF_TRY(dev_alloc(ctx, &ctx->items, plane));
+        RSLF_TRY(dev_alloc(ctx, &ctx->items, plane + 4 * (size_t)ctx->U));     /* + the border list of sharded passes */
         RSLF_TRY(dev_alloc(ctx, &ctx->filtered, plane));
         RSLF_TRY(dev_alloc(ctx, &ctx->arrive, plane));
         RSLF_TRY(dev_alloc(ctx, &ctx->pile_depth_raw, plane));
@@ -290,7 +290,7 @@ extern "C" void rslf_cuda_destroy(rslf_ctx* ctx)
     for (int p = 0; p < RSLF_MAX_LEVELS; ++p) free_level(ctx->lv[p]);
     free_scratch(ctx);
     if (ctx->raw_in && !ctx->raw_borrowed) cudaFree(ctx->raw_in);
-    dev_free(&ctx->count); dev_free(&ctx->total_px); dev_free(&ctx->minmax);
+    dev_free(&ctx->count); dev_free(&ctx->total_px); dev_free(&ctx->minmax); dev_free(&ctx->rowwork);
     if (ctx->l2_flush) cudaFree(ctx->l2_flush);
     for (auto e : ctx->clk.pool) cudaEventDestroy(e);
     if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
@@ -340,7 +340,7 @@ static int set_dims(rslf_ctx* ctx, int V, int S, int U, int C, int cv_depth, flo
     if (cv_depth != RSLF_DEPTH_8U && cv_depth != RSLF_DEPTH_32F) {
         snprintf(ctx->err, sizeof(ctx->err), "only CV_8U and CV_32F inputs are implemented"); return RSLF_ERR_UNSUPPORTED;
     }
-    if ((size_t)S * 2 > RSLF_COUNT_SLOTS / RSLF_MAX_LEVELS) { snprintf(ctx->err, sizeof(ctx->err), "S too large"); return RSLF_ERR_UNSUPPORTED; }
+    if ((size_t)S * 4 > RSLF_COUNT_SLOTS / RSLF_MAX_LEVELS) { snprintf(ctx->err, sizeof(ctx->err), "S too large"); return RSLF_ERR_UNSUPPORTED; }
     ctx->V = V; ctx->S = S; ctx->U = U; ctx->C = C; ctx->cv_depth = cv_depth; ctx->scale_factor = scale;
     if (ctx->V_total == 0 || ctx->world == 1) { ctx->v0 = 0; ctx->V_total = V; }
     return RSLF_OK;
@@ -498,13 +498,30 @@ static int run_depth_pass(rslf_ctx* ctx, const rslf_params& P, const pass_io& io
     const size_t plane = (size_t)V * U;
     const size_t po = io.pile ? 0 : (size_t)io.s_hat * plane;
     int* count = ctx->count + io.count_slot;
-    {
+    int* count2 = ctx->count + RSLF_COUNT_SLOTS / 2 + io.count_slot;
+    const bool sharded = (ctx->world > 1 && !L.replicated);
+    const float* colour0 = L.epi + (size_t)io.s_hat * U * C;      /* colours of line s_hat: row v at + v * S*U*C */
+    const uint8_t* fresh = io.pile ? nullptr : L.remaining + po;
+    const int* rdv = io.pile ? nullptr : L.rowdark + (size_t)S * V;
+    /* row-sharded level: how the rows next to the block reach the neighbours */
+    shard_tab t; bool halo_path = false;
+    if (sharded) {
+        t = level_shards(ctx, io.level, L.Vtot);
+        int min_rows = L.Vtot;
+        for (int q = 0; q < t.n; ++q) min_rows = std::min(min_rows, t.b[q + 1] - t.b[q]);
+        const char* force_full = getenv("RSLF_MEDIAN_GATHER");         /* "full": test hook for the fallback */
+        halo_path = (P.median_filter_size - 1) / 2 <= 2 && min_rows >= 2 && !(force_full && force_full[0] == 'f');
+    }
+    auto compact = [&](int select, int* items, int* cnt) -> int {
         stage_scope sc(ctx, ST_REDUCE);
         compact_kernel<<<stream_grid(ctx, plane), 256, 0, ctx->stream>>>(
-            L.emask + po, io.pile ? nullptr : L.remaining + po, (int)plane, ctx->items, count, ctx->total_px + (L.replicated ? 1 : 0));
+            L.emask + po, io.pile ? nullptr : L.remaining + po, (int)plane, items, cnt, ctx->total_px + (L.replicated ? 1 : 0),
+            L.replicated ? nullptr : ctx->rowwork, U, L.v0, io.level, ctx->v0, ctx->V,
+            V, (sharded && ctx->rank > 0) ? 2 : 0, (sharded && ctx->rank + 1 < ctx->world) ? 2 : 0, select);
         RSLF_CUDA_TRY(ctx, cudaGetLastError());
         ctx->timing.kernel_launches += 1;
-    }
+        return RSLF_OK;
+    };
     depth_plan plan = plan_depth(ctx, S, C, io.D, io.s_hat, io.dmin, io.dmax, P.slope_factor);
     if (plan.chunks > 1) RSLF_TRY(ensure_partials(ctx, plane * plan.chunks));
     depth_args a;
@@ -520,44 +537,62 @@ static int run_depth_pass(rslf_ctx* ctx, const rslf_params& P, const pass_io& io
     a.raw_thr = P.raw_score_threshold;
     a.wpv_q16 = plan.wpv_q16;
     a.chunks = plan.chunks; a.partials = (rslf_partial*)ctx->partials; a.arrive = ctx->arrive;
+    median_halo halo; memset(&halo, 0, sizeof(halo));
+    ctx->pass_items2 = nullptr; ctx->pass_count2 = nullptr;
+    const char* bf = getenv("RSLF_BORDER_FIRST");
+    const bool border_first = halo_path && bf && bf[0] == '1';
+    if (border_first) {
+        /* Border rows first (optional, RSLF_BORDER_FIRST=1; measured on 4 GPUs it does not pay: the ranks stay in
+         * lock-step through the largest pass anyway and the extra launches cost 4 %).  The only cross-row step of a pass is the 5x5 selective median (core.hpp:698-709),
+         * which reads the two rows next to the block.  Those rows are computed by a first small launch and sent to
+         * the neighbours at once, so that a neighbour's median never waits for this rank's whole depth kernel:
+         * the ranks may then drift by up to a pass instead of advancing in lock-step. */
+        int* items_b = ctx->items + ctx->scratch_plane;             /* the tail of the list buffer holds the border list */
+        RSLF_TRY(compact(1, items_b, count2));
+        {
+            stage_scope sc(ctx, ST_DEPTH);
+            depth_args ab = a; ab.items = items_b; ab.count = count2;
+            RSLF_TRY(launch_depth(ctx, C, L.nonneg != 0, ab, plan));
+        }
+        {
+            stage_scope sc(ctx, ST_MEDIAN);
+            /* peer-to-peer stores over NVLink when CUDA IPC between the ranks works, else one small all-gather */
+            if (comm_p2p_setup(ctx, ctx->U, C) == RSLF_OK)
+                RSLF_TRY(comm_p2p_exchange_median_halo(ctx, a.depth, L.emask + po, colour0, (size_t)S * U * C, U, C, t, &halo));
+            else
+                RSLF_TRY(comm_exchange_median_halo(ctx, a.depth, L.emask + po, colour0, (size_t)S * U * C, U, C, t, &halo));
+        }
+        RSLF_TRY(compact(2, ctx->items, count));
+        ctx->pass_items2 = items_b; ctx->pass_count2 = count2;
+    } else {
+        RSLF_TRY(compact(0, ctx->items, count));
+    }
     {
         stage_scope sc(ctx, ST_DEPTH);
         RSLF_TRY(launch_depth(ctx, C, L.nonneg != 0, a, plan));
     }
     {
         stage_scope sc(ctx, ST_MEDIAN);
-        if (ctx->world > 1 && !L.replicated) {
-            /* the only cross-row step of a pass (core.hpp:698-709): the window reaches (size-1)/2 rows into the
-             * neighbouring ranks' blocks */
-            const shard_tab t = level_shards(ctx, io.level, L.Vtot);
-            int min_rows = L.Vtot;
-            for (int q = 0; q < t.n; ++q) min_rows = std::min(min_rows, t.b[q + 1] - t.b[q]);
-            const float* colour0 = L.epi + (size_t)io.s_hat * U * C;
-            const uint8_t* fresh = io.pile ? nullptr : L.remaining + po;
-            const int* rdv = io.pile ? nullptr : L.rowdark + (size_t)S * V;
-            const char* force_full = getenv("RSLF_MEDIAN_GATHER");     /* "full": test hook for the fallback below */
-            if ((P.median_filter_size - 1) / 2 <= 2 && min_rows >= 2 && !(force_full && force_full[0] == 'f')) {
-                /* halo exchange: 2 + 2 rows per rank in one small all-gather, read in place by the median */
-                median_halo halo;
-                /* peer-to-peer stores over NVLink when CUDA IPC between the ranks works, else one small all-gather */
-                if (comm_p2p_setup(ctx, ctx->U, C) == RSLF_OK)
-                    RSLF_TRY(comm_p2p_exchange_median_halo(ctx, a.depth, L.emask + po, colour0, (size_t)S * U * C, U, C, t, &halo));
-                else
-                    RSLF_TRY(comm_exchange_median_halo(ctx, a.depth, L.emask + po, colour0, (size_t)S * U * C, U, C, t, &halo));
-                RSLF_TRY(launch_selective_median(ctx, a.depth, L.emask + po, colour0, (size_t)S * U * C, V, U, C,
-                                                 P.median_filter_size, P.median_filter_epsilon, ctx->filtered, 0, -1, fresh, rdv, &halo));
-            } else {
-                /* thin blocks (coarse levels) or wide windows: gather the whole planes of line s_hat */
-                RSLF_TRY(ensure_gather_planes(ctx, (size_t)L.Vtot * U));
-                RSLF_TRY(comm_gather_median_planes(ctx, a.depth, L.emask + po, colour0, (size_t)S * U * C, U, C, t));
-                RSLF_TRY(launch_selective_median(ctx, ctx->g_depth, ctx->g_mask, ctx->g_colour, (size_t)U * C, L.Vtot, U, C,
-                                                 P.median_filter_size, P.median_filter_epsilon, ctx->filtered, L.v0, V, fresh, rdv));
-            }
+        if (halo_path && !border_first) {
+            /* the rows next to the block go to the neighbours: peer-to-peer stores over NVLink when CUDA IPC between
+             * the ranks works, else one small all-gather */
+            if (comm_p2p_setup(ctx, ctx->U, C) == RSLF_OK)
+                RSLF_TRY(comm_p2p_exchange_median_halo(ctx, a.depth, L.emask + po, colour0, (size_t)S * U * C, U, C, t, &halo));
+            else
+                RSLF_TRY(comm_exchange_median_halo(ctx, a.depth, L.emask + po, colour0, (size_t)S * U * C, U, C, t, &halo));
+        }
+        if (halo_path) {
+            RSLF_TRY(launch_selective_median(ctx, a.depth, L.emask + po, colour0, (size_t)S * U * C, V, U, C,
+                                             P.median_filter_size, P.median_filter_epsilon, ctx->filtered, 0, -1, fresh, rdv, &halo));
+        } else if (sharded) {
+            /* thin blocks or wide windows: gather the whole planes of line s_hat */
+            RSLF_TRY(ensure_gather_planes(ctx, (size_t)L.Vtot * U));
+            RSLF_TRY(comm_gather_median_planes(ctx, a.depth, L.emask + po, colour0, (size_t)S * U * C, U, C, t));
+            RSLF_TRY(launch_selective_median(ctx, ctx->g_depth, ctx->g_mask, ctx->g_colour, (size_t)U * C, L.Vtot, U, C,
+                                             P.median_filter_size, P.median_filter_epsilon, ctx->filtered, L.v0, V, fresh, rdv));
         } else {
-            /* colours of line s_hat: row v starts at epi + (v*S + s_hat)*U*C */
-            RSLF_TRY(launch_selective_median(ctx, a.depth, L.emask + po, L.epi + (size_t)io.s_hat * U * C, (size_t)S * U * C,
-                                             V, U, C, P.median_filter_size, P.median_filter_epsilon, ctx->filtered, 0, -1,
-                                             io.pile ? nullptr : L.remaining + po, io.pile ? nullptr : L.rowdark + (size_t)S * V));
+            RSLF_TRY(launch_selective_median(ctx, a.depth, L.emask + po, colour0, (size_t)S * U * C,
+                                             V, U, C, P.median_filter_size, P.median_filter_epsilon, ctx->filtered, 0, -1, fresh, rdv));
         }
     }
     return RSLF_OK;
@@ -612,6 +647,7 @@ static int run_depth2d_level(rslf_ctx* ctx, int p, const rslf_params& P, float d
             a.rbar_p = L.rbar + (size_t)s_hat * plane * C; a.cd_p = L.cd + (size_t)s_hat * plane;
             a.depth = L.depth; a.cd = L.cd; a.remaining = L.remaining; a.winner = ctx->winner;
             a.items = ctx->items; a.count = ctx->count + io.count_slot; a.rowdark = L.rowdark;
+            a.items2 = ctx->pass_items2; a.count2 = ctx->pass_count2;
             RSLF_TRY(launch_propagate(ctx, C, a));
         }
         ++pass;
@@ -629,6 +665,11 @@ static int begin_run(rslf_ctx* ctx)
     clk_reset(ctx);
     RSLF_CUDA_TRY(ctx, cudaMemsetAsync(ctx->count, 0, RSLF_COUNT_SLOTS * sizeof(int), ctx->stream));
     RSLF_CUDA_TRY(ctx, cudaMemsetAsync(ctx->total_px, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    if (ctx->rowwork_cap < (size_t)ctx->V) {
+        RSLF_TRY(dev_alloc(ctx, &ctx->rowwork, (size_t)ctx->V));
+        ctx->rowwork_cap = (size_t)ctx->V;
+    }
+    RSLF_CUDA_TRY(ctx, cudaMemsetAsync(ctx->rowwork, 0, (size_t)ctx->V * sizeof(unsigned), ctx->stream));
     RSLF_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_a, ctx->stream));
     return RSLF_OK;
 }
@@ -1265,4 +1306,17 @@ extern "C" int rslf_cuda_measure_fp32x2_peak(rslf_ctx* ctx, double* gops_nofma_p
     if (!ctx) return RSLF_ERR_ARG;
     RSLF_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     return measure_fp32x2_peak(ctx, gops_nofma_packed);
+}
+
+/* Pixels evaluated per image row of this rank's block in the last run (all passes; pyramid levels mapped back to
+ * level-0 rows; replicated coarse levels excluded).  The cost of a pixel is D x S samples whatever its level, so
+ * this is the work profile a caller needs to balance the row blocks of a multi-GPU run. */
+extern "C" int rslf_cuda_get_row_work(rslf_ctx* ctx, unsigned* rows_out)
+{
+    if (!ctx || !rows_out) return RSLF_ERR_ARG;
+    if (!ctx->rowwork || ctx->last_kind == 0) return RSLF_ERR_STATE;
+    RSLF_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(rows_out, ctx->rowwork, (size_t)ctx->V * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+    RSLF_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return RSLF_OK;
 }

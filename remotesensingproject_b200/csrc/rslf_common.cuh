@@ -77,7 +77,8 @@ struct rslf_ctx {
 
     /* scratch */
     int* items = nullptr;        /* compacted pixel list of a pass                            */
-    int* count = nullptr;        /* [0] = items in list; device scalar                        */
+    int* count = nullptr;        /* list lengths, one slot per pass (second half: border lists) */
+    const int* pass_items2 = nullptr; const int* pass_count2 = nullptr;   /* border list of the current pass */
     unsigned long long* total_px = nullptr;  /* [0] computed pixels of sharded levels, [1] of replicated levels */
     float* filtered = nullptr;   /* selective-median output plane [V][U]                      */
     int* winner = nullptr;       /* propagation arbitration [S][V][U], INT_MAX when idle      */
@@ -92,6 +93,7 @@ struct rslf_ctx {
     float* out_map = nullptr; uint8_t* out_valid = nullptr;
     size_t scratch_px = 0;       /* S*V*U the scratch was sized for                           */
     size_t scratch_plane = 0;    /* V*U the scratch was sized for                             */
+    unsigned* rowwork = nullptr; size_t rowwork_cap = 0;   /* pixels evaluated per level-0 row of this rank (last run) */
     void* l2_flush = nullptr;
     /* row-sharded runs: gathered planes of line s_hat for the cross-row median, staging */
     float* g_depth = nullptr; float* g_colour = nullptr; uint8_t* g_mask = nullptr;

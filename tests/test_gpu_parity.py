@@ -346,6 +346,16 @@ def test_upload_images_builds_epis(gpu_ctx):
     np.testing.assert_array_equal(m_a, m_b)
 
 
+def test_row_work_profile(gpu_ctx):
+    """rslf_cuda_get_row_work: per-row counts of evaluated pixels, all passes and levels, sum = computed pixels."""
+    epis = lf(5, 44, 60, 3, seed=58)
+    api.FineToCoarse(epis, -1.0, 2.0, 16, epi_scale_factor=1.0, ctx=gpu_ctx).run()
+    w = gpu_ctx.row_work()
+    assert w.shape == (44,) and int(w.sum()) == int(gpu_ctx.timing()["computed_pixels"])
+    ref = oracle.fine_to_coarse(epis, -1.0, 2.0, 16, scale_factor=1.0)
+    assert int(w.sum()) == int(ref["computed_pixels"])
+
+
 def test_row_sharded_run_equals_single_gpu():
     """Two ranks on two GPUs (torchrun + NCCL): every output block is bit-identical to the one-GPU result.
     Skipped on boxes with a single GPU (the driver's -m gpu run); tools/multigpu_check.py is the same check."""

@@ -17,7 +17,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-from remotesensingproject_b200.shard import pyramid_levels, row_shards, shard_table  # noqa: E402
+from remotesensingproject_b200.shard import balanced_blocks, pyramid_levels, row_shards, shard_table  # noqa: E402
 
 
 def test_shard_tables():
@@ -37,6 +37,27 @@ def test_shard_tables():
     assert shard_table(540, 960, 4, pyramid=False) == [0, 135, 270, 405, 540]
     with pytest.raises(ValueError):
         shard_table(12, 60, 16)           # fewer rows than ranks
+
+
+def test_work_balanced_blocks():
+    rng = np.random.default_rng(0)
+    for _ in range(100):
+        V = int(rng.integers(40, 1200))
+        world = int(rng.choice([2, 3, 4, 8]))
+        align = int(rng.choice([1, 2, 4, 8, 16]))
+        if (V + align - 1) // align < world:
+            continue
+        w = rng.random(V) ** 3 * 10 + 0.01
+        st = balanced_blocks(list(w), world, align)
+        assert len(st) == world + 1 and st[0] == 0 and st[-1] == V
+        assert all(b > a for a, b in zip(st[:-1], st[1:])) and all(x % align == 0 for x in st[1:-1])
+        heavy = max(w[a:b].sum() for a, b in zip(st[:-1], st[1:]))
+        even = max(w[a:b].sum() for a, b in row_shards(V, world, align))
+        assert heavy <= even * 1.0001          # never worse than equal row counts
+    # a skewed profile: the balanced cut gives the heavy rows to a smaller block
+    w = [10.0] * 100 + [1.0] * 900
+    st = shard_table(1000, 1500, 4, weights=w)
+    assert st[1] < 250 and st[-1] == 1000
 
 
 def _free_port():

@@ -27,10 +27,14 @@ def main():
              dict(S=6, V=80, U=90, C=3, D=20, mode="ftc", scale=1.0, halo="nccl"),
              # boundary 50 is a multiple of 2 only: levels 0-1 sharded, levels 2-3 replicated on every rank
              dict(S=5, V=100, U=90, C=3, D=16, mode="ftc", scale=-1.0),
-             dict(S=4, V=100, U=90, C=1, D=24, mode="ftc", scale=1.0, u8=True)]
+             dict(S=4, V=100, U=90, C=1, D=24, mode="ftc", scale=1.0, u8=True),
+             dict(S=6, V=96, U=80, C=3, D=24, mode="ftc", scale=1.0, border_first="1")]
     for i, c in enumerate(cases):
         os.environ.pop("RSLF_MEDIAN_GATHER", None)
         os.environ.pop("RSLF_HALO", None)
+        os.environ.pop("RSLF_BORDER_FIRST", None)
+        if c.get("border_first"):
+            os.environ["RSLF_BORDER_FIRST"] = c["border_first"]   # border rows computed and sent first
         if c.get("halo"):
             os.environ["RSLF_HALO"] = c["halo"]                 # "nccl": small all-gather instead of peer-to-peer stores
         if c.get("gather"):

@@ -4,7 +4,7 @@
 set -u
 OUT=${1:-gpurun_out}
 CMD="python bench.py --steps 1 --warmup 3 --no-cpu --no-e2e"
-OURS='regex:^(depth_kernel|compact_kernel|selective_median_kernel|propagate_list_kernel|propagate_dark_kernel|edge_confidence_kernel|downsample_kernel|nearest_valid_kernel|set_bounds_kernel|fuse_level_kernel|median3x3_kernel|valid_mask_kernel|fill_f32_kernel|normalise_f32_kernel|normalise_u8_kernel|stack_minmax_kernel|row_sum_kernel)'
+OURS='regex:^(depth_kernel|compact_kernel|selective_median_kernel|propagate_kernel|edge_confidence_kernel|downsample_kernel|nearest_valid_kernel|set_bounds_kernel|fuse_level_kernel|median3x3_kernel|valid_mask_kernel|fill_f32_kernel|normalise_f32_kernel|normalise_u8_kernel|stack_minmax_kernel|row_sum_kernel)'
 $CMD > $OUT/plain.log 2>&1 || { echo "plain run failed"; tail -5 $OUT/plain.log; exit 1; }
 tail -c 600 $OUT/plain.log
 # one step's worth of launches (the first warm-up step); cold-cache, serialised: compare SHARES
