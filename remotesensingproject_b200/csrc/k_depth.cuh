@@ -58,6 +58,7 @@ struct depth_args {
     const float* epi; int V, S, U, D; int s_hat; float slope; float inv; int iters;
     float negzero;                /* -0.0f, opaque to the compiler: addend of the packed multiplies */
     int wpv_q16;                  /* pixels a chunk's hypotheses spread per view step, 16.16 fixed point (row sizing) */
+    int reg_last;                 /* register-resident views: 0 = the first RV views, 1 = the last RV (padded) views */
     const int* items; const int* count;
     const float* dmin_map; const float* dmax_map; float dmin_c, dmax_c;
     float* ce; uint8_t* emask; float* cd; float* depth; float* rbar;   /* planes of line s_hat */
@@ -127,18 +128,29 @@ static __host__ __device__ inline int depth_segment_floats(int s, int S, int s_h
     long long f = (span * C + 4 + 3) & ~3LL;
     return (int)(f > DEPTH_MAX_ROW_FLOATS ? DEPTH_MAX_ROW_FLOATS : f);
 }
-/* Shared memory is organised in blocks of DEPTH_UNR rows.  Block b hosts the views DEPTH_UNR*b .. +3 of
- * staging round 0 (if below RV) and the views RV + DEPTH_UNR*b .. +3 of round 1.  While staged, view j of the
- * block owns the sub-area [j * pitch, (j + 1) * pitch) with pitch = max(C * 32 * H, longest segment of the
- * block); after the conversion the block's first DEPTH_UNR * C * 32 * H floats hold the radiances transposed
- * as [c][h][lane][view j], so that ONE LDS.128 of a lane fetches a channel of all four views. */
-static __host__ __device__ inline int depth_block_pitch(int b, int S, int Spad, int RV, int s_hat, int wpv_q16, int C, int W)
+/* Shared memory is organised in blocks of DEPTH_UNR views, one table of block offsets per staging round.
+ * Round 0 (only if RV > 0) stages the RV register-resident views, round 1 the other Spad - RV views; both
+ * rounds use the same area from its start, so the area is as large as the larger round.  The register views
+ * are the first RV views (reg_last = 0) or the last RV views of the padded range (reg_last = 1): the host
+ * picks the end that is farther from s_hat, whose segments are the longest, so that the views that stay in
+ * shared memory are the ones with short segments (a pass at the rim of the stack then needs hardly more shared
+ * memory than the centre pass, and as many warps stay resident).  While staged, view j of a block owns the
+ * sub-area [j * pitch, (j + 1) * pitch) with pitch = max(C * 32 * H, longest segment of the block); after the
+ * conversion the block's first DEPTH_UNR * C * 32 * H floats hold the radiances transposed as
+ * [c][h][lane][view j], so that ONE LDS.128 of a lane fetches a channel of all four views. */
+static __host__ __device__ inline int depth_round_base(int round, int Spad, int RV, int reg_last)
 {
+    return round == 0 ? (reg_last ? Spad - RV : 0) : (reg_last ? 0 : RV);
+}
+static __host__ __device__ inline int depth_block_pitch(int round, int b, int S, int Spad, int RV, int reg_last, int s_hat,
+                                                        int wpv_q16, int C, int W)
+{
+    const int base = depth_round_base(round, Spad, RV, reg_last);
+    const int nviews = round == 0 ? RV : Spad - RV;
     int f = C * W;
     for (int j = 0; j < DEPTH_UNR; ++j) {
         const int r = b * DEPTH_UNR + j;
-        if (r < RV) { int g = depth_segment_floats(r, S, s_hat, wpv_q16, C); f = g > f ? g : f; }
-        if (RV + r < Spad) { int g = depth_segment_floats(RV + r, S, s_hat, wpv_q16, C); f = g > f ? g : f; }
+        if (r < nviews) { int g = depth_segment_floats(base + r, S, s_hat, wpv_q16, C); f = g > f ? g : f; }
     }
     return f;
 }
@@ -422,10 +434,13 @@ depth_kernel(const depth_args a)
     const int nrows = depth_num_rows(Spad, RV);
     const int nblk = (Spad - RV) / DEPTH_UNR;               /* blocks of DEPTH_UNR shared-memory views */
     constexpr int W = 32 * H;
-    /* [mbarrier, 16 B][block offsets: nblocks + 1 ints, padded to 16 B][per-row staging records: nrows int4][blocks] */
-    const int nblocks = nrows / DEPTH_UNR;
-    int* blk_off = reinterpret_cast<int*>(smem_raw) + 4;
-    int4* meta = reinterpret_cast<int4*>(blk_off + ((nblocks + 1 + 3) & ~3));
+    /* [mbarrier, 16 B][block offsets of round 0: nb0 + 1 ints, padded to 16 B][block offsets of round 1: nblk + 1 ints,
+     *  padded][per-row staging records: nrows int4][staging area / radiance blocks] */
+    constexpr int nb0 = RV / DEPTH_UNR;
+    const int rlast = a.reg_last;
+    int* blk_off0 = reinterpret_cast<int*>(smem_raw) + 4;
+    int* blk_off1 = blk_off0 + ((nb0 + 1 + 3) & ~3);
+    int4* meta = reinterpret_cast<int4*>(blk_off1 + ((nblk + 1 + 3) & ~3));
     float* rows = reinterpret_cast<float*>(meta + nrows);
     const unsigned bar = smem_u32(smem_raw);
     const long long total = (long long)(*a.count) * a.chunks;
@@ -433,26 +448,29 @@ depth_kernel(const depth_args a)
     const f32x2 NZ = pk2(a.negzero, a.negzero);          /* -0.0 the compiler cannot see (see mul2) */
     const float Um1f = (float)(U - 1);
 
-    /* prologue: mbarrier and the block offset table (exclusive prefix sum of the block sizes) */
+    /* prologue: mbarrier and the block offset tables (exclusive prefix sums of the block sizes) */
     if (lane == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    {
+#pragma unroll 1
+    for (int round = (RV > 0 ? 0 : 1); round < 2; ++round) {
+        int* tab = round ? blk_off1 : blk_off0;
+        const int nb = round ? nblk : nb0;
         int carry = 0;
-        for (int base = 0; base < nblocks; base += 32) {
+        for (int base = 0; base < nb; base += 32) {
             const int b = base + lane;
-            int f = (b < nblocks) ? DEPTH_UNR * depth_block_pitch(b, S, Spad, RV, a.s_hat, a.wpv_q16, C, W) : 0;
+            int f = (b < nb) ? DEPTH_UNR * depth_block_pitch(round, b, S, Spad, RV, rlast, a.s_hat, a.wpv_q16, C, W) : 0;
             int incl = f;
 #pragma unroll
             for (int off = 1; off < 32; off <<= 1) {
                 const int t = __shfl_up_sync(0xffffffffu, incl, off);
                 if (lane >= off) incl += t;
             }
-            if (b < nblocks) blk_off[b] = carry + incl - f;
+            if (b < nb) tab[b] = carry + incl - f;
             carry += __shfl_sync(0xffffffffu, incl, 31);
         }
-        if (lane == 0) blk_off[nblocks] = carry;
+        if (lane == 0) tab[nb] = carry;
     }
     __syncwarp();
     unsigned phase = 0;                                     /* mbarrier phase parity */
@@ -495,13 +513,14 @@ depth_kernel(const depth_args a)
         }
         float rr[RV > 0 ? RV : 1][C][H];
 
-        /* ---- radiances (interp.hpp:155-193) and card_R.  Round 0 (RV > 0): views [0, RV) -> registers;
-         *      round 1: views [RV, Spad) -> shared-memory rows.  Per round: the lanes issue one TMA bulk
+        /* ---- radiances (interp.hpp:155-193) and card_R.  Round 0 (RV > 0): the RV register views (the first or
+         *      the last RV views, a.reg_last) -> registers; round 1: the other views -> shared-memory blocks.  Per round: the lanes issue one TMA bulk
          *      copy per view into that view's row, wait once, then convert the rows in place. ---- */
 #pragma unroll 1
         for (int round = (RV > 0 ? 0 : 1); round < 2; ++round) {
-            const int vbase = round ? RV : 0;
+            const int vbase = depth_round_base(round, Spad, RV, rlast);
             const int nviews = round ? (Spad - RV) : RV;
+            const int* blk_off = round ? blk_off1 : blk_off0;
             bool any_cut = false;
             __syncwarp();
             {
@@ -581,7 +600,7 @@ depth_kernel(const depth_args a)
             }
             float ba[DEPTH_UNR][C][H], bb[DEPTH_UNR][C][H];
             auto load_block = [&](int bi, float (&dst)[DEPTH_UNR][C][H]) {
-                const float* blk = rows + blk_off[bi] + lane * DEPTH_UNR;
+                const float* blk = rows + blk_off1[bi] + lane * DEPTH_UNR;
 #pragma unroll
                 for (int c = 0; c < C; ++c)
 #pragma unroll
@@ -591,20 +610,27 @@ depth_kernel(const depth_args a)
                     }
             };
             if (nblk > 0) load_block(0, ba);
+            /* views in ascending s (the order of cv::reduce): register views first, or last (a.reg_last) */
+#pragma unroll 1
+            for (int part = 0; part < 2; ++part) {
+                if ((part == 1) == (rlast != 0)) {
 #pragma unroll
-            for (int j = 0; j < RV; j += 2) ms_accumulate_pair<C, H, NONNEG>(rr[j], rr[RV > 1 ? j + 1 : 0], rb, inv, NZ, sR, sK);
-            int bi = 0;
-            for (; bi + 2 <= nblk; bi += 2) {
-                load_block(bi + 1, bb);
+                    for (int j = 0; j < RV; j += 2) ms_accumulate_pair<C, H, NONNEG>(rr[j], rr[RV > 1 ? j + 1 : 0], rb, inv, NZ, sR, sK);
+                } else {
+                    int bi = 0;
+                    for (; bi + 2 <= nblk; bi += 2) {
+                        load_block(bi + 1, bb);
 #pragma unroll
-                for (int j = 0; j < DEPTH_UNR; j += 2) ms_accumulate_pair<C, H, NONNEG>(ba[j], ba[j + 1], rb, inv, NZ, sR, sK);
-                load_block(min(bi + 2, nblk - 1), ba);                   /* last: harmless re-read */
+                        for (int j = 0; j < DEPTH_UNR; j += 2) ms_accumulate_pair<C, H, NONNEG>(ba[j], ba[j + 1], rb, inv, NZ, sR, sK);
+                        load_block(min(bi + 2, nblk - 1), ba);                   /* last: harmless re-read */
 #pragma unroll
-                for (int j = 0; j < DEPTH_UNR; j += 2) ms_accumulate_pair<C, H, NONNEG>(bb[j], bb[j + 1], rb, inv, NZ, sR, sK);
-            }
-            if (bi < nblk) {
+                        for (int j = 0; j < DEPTH_UNR; j += 2) ms_accumulate_pair<C, H, NONNEG>(bb[j], bb[j + 1], rb, inv, NZ, sR, sK);
+                    }
+                    if (bi < nblk) {
 #pragma unroll
-                for (int j = 0; j < DEPTH_UNR; j += 2) ms_accumulate_pair<C, H, NONNEG>(ba[j], ba[j + 1], rb, inv, NZ, sR, sK);
+                        for (int j = 0; j < DEPTH_UNR; j += 2) ms_accumulate_pair<C, H, NONNEG>(ba[j], ba[j + 1], rb, inv, NZ, sR, sK);
+                    }
+                }
             }
             /* r_bar = sum_rK / sum_K (x / 0 = 0 as in OpenCV 3), then max(., 0) (core.hpp:606-609) */
 #pragma unroll
@@ -696,7 +722,7 @@ depth_kernel(const depth_args a)
     }
 }
 
-struct depth_plan { int H; int RV; int blocks_per_sm; size_t smem; int chunks; int wpv_q16; };
+struct depth_plan { int H; int RV; int reg_last; int blocks_per_sm; size_t smem; int chunks; int wpv_q16; };
 
 /* pixels a chunk of 32*H hypotheses spreads per view step, 16.16 fixed point, rounded up */
 static inline int depth_wpv_q16(int D, int H, float dmin, float dmax, float slope)
@@ -706,14 +732,16 @@ static inline int depth_wpv_q16(int D, int H, float dmin, float dmax, float slop
     return (int)std::ceil(per_view * 65536.0);
 }
 
-static inline size_t depth_smem_bytes(int S, int C, int H, int RV, int s_hat, int wpv_q16)
+static inline size_t depth_smem_bytes(int S, int C, int H, int RV, int reg_last, int s_hat, int wpv_q16)
 {
     int spad = depth_padded_views(S);
     if (spad < RV) spad = RV;
-    const int nrows = depth_num_rows(spad, RV), nblocks = nrows / DEPTH_UNR;
-    size_t fl = 4 + ((nblocks + 1 + 3) & ~3) + 4 * (size_t)nrows;       /* mbarrier, block offsets, staging records */
-    for (int b = 0; b < nblocks; ++b) fl += (size_t)DEPTH_UNR * depth_block_pitch(b, S, spad, RV, s_hat, wpv_q16, C, 32 * H);
-    return fl * sizeof(float);
+    const int nrows = depth_num_rows(spad, RV), nb0 = RV / DEPTH_UNR, nb1 = (spad - RV) / DEPTH_UNR;
+    size_t fl = 4 + ((nb0 + 1 + 3) & ~3) + ((nb1 + 1 + 3) & ~3) + 4 * (size_t)nrows;   /* mbarrier, block offsets, staging records */
+    size_t area0 = 0, area1 = 0;
+    for (int b = 0; b < nb0; ++b) area0 += (size_t)DEPTH_UNR * depth_block_pitch(0, b, S, spad, RV, reg_last, s_hat, wpv_q16, C, 32 * H);
+    for (int b = 0; b < nb1; ++b) area1 += (size_t)DEPTH_UNR * depth_block_pitch(1, b, S, spad, RV, reg_last, s_hat, wpv_q16, C, 32 * H);
+    return (fl + (area0 > area1 ? area0 : area1)) * sizeof(float);
 }
 
 /* (H, RV) variants that are instantiated */
@@ -740,9 +768,11 @@ static depth_plan plan_depth(const rslf_ctx* ctx, int S, int C, int D, int s_hat
     const char* eh = getenv("RSLF_DEPTH_H");
     const char* er = getenv("RSLF_DEPTH_RV");
     const int fH = eh ? atoi(eh) : 0, fRV = er ? atoi(er) : -1;
-    depth_plan best; best.H = 1; best.RV = 0; best.blocks_per_sm = 1;
+    const char* el = getenv("RSLF_DEPTH_REG_LAST");
+    const int fL = el ? atoi(el) : -1;
+    depth_plan best; best.H = 1; best.RV = 0; best.reg_last = 0; best.blocks_per_sm = 1;
     best.wpv_q16 = depth_wpv_q16(D, 1, dmin, dmax, slope);
-    best.smem = depth_smem_bytes(S, C, 1, 0, s_hat, best.wpv_q16);
+    best.smem = depth_smem_bytes(S, C, 1, 0, 0, s_hat, best.wpv_q16);
     double bestScore = -1;
     for (auto& var : k_depth_variants) {
         const int H = var[0], RV = var[1];
@@ -753,14 +783,20 @@ static depth_plan plan_depth(const rslf_ctx* ctx, int S, int C, int D, int s_hat
         if (!fH && fRV < 0 && C == 3 && H != 1) continue;
         if (!fH && fRV < 0 && C == 1 && RV != 0) continue;
         const int wpv = depth_wpv_q16(D, H, dmin, dmax, slope);
-        const size_t sm = depth_smem_bytes(S, C, H, RV, s_hat, wpv);
+        /* register views at the end of the stack that is farther from s_hat (the smaller shared-memory need) */
+        size_t sm = depth_smem_bytes(S, C, H, RV, 0, s_hat, wpv);
+        int rl = 0;
+        if (RV > 0 && fL != 0) {
+            const size_t sm1 = depth_smem_bytes(S, C, H, RV, 1, s_hat, wpv);
+            if (sm1 < sm || fL == 1) { sm = sm1; rl = 1; }
+        }
         if (sm > ctx->smem_optin) continue;
         int w_smem = (int)(budget / (sm + 1024));
         int w_regs = depth_reg_warps(C, H, RV);
         int w = std::min(std::min(w_smem, w_regs), 32);
         if (w < 1) w = 1;
         double score = 1000.0 * std::min(w, 8) + 10.0 * RV + 100.0 * H + 0.1 * w;
-        if (score > bestScore) { bestScore = score; best.H = H; best.RV = RV; best.blocks_per_sm = w; best.smem = sm; best.wpv_q16 = wpv; }
+        if (score > bestScore) { bestScore = score; best.H = H; best.RV = RV; best.reg_last = rl; best.blocks_per_sm = w; best.smem = sm; best.wpv_q16 = wpv; }
     }
     best.chunks = rslf_div_up(D, 32 * best.H);
     return best;

@@ -535,7 +535,7 @@ static int run_depth_pass(rslf_ctx* ctx, const rslf_params& P, const pass_io& io
     a.depth = io.pile ? ctx->pile_depth_raw : L.depth + po;
     a.rbar = L.rbar + po * C;
     a.raw_thr = P.raw_score_threshold;
-    a.wpv_q16 = plan.wpv_q16;
+    a.wpv_q16 = plan.wpv_q16; a.reg_last = plan.reg_last;
     a.chunks = plan.chunks; a.partials = (rslf_partial*)ctx->partials; a.arrive = ctx->arrive;
     median_halo halo; memset(&halo, 0, sizeof(halo));
     ctx->pass_items2 = nullptr; ctx->pass_count2 = nullptr;

@@ -98,6 +98,32 @@ def test_depth1d_pile(gpu_ctx, monkeypatch, S, V, U, C, D, H, RV):
     assert_maps_equal(gpu, ref, ["edge_mask", "edge_conf", "raw_depth", "best_depth", "rbar", "disp_conf"])
 
 
+# register-resident views at either end of the stack (the planner picks the end farther from s_hat), forced both ways
+REG_LAST_CASES = [
+    # S, C, D, H, RV, reg_last, s_hat
+    (21, 3, 40, 1, 16, 0, 2), (21, 3, 40, 1, 16, 1, 2), (21, 3, 40, 1, 16, 1, 18), (21, 3, 40, 1, 16, -1, 0),
+    (37, 3, 40, 1, 32, 1, 3), (37, 3, 40, 1, 32, 0, 35), (37, 3, 70, 1, 32, -1, 36), (38, 3, 33, 1, 32, 1, 19),
+    (19, 3, 70, 2, 16, 1, 1), (33, 1, 70, 2, 16, 1, 30), (20, 1, 40, 1, 16, 1, 0), (9, 3, 20, 1, 16, 1, 4),
+]
+
+
+@pytest.mark.parametrize("S,C,D,H,RV,RL,s_hat", REG_LAST_CASES)
+def test_depth1d_pile_register_views_at_either_end(gpu_ctx, monkeypatch, S, C, D, H, RV, RL, s_hat):
+    monkeypatch.setenv("RSLF_DEPTH_H", str(H))
+    monkeypatch.setenv("RSLF_DEPTH_RV", str(RV))
+    monkeypatch.delenv("RSLF_DEPTH_REG_LAST", raising=False)
+    if RL >= 0:
+        monkeypatch.setenv("RSLF_DEPTH_REG_LAST", str(RL))
+    epis = lf(S, 4, 48, C, seed=300 + S + D + s_hat)
+    comp = api.Depth1DComputer_pile(epis, -1.0, 2.0, D, s_hat=s_hat, epi_scale_factor=1.0, ctx=gpu_ctx).run()
+    ref = oracle.depth1d_pile(oracle.normalise(epis, 1.0), -1.0, 2.0, D, s_hat=s_hat)
+    gpu = dict(best_depth=comp.m_best_depth_v_u, edge_conf=comp.m_edge_confidence_v_u,
+               edge_mask=comp.m_edge_confidence_mask_v_u, disp_conf=comp.m_disp_confidence_v_u,
+               rbar=comp.m_rbar_v_u, raw_depth=comp.m_raw_depth_v_u)
+    assert ref["computed_pixels"] > 0
+    assert_maps_equal(gpu, ref, ["edge_mask", "edge_conf", "raw_depth", "best_depth", "rbar", "disp_conf"])
+
+
 def test_depth1d_pile_uint8_and_max_scale(gpu_ctx):
     epis = lf(7, 6, 48, 3, seed=5)
     u8 = np.clip(np.rint(epis * 255.0), 0, 255).astype(np.uint8)
