@@ -14,7 +14,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librslf_b200.so")
+# RSLF_B200_LIB: developer hook to time an alternative build of the same library (A/B experiments)
+LIB_PATH = os.environ.get("RSLF_B200_LIB") or os.path.join(_HERE, "librslf_b200.so")
 
 RSLF_DEPTH_8U = 0
 RSLF_DEPTH_32F = 5

@@ -50,6 +50,27 @@
 
 #define RSLF_RAD_SENTINEL 1.0e18f
 
+/* Staging of the scanline segments: 0 = one TMA bulk copy per view (UBLKCP, issued lane by lane through the
+ * uniform datapath), 1 = 16-byte cp.async copies (LDGSTS), half a warp per view, all lanes in parallel. */
+#ifndef RSLF_STAGE_CPASYNC
+#define RSLF_STAGE_CPASYNC 0
+#endif
+/* 1 = the converted radiance blocks are packed at a uniform stride of DEPTH_UNR * C * 32 * H floats (block b's
+ * destination only overlaps the staging sub-areas of blocks <= b, which have been consumed by then), so the
+ * mean shift needs no block-offset look-ups. */
+#ifndef RSLF_COMPACT_BLOCKS
+#define RSLF_COMPACT_BLOCKS 1
+#endif
+/* unroll factor of the mean-shift loop over shared-memory block pairs (1 = 8 views per loop iteration) */
+#ifndef RSLF_MS_UNROLL
+#define RSLF_MS_UNROLL 1
+#endif
+#ifndef RSLF_PREFETCH_ITEM
+#define RSLF_PREFETCH_ITEM 0
+#endif
+#define RSLF_PRAGMA_(x) _Pragma(#x)
+#define RSLF_PRAGMA(x) RSLF_PRAGMA_(x)
+
 struct __align__(16) rslf_partial {
     float mx; int idx; float dv; float rb[3]; double sum;
 };
@@ -179,6 +200,10 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
     }
     __trap();
 }
+__device__ __forceinline__ void cp_async16(unsigned dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void tma_bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
@@ -357,6 +382,17 @@ __device__ __forceinline__ void ms_accumulate_pair(const float (&va)[C][H], cons
  * (interp.hpp:171-185).  Views >= S (padding) and out-of-image samples become the sentinel.
  * ufl = u as float, NaN for lanes whose hypothesis index is >= D (they then fail every test).
  */
+/* float offset of radiance block b inside the area */
+template <int C, int H>
+__device__ __forceinline__ int rad_block(const int* blk_off, int b)
+{
+#if RSLF_COMPACT_BLOCKS
+    return b * (DEPTH_UNR * C * 32 * H);
+#else
+    return blk_off[b];
+#endif
+}
+
 template <int C, int H, bool FALLBACK>
 __device__ __forceinline__ void convert_rows(const depth_args& a, const int4* meta, const int* blk_off, float* rows, int vbase, int nviews,
                                              int lane, long long row0, const float (&ufl)[H], float Um1f,
@@ -405,7 +441,7 @@ __device__ __forceinline__ void convert_rows(const depth_args& a, const int4* me
         }
         __syncwarp();                                               /* every lane has read the segments */
         /* radiances of the block, transposed: [c][h][lane][view j] */
-        float* blk = rows + blk_off[rb0 / DEPTH_UNR];
+        float* blk = rows + rad_block<C, H>(blk_off, rb0 / DEPTH_UNR);
 #pragma unroll
         for (int c = 0; c < C; ++c)
 #pragma unroll
@@ -475,13 +511,32 @@ depth_kernel(const depth_args a)
     __syncwarp();
     unsigned phase = 0;                                     /* mbarrier phase parity */
 
+#if RSLF_PREFETCH_ITEM
+    /* the list entry and the bounds of the NEXT item are loaded while the current one is computed */
+    int pix_n = 0; float dmin_n = a.dmin_c, dmax_n = a.dmax_c;
+    if ((long long)blockIdx.x < total) {
+        pix_n = a.items[(int)((long long)blockIdx.x / a.chunks)];
+        if (a.dmin_map) dmin_n = a.dmin_map[pix_n];
+        if (a.dmax_map) dmax_n = a.dmax_map[pix_n];
+    }
+#endif
     for (long long w = blockIdx.x; w < total; w += gridDim.x) {
         const int item = (int)(w / a.chunks);
         const int chunk = (int)(w - (long long)item * a.chunks);
+#if RSLF_PREFETCH_ITEM
+        const int pix = pix_n;
+        const float dmin = dmin_n, dmax = dmax_n;
+        if (w + gridDim.x < total) {
+            pix_n = a.items[(int)((w + gridDim.x) / a.chunks)];
+            if (a.dmin_map) dmin_n = a.dmin_map[pix_n];
+            if (a.dmax_map) dmax_n = a.dmax_map[pix_n];
+        }
+#else
         const int pix = a.items[item];
-        const int v = pix / U, u = pix - v * U;
         const float dmin = a.dmin_map ? a.dmin_map[pix] : a.dmin_c;
         const float dmax = a.dmax_map ? a.dmax_map[pix] : a.dmax_c;
+#endif
+        const int v = pix / U, u = pix - v * U;
         const int dbase = chunk * W + lane * H;
         const float uf = (float)u;
         float ufl[H];                                          /* u, or NaN for padding hypotheses (d >= D) */
@@ -541,10 +596,28 @@ depth_kernel(const depth_args a)
                     }
                     meta[r] = m;
                 }
+                any_cut = __any_sync(0xffffffffu, cut != 0);
+#if RSLF_STAGE_CPASYNC
+                (void)bytes;
+                __syncwarp();                                           /* the staging records are read by other lanes */
+                /* half a warp per view, lane q of the half copies the 16-byte pieces q, q + 16, ... of the segment */
+                const int half = lane >> 4, l16 = lane & 15;
+#pragma unroll 1
+                for (int r0 = 0; r0 < nviews; r0 += 2) {
+                    const int r = r0 + half;
+                    const int4 m = meta[r < nviews ? r : r0];
+                    const int n4 = (r < nviews) ? (m.y >> 2) : 0;
+                    const float* src = a.epi + ((row0 + (long long)(vbase + r) * U) * C - m.x);
+                    const unsigned dst = smem_u32(rows + m.z);
+                    for (int q = l16; q < n4; q += 16) cp_async16(dst + 16u * (unsigned)q, src + 4 * q);
+                }
+            }
+            cp_async_wait_all();
+            __syncwarp();
+#else
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, off);
                 if (lane == 0) mbar_arrive_expect_tx(bar, bytes);
-                any_cut = __any_sync(0xffffffffu, cut != 0);
                 for (int r = lane; r < nviews; r += 32) {
                     const int4 m = meta[r];
                     /* segment start in the stack: (row0 + s*U) * C - m.x floats, 16-byte aligned by construction */
@@ -554,6 +627,7 @@ depth_kernel(const depth_args a)
             }
             mbar_wait(bar, phase);
             phase ^= 1u;
+#endif
             /* in-place conversion of the rows; the variant with the global-memory fallback is only needed when a
              * segment was cut to its row (user-edited bounds wider than the global range) */
             if (any_cut) convert_rows<C, H, true>(a, meta, blk_off, rows, vbase, nviews, lane, row0, ufl, Um1f, Dv, cardi);
@@ -565,7 +639,7 @@ depth_kernel(const depth_args a)
                 for (int c = 0; c < C; ++c)
 #pragma unroll
                     for (int h = 0; h < H; ++h)
-                        rb[c][h] = rows[blk_off[(a.s_hat - vbase) / DEPTH_UNR] + ((c * H + h) * 32 + lane) * DEPTH_UNR + (a.s_hat - vbase) % DEPTH_UNR];
+                        rb[c][h] = rows[rad_block<C, H>(blk_off, (a.s_hat - vbase) / DEPTH_UNR) + ((c * H + h) * 32 + lane) * DEPTH_UNR + (a.s_hat - vbase) % DEPTH_UNR];
             }
             if (RV > 0 && round == 0) {
 #pragma unroll
@@ -574,7 +648,7 @@ depth_kernel(const depth_args a)
                     for (int c = 0; c < C; ++c)
 #pragma unroll
                         for (int h = 0; h < H; ++h) {
-                            const float4 t = *reinterpret_cast<const float4*>(rows + blk_off[b] + ((c * H + h) * 32 + lane) * DEPTH_UNR);
+                            const float4 t = *reinterpret_cast<const float4*>(rows + rad_block<C, H>(blk_off, b) + ((c * H + h) * 32 + lane) * DEPTH_UNR);
                             rr[b * DEPTH_UNR + 0][c][h] = t.x; rr[b * DEPTH_UNR + 1][c][h] = t.y;
                             rr[b * DEPTH_UNR + 2][c][h] = t.z; rr[b * DEPTH_UNR + 3][c][h] = t.w;
                         }
@@ -599,8 +673,7 @@ depth_kernel(const depth_args a)
                 for (int c = 0; c < C; ++c) sR[c][h] = 0.f;
             }
             float ba[DEPTH_UNR][C][H], bb[DEPTH_UNR][C][H];
-            auto load_block = [&](int bi, float (&dst)[DEPTH_UNR][C][H]) {
-                const float* blk = rows + blk_off1[bi] + lane * DEPTH_UNR;
+            auto load_block = [&](const float* blk, float (&dst)[DEPTH_UNR][C][H]) {
 #pragma unroll
                 for (int c = 0; c < C; ++c)
 #pragma unroll
@@ -609,7 +682,15 @@ depth_kernel(const depth_args a)
                         dst[0][c][h] = t.x; dst[1][c][h] = t.y; dst[2][c][h] = t.z; dst[3][c][h] = t.w;
                     }
             };
-            if (nblk > 0) load_block(0, ba);
+#if RSLF_COMPACT_BLOCKS
+            constexpr int BLK = DEPTH_UNR * C * 32 * H;                 /* floats per radiance block */
+            const float* const p0 = rows + lane * DEPTH_UNR;
+            const float* const plast = p0 + (nblk > 0 ? nblk - 1 : 0) * BLK;
+#define RSLF_BLOCK_PTR(bi) (p0 + (bi) * BLK)
+#else
+#define RSLF_BLOCK_PTR(bi) (rows + blk_off1[bi] + lane * DEPTH_UNR)
+#endif
+            if (nblk > 0) load_block(RSLF_BLOCK_PTR(0), ba);
             /* views in ascending s (the order of cv::reduce): register views first, or last (a.reg_last) */
 #pragma unroll 1
             for (int part = 0; part < 2; ++part) {
@@ -617,12 +698,30 @@ depth_kernel(const depth_args a)
 #pragma unroll
                     for (int j = 0; j < RV; j += 2) ms_accumulate_pair<C, H, NONNEG>(rr[j], rr[RV > 1 ? j + 1 : 0], rb, inv, NZ, sR, sK);
                 } else {
-                    int bi = 0;
-                    for (; bi + 2 <= nblk; bi += 2) {
-                        load_block(bi + 1, bb);
+#if RSLF_COMPACT_BLOCKS
+                    /* two blocks per step, running pointer, the prefetch of the step after the last clamped to the last block */
+                    const float* p = p0;
+RSLF_PRAGMA(unroll RSLF_MS_UNROLL)
+                    for (int n = nblk >> 1; n > 0; --n) {
+                        load_block(p + BLK, bb);
 #pragma unroll
                         for (int j = 0; j < DEPTH_UNR; j += 2) ms_accumulate_pair<C, H, NONNEG>(ba[j], ba[j + 1], rb, inv, NZ, sR, sK);
-                        load_block(min(bi + 2, nblk - 1), ba);                   /* last: harmless re-read */
+                        p += 2 * BLK;
+                        load_block(p < plast ? p : plast, ba);
+#pragma unroll
+                        for (int j = 0; j < DEPTH_UNR; j += 2) ms_accumulate_pair<C, H, NONNEG>(bb[j], bb[j + 1], rb, inv, NZ, sR, sK);
+                    }
+                    if (nblk & 1) {
+#pragma unroll
+                        for (int j = 0; j < DEPTH_UNR; j += 2) ms_accumulate_pair<C, H, NONNEG>(ba[j], ba[j + 1], rb, inv, NZ, sR, sK);
+                    }
+#else
+                    int bi = 0;
+                    for (; bi + 2 <= nblk; bi += 2) {
+                        load_block(RSLF_BLOCK_PTR(bi + 1), bb);
+#pragma unroll
+                        for (int j = 0; j < DEPTH_UNR; j += 2) ms_accumulate_pair<C, H, NONNEG>(ba[j], ba[j + 1], rb, inv, NZ, sR, sK);
+                        load_block(RSLF_BLOCK_PTR(min(bi + 2, nblk - 1)), ba);   /* last: harmless re-read */
 #pragma unroll
                         for (int j = 0; j < DEPTH_UNR; j += 2) ms_accumulate_pair<C, H, NONNEG>(bb[j], bb[j + 1], rb, inv, NZ, sR, sK);
                     }
@@ -630,8 +729,10 @@ depth_kernel(const depth_args a)
 #pragma unroll
                         for (int j = 0; j < DEPTH_UNR; j += 2) ms_accumulate_pair<C, H, NONNEG>(ba[j], ba[j + 1], rb, inv, NZ, sR, sK);
                     }
+#endif
                 }
             }
+#undef RSLF_BLOCK_PTR
             /* r_bar = sum_rK / sum_K (x / 0 = 0 as in OpenCV 3), then max(., 0) (core.hpp:606-609) */
 #pragma unroll
             for (int h = 0; h < H; ++h) {
