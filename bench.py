@@ -13,9 +13,10 @@ device-side work lists and equals the oracle's.
   e2e   : the same through the host-facing API (FineToCoarse / Depth2DComputer
           mirror classes -> C ABI) with pinned HOST buffers: H2D of the stack and
           D2H of the result maps inside the timed region
-  --impl reference : the CPU path (oracle/, the line-by-line restatement of the
-          reference's OpenMP path — the reference itself needs OpenCV 3.x C++ and
-          cannot be built in this image) on a bounded sample, all host threads.
+  --impl reference : the reference's CPU/OpenMP path on a bounded sample, all host
+          threads: its own sources compiled against the stand-in OpenCV headers of
+          oracle/cvshim (oracle/_ref/librslf_ref.so, built where /root/reference exists
+          and shipped with the snapshot), else the restated oracle (oracle/).
 """
 import argparse
 import json
@@ -94,8 +95,32 @@ def cpu_sample(cfg, rows):
     return epis
 
 
-def run_cpu(cfg, epis):
+def cpu_kind():
+    """"reference": the reference's own sources (oracle/_ref/librslf_ref.so, built in the CPU container from
+    /root/reference against the stand-in OpenCV headers of oracle/cvshim and shipped with the snapshot);
+    "port": the restated oracle (oracle/rslf_oracle.cpp) when that library is absent.  RSLF_CPU_BASELINE overrides."""
+    from oracle import ref
+    want = os.environ.get("RSLF_CPU_BASELINE", "")
+    if want in ("port", "reference"):
+        return want
+    return "reference" if os.path.exists(ref.LIB_PATH) else "port"
+
+
+def run_cpu(cfg, epis, kind="port", samples=None):
+    """One CPU pass over the sample; returns (samples evaluated, seconds).  The reference build does not count its
+    work: its sample count is the oracle's on the same input (identical results, counted once, untimed)."""
     import oracle
+    if kind == "reference":
+        from oracle import ref
+        t0 = time.perf_counter()
+        if cfg["mode"] == "ftc":
+            ref.fine_to_coarse(epis, DMIN, DMAX, cfg["D"], scale_factor=cfg["scale"])
+        else:
+            ref.depth2d(epis, DMIN, DMAX, cfg["D"], scale_factor=cfg["scale"])
+        t = time.perf_counter() - t0
+        if samples is None:
+            samples = run_cpu(cfg, epis, "port")[0]
+        return samples, t
     t0 = time.perf_counter()
     if cfg["mode"] == "ftc":
         r = oracle.fine_to_coarse(epis, DMIN, DMAX, cfg["D"], scale_factor=cfg["scale"], want_levels=False)
@@ -106,42 +131,58 @@ def run_cpu(cfg, epis):
     return samples, time.perf_counter() - t0
 
 
-def cpu_rows(cfg, budget_s=15.0):
+def cpu_threads(kind):
+    """All host cores for the CPU arm (torchrun exports OMP_NUM_THREADS=1)."""
+    import oracle
+    n = os.cpu_count() or 1
+    oracle.set_num_threads(n)
+    if kind == "reference":
+        from oracle import ref
+        ref.set_num_threads(n)
+        return ref.num_threads()
+    return oracle.num_threads()
+
+
+def cpu_rows(cfg, budget_s=15.0, kind="port"):
     """Rows of the CPU sample: sized from a probe so that one pass takes roughly budget_s."""
-    probe_rows = 12 if cfg["mode"] == "ftc" else 4
+    # the reference parallelises over image rows (core.hpp:743, 799, 1088): at least one row per host thread
+    cores = os.cpu_count() or 1
+    probe_rows = max(12, min(cores, cfg["V"])) if cfg["mode"] == "ftc" else max(4, min(cores, cfg["V"]))
     epis = cpu_sample(cfg, probe_rows)
-    _, t = run_cpu(cfg, epis)
+    _, t = run_cpu(cfg, epis, kind, samples=0.0)
     rows = int(max(probe_rows, min(cfg["V"], probe_rows * budget_s / max(t, 1e-3))))
-    if cfg["mode"] == "ftc":
-        rows = max(12, rows)
+    if rows > cores:
+        rows -= rows % cores                       # whole rounds of rows over the threads
     return rows
 
 
 def reference_arm(args, cfg, name):
-    """The reference's CPU/OpenMP path (restated in oracle/) on the host cores, bounded sample per step."""
+    """The reference's CPU/OpenMP path on the host cores (its own sources when oracle/_ref was shipped, else the
+    restated oracle), bounded sample per step."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import oracle
-    oracle.set_num_threads(os.cpu_count() or 1)      # torchrun exports OMP_NUM_THREADS=1; the arm uses every host core
-    cores = oracle.num_threads()
-    rows = cpu_rows(cfg, budget_s=max(3.0, 60.0 / max(1, args.steps + args.warmup)))
+    kind = cpu_kind()
+    cores = cpu_threads(kind)
+    rows = cpu_rows(cfg, budget_s=max(3.0, 60.0 / max(1, args.steps + args.warmup)), kind=kind)
     epis = cpu_sample(cfg, rows)
+    count = run_cpu(cfg, epis, "port")[0]                 # samples of one pass (the oracle counts; results are identical)
     for _ in range(args.warmup):
-        run_cpu(cfg, epis)
+        run_cpu(cfg, epis, kind, samples=count)
     tot_s, tot_t = 0.0, 0.0
     for _ in range(args.steps):
-        s, t = run_cpu(cfg, epis)
+        s, t = run_cpu(cfg, epis, kind, samples=count)
         tot_s += s
         tot_t += t
     v = tot_s / tot_t
-    sample = "%d-row band of the %s light field (all %d views, all %d columns, D=%d, %s)" % (
-        rows, name, cfg["S"], cfg["U"], cfg["D"], cfg["mode"])
+    sample = "%d-row band of the %s light field (all %d views, all %d columns, D=%d, %s)%s" % (
+        rows, name, cfg["S"], cfg["U"], cfg["D"], cfg["mode"],
+        "; reference sources + stand-in OpenCV primitives (oracle/cvshim)" if kind == "reference" else "; restated oracle")
     line = {"impl": "reference", "metric": "EPI samples/sec (pixel x disparity x view)", "value": v, "unit": "samples/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot_t / args.steps * 1e3,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": name + ": " + cfg["desc"], "sample": sample},
-            "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -338,14 +379,16 @@ def main():
         }
         cpu = None
         if not args.no_cpu and world == 1:          # the CPU baseline is timed at N = 1 only
-            import oracle
-            oracle.set_num_threads(os.cpu_count() or 1)
-            rows = cpu_rows(cfg, budget_s=15.0)
+            kind = cpu_kind()
+            cores = cpu_threads(kind)
+            rows = cpu_rows(cfg, budget_s=15.0, kind=kind)
             ce = cpu_sample(cfg, rows)
-            cs, ct = run_cpu(cfg, ce)
-            cpu = {"value": cs / ct, "unit": "samples/s", "cores": oracle.num_threads(), "kind": "port",
-                   "sample": "%d-row band of the %s light field (all views, all columns, D=%d, %s), %.1f s" % (
-                       rows, name, D, cfg["mode"], ct)}
+            cs, ct = run_cpu(cfg, ce, kind)
+            cpu = {"value": cs / ct, "unit": "samples/s", "cores": cores, "kind": kind,
+                   "sample": "%d-row band of the %s light field (all views, all columns, D=%d, %s), %.1f s; %s" % (
+                       rows, name, D, cfg["mode"], ct,
+                       "the reference's own sources + stand-in OpenCV primitives (oracle/_ref, oracle/cvshim)"
+                       if kind == "reference" else "restated oracle (oracle/rslf_oracle.cpp)")}
         line = {
             "metric": "EPI samples/sec (pixel x disparity x view)", "value": value, "unit": "samples/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / args.steps * 1e3,

@@ -6,12 +6,19 @@
  * this file; it is used by tests/, __graft_entry__.smoke() and bench.py's
  * cpu_baseline / --impl reference legs as the checker and the timed CPU arm.
  *
- * PARITY PIN STATUS: the reference cannot be compiled here (it needs OpenCV 3.x
- * C++ headers/libs; only the cv2 4.13 Python wheel exists) and its repository
- * holds no golden vectors or asserting tests ("parity unpinned" by the
- * reference's own tests).  This restatement is pinned instead against a cv2
- * mirror of the reference's exact OpenCV call sequence (oracle/cv2_mirror.py,
- * fixtures in tests/golden/, checked by tests/test_oracle_vs_cv2.py).
+ * PARITY PIN STATUS: the reference's repository holds no golden vectors or
+ * asserting tests, and it cannot be linked against the real OpenCV here (no
+ * OpenCV C++ headers/libs in the image, only the cv2 4.13 Python wheel).  This
+ * restatement is pinned two ways:
+ *  (1) against the REFERENCE'S OWN SOURCES, compiled where they lie against a
+ *      stand-in for the OpenCV calls they make (oracle/cvshim, oracle/ref_driver.cpp
+ *      -> oracle/_ref/librslf_ref.so): every map of Depth1DComputer_pile,
+ *      Depth2DComputer and FineToCoarse bit-identical (tests/test_oracle_vs_reference.py,
+ *      fixtures tests/golden/ref_*.npz).  This pins all control flow of the path;
+ *  (2) the OpenCV primitives themselves (which (1) takes from the stand-in) against
+ *      the real library: a cv2 4.13 replay of the reference's exact call sequence
+ *      (oracle/cv2_mirror.py, tests/golden/px_*, down_*, fuse_*, tests/test_oracle_vs_cv2.py).
+ * What stays unpinned: OpenCV 3.x-vs-4.x differences inside primitives.
  *
  * Every function cites the reference lines it follows (paths relative to
  * /root/reference/RSLightFields).  All arithmetic is float32 with one rounding

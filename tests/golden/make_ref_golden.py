@@ -1,0 +1,92 @@
+"""Writes tests/golden/ref_*.npz: outputs of the REFERENCE'S OWN code (oracle/_ref/librslf_ref.so = the sources under
+/root/reference/RSLightFields compiled against oracle/cvshim) on small seeded inputs.  Run in the CPU container:
+
+    python tests/golden/make_ref_golden.py
+
+`run_case` is shared with the tests so that the oracle and the CUDA path are run with exactly the same arguments:
+side "ref" = the reference build, "oracle" = oracle/rslf_oracle.cpp, "gpu" = the CUDA library through api.py.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# name -> (kind, S, V, U, C, uint8 input, scale factor, dmin, dmax, D, seed)
+CASES = {
+    "ref_pile_c3": ("pile", 9, 6, 48, 3, False, 1.0, -1.0, 2.0, 40, 901),
+    "ref_pile_c1_u8": ("pile", 8, 6, 48, 1, True, -1.0, -1.0, 2.0, 33, 902),
+    "ref_2d_c3": ("2d", 5, 8, 40, 3, False, 1.0, -1.0, 2.0, 24, 903),
+    "ref_ftc_c1": ("ftc", 4, 26, 44, 1, False, -1.0, -1.0, 2.0, 20, 904),
+    "ref_ftc_c3_u8": ("ftc", 3, 24, 40, 3, True, -1.0, -1.0, 2.0, 16, 905),
+}
+PILE_KEYS = ["best_depth", "edge_conf", "edge_mask", "disp_conf", "rbar"]
+
+
+def make_input(name):
+    from remotesensingproject_b200.synth import make_light_field_np
+    kind, S, V, U, C, as_u8, scale, dmin, dmax, D, seed = CASES[name]
+    epis, _ = make_light_field_np(S, V, U, C, dmin=dmin, dmax=dmax, seed=seed, layers=5)
+    if as_u8:
+        return np.clip(np.rint(epis * 255.0), 0, 255).astype(np.uint8)
+    if scale < 0:
+        return (epis * 200.0 + 3.0).astype(np.float32)
+    return epis
+
+
+def run_case(name, epis, side="ref", oracle_side=False, ctx=None):
+    kind, S, V, U, C, as_u8, scale, dmin, dmax, D, seed = CASES[name]
+    if oracle_side:
+        side = "oracle"
+    if side == "ref":
+        from oracle import ref
+        if kind == "pile":
+            r = ref.depth1d_pile(epis, dmin, dmax, D, scale_factor=scale)
+            return {k: r[k] for k in PILE_KEYS}
+        if kind == "2d":
+            r = ref.depth2d(epis, dmin, dmax, D, scale_factor=scale)
+            return {k: r[k] for k in PILE_KEYS + ["valid"]}
+        r = ref.fine_to_coarse(epis, dmin, dmax, D, scale_factor=scale)
+        return dict(map=r["map"], valid=r["valid"])
+    if side == "oracle":
+        import oracle
+        if kind == "pile":
+            r = oracle.depth1d_pile(oracle.normalise(epis, scale), dmin, dmax, D)
+            return {k: r[k] for k in PILE_KEYS}
+        if kind == "2d":
+            r = oracle.depth2d(oracle.normalise(epis, scale), dmin, dmax, D)
+            out = {k: r[k] for k in PILE_KEYS}
+            out["valid"] = np.where(r["edge_conf"] > np.float32(0.02), 255, 0).astype(np.uint8)
+            return out
+        r = oracle.fine_to_coarse(epis, dmin, dmax, D, scale_factor=scale)
+        return dict(map=r["map"], valid=r["valid"])
+    from remotesensingproject_b200 import api
+    if kind == "pile":
+        c = api.Depth1DComputer_pile(epis, dmin, dmax, D, epi_scale_factor=scale, ctx=ctx).run()
+        return dict(best_depth=c.m_best_depth_v_u, edge_conf=c.m_edge_confidence_v_u, edge_mask=c.m_edge_confidence_mask_v_u,
+                    disp_conf=c.m_disp_confidence_v_u, rbar=c.m_rbar_v_u)
+    if kind == "2d":
+        c = api.Depth2DComputer(epis, dmin, dmax, D, epi_scale_factor=scale, ctx=ctx).run()
+        return dict(best_depth=c.m_best_depth_s_v_u, edge_conf=c.m_edge_confidence_s_v_u,
+                    edge_mask=c.m_edge_confidence_mask_s_v_u, disp_conf=c.m_disp_confidence_s_v_u, rbar=c.m_rbar_s_v_u,
+                    valid=c.get_valid_depths_mask_s_v_u())
+    f = api.FineToCoarse(epis, dmin, dmax, D, epi_scale_factor=scale, ctx=ctx).run()
+    m, v = f.get_results()
+    return dict(map=m, valid=v)
+
+
+def main():
+    here = os.path.dirname(os.path.abspath(__file__))
+    for name in CASES:
+        epis = make_input(name)
+        out = run_case(name, epis, side="ref")
+        path = os.path.join(here, name + ".npz")
+        np.savez_compressed(path, epis=epis, **out)
+        print("%s: %d bytes, %d confident pixels" % (path, os.path.getsize(path), int((out.get("edge_mask", out.get("valid")) > 0).sum())))
+
+
+if __name__ == "__main__":
+    main()

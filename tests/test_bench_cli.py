@@ -17,9 +17,19 @@ def test_reference_arm_prints_contract_line():
               "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert k in line, k
     assert line["unit"] == "samples/s" and line["value"] > 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    shipped = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "librslf_ref.so"))
+    assert line["cpu_baseline"]["kind"] == ("reference" if shipped else "port") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in line["config"]
+
+
+def test_reference_arm_falls_back_to_the_port():
+    env = dict(os.environ, RSLF_CPU_BASELINE="port")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", "tiny",
+                        "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stderr
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["cpu_baseline"]["kind"] == "port" and line["value"] > 0
 
 
 def test_reference_arm_other_ranks_stay_silent():

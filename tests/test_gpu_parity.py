@@ -382,6 +382,51 @@ def test_row_work_profile(gpu_ctx):
     assert int(w.sum()) == int(ref["computed_pixels"])
 
 
+# --------------------------------------------------------------------------- against the reference's own code
+def _ref_cases():
+    import importlib.util
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "make_ref_golden.py")
+    spec = importlib.util.spec_from_file_location("make_ref_golden", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.parametrize("name", ["ref_pile_c3", "ref_pile_c1_u8", "ref_2d_c3", "ref_ftc_c1", "ref_ftc_c3_u8"])
+def test_against_reference_fixtures(gpu_ctx, golden_dir, name):
+    """tests/golden/ref_*.npz were written by the reference's own sources (compiled against oracle/cvshim):
+    every map of the CUDA path must be bit-identical to them."""
+    mod = _ref_cases()
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    out = mod.run_case(name, g["epis"], side="gpu", ctx=gpu_ctx)
+    for k in g.files:
+        if k != "epis":
+            np.testing.assert_array_equal(out[k], g[k], err_msg="%s:%s" % (name, k))
+
+
+@pytest.mark.parametrize("S,V,U,C,D,as_u8", [(12, 48, 96, 3, 64, False), (9, 52, 110, 1, 48, True), (16, 40, 72, 3, 40, True)])
+def test_against_reference_build(gpu_ctx, S, V, U, C, D, as_u8):
+    """The reference build itself (oracle/_ref/librslf_ref.so travels with the snapshot): larger fine-to-coarse runs than
+    the fixtures hold, all levels and the fused result bit-identical."""
+    from oracle import ref
+    if not os.path.exists(ref.LIB_PATH):
+        pytest.skip("oracle/_ref/librslf_ref.so was not shipped")
+    epis = lf(S, V, U, C, seed=700 + V)
+    if as_u8:
+        epis = np.clip(np.rint(epis * 255.0), 0, 255).astype(np.uint8)
+    dims = oracle.pyramid_dims(V, U)
+    r = ref.fine_to_coarse(epis, -1.0, 2.0, D, scale_factor=-1.0 if as_u8 else 1.0, dims=dims)
+    f = api.FineToCoarse(epis, -1.0, 2.0, D, epi_scale_factor=-1.0 if as_u8 else 1.0, ctx=gpu_ctx).run()
+    m, v = f.get_results()
+    np.testing.assert_array_equal(v, r["valid"])
+    np.testing.assert_array_equal(m, r["map"])
+    levels = f.get_levels()
+    assert len(levels) == len(dims)
+    for p, lv in enumerate(levels):
+        for k in ("edge_mask", "best_depth", "disp_conf"):
+            np.testing.assert_array_equal(lv[k], r["levels"][p][k], err_msg="level %d %s" % (p, k))
+
+
 def test_row_sharded_run_equals_single_gpu():
     """Two ranks on two GPUs (torchrun + NCCL): every output block is bit-identical to the one-GPU result.
     Skipped on boxes with a single GPU (the driver's -m gpu run); tools/multigpu_check.py is the same check."""
