@@ -12,6 +12,10 @@
 #include "rslf_common.cuh"
 #include "k_edge.cuh"
 #include "k_depth.cuh"
+#ifndef RSLF_DEPTH_TMEM_DEFAULT
+#define RSLF_DEPTH_TMEM_DEFAULT 1
+#endif
+#include "k_depth_tm.cuh"
 #include "k_median.cuh"
 #include "k_propagate.cuh"
 #include "k_pyramid.cuh"
@@ -523,6 +527,21 @@ static int run_depth_pass(rslf_ctx* ctx, const rslf_params& P, const pass_io& io
         return RSLF_OK;
     };
     depth_plan plan = plan_depth(ctx, S, C, io.D, io.s_hat, io.dmin, io.dmax, P.slope_factor);
+    /* tensor-memory variant (k_depth_tm.cuh): RSLF_DEPTH_TMEM = 0 off, 1 RGB stacks (the planner's H = 1 case), 2 every stack */
+    depth_tm_layout tml; bool use_tm = false;
+    {
+        const char* et = getenv("RSLF_DEPTH_TMEM");
+        const int mode = et ? atoi(et) : RSLF_DEPTH_TMEM_DEFAULT;
+        const bool forced = getenv("RSLF_DEPTH_H") || getenv("RSLF_DEPTH_RV");
+        if (mode > 0 && !forced && (mode >= 2 || C == 3)) {
+            const int wpv1 = depth_wpv_q16(io.D, 1, io.dmin, io.dmax, P.slope_factor);
+            if (depth_tm_build(tml, S, C, io.s_hat, wpv1, ctx->smem_optin)) {
+                use_tm = true;
+                plan.H = 1; plan.RV = DEPTH_TM_RV; plan.reg_last = tml.reg_last; plan.wpv_q16 = wpv1;
+                plan.chunks = rslf_div_up(io.D, 32);
+            }
+        }
+    }
     if (plan.chunks > 1) RSLF_TRY(ensure_partials(ctx, plane * plan.chunks));
     depth_args a;
     a.epi = L.epi; a.V = V; a.S = S; a.U = U; a.D = io.D; a.s_hat = io.s_hat; a.slope = P.slope_factor;
@@ -552,7 +571,8 @@ static int run_depth_pass(rslf_ctx* ctx, const rslf_params& P, const pass_io& io
         {
             stage_scope sc(ctx, ST_DEPTH);
             depth_args ab = a; ab.items = items_b; ab.count = count2;
-            RSLF_TRY(launch_depth(ctx, C, L.nonneg != 0, ab, plan));
+            if (use_tm) RSLF_TRY(launch_depth_tm(ctx, C, L.nonneg != 0, ab, tml));
+            else RSLF_TRY(launch_depth(ctx, C, L.nonneg != 0, ab, plan));
         }
         {
             stage_scope sc(ctx, ST_MEDIAN);
@@ -569,7 +589,8 @@ static int run_depth_pass(rslf_ctx* ctx, const rslf_params& P, const pass_io& io
     }
     {
         stage_scope sc(ctx, ST_DEPTH);
-        RSLF_TRY(launch_depth(ctx, C, L.nonneg != 0, a, plan));
+        if (use_tm) RSLF_TRY(launch_depth_tm(ctx, C, L.nonneg != 0, a, tml));
+        else RSLF_TRY(launch_depth(ctx, C, L.nonneg != 0, a, plan));
     }
     {
         stage_scope sc(ctx, ST_MEDIAN);

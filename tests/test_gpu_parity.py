@@ -124,6 +124,43 @@ def test_depth1d_pile_register_views_at_either_end(gpu_ctx, monkeypatch, S, C, D
     assert_maps_equal(gpu, ref, ["edge_mask", "edge_conf", "raw_depth", "best_depth", "rbar", "disp_conf"])
 
 
+# tensor-memory variant of the depth kernel (k_depth_tm.cuh): 16 views in registers, up to 128 / (4 C) * 4 views in
+# TMEM, the rest in shared memory; RSLF_DEPTH_TMEM=2 selects it for every stack it fits
+TMEM_CASES = [
+    # S, C, D, s_hat (-1 = centre), U
+    (24, 3, 40, -1, 48), (37, 3, 70, 3, 48), (37, 3, 33, 35, 48), (60, 3, 40, -1, 40), (60, 3, 100, 0, 40), (60, 3, 64, 59, 40),
+    (100, 3, 48, -1, 64), (100, 3, 40, 99, 64), (100, 3, 40, 2, 64), (21, 3, 20, 10, 40), (19, 3, 20, 4, 40),
+    (40, 1, 70, -1, 48), (150, 1, 40, 7, 40), (200, 1, 36, -1, 40),
+]
+
+
+@pytest.mark.parametrize("S,C,D,s_hat,U", TMEM_CASES)
+def test_depth1d_pile_tensor_memory_variant(gpu_ctx, monkeypatch, S, C, D, s_hat, U):
+    monkeypatch.delenv("RSLF_DEPTH_H", raising=False)
+    monkeypatch.delenv("RSLF_DEPTH_RV", raising=False)
+    monkeypatch.setenv("RSLF_DEPTH_TMEM", "2")
+    epis = lf(S, 3, U, C, seed=500 + S + D, dmin=-1.0, dmax=1.5)
+    comp = api.Depth1DComputer_pile(epis, -1.0, 1.5, D, s_hat=s_hat, epi_scale_factor=1.0, ctx=gpu_ctx).run()
+    ref = oracle.depth1d_pile(oracle.normalise(epis, 1.0), -1.0, 1.5, D, s_hat=s_hat)
+    gpu = dict(best_depth=comp.m_best_depth_v_u, edge_conf=comp.m_edge_confidence_v_u,
+               edge_mask=comp.m_edge_confidence_mask_v_u, disp_conf=comp.m_disp_confidence_v_u,
+               rbar=comp.m_rbar_v_u, raw_depth=comp.m_raw_depth_v_u)
+    assert ref["computed_pixels"] > 0
+    assert_maps_equal(gpu, ref, ["edge_mask", "edge_conf", "raw_depth", "best_depth", "rbar", "disp_conf"])
+
+
+def test_fine_to_coarse_tensor_memory_variant(gpu_ctx, monkeypatch):
+    """Whole pipeline with the tensor-memory kernel: per-pixel bounds (coarse levels), negative radiances."""
+    monkeypatch.setenv("RSLF_DEPTH_TMEM", "2")
+    for C, shift in ((3, 0.0), (1, 0.0), (3, -0.15)):
+        epis = lf(28, 30, 60, C, seed=640 + C) + np.float32(shift)
+        f = api.FineToCoarse(epis, -1.0, 2.0, 40, epi_scale_factor=1.0, ctx=gpu_ctx).run()
+        m, v = f.get_results()
+        r = oracle.fine_to_coarse(epis, -1.0, 2.0, 40, scale_factor=1.0)
+        np.testing.assert_array_equal(v, r["valid"])
+        np.testing.assert_array_equal(m, r["map"])
+
+
 def test_depth1d_pile_uint8_and_max_scale(gpu_ctx):
     epis = lf(7, 6, 48, 3, seed=5)
     u8 = np.clip(np.rint(epis * 255.0), 0, 255).astype(np.uint8)
