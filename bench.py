@@ -364,8 +364,17 @@ def main():
         flops = FLOPS_PER_SAMPLE[C]
         depth_s = acc["ms_depth"] * 1e-3
         achieved = (acc["samples"] * flops / depth_s) * 1e-12 if depth_s > 0 else None
+        # DRAM traffic of the dominant kernel: bytes per sample of the ncu --set full capture (profiles/), scaled to the
+        # average launch of this run (the capture is one launch on a band of the same light field, see profiles/README.md)
+        traffic, traffic_note = None, None
+        cap = os.path.join(ROOT, "profiles", "depth_kernel_capture_r01c.json")
+        if C == 3 and os.path.exists(cap):
+            bps = json.load(open(cap))["dram_bytes_per_sample"]
+            traffic = bps * acc["samples"] / max(1.0, acc["depth_launches"])
+            traffic_note = ("%.4f B/sample (dram__bytes_read+write of profiles/depth_kernel_capture_r01c.json) x samples_per_launch; "
+                            "algorithmic HBM bytes are the scanline segments, shared by neighbouring pixels through L2" % bps)
         roofline = {
-            "kernel": "depth_kernel (radiance sampling + mean shift + score + argmax)",
+            "kernel": "depth_kernel_tm / depth_kernel (radiance sampling + mean shift + score + argmax)",
             "bound": "fp32", "unit": "TFLOP/s", "achieved": achieved, "peak": fma * 1e-3,
             "frac": (achieved / (fma * 1e-3)) if achieved else None,
             "peak_kind": "measured in this run: FFMA micro-benchmark x2 flops (MEASURED_PEAKS.json holds only HBM / "
@@ -374,7 +383,8 @@ def main():
             "frac_of_nofma_issue": (achieved / (nofma * 1e-3)) if achieved else None,
             "flops_per_sample": flops, "samples_per_launch": acc["samples"] / max(1.0, acc["depth_launches"]),
             "avg_launch_ms": acc["ms_depth"] / max(1.0, acc["depth_launches"]),
-            "share_of_step": acc["ms_depth"] / acc["ms_total"], "traffic": None,
+            "share_of_step": acc["ms_depth"] / acc["ms_total"], "traffic": traffic, "traffic_note": traffic_note,
+            "hbm_gbs_of_kernel": (traffic / (acc["ms_depth"] / max(1.0, acc["depth_launches"]) * 1e-3) * 1e-9) if traffic else None,
             "hbm_peak_gbs": peaks.get("hbm_gbs"), "hbm_peak_kind": peak_kind,
         }
         cpu = None
