@@ -256,6 +256,14 @@ int rslf_cuda_get_row_work(rslf_ctx* ctx, unsigned* rows_out /* V entries */);
 int rslf_cuda_measure_fp32_peak(rslf_ctx* ctx, double* gops_nofma, double* gflops_fma);
 /* The same separately rounded multiply / add mix issued as packed FP32x2 instructions (FFMA2 / FADD2). */
 int rslf_cuda_measure_fp32x2_peak(rslf_ctx* ctx, double* gops_nofma_packed);
+/* Host-side planning of the tensor-memory depth kernel for one pass (no device needed): how the S views of a
+ * warp item are split over registers / tensor memory / shared memory and packed into staging rounds.
+ * out[0..7] = {fits (0/1), register views, tensor-memory views, shared-memory views, registers at the high end
+ * (0/1), staging rounds, shared-memory bytes per warp, warps per SM}; rounds (optional, 3 ints per round) =
+ * {first 4-view block, number of blocks, destination kind 0 registers / 1 tensor memory / 2 shared memory};
+ * blocks (optional, 2 ints per 4-view block) = {staging offset in floats inside its round, floats per staged view}. */
+int rslf_plan_depth_tm(int S, int C, int D, int s_hat, float dmin, float dmax, float slope, size_t smem_limit,
+                       int* out8, int* rounds, int* blocks);
 /* Writes >126 MB on the device so the next timed step starts with a cold L2. */
 int rslf_cuda_flush_l2(rslf_ctx* ctx);
 int rslf_cuda_sync(rslf_ctx* ctx);

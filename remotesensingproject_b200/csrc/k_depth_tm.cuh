@@ -85,6 +85,13 @@ static inline bool depth_tm_build(depth_tm_layout& L, int S, int C, int s_hat, i
         int area = std::max(areaS, areaR);
         /* tensor-memory rounds: greedy packing into the area (grown if a single block needs more) */
         for (int i = 0; i < nbT; ++i) area = std::max(area, DEPTH_UNR * maxseg(T.tm_b0 + i));
+        /* the area may as well be as large as twelve warps allow: fewer tensor-memory rounds, i.e. fewer TMA waits */
+        {
+            const int meta_cap = std::max(RV, std::max(T.TV, T.SV));
+            const long long per_warp = ((long long)smem_limit - 64) / DEPTH_TM_WARPS - 16 - 16LL * meta_cap;
+            const int cap = (int)std::min<long long>(per_warp / 4, 4LL * 65535) & ~3;
+            if (cap > area) area = cap;
+        }
         int nr = 0, meta = std::max(RV, T.SV);
         auto push_round = [&](int b0, int nb, int kind) {
             if (nb <= 0) return true;
@@ -115,7 +122,9 @@ static inline bool depth_tm_build(depth_tm_layout& L, int S, int C, int s_hat, i
         T.warp_bytes = 16 + 16 * meta + 4 * area;
         T.warp_bytes = (T.warp_bytes + 15) & ~15;
         if (area / 4 > 65535) continue;
-        if (!have || T.warp_bytes < best.warp_bytes) { best = T; have = true; }
+        if ((size_t)T.warp_bytes * DEPTH_TM_WARPS + 64 > smem_limit) continue;
+        /* fewer staging rounds first, then the smaller footprint */
+        if (!have || T.nrounds < best.nrounds || (T.nrounds == best.nrounds && T.warp_bytes < best.warp_bytes)) { best = T; have = true; }
     }
     if (!have) return false;
     if ((size_t)best.warp_bytes * DEPTH_TM_WARPS + 64 > smem_limit) return false;

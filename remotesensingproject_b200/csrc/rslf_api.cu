@@ -1314,6 +1314,23 @@ extern "C" int rslf_cuda_fuse_disp_maps(rslf_ctx* ctx, int levels, int S, const 
 }
 
 /* ------------------------------------------------------------------ measurement */
+extern "C" int rslf_plan_depth_tm(int S, int C, int D, int s_hat, float dmin, float dmax, float slope, size_t smem_limit,
+                                  int* out8, int* rounds, int* blocks)
+{
+    if (!out8 || S < 1 || (C != 1 && C != 3) || D < 2) return RSLF_ERR_ARG;
+    depth_tm_layout L; memset(&L, 0, sizeof(L));
+    const int wpv = depth_wpv_q16(D, 1, dmin, dmax, slope);
+    const bool ok = depth_tm_build(L, S, C, s_hat, wpv, smem_limit);
+    out8[0] = ok ? 1 : 0; out8[1] = DEPTH_TM_RV; out8[2] = L.TV; out8[3] = L.SV; out8[4] = L.reg_last;
+    out8[5] = L.nrounds; out8[6] = L.warp_bytes; out8[7] = DEPTH_TM_WARPS;
+    if (!ok) return RSLF_OK;
+    if (rounds)
+        for (int r = 0; r < L.nrounds; ++r) { rounds[3 * r] = L.round_b0[r]; rounds[3 * r + 1] = L.round_nb[r]; rounds[3 * r + 2] = L.round_kind[r]; }
+    if (blocks)
+        for (int b = 0; b < depth_padded_views(S) / DEPTH_UNR; ++b) { blocks[2 * b] = 4 * (int)L.blk_off4[b]; blocks[2 * b + 1] = L.blk_pitch[b]; }
+    return RSLF_OK;
+}
+
 extern "C" int rslf_cuda_measure_fp32_peak(rslf_ctx* ctx, double* gops_nofma, double* gflops_fma)
 {
     if (!ctx) return RSLF_ERR_ARG;

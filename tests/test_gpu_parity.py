@@ -255,6 +255,30 @@ def test_depth2d_bounds_wider_than_global_range(gpu_ctx):
     np.testing.assert_array_equal(comp.m_rbar_s_v_u, ref["rbar"])
 
 
+@pytest.mark.parametrize("C", [3, 1])
+def test_depth2d_bounds_tensor_memory_variant(gpu_ctx, monkeypatch, C):
+    """Per-pixel bounds (incl. dmin == dmax) and bounds far wider than the constructor's range (segments cut to their
+    staging rows -> global-memory fallback) through the tensor-memory kernel."""
+    monkeypatch.setenv("RSLF_DEPTH_TMEM", "2")
+    S, V, U, D = 24, 3, 120, 40
+    epis = lf(S, V, U, C, seed=91 + C, dmin=-2.0, dmax=2.0)
+    rng = np.random.default_rng(5)
+    lo = rng.uniform(-1.0, 0.5, (S, V, U)).astype(np.float32)
+    hi = (lo + rng.uniform(0.0, 1.5, (S, V, U))).astype(np.float32)
+    hi[0, 0, :8] = lo[0, 0, :8]
+    for (a, b, gmin, gmax) in ((lo, hi, -1.0, 2.0),
+                               (np.full((S, V, U), -9.0, np.float32), np.full((S, V, U), 9.0, np.float32), 0.0, 0.25)):
+        comp = api.Depth2DComputer(epis, gmin, gmax, D, epi_scale_factor=1.0, ctx=gpu_ctx)
+        comp.edit_dmin()[:] = a
+        comp.edit_dmax()[:] = b
+        comp.run()
+        ref = oracle.depth2d(oracle.normalise(epis, 1.0), gmin, gmax, D, dmin_svu=a, dmax_svu=b)
+        np.testing.assert_array_equal(comp.m_edge_confidence_mask_s_v_u, ref["edge_mask"])
+        np.testing.assert_array_equal(comp.m_best_depth_s_v_u, ref["best_depth"])
+        np.testing.assert_array_equal(comp.m_disp_confidence_s_v_u, ref["disp_conf"])
+        np.testing.assert_array_equal(comp.m_rbar_s_v_u, ref["rbar"])
+
+
 # --------------------------------------------------------------------------- FineToCoarse
 @pytest.mark.parametrize("S,V,U,C,D,scale", [(5, 44, 60, 3, 16, 1.0), (4, 27, 90, 1, 24, -1.0)])
 def test_fine_to_coarse(gpu_ctx, S, V, U, C, D, scale):
