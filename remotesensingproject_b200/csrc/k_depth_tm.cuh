@@ -257,7 +257,9 @@ depth_kernel_tm(const depth_args a, const depth_tm_layout L)
     const float Um1f = (float)(U - 1);
     const int nbT = L.TV / DEPTH_UNR, nbS = L.SV / DEPTH_UNR;
 
-    for (long long w = (long long)blockIdx.x * DEPTH_TM_WARPS + wid; w < total; w += (long long)gridDim.x * DEPTH_TM_WARPS) {
+    /* consecutive items go to different SMs (and, within a CTA, to different schedulers): a pass with few items then
+     * spreads over the whole GPU instead of filling the twelve warps of a few CTAs */
+    for (long long w = (long long)blockIdx.x + (long long)gridDim.x * wid; w < total; w += (long long)gridDim.x * DEPTH_TM_WARPS) {
         const int item = (int)(w / a.chunks);
         const int chunk = (int)(w - (long long)item * a.chunks);
         const int pix = a.items[item];
