@@ -101,6 +101,21 @@ def edge_confidence(epis, s, params=None):
     return ce, mask
 
 
+def structuring_element(shape, k):
+    """cv::getStructuringElement(shape, (k, k)) as the edge-mask opening builds it (core.hpp:762-766)."""
+    out = np.zeros((k, k), np.uint8)
+    lib().orc_structuring_element(int(shape), int(k), _b(out))
+    return out
+
+
+def morph_open(mask, shape, k):
+    """cv::morphologyEx(mask, mask, MORPH_OPEN, getStructuringElement(shape, (k, k))) (core.hpp:768)."""
+    out = np.ascontiguousarray(mask, np.uint8).copy()
+    V, U = out.shape
+    lib().orc_morph_open(_b(out), V, U, int(shape), int(k))
+    return out
+
+
 def pixel_scores(epi, s_hat, u, dmin, dmax, D, params=None):
     """epi: [S][U][C] normalised.  Returns scores[D], rbar[D][C], dvals[D]."""
     epi = _c32(epi)

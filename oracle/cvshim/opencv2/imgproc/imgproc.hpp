@@ -227,9 +227,63 @@ inline void medianBlur(const Mat& src, Mat& dst, int ksize)
     dst = out;
 }
 
-/* declared, outside the depth path (the opening is disabled by default: core.hpp:29, :759) */
-inline Mat getStructuringElement(int, Size, Point = Point(-1, -1)) { shim_abort("getStructuringElement"); }
-inline void morphologyEx(const Mat&, Mat&, int, const Mat&) { shim_abort("morphologyEx"); }
+/* cv::getStructuringElement (anchor at the centre, ksize / 2): MORPH_RECT all ones; MORPH_CROSS the anchor's row and
+ * column; MORPH_ELLIPSE row i covers [c - dx, c + dx] with dx = cvRound(c * sqrt((r^2 - (i - r)^2) / r^2)), r = c = ksize / 2.
+ * Pinned against cv2 4.13 for sizes 1..15 (tests/test_oracle_vs_cv2.py). */
+inline Mat getStructuringElement(int shape, Size ksize, Point anchor = Point(-1, -1))
+{
+    shim_check(shape == MORPH_RECT || shape == MORPH_CROSS || shape == MORPH_ELLIPSE, "getStructuringElement: shape");
+    shim_check(anchor.x == -1 && anchor.y == -1, "getStructuringElement: default anchor");
+    const int ax = ksize.width / 2, ay = ksize.height / 2;
+    const int r = ksize.height / 2, c = ksize.width / 2;
+    const double inv_r2 = r ? 1.0 / ((double)r * r) : 0.0;
+    Mat K(ksize.height, ksize.width, CV_8UC1);
+    for (int i = 0; i < ksize.height; ++i) {
+        int j1 = 0, j2 = 0;
+        if (shape == MORPH_RECT || (shape == MORPH_CROSS && i == ay)) j2 = ksize.width;
+        else if (shape == MORPH_CROSS) { j1 = ax; j2 = j1 + 1; }
+        else {
+            const int dy = i - r;
+            if (std::abs(dy) <= r) {
+                const int dx = detail::cv_round(c * std::sqrt((r * r - dy * dy) * inv_r2));
+                j1 = std::max(c - dx, 0); j2 = std::min(c + dx + 1, ksize.width);
+            }
+        }
+        uchar* row = K.ptr<uchar>(i);
+        for (int j = 0; j < ksize.width; ++j) row[j] = (j >= j1 && j < j2) ? 1 : 0;
+    }
+    return K;
+}
+
+/* cv::morphologyEx(MORPH_OPEN) on CV_8UC1, one iteration, default anchor, BORDER_CONSTANT with
+ * morphologyDefaultBorderValue(): erosion then dilation, dst(y, x) = min / max over the element's non-zero (ky, kx) of
+ * src(y + ky - ay, x + kx - ax), positions outside the image ignored.  Pinned against cv2 4.13 (odd and even sizes). */
+inline void morphologyEx(const Mat& src, Mat& dst, int op, const Mat& kernel)
+{
+    shim_check(op == MORPH_OPEN && src.type() == CV_8UC1 && kernel.type() == CV_8UC1, "morphologyEx: MORPH_OPEN on CV_8UC1");
+    Mat S = src, K = kernel;
+    const int V = S.rows, U = S.cols, ay = K.rows / 2, ax = K.cols / 2;
+    auto pass = [&](const Mat& in, bool erode) {
+        Mat out(V, U, CV_8UC1);
+        for (int y = 0; y < V; ++y)
+            for (int x = 0; x < U; ++x) {
+                int acc = erode ? 255 : 0;
+                for (int ky = 0; ky < K.rows; ++ky)
+                    for (int kx = 0; kx < K.cols; ++kx) {
+                        if (!K.ptr<uchar>(ky)[kx]) continue;
+                        const int yy = y + ky - ay, xx = x + kx - ax;
+                        if (yy < 0 || yy >= V || xx < 0 || xx >= U) continue;
+                        const int v = in.ptr<uchar>(yy)[xx];
+                        acc = erode ? std::min(acc, v) : std::max(acc, v);
+                    }
+                out.ptr<uchar>(y)[x] = (uchar)acc;
+            }
+        return out;
+    };
+    Mat out = pass(pass(S, true), false);
+    if (dst.rows == V && dst.cols == U && dst.type() == CV_8UC1 && dst.data) out.copyTo(dst);
+    else dst = out;
+}
 inline void applyColorMap(const Mat&, Mat&, int) { shim_abort("applyColorMap"); }
 inline void cvtColor(const Mat&, Mat&, int, int = 0) { shim_abort("cvtColor"); }
 inline void line(Mat&, Point, Point, const Scalar&, int = 1, int = 8, int = 0) { shim_abort("line"); }

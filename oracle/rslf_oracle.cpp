@@ -331,13 +331,67 @@ void selective_median(const float* src, float* dst, const float* epis, const Dim
     }
 }
 
-/* compute_1D_edge_confidence_pile (core.hpp:728-770); opening is disabled for size <= 1 */
+/* cv::getStructuringElement(shape, Size(k, k)) with the default anchor (k/2, k/2): 0 = MORPH_RECT, 1 = MORPH_CROSS,
+ * 2 = MORPH_ELLIPSE (row i spans c -+ cvRound(c * sqrt((r^2 - (i-r)^2) / r^2)), r = c = k/2).  k x k bytes, 0 / 1. */
+std::vector<uint8_t> structuring_element(int shape, int k) {
+    std::vector<uint8_t> K((size_t)k * k, 0);
+    const int r = k / 2, c = k / 2;
+    const double inv_r2 = r ? 1.0 / ((double)r * r) : 0.0;
+    for (int i = 0; i < k; ++i) {
+        int j1 = 0, j2 = 0;
+        if (shape == 0 || (shape == 1 && i == r)) j2 = k;
+        else if (shape == 1) { j1 = c; j2 = c + 1; }
+        else {
+            const int dy = i - r;
+            if (std::abs(dy) <= r) {
+                const int dx = (int)std::nearbyint(c * std::sqrt((r * r - dy * dy) * inv_r2));
+                j1 = std::max(c - dx, 0); j2 = std::min(c + dx + 1, k);
+            }
+        }
+        for (int j = j1; j < j2; ++j) K[(size_t)i * k + j] = 1;
+    }
+    return K;
+}
+
+/* cv::morphologyEx(mask, mask, MORPH_OPEN, kernel) (core.hpp:759-769): erosion then dilation of a V x U uint8 image,
+ * min / max over the element's non-zero offsets (ky - k/2, kx - k/2); positions outside the image do not take part
+ * (BORDER_CONSTANT with morphologyDefaultBorderValue). */
+void morph_open(uint8_t* mask, int V, int U, int shape, int k) {
+    const std::vector<uint8_t> K = structuring_element(shape, k);
+    const int a = k / 2;
+    std::vector<uint8_t> tmp((size_t)V * U);
+    for (int phase = 0; phase < 2; ++phase) {
+        const uint8_t* in = phase == 0 ? mask : tmp.data();
+        uint8_t* out = phase == 0 ? tmp.data() : mask;
+#pragma omp parallel for schedule(static)
+        for (int y = 0; y < V; ++y)
+            for (int x = 0; x < U; ++x) {
+                int acc = phase == 0 ? 255 : 0;
+                for (int ky = 0; ky < k; ++ky) {
+                    const int yy = y + ky - a;
+                    if (yy < 0 || yy >= V) continue;
+                    for (int kx = 0; kx < k; ++kx) {
+                        const int xx = x + kx - a;
+                        if (!K[(size_t)ky * k + kx] || xx < 0 || xx >= U) continue;
+                        const int v = in[(size_t)yy * U + xx];
+                        acc = phase == 0 ? std::min(acc, v) : std::max(acc, v);
+                    }
+                }
+                out[(size_t)y * U + x] = (uint8_t)acc;
+            }
+    }
+}
+
+/* compute_1D_edge_confidence_pile (core.hpp:728-770): every row, then the optional morphological opening of the
+ * V x U mask (size > 1; disabled by default, core.hpp:29) */
 void edge_confidence_plane(const float* epis, const Dims& g, int s, const rslf_params& P,
                            float* ce, uint8_t* mask) {
 #pragma omp parallel for schedule(static)
     for (int v = 0; v < g.V; ++v)
         edge_confidence_row(epis + epi_off(g, v, s, 0), g.U, g.C, P,
                             ce + (size_t)v * g.U, mask + (size_t)v * g.U);
+    if (P.edge_confidence_opening_size > 1)
+        morph_open(mask, g.V, g.U, P.edge_confidence_opening_type, P.edge_confidence_opening_size);
 }
 
 /* The s_hat visiting order of compute_2D_depth_epi (core.hpp:953, 981-990). */
@@ -737,6 +791,13 @@ void orc_pixel_scores(const float* epi_su, int S, int U, int C, int D, int s_hat
         for (int c = 0; c < C; ++c) rbar_dc[(size_t)d * C + c] = w.rbar[(size_t)c * D + d];
     }
 }
+
+/* getStructuringElement / morphologyEx(MORPH_OPEN) as the edge-mask opening uses them (core.hpp:759-769) */
+void orc_structuring_element(int shape, int k, uint8_t* out_kk) {
+    std::vector<uint8_t> K = structuring_element(shape, k);
+    std::memcpy(out_kk, K.data(), K.size());
+}
+void orc_morph_open(uint8_t* mask_vu, int V, int U, int shape, int k) { morph_open(mask_vu, V, U, shape, k); }
 
 void orc_selective_median(const float* src_vu, const uint8_t* mask_vu, const float* epis, int V, int S, int U, int C,
                           int s_hat, int size, float eps, float* dst_vu) {

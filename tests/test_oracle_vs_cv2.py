@@ -81,3 +81,20 @@ def test_constants():
     p = oracle.default_params()
     assert np.float32(p.shadow_level) == np.float32(0.05 * 1.73205080757)
     assert np.float32(1.0 / float(np.float32(0.2) * np.float32(0.2))) == np.float32(24.999998)
+
+
+def test_structuring_element_and_opening_match_cv2():
+    """The optional opening of the edge mask (core.hpp:759-769): getStructuringElement and
+    morphologyEx(MORPH_OPEN) of the real OpenCV (cv2 4.13), odd and even sizes, thin images."""
+    cv2 = pytest.importorskip("cv2")
+    cv2.setNumThreads(1)
+    for shape in (cv2.MORPH_RECT, cv2.MORPH_CROSS, cv2.MORPH_ELLIPSE):
+        for k in range(1, 16):
+            np.testing.assert_array_equal(oracle.structuring_element(shape, k), cv2.getStructuringElement(shape, (k, k)))
+    rng = np.random.default_rng(11)
+    for shape in (0, 1, 2):
+        for k in (2, 3, 4, 5, 7, 9):
+            for (V, U) in ((1, 9), (7, 1), (6, 11), (23, 37)):
+                m = np.where(rng.random((V, U)) < 0.75, 255, 0).astype(np.uint8)
+                want = cv2.morphologyEx(m, cv2.MORPH_OPEN, cv2.getStructuringElement(shape, (k, k)))
+                np.testing.assert_array_equal(oracle.morph_open(m, shape, k), want, err_msg="shape %d k %d %dx%d" % (shape, k, V, U))

@@ -167,6 +167,32 @@ def test_free_functions():
     np.testing.assert_array_equal(m_r, m_o)
 
 
+@needs_ref
+@pytest.mark.parametrize("shape,size", [(2, 3), (0, 2), (1, 5), (2, 4)])
+def test_edge_mask_opening(shape, size):
+    """par_edge_confidence_opening_size > 1: morphological opening of every V x U edge mask (core.hpp:759-769),
+    through the pile, the 2D computer and the pyramid."""
+    p = oracle.default_params(edge_confidence_opening_type=shape, edge_confidence_opening_size=size)
+    epis = lf(7, 14, 60, 3, seed=40 + size)
+    ce_r, m_r = ref.edge_confidence(epis, 3, params=p)
+    ce_o, m_o = oracle.edge_confidence(epis, 3, params=p)
+    _, m_plain = oracle.edge_confidence(epis, 3)
+    np.testing.assert_array_equal(m_r, m_o)
+    np.testing.assert_array_equal(ce_r, ce_o)
+    assert (m_o != m_plain).any() and m_o.any()
+    if size % 2:                         # even elements are anchored off-centre: cv2's opening then shifts the mask
+        assert (m_o <= m_plain).all()
+    assert_same(ref.depth1d_pile(epis, -1.0, 2.0, 24, scale_factor=1.0, params=p),
+                oracle.depth1d_pile(oracle.normalise(epis, 1.0), -1.0, 2.0, 24, params=p), MAPS, "pile opening")
+    assert_same(ref.depth2d(epis, -1.0, 2.0, 24, scale_factor=1.0, params=p),
+                oracle.depth2d(oracle.normalise(epis, 1.0), -1.0, 2.0, 24, params=p), MAPS, "2d opening")
+    epis = lf(5, 24, 64, 1, seed=41 + size)
+    dims = oracle.pyramid_dims(24, 64)
+    r = ref.fine_to_coarse(epis, -1.0, 2.0, 16, scale_factor=1.0, params=p, dims=dims)
+    o = oracle.fine_to_coarse(epis, -1.0, 2.0, 16, scale_factor=1.0, params=p)
+    assert_same(r, o, ["valid", "map"], "ftc opening")
+
+
 GOLDEN = ["ref_pile_c3", "ref_pile_c1_u8", "ref_2d_c3", "ref_ftc_c1", "ref_ftc_c3_u8"]
 
 
