@@ -91,21 +91,123 @@ edge_confidence_kernel(const float* __restrict__ epi, int V, int S, int U, int s
     }
 }
 
+/*
+ * Optional morphological opening of every V x U edge mask (core.hpp:759-769):
+ * cv::morphologyEx(mask, mask, MORPH_OPEN, getStructuringElement(type, Size(k, k))), i.e. an erosion followed by a
+ * dilation with the same element, anchor (k/2, k/2), BORDER_CONSTANT with morphologyDefaultBorderValue() (positions
+ * outside the image take no part).  Every row of a RECT / CROSS / ELLIPSE element is one contiguous span
+ * [j1, j2), so the element travels in the kernel arguments as k spans.  HBM-bound byte stream: the k x k
+ * neighbourhood of a pixel comes out of L1/L2, 1 B read + 1 B written per pixel and pass from HBM.
+ */
+#define MORPH_MAX_K 31
+#define MORPH_THREADS 128
+struct morph_elem { int k; signed char j1[MORPH_MAX_K]; signed char j2[MORPH_MAX_K]; };
+
+/* cv::getStructuringElement(shape, Size(k, k)), default anchor: 0 = MORPH_RECT, 1 = MORPH_CROSS, 2 = MORPH_ELLIPSE */
+static bool morph_build(morph_elem& e, int shape, int k)
+{
+    if (k < 1 || k > MORPH_MAX_K || shape < 0 || shape > 2) return false;
+    e.k = k;
+    const int r = k / 2, c = k / 2;
+    const double inv_r2 = r ? 1.0 / ((double)r * r) : 0.0;
+    for (int i = 0; i < MORPH_MAX_K; ++i) { e.j1[i] = 0; e.j2[i] = 0; }
+    for (int i = 0; i < k; ++i) {
+        int j1 = 0, j2 = 0;
+        if (shape == 0 || (shape == 1 && i == r)) j2 = k;
+        else if (shape == 1) { j1 = c; j2 = c + 1; }
+        else {
+            const int dy = i - r;
+            if (abs(dy) <= r) {
+                const int dx = (int)nearbyint(c * sqrt((r * r - dy * dy) * inv_r2));     /* cvRound: half to even */
+                j1 = c - dx > 0 ? c - dx : 0;
+                j2 = c + dx + 1 < k ? c + dx + 1 : k;
+            }
+        }
+        e.j1[i] = (signed char)j1; e.j2[i] = (signed char)j2;
+    }
+    return true;
+}
+
+/* grid (U tiles, V, planes); ERODE: min over the element, else max */
+template <int ERODE>
+__global__ void __launch_bounds__(MORPH_THREADS)
+morph_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int V, int U, const morph_elem e)
+{
+    const int u = blockIdx.x * MORPH_THREADS + threadIdx.x;
+    if (u >= U) return;
+    const int v = blockIdx.y;
+    const size_t plane_off = (size_t)blockIdx.z * (size_t)V * U;
+    const int a = e.k / 2;
+    int acc = ERODE ? 255 : 0;
+    for (int ky = 0; ky < e.k; ++ky) {
+        const int yy = v + ky - a;
+        if (yy < 0 || yy >= V) continue;
+        const uint8_t* row = in + plane_off + (size_t)yy * U;
+        const int x0 = max(u + (int)e.j1[ky] - a, 0), x1 = min(u + (int)e.j2[ky] - a, U);
+        for (int x = x0; x < x1; ++x) {
+            const int val = row[x];
+            acc = ERODE ? min(acc, val) : max(acc, val);
+        }
+    }
+    out[plane_off + (size_t)v * U + u] = (uint8_t)acc;
+}
+
+/* confident-and-dark pixels per (line, row) of a mask that was opened after the edge kernel (same count as the edge
+ * kernel's `rowdark`); one block per (v, si) row like the edge kernel */
+template <int C>
+__global__ void __launch_bounds__(EDGE_THREADS)
+rowdark_count_kernel(const float* __restrict__ epi, const uint8_t* __restrict__ mask, int V, int S, int U, int s_first,
+                     int s_count, float dark_eps, double dark_T, int* __restrict__ rowdark)
+{
+    const int row = blockIdx.x;
+    const int v = row / s_count, si = row % s_count;
+    const float* src = epi + ((size_t)v * S + (s_first + si)) * (size_t)U * C;
+    const uint8_t* m = mask + ((size_t)si * V + v) * (size_t)U;
+    int ndark = 0;
+    for (int u = threadIdx.x; u < U; u += EDGE_THREADS) {
+        if (!m[u]) continue;
+        float x[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) x[c] = __ldg(src + (size_t)u * C + c);
+        bool dk;
+        if (C == 1) dk = rslf_norm1_lt(x[0], dark_eps);
+        else dk = rslf_norm3_lt(x[0], x[C > 1 ? 1 : 0], x[C > 2 ? 2 : 0], dark_T);
+        ndark += dk ? 1 : 0;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) ndark += __shfl_xor_sync(0xffffffffu, ndark, off);
+    if ((threadIdx.x & 31) == 0 && ndark) atomicAdd(rowdark + (size_t)si * V + v, ndark);
+}
+
 /* Launch for lines [s_first, s_first + s_count) of every row; output planes are
- * [s_count][V][U] starting at ce_out / mask_out. */
+ * [s_count][V][U] starting at ce_out / mask_out.  mask_tmp: scratch of the same size as mask_out, needed only
+ * when the opening is enabled (edge_confidence_opening_size > 1). */
 static int launch_edge_confidence(rslf_ctx* ctx, const float* epi, int V, int S, int U, int C, int s_first,
                                   int s_count, const rslf_params& P, float* ce_out, uint8_t* mask_out,
-                                  int* rowdark = nullptr)
+                                  int* rowdark = nullptr, uint8_t* mask_tmp = nullptr)
 {
     int fs = P.edge_confidence_filter_size;
     if (fs < 1 || fs > EDGE_MAX_FS) {
         snprintf(ctx->err, sizeof(ctx->err), "edge_confidence_filter_size %d outside [1,%d]", fs, EDGE_MAX_FS);
         return RSLF_ERR_UNSUPPORTED;
     }
-    if (P.edge_confidence_opening_size > 1) {
-        snprintf(ctx->err, sizeof(ctx->err), "morphological opening of the edge mask is not implemented");
-        return RSLF_ERR_UNSUPPORTED;
+    const bool opening = P.edge_confidence_opening_size > 1;
+    morph_elem elem;
+    if (opening) {
+        if (ctx->world > 1) {
+            /* the element reaches k/2 rows beyond a rank's block in every view: not exchanged */
+            snprintf(ctx->err, sizeof(ctx->err), "morphological opening of the edge mask is not implemented for row-sharded runs");
+            return RSLF_ERR_UNSUPPORTED;
+        }
+        if (!morph_build(elem, P.edge_confidence_opening_type, P.edge_confidence_opening_size)) {
+            snprintf(ctx->err, sizeof(ctx->err), "edge_confidence_opening: type %d (0..2), size %d (<= %d)",
+                     P.edge_confidence_opening_type, P.edge_confidence_opening_size, MORPH_MAX_K);
+            return RSLF_ERR_UNSUPPORTED;
+        }
+        if (!mask_tmp || V > 65535 || s_count > 65535) { snprintf(ctx->err, sizeof(ctx->err), "edge_confidence_opening: no scratch mask"); return RSLF_ERR_STATE; }
     }
+    int* rowdark_late = opening ? rowdark : nullptr;      /* counted on the opened mask instead */
+    if (opening) rowdark = nullptr;
     dim3 grid((unsigned)((size_t)V * s_count), rslf_div_up(U, EDGE_TILE));
     size_t smem = (size_t)(EDGE_TILE + fs - 1) * C * sizeof(float);
     double T = rslf_sq_threshold(P.shadow_level);
@@ -120,5 +222,18 @@ static int launch_edge_confidence(rslf_ctx* ctx, const float* epi, int V, int S,
             P.propagation_epsilon, dT, rowdark);
     RSLF_CUDA_TRY(ctx, cudaGetLastError());
     ctx->timing.kernel_launches += 1;
+    if (opening) {
+        dim3 mg(rslf_div_up(U, MORPH_THREADS), V, s_count);
+        morph_kernel<1><<<mg, MORPH_THREADS, 0, ctx->stream>>>(mask_out, mask_tmp, V, U, elem);
+        morph_kernel<0><<<mg, MORPH_THREADS, 0, ctx->stream>>>(mask_tmp, mask_out, V, U, elem);
+        ctx->timing.kernel_launches += 2;
+        if (rowdark_late) {
+            const unsigned rows = (unsigned)((size_t)V * s_count);
+            if (C == 1) rowdark_count_kernel<1><<<rows, EDGE_THREADS, 0, ctx->stream>>>(epi, mask_out, V, S, U, s_first, s_count, P.propagation_epsilon, dT, rowdark_late);
+            else rowdark_count_kernel<3><<<rows, EDGE_THREADS, 0, ctx->stream>>>(epi, mask_out, V, S, U, s_first, s_count, P.propagation_epsilon, dT, rowdark_late);
+            ctx->timing.kernel_launches += 1;
+        }
+        RSLF_CUDA_TRY(ctx, cudaGetLastError());
+    }
     return RSLF_OK;
 }

@@ -645,7 +645,7 @@ static int run_depth2d_level(rslf_ctx* ctx, int p, const rslf_params& P, float d
     RSLF_CUDA_TRY(ctx, cudaMemsetAsync(L.rowdark, 0, ((size_t)S + 1) * V * sizeof(int), ctx->stream));
     {
         stage_scope sc(ctx, ST_EDGE);
-        RSLF_TRY(launch_edge_confidence(ctx, L.epi, V, S, U, C, 0, S, P, L.ce, L.emask, L.rowdark));
+        RSLF_TRY(launch_edge_confidence(ctx, L.epi, V, S, U, C, 0, S, P, L.ce, L.emask, L.rowdark, L.remaining));   /* L.remaining is free until core.hpp:958-963 below */
         /* rows that hold a dark target in any view: rowdark[S][v] = sum over s (an upper bound for the whole level) */
         row_sum_kernel<<<rslf_div_up(V, 256), 256, 0, ctx->stream>>>(L.rowdark, S, V, L.rowdark + (size_t)S * V);
         RSLF_CUDA_TRY(ctx, cudaGetLastError());
@@ -742,7 +742,7 @@ extern "C" int rslf_cuda_depth1d_pile_run(rslf_ctx* ctx, float dmin, float dmax,
     RSLF_CUDA_TRY(ctx, cudaMemsetAsync(L.rbar, 0, plane * C * sizeof(float), ctx->stream));
     {
         stage_scope sc(ctx, ST_EDGE);
-        RSLF_TRY(launch_edge_confidence(ctx, L.epi, V, S, U, C, s_hat, 1, P, L.ce, L.emask));
+        RSLF_TRY(launch_edge_confidence(ctx, L.epi, V, S, U, C, s_hat, 1, P, L.ce, L.emask, nullptr, L.remaining));
     }
     pass_io io;
     io.level = 0; io.s_hat = s_hat; io.D = dim_d; io.dmin = dmin; io.dmax = dmax; io.use_bound_maps = false;
@@ -1153,7 +1153,7 @@ extern "C" int rslf_cuda_edge_confidence(rslf_ctx* ctx, int s, const rslf_params
     ctx->last_kind = 0;
     RSLF_TRY(normalise_level(ctx, 0, ctx->raw_in, ctx->cv_depth));
     rslf_level& L = ctx->lv[0];
-    RSLF_TRY(launch_edge_confidence(ctx, L.epi, ctx->V, ctx->S, ctx->U, ctx->C, s, 1, *params, L.ce, L.emask));
+    RSLF_TRY(launch_edge_confidence(ctx, L.epi, ctx->V, ctx->S, ctx->U, ctx->C, s, 1, *params, L.ce, L.emask, nullptr, L.remaining));
     const size_t plane = (size_t)ctx->V * ctx->U;
     RSLF_TRY(copy_out(ctx, edge_conf_vu, L.ce, plane * 4));
     RSLF_TRY(copy_out(ctx, edge_mask_vu, L.emask, plane));
