@@ -30,6 +30,7 @@ extern "C" {
 
 /* OpenCV depth codes accepted by rslf_cuda_upload_epis (CV_8U = 0, CV_32F = 5). */
 #define RSLF_DEPTH_8U  0
+#define RSLF_DEPTH_16U 2
 #define RSLF_DEPTH_32F 5
 
 enum {

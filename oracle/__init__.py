@@ -71,6 +71,11 @@ def _c32(a):
     return a
 
 
+def _cv_depth(a):
+    """OpenCV depth code of a raw stack: CV_8U = 0, CV_16U = 2, CV_32F = 5 (anything else is converted to float32)."""
+    return {np.dtype(np.uint8): 0, np.dtype(np.uint16): 2}.get(a.dtype, 5)
+
+
 def num_threads():
     return lib().orc_num_threads()
 
@@ -83,7 +88,7 @@ def normalise(raw, scale_factor=-1.0):
     """Computer ctor input normalisation.  raw: [V][S][U][C] uint8 or float32."""
     raw = np.ascontiguousarray(raw)
     V, S, U, Cc = raw.shape
-    depth = 0 if raw.dtype == np.uint8 else 5
+    depth = _cv_depth(raw)
     if depth == 5:
         raw = _c32(raw)
     out = np.empty(raw.shape, np.float32)
@@ -196,6 +201,11 @@ def downsample(raw):
         out = np.zeros((half_size(V), S, half_size(U), Cc), np.uint8)
         lib().orc_downsample_u8(_b(raw), V, S, U, Cc, _b(out))
         return out
+    if raw.dtype == np.uint16:
+        V, S, U, Cc = raw.shape
+        out = np.zeros((half_size(V), S, half_size(U), Cc), np.uint16)
+        lib().orc_downsample_u16(raw.ctypes.data_as(C.c_void_p), V, S, U, Cc, out.ctypes.data_as(C.c_void_p))
+        return out
     raw = _c32(raw)
     V, S, U, Cc = raw.shape
     out = np.zeros((half_size(V), S, half_size(U), Cc), np.float32)
@@ -255,7 +265,7 @@ def fine_to_coarse(raw, dmin, dmax, D, scale_factor=-1.0, params=None, max_pyr_d
     """FineToCoarse ctor + run + get_results on a raw [V][S][U][C] stack."""
     raw = np.ascontiguousarray(raw)
     V, S, U, Cc = raw.shape
-    depth = 0 if raw.dtype == np.uint8 else 5
+    depth = _cv_depth(raw)
     if depth == 5:
         raw = _c32(raw)
     p = params or default_params()

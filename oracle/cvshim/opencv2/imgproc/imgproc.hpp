@@ -63,7 +63,7 @@ inline void filter2D(const Mat& src, Mat& dst, int ddepth, const Mat& kernel, Po
 /* cv::GaussianBlur, ksize 7x7, sigma 0 (-> sigma 1.4, the fixed small-kernel table [0.03125, 0.109375, 0.21875,
  * 0.28125, ...]), separable: rows, then columns.
  * CV_32F: symmetric row / column filters, k0*x0 + k1*(x-1 + x+1) + k2*(x-2 + x+2) + k3*(x-3 + x+3) in float.
- * CV_8U: fixed-point kernel [8, 28, 56, 72, 56, 28, 8] / 256 in both passes, result (acc + 2^15) >> 16. */
+ * CV_8U / CV_16U: fixed-point kernel [8, 28, 56, 72, 56, 28, 8] / 256 in both passes, result (acc + 2^15) >> 16. */
 inline void GaussianBlur(const Mat& src, Mat& dst, Size ksize, double sigmaX, double sigmaY = 0, int borderType = BORDER_DEFAULT)
 {
     shim_check(ksize.width == 7 && ksize.height == 7 && sigmaX == 0 && sigmaY == 0, "GaussianBlur: 7x7, sigma 0");
@@ -93,22 +93,27 @@ inline void GaussianBlur(const Mat& src, Mat& dst, Size ksize, double sigmaX, do
                     float t3 = px(v - 3) + px(v + 3); t3 = k3 * t3; acc = acc + t3;
                     out.ptr<float>(v)[u * cn + c] = acc;
                 }
-    } else if (S.depth() == CV_8U) {
-        static const int K[7] = {8, 28, 56, 72, 56, 28, 8};
-        std::vector<int32_t> h((size_t)V * U * cn);
+    } else if (S.depth() == CV_8U || S.depth() == CV_16U) {
+        /* the same fixed-point kernel for both integer depths (pinned against cv2 4.13 incl. exact ties);
+         * unsigned 32-bit: 256 * 256 * 65535 + 2^15 < 2^32 */
+        const bool wide = S.depth() == CV_16U;
+        static const uint32_t K[7] = {8, 28, 56, 72, 56, 28, 8};
+        auto px = [&](int v, int i) -> uint32_t { return wide ? (uint32_t)S.ptr<ushort>(v)[i] : (uint32_t)S.ptr<uchar>(v)[i]; };
+        std::vector<uint32_t> h((size_t)V * U * cn);
         for (int v = 0; v < V; ++v)
             for (int u = 0; u < U; ++u)
                 for (int c = 0; c < cn; ++c) {
-                    int32_t acc = 0;
-                    for (int j = 0; j < 7; ++j) acc += K[j] * (int32_t)S.ptr<uchar>(v)[detail::border(u + j - 3, U, borderType) * cn + c];
+                    uint32_t acc = 0;
+                    for (int j = 0; j < 7; ++j) acc += K[j] * px(v, detail::border(u + j - 3, U, borderType) * cn + c);
                     h[((size_t)v * U + u) * cn + c] = acc;
                 }
         for (int v = 0; v < V; ++v)
             for (int u = 0; u < U; ++u)
                 for (int c = 0; c < cn; ++c) {
-                    int32_t acc = 0;
+                    uint32_t acc = 0;
                     for (int j = 0; j < 7; ++j) acc += K[j] * h[((size_t)detail::border(v + j - 3, V, borderType) * U + u) * cn + c];
-                    out.ptr<uchar>(v)[u * cn + c] = (uchar)((acc + 32768) >> 16);
+                    const uint32_t r = (acc + 32768u) >> 16;
+                    if (wide) out.ptr<ushort>(v)[u * cn + c] = (ushort)r; else out.ptr<uchar>(v)[u * cn + c] = (uchar)r;
                 }
     } else shim_abort("GaussianBlur on this depth");
     dst = out;
@@ -154,7 +159,9 @@ inline void resize(const Mat& src, Mat& dst, Size dsize, double fx = 0, double f
                     }
                 }
             }
-        } else if (S.depth() == CV_8U) {
+        } else if (S.depth() == CV_8U || S.depth() == CV_16U) {
+            /* CV_16U: OpenCV's own code path (an IPP build rounds the 2x2 ties half to even instead) */
+            const bool wide = S.depth() == CV_16U;
             for (int v = 0; v < Vd; ++v) {
                 const int nr = (2 * v + 1 < Vs) ? 2 : 1;
                 for (int u = 0; u < Ud; ++u) {
@@ -162,13 +169,16 @@ inline void resize(const Mat& src, Mat& dst, Size dsize, double fx = 0, double f
                     for (int c = 0; c < cn; ++c) {
                         int sum = 0;
                         for (int a = 0; a < nr; ++a)
-                            for (int b = 0; b < nc; ++b) sum += S.ptr<uchar>(std::min(2 * v + a, Vs - 1))[std::min(2 * u + b, Us - 1) * cn + c];
+                            for (int b = 0; b < nc; ++b) {
+                                const int yy = std::min(2 * v + a, Vs - 1), ii = std::min(2 * u + b, Us - 1) * cn + c;
+                                sum += wide ? (int)S.ptr<ushort>(yy)[ii] : (int)S.ptr<uchar>(yy)[ii];
+                            }
                         const int n = nr * nc;
                         int r;
                         if (n == 4) r = (sum + 2) >> 2;
                         else if (n == 2) r = (sum + ((sum >> 1) & 1)) >> 1;
                         else r = sum;
-                        out.ptr<uchar>(v)[u * cn + c] = (uchar)r;
+                        if (wide) out.ptr<ushort>(v)[u * cn + c] = (ushort)r; else out.ptr<uchar>(v)[u * cn + c] = (uchar)r;
                     }
                 }
             }

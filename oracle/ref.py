@@ -59,9 +59,9 @@ def _b(a):
 
 def _raw(raw):
     raw = np.ascontiguousarray(raw)
-    if raw.dtype != np.uint8:
+    if raw.dtype not in (np.uint8, np.uint16):
         raw = np.ascontiguousarray(raw, dtype=np.float32)
-    return raw, (0 if raw.dtype == np.uint8 else 5)
+    return raw, {np.dtype(np.uint8): 0, np.dtype(np.uint16): 2}.get(raw.dtype, 5)      # CV_8U, CV_16U, CV_32F
 
 
 def depth1d_pile(raw, dmin, dmax, D, s_hat=-1, scale_factor=-1.0, params=None):

@@ -58,7 +58,7 @@ struct QuietCout {
 RVec<Mat> make_epis(const void* raw, int cv_depth, int V, int S, int U, int C)
 {
     const int type = CV_MAKETYPE(cv_depth, C);
-    const size_t esz = (cv_depth == CV_8U ? 1 : 4) * (size_t)C;
+    const size_t esz = (cv_depth == CV_8U ? 1 : cv_depth == CV_16U ? 2 : 4) * (size_t)C;
     RVec<Mat> epis;
     for (int v = 0; v < V; ++v) {
         Mat m(S, U, type);
@@ -202,7 +202,7 @@ extern "C" {
 int ref_num_threads(void) { return omp_get_max_threads(); }
 void ref_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 
-/* Depth1DComputer_pile ctor + run.  raw: [V][S][U][C], cv_depth 0 (CV_8U) or 5 (CV_32F).  Returns the s_hat used. */
+/* Depth1DComputer_pile ctor + run.  raw: [V][S][U][C], cv_depth 0 (CV_8U), 2 (CV_16U) or 5 (CV_32F).  Returns the s_hat used. */
 int ref_depth1d_pile(const void* raw, int cv_depth, int V, int S, int U, int C, float scale, float dmin, float dmax, int D,
                      int s_hat, const rslf_params* P, float* best_depth, float* edge_conf, uint8_t* edge_mask,
                      float* disp_conf, float* rbar)
@@ -242,7 +242,7 @@ int ref_downsample(const void* raw, int cv_depth, int V, int S, int U, int C, vo
 {
     RVec<Mat> epis = make_epis(raw, cv_depth, V, S, U, C), down;
     rslf::downsample_EPIs(epis, down);
-    const size_t esz = (cv_depth == CV_8U ? 1 : 4) * (size_t)C;
+    const size_t esz = (cv_depth == CV_8U ? 1 : cv_depth == CV_16U ? 2 : 4) * (size_t)C;
     if (V2) *V2 = (int)down.size();
     if (U2) *U2 = down.empty() ? 0 : down[0].cols;
     if (out)

@@ -539,56 +539,62 @@ void downsample(const float* in, const Dims& g, float* out, int V2, int U2) {
 }
 
 /*
- * downsample_EPIs (ftc_core.cpp:14-60) for 8-bit stacks, which stay 8-bit between pyramid levels
- * (ftc.hpp:142-147 normalises each level from the un-normalised stack).  OpenCV's CV_8U paths, bit-exact
- * against cv2 (oracle/cv2_mirror.py, tests/golden/down_u8_*.npz): GaussianBlur 7x7 sigma 0 = integer kernel
- * [8,28,56,72,56,28,8] (sum 256) along rows, then along columns, result (acc + 2^15) >> 16, BORDER_REFLECT;
- * resize fx=fy=0.5 = (a+b+c+d+2) >> 2, and where an odd dimension leaves only one source row / column the
- * exact mean of the available pixels rounded half to even.
+ * downsample_EPIs (ftc_core.cpp:14-60) for 8-bit and 16-bit stacks, which keep their depth between pyramid
+ * levels (ftc.hpp:142-147 normalises each level from the un-normalised stack).  OpenCV's integer paths, bit-exact
+ * against cv2 (oracle/cv2_mirror.py, tests/golden/down_u8_*.npz; tests/test_oracle_vs_cv2.py for CV_16U):
+ * GaussianBlur 7x7 sigma 0 = integer kernel [8,28,56,72,56,28,8] (sum 256) along rows, then along columns,
+ * result (acc + 2^15) >> 16 (the exact value rounded half up), BORDER_REFLECT; resize fx=fy=0.5 =
+ * (a+b+c+d+2) >> 2, and where an odd dimension leaves only one source row / column the exact mean of the
+ * available pixels rounded half to even.  (CV_16U resize: OpenCV's own code; an IPP build rounds the 2x2 ties
+ * half to even instead.)  Unsigned 32-bit accumulators: 256 * 256 * 65535 + 2^15 < 2^32.
  */
-void downsample_u8(const uint8_t* in, const Dims& g, uint8_t* out, int V2, int U2) {
+template <typename T>
+void downsample_int(const T* in, const Dims& g, T* out, int V2, int U2) {
     const int V = g.V, S = g.S, U = g.U, C = g.C;
-    static const int K[7] = {8, 28, 56, 72, 56, 28, 8};
+    static const uint32_t K[7] = {8, 28, 56, 72, 56, 28, 8};
     Dims go{V2, S, U2, C};
 #pragma omp parallel
     {
-        std::vector<int32_t> hbuf((size_t)V * U * C);
-        std::vector<uint8_t> blur((size_t)V * U * C);
+        std::vector<uint32_t> hbuf((size_t)V * U * C);
+        std::vector<T> blur((size_t)V * U * C);
 #pragma omp for schedule(dynamic, 1)
         for (int s = 0; s < S; ++s) {
             for (int v = 0; v < V; ++v)
                 for (int u = 0; u < U; ++u)
                     for (int c = 0; c < C; ++c) {
-                        int32_t acc = 0;
-                        for (int j = 0; j < 7; ++j) acc += K[j] * (int32_t)in[epi_off(g, v, s, reflect(u + j - 3, U)) + c];
+                        uint32_t acc = 0;
+                        for (int j = 0; j < 7; ++j) acc += K[j] * (uint32_t)in[epi_off(g, v, s, reflect(u + j - 3, U)) + c];
                         hbuf[((size_t)v * U + u) * C + c] = acc;
                     }
             for (int v = 0; v < V; ++v)
                 for (int u = 0; u < U; ++u)
                     for (int c = 0; c < C; ++c) {
-                        int32_t acc = 0;
+                        uint32_t acc = 0;
                         for (int j = 0; j < 7; ++j) acc += K[j] * hbuf[((size_t)reflect(v + j - 3, V) * U + u) * C + c];
-                        blur[((size_t)v * U + u) * C + c] = (uint8_t)((acc + 32768) >> 16);
+                        blur[((size_t)v * U + u) * C + c] = (T)((acc + 32768u) >> 16);
                     }
             for (int v = 0; v < V2; ++v) {
                 const int nr = (2 * v + 1 < V) ? 2 : 1;
                 for (int u = 0; u < U2; ++u) {
                     const int nc = (2 * u + 1 < U) ? 2 : 1;
                     for (int c = 0; c < C; ++c) {
-                        int sum = 0;
+                        uint32_t sum = 0;
                         for (int a = 0; a < nr; ++a)
                             for (int b = 0; b < nc; ++b) sum += blur[((size_t)(2 * v + a) * U + (2 * u + b)) * C + c];
-                        int n = nr * nc, r;
+                        const int n = nr * nc;
+                        uint32_t r;
                         if (n == 4) r = (sum + 2) >> 2;
                         else if (n == 2) r = (sum + ((sum >> 1) & 1)) >> 1;      /* half to even */
                         else r = sum;
-                        out[epi_off(go, v, s, u) + c] = (uint8_t)r;
+                        out[epi_off(go, v, s, u) + c] = (T)r;
                     }
                 }
             }
         }
     }
 }
+void downsample_u8(const uint8_t* in, const Dims& g, uint8_t* out, int V2, int U2) { downsample_int<uint8_t>(in, g, out, V2, U2); }
+void downsample_u16(const uint16_t* in, const Dims& g, uint16_t* out, int V2, int U2) { downsample_int<uint16_t>(in, g, out, V2, U2); }
 
 /*
  * FineToCoarse::run bound propagation (ftc.hpp:201-294) from level p (up) to
@@ -727,6 +733,21 @@ float normalise(const void* raw, int cv_depth, size_t n, float scale_factor, flo
 #pragma omp parallel for schedule(static)
         for (long long i = 0; i < (long long)n; ++i) out[i] = (float)p[i] * a;
         return 255.f;
+    }
+    if (cv_depth == RSLF_DEPTH_16U) {
+        /* minMaxLoc -> (float)max (dc.hpp:453-456); convertTo(CV_32F, 1.0 / scale): float(x) * float(alpha) */
+        const uint16_t* p = (const uint16_t*)raw;
+        float sf = scale_factor;
+        if (sf < 0) {
+            float mx = sf;
+#pragma omp parallel for reduction(max : mx) schedule(static)
+            for (long long i = 0; i < (long long)n; ++i) mx = std::max(mx, (float)p[i]);
+            sf = mx;
+        }
+        const float a = (float)(1.0 / (double)sf);
+#pragma omp parallel for schedule(static)
+        for (long long i = 0; i < (long long)n; ++i) out[i] = (float)p[i] * a;
+        return sf;
     }
     const float* p = (const float*)raw;
     float sf = scale_factor;
@@ -874,6 +895,11 @@ void orc_downsample_u8(const uint8_t* in, int V, int S, int U, int C, uint8_t* o
     downsample_u8(in, g, out, cv_round(V * 0.5), cv_round(U * 0.5));
 }
 
+void orc_downsample_u16(const uint16_t* in, int V, int S, int U, int C, uint16_t* out) {
+    Dims g{V, S, U, C};
+    downsample_u16(in, g, out, cv_round(V * 0.5), cv_round(U * 0.5));
+}
+
 void orc_set_bounds(const float* depth_up, const uint8_t* valid_up, int S, int Vu, int Uu, int Vd, int Ud,
                     float* dmin_map, float* dmax_map) {
     set_bounds(depth_up, valid_up, S, Vu, Uu, Vd, Ud, dmin_map, dmax_map);
@@ -913,11 +939,12 @@ double orc_fine_to_coarse(const void* raw, int cv_depth, int V, int S, int U, in
     int Vp[32], Up[32];
     int levels = orc_pyramid_dims(V, U, max_pyr_depth, Vp, Up);
     if (levels == 0) return 0;
-    if (cv_depth != RSLF_DEPTH_32F && cv_depth != RSLF_DEPTH_8U) return -1;
+    if (cv_depth != RSLF_DEPTH_32F && cv_depth != RSLF_DEPTH_8U && cv_depth != RSLF_DEPTH_16U) return -1;
     std::vector<std::vector<float>> depth(levels), ce(levels), cd(levels), dmn(levels), dmx(levels);
     std::vector<std::vector<uint8_t>> emask(levels), valid(levels);
     std::vector<float> raw_cur, raw_next, norm, rbar;
     std::vector<uint8_t> raw8_cur, raw8_next;
+    std::vector<uint16_t> raw16_cur, raw16_next;
     size_t n0 = (size_t)V * S * U * C;
     const void* cur_raw = raw;
     double total = 0;
@@ -946,6 +973,9 @@ double orc_fine_to_coarse(const void* raw, int cv_depth, int V, int S, int U, in
             if (cv_depth == RSLF_DEPTH_8U) {
                 raw8_next.resize((size_t)Vp[p + 1] * S * Up[p + 1] * C);
                 downsample_u8((const uint8_t*)cur_raw, g, raw8_next.data(), Vp[p + 1], Up[p + 1]);
+            } else if (cv_depth == RSLF_DEPTH_16U) {
+                raw16_next.resize((size_t)Vp[p + 1] * S * Up[p + 1] * C);
+                downsample_u16((const uint16_t*)cur_raw, g, raw16_next.data(), Vp[p + 1], Up[p + 1]);
             } else {
                 raw_next.resize((size_t)Vp[p + 1] * S * Up[p + 1] * C);
                 downsample((const float*)cur_raw, g, raw_next.data(), Vp[p + 1], Up[p + 1]);
@@ -956,6 +986,7 @@ double orc_fine_to_coarse(const void* raw, int cv_depth, int V, int S, int U, in
             set_bounds(depth[p].data(), valid[p].data(), S, Vp[p], Up[p], Vp[p + 1], Up[p + 1], dmn[p + 1].data(),
                        dmx[p + 1].data());
             if (cv_depth == RSLF_DEPTH_8U) { raw8_cur.swap(raw8_next); cur_raw = raw8_cur.data(); }
+            else if (cv_depth == RSLF_DEPTH_16U) { raw16_cur.swap(raw16_next); cur_raw = raw16_cur.data(); }
             else { raw_cur.swap(raw_next); cur_raw = raw_cur.data(); }
         }
     }

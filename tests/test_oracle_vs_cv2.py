@@ -98,3 +98,30 @@ def test_structuring_element_and_opening_match_cv2():
                 m = np.where(rng.random((V, U)) < 0.75, 255, 0).astype(np.uint8)
                 want = cv2.morphologyEx(m, cv2.MORPH_OPEN, cv2.getStructuringElement(shape, (k, k)))
                 np.testing.assert_array_equal(oracle.morph_open(m, shape, k), want, err_msg="shape %d k %d %dx%d" % (shape, k, V, U))
+
+
+def test_downsample_uint16_matches_cv2():
+    """CV_16U pyramids (they stay 16-bit, ftc.hpp:142-147): GaussianBlur 7x7 + resize 0.5 of the real OpenCV, incl.
+    exact .5 ties of the blur (values that are multiples of 128), odd sizes and images smaller than the kernel.
+    IPP is switched off: OpenCV's own 2x2 resize rounds ties up ((a+b+c+d+2) >> 2), the IPP build of the wheel rounds
+    them to even; the blur is identical either way."""
+    cv2 = pytest.importorskip("cv2")
+    cv2.setNumThreads(1)
+    ipp = cv2.ipp.useIPP()
+    cv2.ipp.setUseIPP(False)
+    try:
+        rng = np.random.default_rng(5)
+        for t in range(14):
+            V, U, S = int(rng.integers(2, 40)), int(rng.integers(2, 40)), 2
+            C = int(rng.choice([1, 3]))
+            raw = rng.integers(0, 65536, size=(V, S, U, C)).astype(np.uint16)
+            if t % 3 == 0:
+                raw = (raw // 128 * 128).astype(np.uint16)
+            out = oracle.downsample(raw)
+            assert out.dtype == np.uint16
+            for s in range(S):
+                b = cv2.GaussianBlur(np.ascontiguousarray(raw[:, s]), (7, 7), 0, borderType=cv2.BORDER_REFLECT)
+                r = cv2.resize(b, None, fx=0.5, fy=0.5, interpolation=cv2.INTER_LINEAR).reshape(out[:, s].shape)
+                np.testing.assert_array_equal(out[:, s], r, err_msg="%dx%dx%d" % (V, U, C))
+    finally:
+        cv2.ipp.setUseIPP(ipp)

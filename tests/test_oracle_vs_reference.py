@@ -193,6 +193,25 @@ def test_edge_mask_opening(shape, size):
     assert_same(r, o, ["valid", "map"], "ftc opening")
 
 
+@needs_ref
+@pytest.mark.parametrize("S,V,U,C,scale", [(5, 44, 70, 3, -1.0), (4, 27, 135, 1, -1.0), (5, 24, 50, 3, 4095.0)])
+def test_16_bit_input(S, V, U, C, scale):
+    """CV_16U stacks: x float(1 / scale) with scale = the stack maximum or a given factor (dc.hpp:442-477); the pyramid
+    stays 16-bit between levels (ftc.hpp:142-147; integer Gaussian and half-size resize)."""
+    epis = lf(S, V, U, C, seed=V)
+    u16 = np.clip(np.rint(epis * (4095.0 if scale > 0 else 60000.0)), 0, 65535).astype(np.uint16)
+    np.testing.assert_array_equal(ref.downsample(u16), oracle.downsample(u16))
+    assert_same(ref.depth1d_pile(u16, -1.0, 2.0, 24, scale_factor=scale),
+                oracle.depth1d_pile(oracle.normalise(u16, scale), -1.0, 2.0, 24), MAPS, "u16 pile")
+    dims = oracle.pyramid_dims(V, U)
+    r = ref.fine_to_coarse(u16, -1.0, 2.0, 16, scale_factor=scale, dims=dims)
+    o = oracle.fine_to_coarse(u16, -1.0, 2.0, 16, scale_factor=scale)
+    assert len(dims) >= 2 and o["computed_pixels"] > 0
+    for p in range(len(dims)):
+        assert_same(r["levels"][p], o["levels"][p], ["edge_mask", "edge_conf", "dmin", "dmax", "best_depth", "disp_conf"], "u16 level %d" % p)
+    assert_same(r, o, ["valid", "map"], "u16 fused")
+
+
 GOLDEN = ["ref_pile_c3", "ref_pile_c1_u8", "ref_2d_c3", "ref_ftc_c1", "ref_ftc_c3_u8"]
 
 
