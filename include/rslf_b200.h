@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-/* OpenCV depth codes accepted by rslf_cuda_upload_epis (CV_8U = 0, CV_32F = 5). */
+/* OpenCV depth codes accepted by rslf_cuda_upload_epis (CV_8U = 0, CV_16U = 2, CV_32F = 5). */
 #define RSLF_DEPTH_8U  0
 #define RSLF_DEPTH_16U 2
 #define RSLF_DEPTH_32F 5
@@ -207,6 +207,10 @@ int rslf_cuda_downsample_epis(rslf_ctx* ctx, const float* in_epis, int V, int S,
  * ([8,28,56,72,56,28,8]/256 twice, (acc + 2^15) >> 16) and integer half-size resize, bit-exact to cv2. */
 int rslf_cuda_downsample_epis_u8(rslf_ctx* ctx, const uint8_t* in_epis, int V, int S,
                                  int U, int C, uint8_t* out_epis, int* V2, int* U2);
+/* The same for CV_16U stacks (they stay 16-bit): the same integer Gaussian and integer half-size resize
+ * ((a+b+c+d+2) >> 2: OpenCV's own code; an IPP build of OpenCV rounds the 2x2 ties to even instead). */
+int rslf_cuda_downsample_epis_u16(rslf_ctx* ctx, const uint16_t* in_epis, int V, int S,
+                                  int U, int C, uint16_t* out_epis, int* V2, int* U2);
 /* rslf::fuse_disp_maps (src/rslf_fine_to_coarse_core.cpp:69-135).  disp_p[p] and
  * valid_p[p] are dense [S][V_p][U_p] host maps, finest first. */
 int rslf_cuda_fuse_disp_maps(rslf_ctx* ctx, int levels, int S, const int* Vp,

@@ -47,11 +47,14 @@ using Vec3f = cv::Vec3f;
 /* ---- minimal cv::Mat stand-in (layout-compatible subset) ---- */
 #ifndef CV_8U
 #define CV_8U 0
+#define CV_16U 2
 #define CV_32F 5
 #define CV_CN_SHIFT 3
 #define CV_MAKETYPE(depth, cn) (((depth) & 7) + (((cn) - 1) << CV_CN_SHIFT))
 #define CV_8UC1 CV_MAKETYPE(CV_8U, 1)
 #define CV_8UC3 CV_MAKETYPE(CV_8U, 3)
+#define CV_16UC1 CV_MAKETYPE(CV_16U, 1)
+#define CV_16UC3 CV_MAKETYPE(CV_16U, 3)
 #define CV_32FC1 CV_MAKETYPE(CV_32F, 1)
 #define CV_32FC3 CV_MAKETYPE(CV_32F, 3)
 #endif
@@ -83,7 +86,7 @@ public:
     int type() const { return m_type; }
     int depth() const { return m_type & 7; }
     int channels() const { return (m_type >> CV_CN_SHIFT) + 1; }
-    size_t elemSize1() const { return depth() == CV_8U ? 1 : 4; }
+    size_t elemSize1() const { return depth() == CV_8U ? 1 : depth() == CV_16U ? 2 : 4; }
     size_t elemSize() const { return elemSize1() * channels(); }
     bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
     bool isContinuous() const { return step == (size_t)cols * elemSize(); }

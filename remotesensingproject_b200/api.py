@@ -18,7 +18,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RSLF_B200_LIB") or os.path.join(_HERE, "librslf_b200.so")
 
 RSLF_DEPTH_8U = 0
+RSLF_DEPTH_16U = 2
 RSLF_DEPTH_32F = 5
+_DEPTH_OF = {np.dtype(np.uint8): RSLF_DEPTH_8U, np.dtype(np.uint16): RSLF_DEPTH_16U, np.dtype(np.float32): RSLF_DEPTH_32F}
 
 
 class RslfError(RuntimeError):
@@ -117,11 +119,11 @@ class Context:
     # ---- input ----------------------------------------------------------------
     def upload_epis(self, epis, epi_scale_factor=-1.0):
         """epis: the reference's Vec<Mat> — a [V][S][U][C] (or [V][S][U]) array or a list of V
-        [S][U][C] arrays; uint8 or float32 host memory (numpy, or a pinned CPU torch tensor)."""
+        [S][U][C] arrays; uint8, uint16 or float32 host memory (numpy, or a pinned CPU torch tensor)."""
         mats = _as_mats(epis)
         V = len(mats)
         S, U, Cc = mats[0].shape
-        depth = RSLF_DEPTH_8U if mats[0].dtype == np.uint8 else RSLF_DEPTH_32F
+        depth = _DEPTH_OF[mats[0].dtype]
         ptrs = (C.c_void_p * V)(*[m.ctypes.data for m in mats])
         step = mats[0].strides[0]
         self.check(lib().rslf_cuda_upload_epis(self._h, ptrs, V, S, U, Cc, depth, C.c_size_t(step),
@@ -134,7 +136,7 @@ class Context:
         mats = _as_mats(imgs)
         S = len(mats)
         V, U, Cc = mats[0].shape
-        depth = RSLF_DEPTH_8U if mats[0].dtype == np.uint8 else RSLF_DEPTH_32F
+        depth = _DEPTH_OF[mats[0].dtype]
         ptrs = (C.c_void_p * S)(*[m.ctypes.data for m in mats])
         self.check(lib().rslf_cuda_upload_images(self._h, ptrs, S, V, U, Cc, depth, C.c_size_t(mats[0].strides[0]),
                                                  C.c_float(epi_scale_factor)), "rslf_cuda_upload_images")
@@ -142,11 +144,11 @@ class Context:
         self._keep = None
 
     def set_epis_device(self, t, epi_scale_factor=-1.0):
-        """t: a CUDA torch tensor [V][S][U][C], float32 or uint8, contiguous, on this ctx's device."""
+        """t: a CUDA torch tensor [V][S][U][C], float32, uint16 or uint8, contiguous, on this ctx's device."""
         if not (t.is_cuda and t.is_contiguous() and t.dim() == 4):
             raise RslfError("set_epis_device needs a contiguous 4-d CUDA tensor")
         V, S, U, Cc = t.shape
-        depth = RSLF_DEPTH_8U if t.element_size() == 1 else RSLF_DEPTH_32F
+        depth = {1: RSLF_DEPTH_8U, 2: RSLF_DEPTH_16U}.get(t.element_size(), RSLF_DEPTH_32F)
         self.check(lib().rslf_cuda_set_epis_device(self._h, C.c_void_p(t.data_ptr()), V, S, U, Cc, depth,
                                                    C.c_float(epi_scale_factor)), "rslf_cuda_set_epis_device")
         self.dims = (V, S, U, Cc)
@@ -257,6 +259,12 @@ class Context:
             self.check(lib().rslf_cuda_downsample_epis_u8(self._h, _bp(raw), V, S, U, Cc, _bp(out), C.byref(v2),
                                                           C.byref(u2)), "rslf_cuda_downsample_epis_u8")
             return out
+        if raw.dtype == np.uint16:
+            out = np.empty((int(np.rint(V * 0.5)), S, int(np.rint(U * 0.5)), Cc), np.uint16)
+            self.check(lib().rslf_cuda_downsample_epis_u16(self._h, C.c_void_p(raw.ctypes.data), V, S, U, Cc,
+                                                           C.c_void_p(out.ctypes.data), C.byref(v2), C.byref(u2)),
+                       "rslf_cuda_downsample_epis_u16")
+            return out
         raw = np.ascontiguousarray(raw, np.float32)
         out = np.empty((int(np.rint(V * 0.5)), S, int(np.rint(U * 0.5)), Cc), np.float32)
         self.check(lib().rslf_cuda_downsample_epis(self._h, _fp(raw), V, S, U, Cc, _fp(out), C.byref(v2), C.byref(u2)),
@@ -350,8 +358,8 @@ def _as_mats(epis):
             epis = epis[..., None]
         if epis.ndim != 4:
             raise RslfError("expected [V][S][U][C] or [V][S][U]")
-        if epis.dtype not in (np.uint8, np.float32):
-            raise RslfError("only uint8 (CV_8U) and float32 (CV_32F) inputs are implemented")
+        if epis.dtype not in _DEPTH_OF:
+            raise RslfError("only uint8 (CV_8U), uint16 (CV_16U) and float32 (CV_32F) inputs are implemented")
         if not epis[0].flags["C_CONTIGUOUS"]:
             epis = np.ascontiguousarray(epis)
         return [epis[v] for v in range(epis.shape[0])]
@@ -361,8 +369,8 @@ def _as_mats(epis):
             m = m.numpy()
         if m.ndim == 2:
             m = m[..., None]
-        if m.dtype not in (np.uint8, np.float32):
-            raise RslfError("only uint8 (CV_8U) and float32 (CV_32F) inputs are implemented")
+        if m.dtype not in _DEPTH_OF:
+            raise RslfError("only uint8 (CV_8U), uint16 (CV_16U) and float32 (CV_32F) inputs are implemented")
         if m.strides[2] != m.itemsize or m.strides[1] != m.itemsize * m.shape[2]:
             m = np.ascontiguousarray(m)
         mats.append(m)

@@ -58,6 +58,23 @@ __global__ void normalise_u8_kernel(const uint8_t* __restrict__ in, size_t n, fl
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         out[i] = (float)in[i] * a;
 }
+/* CV_16U stacks: maximum for scale < 0 (minMaxLoc -> (float)max, dc.hpp:453-456; mm[0] holds the start value) and
+ * convertTo(CV_32F, 1.0 / scale) = float(x) * float(1.0 / scale) (dc.hpp:472-474) */
+__global__ void stack_max_u16_kernel(const uint16_t* __restrict__ x, size_t n, float* __restrict__ mm)
+{
+    unsigned mx = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        mx = max(mx, (unsigned)x[i]);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    if ((threadIdx.x & 31) == 0) atomic_max_float(mm, (float)mx);
+}
+__global__ void normalise_u16_kernel(const uint16_t* __restrict__ in, size_t n, float scale, float* __restrict__ out)
+{
+    const float a = (float)(1.0 / (double)scale);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = (float)in[i] * a;
+}
 
 /* ---- downsample_EPIs, float32 ------------------------------------------------
  * One block = one view s, one tile of DS_TV x DS_TU output pixels.  The input tile
@@ -132,21 +149,22 @@ downsample_kernel(const float* __restrict__ in, int V, int S, int U, float* __re
     }
 }
 
-/* ---- downsample_EPIs, 8-bit stacks (they stay 8-bit between levels, ftc.hpp:142-147) ----------------
- * OpenCV's CV_8U paths, bit-exact against cv2 (tests/golden/down_u8_*.npz): integer kernel
- * [8,28,56,72,56,28,8] (sum 256) along rows then columns, (acc + 2^15) >> 16, BORDER_REFLECT; half-size
+/* ---- downsample_EPIs, 8-bit and 16-bit stacks (they keep their depth between levels, ftc.hpp:142-147) ----
+ * OpenCV's integer paths, bit-exact against cv2 (tests/golden/down_u8_*.npz, tests/test_oracle_vs_cv2.py): integer
+ * kernel [8,28,56,72,56,28,8] (sum 256) along rows then columns, (acc + 2^15) >> 16, BORDER_REFLECT; half-size
  * resize = (a+b+c+d+2) >> 2, or the half-to-even rounded mean where an odd dimension leaves a single
- * source row / column.  Same tiling as the float kernel.
+ * source row / column.  Same tiling as the float kernel.  T = uint8_t / uint16_t; unsigned 32-bit
+ * accumulators (256 * 256 * 65535 + 2^15 < 2^32).
  */
-template <int C>
+template <typename T, int C>
 __global__ void __launch_bounds__(DS_THREADS)
-downsample_u8_kernel(const uint8_t* __restrict__ in, int V, int S, int U, uint8_t* __restrict__ out, int V2, int U2,
-                     int ov_begin, int ov_count)
+downsample_int_kernel(const T* __restrict__ in, int V, int S, int U, T* __restrict__ out, int V2, int U2,
+                      int ov_begin, int ov_count)
 {
     constexpr int IW = 2 * DS_TU + 6, IH = 2 * DS_TV + 6, BW = 2 * DS_TU;
-    __shared__ uint8_t tin[IH][IW * C];
-    __shared__ int hb[IH][BW * C];
-    const int K[7] = {8, 28, 56, 72, 56, 28, 8};
+    __shared__ T tin[IH][IW * C];
+    __shared__ unsigned hb[IH][BW * C];
+    const unsigned K[7] = {8u, 28u, 56u, 72u, 56u, 28u, 8u};
     const int s = blockIdx.z;
     const int ou0 = blockIdx.x * DS_TU, ov0 = ov_begin + blockIdx.y * DS_TV;
     const int iu0 = 2 * ou0 - 3, iv0 = 2 * ov0 - 3;
@@ -161,9 +179,9 @@ downsample_u8_kernel(const uint8_t* __restrict__ in, int V, int S, int U, uint8_
     for (int i = threadIdx.x; i < IH * BW * C; i += DS_THREADS) {
         int r = i / (BW * C), rem = i - r * (BW * C);
         int p = rem / C, c = rem - p * C;
-        int acc = 0;
+        unsigned acc = 0;
 #pragma unroll
-        for (int j = 0; j < 7; ++j) acc += K[j] * (int)tin[r][(p + j) * C + c];
+        for (int j = 0; j < 7; ++j) acc += K[j] * (unsigned)tin[r][(p + j) * C + c];
         hb[r][rem] = acc;
     }
     __syncthreads();
@@ -173,22 +191,22 @@ downsample_u8_kernel(const uint8_t* __restrict__ in, int V, int S, int U, uint8_
         const int ov = ov0 + r, ou = ou0 + p;
         if (ov >= V2 || ov >= ov_begin + ov_count || ou >= U2) continue;
         const int nr = (2 * ov + 1 < V) ? 2 : 1, nc = (2 * ou + 1 < U) ? 2 : 1;
-        int sum = 0;
+        unsigned sum = 0;
         for (int a = 0; a < nr; ++a) {
             const int rr = 2 * ov + a - iv0;
             for (int b = 0; b < nc; ++b) {
                 const int cc = (2 * ou + b - 2 * ou0) * C + c;
-                int acc = 0;
+                unsigned acc = 0;
 #pragma unroll
                 for (int j = 0; j < 7; ++j) acc += K[j] * hb[rr + j - 3][cc];
-                sum += (acc + 32768) >> 16;
+                sum += (acc + 32768u) >> 16;
             }
         }
         const int n = nr * nc;
-        int res = sum;
-        if (n == 4) res = (sum + 2) >> 2;
-        else if (n == 2) res = (sum + ((sum >> 1) & 1)) >> 1;          /* half to even */
-        out[(((size_t)(ov - ov_begin) * S + s) * (size_t)U2 + ou) * C + c] = (uint8_t)res;
+        unsigned res = sum;
+        if (n == 4) res = (sum + 2u) >> 2;
+        else if (n == 2) res = (sum + ((sum >> 1) & 1u)) >> 1;          /* half to even */
+        out[(((size_t)(ov - ov_begin) * S + s) * (size_t)U2 + ou) * C + c] = (T)res;
     }
 }
 

@@ -22,7 +22,7 @@
 #include "rslf_comm.cuh"
 #include "k_peak.cuh"
 
-#define RSLF_ABI_VERSION 2
+#define RSLF_ABI_VERSION 3
 #define RSLF_COUNT_SLOTS 65536
 
 /* ------------------------------------------------------------------ helpers */
@@ -202,6 +202,22 @@ static int normalise_level(rslf_ctx* ctx, int p, const void* raw, int cv_depth)
         normalise_u8_kernel<<<stream_grid(ctx, n), 256, 0, ctx->stream>>>((const uint8_t*)raw, n, L.epi);
         L.nonneg = 1;
         ctx->timing.kernel_launches += 1;
+    } else if (cv_depth == RSLF_DEPTH_16U) {
+        float sf = ctx->scale_factor;
+        if (sf < 0.f) {
+            /* the stack maximum over all ranks (start value = the scale factor, dc.hpp:445) */
+            float init[2] = {sf, 0.f}, mx = sf;
+            RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->minmax, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+            stack_max_u16_kernel<<<stream_grid(ctx, n), 256, 0, ctx->stream>>>((const uint16_t*)raw, n, ctx->minmax);
+            RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(&mx, ctx->minmax, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+            RSLF_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            if (ctx->world > 1 && !L.replicated) RSLF_TRY(comm_allreduce_max(ctx, ctx->minmax, 1, &mx));
+            sf = mx;
+            ctx->timing.kernel_launches += 1;
+        }
+        L.nonneg = (sf > 0.f) ? 1 : 0;
+        normalise_u16_kernel<<<stream_grid(ctx, n), 256, 0, ctx->stream>>>((const uint16_t*)raw, n, sf, L.epi);
+        ctx->timing.kernel_launches += 1;
     } else {
         /* max (start value = the scale factor, dc.hpp:445) and min of the stack */
         float init[2] = {ctx->scale_factor, std::numeric_limits<float>::infinity()};
@@ -341,14 +357,17 @@ extern "C" int rslf_cuda_flush_l2(rslf_ctx* ctx)
 static int set_dims(rslf_ctx* ctx, int V, int S, int U, int C, int cv_depth, float scale)
 {
     if (V < 1 || S < 1 || U < 1 || (C != 1 && C != 3)) { snprintf(ctx->err, sizeof(ctx->err), "bad dimensions"); return RSLF_ERR_ARG; }
-    if (cv_depth != RSLF_DEPTH_8U && cv_depth != RSLF_DEPTH_32F) {
-        snprintf(ctx->err, sizeof(ctx->err), "only CV_8U and CV_32F inputs are implemented"); return RSLF_ERR_UNSUPPORTED;
+    if (cv_depth != RSLF_DEPTH_8U && cv_depth != RSLF_DEPTH_16U && cv_depth != RSLF_DEPTH_32F) {
+        snprintf(ctx->err, sizeof(ctx->err), "only CV_8U, CV_16U and CV_32F inputs are implemented"); return RSLF_ERR_UNSUPPORTED;
     }
     if ((size_t)S * 4 > RSLF_COUNT_SLOTS / RSLF_MAX_LEVELS) { snprintf(ctx->err, sizeof(ctx->err), "S too large"); return RSLF_ERR_UNSUPPORTED; }
     ctx->V = V; ctx->S = S; ctx->U = U; ctx->C = C; ctx->cv_depth = cv_depth; ctx->scale_factor = scale;
     if (ctx->V_total == 0 || ctx->world == 1) { ctx->v0 = 0; ctx->V_total = V; }
     return RSLF_OK;
 }
+
+/* bytes of one value of a raw stack */
+static inline size_t depth_esz(int cv_depth) { return cv_depth == RSLF_DEPTH_8U ? 1 : cv_depth == RSLF_DEPTH_16U ? 2 : 4; }
 
 static int own_raw(rslf_ctx* ctx, size_t bytes)
 {
@@ -369,7 +388,7 @@ extern "C" int rslf_cuda_upload_epis(rslf_ctx* ctx, const void* const* epi_ptrs,
     if (!ctx || !epi_ptrs) return RSLF_ERR_ARG;
     RSLF_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     RSLF_TRY(set_dims(ctx, V, S, U, C, cv_depth, epi_scale_factor));
-    const size_t esz = (cv_depth == RSLF_DEPTH_8U) ? 1 : 4;
+    const size_t esz = depth_esz(cv_depth);
     const size_t row = (size_t)U * C * esz;
     if (row_step_bytes < row) { snprintf(ctx->err, sizeof(ctx->err), "row step smaller than a row"); return RSLF_ERR_ARG; }
     const size_t epi_bytes = row * S;
@@ -423,7 +442,7 @@ extern "C" int rslf_cuda_upload_images(rslf_ctx* ctx, const void* const* img_ptr
     if (!ctx || !img_ptrs) return RSLF_ERR_ARG;
     RSLF_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     RSLF_TRY(set_dims(ctx, V, S, U, C, cv_depth, epi_scale_factor));
-    const size_t esz = (cv_depth == RSLF_DEPTH_8U) ? 1 : 4;
+    const size_t esz = depth_esz(cv_depth);
     const size_t row = (size_t)U * C * esz;
     if (row_step_bytes < row) return RSLF_ERR_ARG;
     const size_t img_bytes = row * V;
@@ -438,6 +457,7 @@ extern "C" int rslf_cuda_upload_images(rslf_ctx* ctx, const void* const* img_ptr
     }
     dim3 grid(std::max(1, std::min(8, rslf_div_up((long long)U * C, 256))), S, V);
     if (esz == 1) build_epis_kernel<uint8_t><<<grid, 256, 0, ctx->stream>>>((const uint8_t*)staging, S, V, (size_t)U * C, (uint8_t*)ctx->raw_in);
+    else if (esz == 2) build_epis_kernel<uint16_t><<<grid, 256, 0, ctx->stream>>>((const uint16_t*)staging, S, V, (size_t)U * C, (uint16_t*)ctx->raw_in);
     else build_epis_kernel<float><<<grid, 256, 0, ctx->stream>>>((const float*)staging, S, V, (size_t)U * C, (float*)ctx->raw_in);
     cudaEventRecord(ctx->ev_b, ctx->stream);
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
@@ -885,13 +905,14 @@ static int launch_downsample(rslf_ctx* ctx, const float* in, int V, int S, int U
     return RSLF_OK;
 }
 
-static int launch_downsample_u8(rslf_ctx* ctx, const uint8_t* in, int V, int S, int U, int C, uint8_t* out, int V2, int U2,
-                                int ov_begin = 0, int ov_count = -1)
+template <typename T>
+static int launch_downsample_int(rslf_ctx* ctx, const T* in, int V, int S, int U, int C, T* out, int V2, int U2,
+                                 int ov_begin = 0, int ov_count = -1)
 {
     if (ov_count < 0) ov_count = V2;
     dim3 grid(rslf_div_up(U2, DS_TU), rslf_div_up(ov_count, DS_TV), S);
-    if (C == 1) downsample_u8_kernel<1><<<grid, DS_THREADS, 0, ctx->stream>>>(in, V, S, U, out, V2, U2, ov_begin, ov_count);
-    else downsample_u8_kernel<3><<<grid, DS_THREADS, 0, ctx->stream>>>(in, V, S, U, out, V2, U2, ov_begin, ov_count);
+    if (C == 1) downsample_int_kernel<T, 1><<<grid, DS_THREADS, 0, ctx->stream>>>(in, V, S, U, out, V2, U2, ov_begin, ov_count);
+    else downsample_int_kernel<T, 3><<<grid, DS_THREADS, 0, ctx->stream>>>(in, V, S, U, out, V2, U2, ov_begin, ov_count);
     RSLF_CUDA_TRY(ctx, cudaGetLastError());
     ctx->timing.kernel_launches += 1;
     return RSLF_OK;
@@ -1030,7 +1051,7 @@ extern "C" int rslf_cuda_fine_to_coarse_run(rslf_ctx* ctx, float dmin, float dma
         rslf_level& L = ctx->lv[p];
         const size_t px = (size_t)S * Vl[p] * Up[p];
         const void* raw = (p == 0) ? ctx->raw_in : (const void*)L.raw;
-        /* 8-bit stacks stay 8-bit between levels (OpenCV's integer blur / resize), float stacks stay float */
+        /* 8-bit / 16-bit stacks keep their depth between levels (OpenCV's integer blur / resize), float stacks stay float */
         RSLF_TRY(normalise_level(ctx, p, raw, ctx->cv_depth));
         rslf_params P = P0;
         P.slope_factor = (float)((0.0 + Up[p]) / Up[0]);                        /* ftc.hpp:139 */
@@ -1052,7 +1073,7 @@ extern "C" int rslf_cuda_fine_to_coarse_run(rslf_ctx* ctx, float dmin, float dma
                 const bool sh = (ctx->world > 1 && !rep[p]);             /* level p is sharded */
                 /* next level's raw stack (ftc.hpp:146): the 7x7 blur reads 3 rows beyond the rank's block, so a
                  * sharded level first gathers its raw rows */
-                const size_t esz = (ctx->cv_depth == RSLF_DEPTH_8U) ? 1 : sizeof(float);
+                const size_t esz = depth_esz(ctx->cv_depth);
                 const void* ds_in = raw;
                 if (sh) {
                     RSLF_TRY(comm_gather_rows(ctx, raw, (size_t)S * Up[p] * C * esz, tabs[p], ctx->g_raw));
@@ -1060,7 +1081,9 @@ extern "C" int rslf_cuda_fine_to_coarse_run(rslf_ctx* ctx, float dmin, float dma
                 }
                 const int ov0 = rep[p + 1] ? 0 : tabs[p + 1].b[r];
                 if (ctx->cv_depth == RSLF_DEPTH_8U)
-                    RSLF_TRY(launch_downsample_u8(ctx, (const uint8_t*)ds_in, Vp[p], S, Up[p], C, (uint8_t*)N.raw, Vp[p + 1], Up[p + 1], ov0, Vl[p + 1]));
+                    RSLF_TRY(launch_downsample_int<uint8_t>(ctx, (const uint8_t*)ds_in, Vp[p], S, Up[p], C, (uint8_t*)N.raw, Vp[p + 1], Up[p + 1], ov0, Vl[p + 1]));
+                else if (ctx->cv_depth == RSLF_DEPTH_16U)
+                    RSLF_TRY(launch_downsample_int<uint16_t>(ctx, (const uint16_t*)ds_in, Vp[p], S, Up[p], C, (uint16_t*)N.raw, Vp[p + 1], Up[p + 1], ov0, Vl[p + 1]));
                 else
                     RSLF_TRY(launch_downsample(ctx, (const float*)ds_in, Vp[p], S, Up[p], C, N.raw, Vp[p + 1], Up[p + 1], ov0, Vl[p + 1]));
                 const size_t npx = (size_t)S * Vl[p + 1] * Up[p + 1];
@@ -1208,8 +1231,8 @@ extern "C" int rslf_cuda_downsample_epis(rslf_ctx* ctx, const float* in_epis, in
     return rc;
 }
 
-extern "C" int rslf_cuda_downsample_epis_u8(rslf_ctx* ctx, const uint8_t* in_epis, int V, int S, int U, int C,
-                                            uint8_t* out_epis, int* V2o, int* U2o)
+template <typename T>
+static int downsample_epis_int(rslf_ctx* ctx, const T* in_epis, int V, int S, int U, int C, T* out_epis, int* V2o, int* U2o)
 {
     if (!ctx || !in_epis || !out_epis || (C != 1 && C != 3) || V < 1 || S < 1 || U < 1) return RSLF_ERR_ARG;
     RSLF_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -1217,20 +1240,32 @@ extern "C" int rslf_cuda_downsample_epis_u8(rslf_ctx* ctx, const uint8_t* in_epi
     if (V2o) *V2o = V2;
     if (U2o) *U2o = U2;
     if (V2 < 1 || U2 < 1) return RSLF_ERR_ARG;
-    uint8_t *din = nullptr, *dout = nullptr;
+    T *din = nullptr, *dout = nullptr;
     const size_t nin = (size_t)V * S * U * C, nout = (size_t)V2 * S * U2 * C;
     RSLF_TRY(dev_alloc(ctx, &din, nin));
     int rc = dev_alloc(ctx, &dout, nout);
     if (rc == RSLF_OK) {
-        cudaMemcpyAsync(din, in_epis, nin, cudaMemcpyHostToDevice, ctx->stream);
-        rc = launch_downsample_u8(ctx, din, V, S, U, C, dout, V2, U2);
+        cudaMemcpyAsync(din, in_epis, nin * sizeof(T), cudaMemcpyHostToDevice, ctx->stream);
+        rc = launch_downsample_int<T>(ctx, din, V, S, U, C, dout, V2, U2);
         if (rc == RSLF_OK) {
-            cudaMemcpyAsync(out_epis, dout, nout, cudaMemcpyDeviceToHost, ctx->stream);
+            cudaMemcpyAsync(out_epis, dout, nout * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream);
             if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = RSLF_ERR_CUDA;
         }
     }
     dev_free(&din); dev_free(&dout);
     return rc;
+}
+
+extern "C" int rslf_cuda_downsample_epis_u8(rslf_ctx* ctx, const uint8_t* in_epis, int V, int S, int U, int C,
+                                            uint8_t* out_epis, int* V2o, int* U2o)
+{
+    return downsample_epis_int<uint8_t>(ctx, in_epis, V, S, U, C, out_epis, V2o, U2o);
+}
+
+extern "C" int rslf_cuda_downsample_epis_u16(rslf_ctx* ctx, const uint16_t* in_epis, int V, int S, int U, int C,
+                                             uint16_t* out_epis, int* V2o, int* U2o)
+{
+    return downsample_epis_int<uint16_t>(ctx, in_epis, V, S, U, C, out_epis, V2o, U2o);
 }
 
 extern "C" int rslf_cuda_set_bounds(rslf_ctx* ctx, const float* depth_up, const uint8_t* valid_up, int S, int Vu, int Uu,

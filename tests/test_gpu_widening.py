@@ -103,3 +103,70 @@ def test_opening_rejects_what_it_cannot_do(gpu_ctx):
         gpu_ctx.edge_confidence(1, api.default_params(edge_confidence_opening_size=33))     # element larger than 31
     with pytest.raises(api.RslfError):
         gpu_ctx.edge_confidence(1, api.default_params(edge_confidence_opening_type=7, edge_confidence_opening_size=3))
+
+
+# --------------------------------------------------------------------------- CV_16U input
+def u16_stack(S, V, U, C, seed, peak):
+    return np.clip(np.rint(lf(S, V, U, C, seed=seed) * peak), 0, 65535).astype(np.uint16)
+
+
+@pytest.mark.parametrize("V,U,C", [(13, 27, 3), (20, 32, 1), (9, 135, 1), (40, 70, 3), (2, 3, 3)])
+def test_downsample_uint16(gpu_ctx, V, U, C):
+    """downsample_EPIs on CV_16U stacks (integer Gaussian, (a+b+c+d+2) >> 2), incl. exact ties of the blur."""
+    rng = np.random.default_rng(V * 1000 + U)
+    raw = rng.integers(0, 65536, size=(V, 3, U, C)).astype(np.uint16)
+    got = gpu_ctx.downsample_epis(raw)
+    want = oracle.downsample(raw)
+    assert got.dtype == np.uint16
+    same(got, want, "u16 downsample")
+    ties = (raw // 128 * 128).astype(np.uint16)
+    same(gpu_ctx.downsample_epis(ties), oracle.downsample(ties), "u16 downsample, tie values")
+    top = np.full((V, 2, U, C), 65535, np.uint16)                       # accumulators at their maximum
+    same(gpu_ctx.downsample_epis(top), oracle.downsample(top), "u16 downsample, saturated")
+
+
+@pytest.mark.parametrize("C,scale", [(3, -1.0), (1, -1.0), (3, 4095.0)])
+def test_uint16_input_through_the_computers(gpu_ctx, C, scale):
+    """dc.hpp:442-477: x float(1 / scale), scale = stack maximum (scale < 0) or the given factor."""
+    raw = u16_stack(7, 10, 56, C, seed=70 + C, peak=4095.0 if scale > 0 else 60000.0)
+    norm = oracle.normalise(raw, scale)
+    comp = api.Depth1DComputer_pile(raw, -1.0, 2.0, 24, epi_scale_factor=scale, ctx=gpu_ctx).run()
+    ref = oracle.depth1d_pile(norm, -1.0, 2.0, 24)
+    gpu = dict(best_depth=comp.m_best_depth_v_u, edge_conf=comp.m_edge_confidence_v_u,
+               edge_mask=comp.m_edge_confidence_mask_v_u, disp_conf=comp.m_disp_confidence_v_u, rbar=comp.m_rbar_v_u)
+    assert ref["computed_pixels"] > 0
+    for k in MAPS:
+        same(gpu[k], ref[k], "u16 pile " + k)
+    c2 = api.Depth2DComputer(raw, -1.0, 2.0, 24, epi_scale_factor=scale, ctx=gpu_ctx).run()
+    r2 = oracle.depth2d(norm, -1.0, 2.0, 24)
+    g2 = dict(best_depth=c2.m_best_depth_s_v_u, edge_conf=c2.m_edge_confidence_s_v_u,
+              edge_mask=c2.m_edge_confidence_mask_s_v_u, disp_conf=c2.m_disp_confidence_s_v_u, rbar=c2.m_rbar_s_v_u)
+    for k in MAPS:
+        same(g2[k], r2[k], "u16 2d " + k)
+
+
+@pytest.mark.parametrize("S,V,U,C,scale", [(5, 44, 70, 3, -1.0), (4, 27, 135, 1, -1.0), (5, 24, 50, 3, 4095.0)])
+def test_uint16_fine_to_coarse(gpu_ctx, S, V, U, C, scale):
+    """The pyramid stays 16-bit between levels (ftc.hpp:142-147); every level is normalised from its own raw stack."""
+    raw = u16_stack(S, V, U, C, seed=V, peak=4095.0 if scale > 0 else 60000.0)
+    f = api.FineToCoarse(raw, -1.0, 2.0, 16, epi_scale_factor=scale, ctx=gpu_ctx).run()
+    m, v = f.get_results()
+    r = oracle.fine_to_coarse(raw, -1.0, 2.0, 16, scale_factor=scale)
+    assert len(r["dims"]) >= 2 and r["computed_pixels"] > 0
+    assert gpu_ctx.timing()["computed_pixels"] == r["computed_pixels"]
+    for p, (g, o) in enumerate(zip(f.get_levels(), r["levels"])):
+        for k in ("edge_mask", "edge_conf", "dmin", "dmax", "best_depth", "disp_conf"):
+            same(g[k], o[k], "u16 level %d %s" % (p, k))
+    same(v, r["valid"], "u16 ftc valid")
+    same(m, r["map"], "u16 ftc map")
+
+
+def test_uint16_images_upload(gpu_ctx):
+    """rslf_cuda_upload_images (build_epis_from_imgs, rslf_io.cpp:194-227) with 16-bit frames."""
+    raw = u16_stack(5, 8, 40, 3, seed=3, peak=50000.0)
+    imgs = np.ascontiguousarray(raw.transpose(1, 0, 2, 3))               # [S][V][U][C]
+    gpu_ctx.upload_images(imgs, epi_scale_factor=-1.0)
+    ce, m = gpu_ctx.edge_confidence(2, api.default_params())
+    ce_o, m_o = oracle.edge_confidence(oracle.normalise(raw, -1.0), 2)
+    same(m, m_o, "u16 images mask")
+    same(ce, ce_o, "u16 images C_e")
