@@ -239,6 +239,22 @@ def fuse(disp_p, valid_p):
     return out_map, out_valid
 
 
+def colour_maps(out_map, out_valid, epis0_norm, lut_bgr, saturate=True, cut_shadows=True):
+    """FineToCoarse::get_coloured_depth_maps (ftc.hpp:324-377) from the fused results of fine_to_coarse():
+    out_map / out_valid [S][V][U], epis0_norm = normalise(raw) [V][S][U][C], lut_bgr = 256 x 3 colour table.
+    Returns ([S][V][U][3] uint8, (fit min, fit max))."""
+    out_map = _c32(out_map)
+    out_valid = np.ascontiguousarray(out_valid, np.uint8)
+    epis0_norm = _c32(epis0_norm)
+    lut = np.ascontiguousarray(lut_bgr, np.uint8).reshape(256, 3)
+    V, S, U, Cc = epis0_norm.shape
+    out = np.zeros((S, V, U, 3), np.uint8)
+    mm = np.zeros(2, np.float64)
+    lib().orc_colour_maps(_f(out_map), _b(out_valid), _f(epis0_norm), V, S, U, Cc, _b(lut), int(bool(saturate)),
+                          int(bool(cut_shadows)), _b(out), mm.ctypes.data_as(C.POINTER(C.c_double)))
+    return out, (float(mm[0]), float(mm[1]))
+
+
 def resize_linear(src, Vd, Ud):
     src = _c32(src)
     dst = np.zeros((Vd, Ud), np.float32)

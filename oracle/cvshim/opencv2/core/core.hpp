@@ -20,6 +20,7 @@
 #define CVSHIM_CORE_HPP
 
 #include <algorithm>
+#include <cassert>
 #include <cmath>
 #include <cstddef>
 #include <cstdint>
@@ -150,6 +151,11 @@ enum { CMP_EQ = 0, CMP_GT = 1, CMP_GE = 2, CMP_LT = 3, CMP_LE = 4, CMP_NE = 5 };
 enum { MORPH_RECT = 0, MORPH_CROSS = 1, MORPH_ELLIPSE = 2 };
 enum { MORPH_ERODE = 0, MORPH_DILATE = 1, MORPH_OPEN = 2, MORPH_CLOSE = 3 };
 enum { COLORMAP_AUTUMN = 0, COLORMAP_BONE = 1, COLORMAP_JET = 2 };
+/* OpenCV 3.x C-API constants still used by the reference (rslf_plot.cpp:71) */
+#define CV_SORT_EVERY_ROW 0
+#define CV_SORT_EVERY_COLUMN 1
+#define CV_SORT_ASCENDING 0
+#define CV_SORT_DESCENDING 16
 enum { ROTATE_90_CLOCKWISE = 0, ROTATE_180 = 1, ROTATE_90_COUNTERCLOCKWISE = 2 };
 enum { DFT_INVERSE = 1, DFT_SCALE = 2, DFT_ROWS = 4, DFT_COMPLEX_OUTPUT = 16, DFT_REAL_OUTPUT = 32 };
 enum { WINDOW_NORMAL = 0, WINDOW_AUTOSIZE = 1 };
@@ -229,6 +235,7 @@ public:
     Mat colRange(const Range& r) const { return r.is_all() ? *this : colRange(r.start, r.end); }
     Mat operator()(const Range& rr, const Range& cr) const { return rowRange(rr).colRange(cr); }
     Mat operator()(const Rect& r) const { return rowRange(r.y, r.y + r.height).colRange(r.x, r.x + r.width); }
+    Mat operator()(const Range* ranges) const { return rowRange(ranges[0]).colRange(ranges[1]); }
 
     template <typename T> T* ptr(int y = 0) { return reinterpret_cast<T*>(data + (size_t)y * step); }
     template <typename T> const T* ptr(int y = 0) const { return reinterpret_cast<const T*>(data + (size_t)y * step); }
@@ -766,8 +773,29 @@ inline std::ostream& operator<<(std::ostream& os, const Size& s) { return os << 
 template <typename T> inline std::ostream& operator<<(std::ostream& os, const Point_<T>& p) { return os << "[" << p.x << ", " << p.y << "]"; }
 
 /* ---------------------------------------------------------------- declared, outside the depth path */
-inline void meanStdDev(const Mat&, Scalar&, Scalar&) { shim_abort("meanStdDev"); }
-inline void sort(const Mat&, Mat&, int) { shim_abort("sort"); }
+/* cv::meanStdDev of a single-channel CV_32F image: double sums, std = sqrt(max(sum(x^2) / N - mean^2, 0)) */
+inline void meanStdDev(const Mat& m, Scalar& mean, Scalar& stddev)
+{
+    shim_check(m.type() == CV_32FC1 && !m.empty(), "meanStdDev: CV_32FC1");
+    double s = 0, sq = 0;
+    for (int y = 0; y < m.rows; ++y)
+        for (int x = 0; x < m.cols; ++x) { const double v = m.ptr<float>(y)[x]; s += v; sq += v * v; }
+    const double n = (double)m.rows * m.cols, mu = s / n;
+    mean = Scalar(mu); stddev = Scalar(std::sqrt(std::max(sq / n - mu * mu, 0.0)));
+}
+/* cv::sort: every column of a CV_32FC1 matrix, ascending (rslf_plot.cpp:71) */
+inline void sort(const Mat& src, Mat& dst, int flags)
+{
+    shim_check(src.type() == CV_32FC1 && flags == (CV_SORT_EVERY_COLUMN + CV_SORT_ASCENDING), "sort: columns of CV_32FC1, ascending");
+    Mat S = src, out(S.rows, S.cols, CV_32FC1);
+    std::vector<float> col(S.rows);
+    for (int x = 0; x < S.cols; ++x) {
+        for (int y = 0; y < S.rows; ++y) col[y] = S.ptr<float>(y)[x];
+        std::sort(col.begin(), col.end());
+        for (int y = 0; y < S.rows; ++y) out.ptr<float>(y)[x] = col[y];
+    }
+    dst = out;
+}
 inline int getOptimalDFTSize(int) { shim_abort("getOptimalDFTSize"); }
 inline void dft(const Mat&, Mat&, int = 0, int = 0) { shim_abort("dft"); }
 inline void idft(const Mat&, Mat&, int = 0, int = 0) { shim_abort("idft"); }

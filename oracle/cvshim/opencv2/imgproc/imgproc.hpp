@@ -294,7 +294,23 @@ inline void morphologyEx(const Mat& src, Mat& dst, int op, const Mat& kernel)
     if (dst.rows == V && dst.cols == U && dst.type() == CV_8UC1 && dst.data) out.copyTo(dst);
     else dst = out;
 }
-inline void applyColorMap(const Mat&, Mat&, int) { shim_abort("applyColorMap"); }
+/* cv::applyColorMap: CV_8UC1 -> CV_8UC3 through a 256-entry BGR table.  OpenCV's tables are data of the real library:
+ * the driver hands in the table it was given (cv2.applyColorMap of a 0..255 ramp, tests/golden/colormap_jet.npy). */
+inline const uchar*& cvshim_colormap_lut() { static const uchar* lut = nullptr; return lut; }
+inline void applyColorMap(const Mat& src, Mat& dst, int)
+{
+    const uchar* lut = cvshim_colormap_lut();
+    shim_check(lut != nullptr, "applyColorMap: no colour table set");
+    shim_check(src.type() == CV_8UC1, "applyColorMap: CV_8UC1");
+    Mat S = src, out(S.rows, S.cols, CV_8UC3);
+    for (int y = 0; y < S.rows; ++y)
+        for (int x = 0; x < S.cols; ++x) {
+            const uchar* e = lut + 3 * (int)S.ptr<uchar>(y)[x];
+            uchar* o = out.ptr<uchar>(y) + 3 * x;
+            o[0] = e[0]; o[1] = e[1]; o[2] = e[2];
+        }
+    dst = out;
+}
 inline void cvtColor(const Mat&, Mat&, int, int = 0) { shim_abort("cvtColor"); }
 inline void line(Mat&, Point, Point, const Scalar&, int = 1, int = 8, int = 0) { shim_abort("line"); }
 

@@ -133,6 +133,22 @@ def fine_to_coarse(raw, dmin, dmax, D, scale_factor=-1.0, params=None, max_pyr_d
     return dict(map=out_map, valid=out_valid, levels=levels, dims=[(lvV[i], lvU[i]) for i in range(n)], seconds_run=secs.value)
 
 
+def fine_to_coarse_coloured(raw, dmin, dmax, D, lut_bgr, scale_factor=-1.0, params=None, saturate=True):
+    """rslf::FineToCoarse<T>: ctor, run, get_coloured_depth_maps(plots, COLORMAP_JET, saturate) with the colour table
+    lut_bgr (256 x 3) standing in for OpenCV's.  Returns [S][V][U][3] uint8 (BGR)."""
+    raw, depth = _raw(raw)
+    V, S, U, Cc = raw.shape
+    p = params or default_params()
+    lut = np.ascontiguousarray(lut_bgr, np.uint8).reshape(256, 3)
+    out = np.zeros((S, V, U, 3), np.uint8)
+    n = lib().ref_fine_to_coarse_coloured(raw.ctypes.data_as(C.c_void_p), depth, V, S, U, Cc, C.c_float(scale_factor),
+                                          C.c_float(dmin), C.c_float(dmax), int(D), C.byref(p), _b(lut),
+                                          int(bool(saturate)), _b(out))
+    if n != S:
+        raise ValueError("reference: get_coloured_depth_maps returned %d maps" % n)
+    return out
+
+
 def downsample(raw):
     """rslf::downsample_EPIs on a RAW stack (uint8 stays uint8)."""
     raw, depth = _raw(raw)

@@ -195,9 +195,41 @@ int ftc_t(const void* raw, int cv_depth, int V, int S, int U, int C, float scale
     return L;
 }
 
+/* FineToCoarse ctor + run + get_coloured_depth_maps (ftc.hpp:324-377): ImageConverter_uchar::fit on the fused map of
+ * view round(S / 2) (rslf_plot.cpp:66-98), copy_and_scale (:100-107), applyColorMap, invalid and shadow pixels black. */
+template <typename T>
+int ftc_coloured_t(const void* raw, int cv_depth, int V, int S, int U, int C, float scale, float dmin, float dmax, int D,
+                   const rslf_params* P, const uint8_t* lut_bgr, int saturate, uint8_t* out_bgr_svu3)
+{
+    rslf::Depth1DParameters<T> q;
+    fill_params(q, P);
+    RVec<Mat> epis = make_epis(raw, cv_depth, V, S, U, C);
+    rslf::FineToCoarse<T> ftc(epis, dmin, dmax, D, scale, q);
+    ftc.run();
+    cv::cvshim_colormap_lut() = lut_bgr;
+    RVec<Mat> plots;
+    ftc.get_coloured_depth_maps(plots, cv::COLORMAP_JET, saturate != 0);
+    cv::cvshim_colormap_lut() = nullptr;
+    for (size_t s = 0; s < plots.size(); ++s)
+        for (int v = 0; v < plots[s].rows; ++v)
+            std::memcpy(out_bgr_svu3 + ((s * V + v) * (size_t)U) * 3, plots[s].ptr(v), (size_t)U * 3);
+    delete q.par_interpolation_class;
+    delete q.par_kernel_class;
+    return (int)plots.size();
+}
+
 }  // namespace
 
 extern "C" {
+
+/* FineToCoarse::get_coloured_depth_maps with the colour table lut_bgr[256][3].  out: [S][V][U][3] uint8 (BGR). */
+int ref_fine_to_coarse_coloured(const void* raw, int cv_depth, int V, int S, int U, int C, float scale, float dmin, float dmax,
+                                int D, const rslf_params* P, const uint8_t* lut_bgr, int saturate, uint8_t* out_bgr_svu3)
+{
+    if (C == 1) return ftc_coloured_t<float>(raw, cv_depth, V, S, U, C, scale, dmin, dmax, D, P, lut_bgr, saturate, out_bgr_svu3);
+    if (C == 3) return ftc_coloured_t<cv::Vec3f>(raw, cv_depth, V, S, U, C, scale, dmin, dmax, D, P, lut_bgr, saturate, out_bgr_svu3);
+    return -1;
+}
 
 int ref_num_threads(void) { return omp_get_max_threads(); }
 void ref_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }

@@ -725,6 +725,60 @@ void fuse(int levels, int S, const int* Vp, const int* Up, const float* const* d
     }
 }
 
+/*
+ * FineToCoarse::get_coloured_depth_maps (ftc.hpp:324-377) after get_results: map / valid [S][V][U] fused results,
+ * epis0 = the normalised level-0 stack (m_computers[0]->get_epis()), lut = 256 x 3 colour table (cv::applyColorMap).
+ *  - ImageConverter_uchar::fit (rslf_plot.cpp:66-98) on the map of view (int)std::round(S / 2.0): saturate -> the
+ *    values of rank floor(0.02 N) and floor(0.98 N) of the sorted plane; else min = true minimum,
+ *    max = min(mean + 12 std, true maximum) (cv::meanStdDev, double sums);
+ *  - copy_and_scale (:100-107): float alpha = 255.0 / (max - min); convertTo(CV_8U, alpha, -alpha * min) =
+ *    saturate_cast<uchar>(cvRound(x * float(alpha) + float(beta))), multiply and add rounded separately (OpenCV 3.x
+ *    cvtScale_<float, uchar, float>; a 4.x build with FMA dispatch fuses them: DESIGN.md section 5);
+ *  - colour table, then black where the validity mask is 0 and, with par_cut_shadows, where
+ *    norm(E(s, u)) < _SHADOW_NORMALIZED_LEVEL (the macro core.hpp:30, not par_shadow_level).
+ * out: [S][V][U][3] uint8; fit_min_max (optional): the fitted min and max.
+ */
+void colour_maps(const float* map, const uint8_t* valid, const float* epis0, const Dims& g, const uint8_t* lut,
+                 bool saturate, bool cut_shadows, uint8_t* out, double* fit_min_max) {
+    const int S = g.S, V = g.V, U = g.U, C = g.C;
+    const size_t plane = (size_t)V * U;
+    const int s_fit = (int)std::round(S / 2.0);
+    const float* fitp = map + (size_t)s_fit * plane;
+    double mn, mx;
+    if (saturate) {
+        std::vector<float> sorted(fitp, fitp + plane);
+        std::sort(sorted.begin(), sorted.end());
+        mn = sorted[(size_t)std::floor(0.02 * (double)plane)];
+        mx = sorted[(size_t)std::floor(0.98 * (double)plane)];
+    } else {
+        double s = 0, sq = 0, tmin = fitp[0], tmax = fitp[0];
+        for (size_t i = 0; i < plane; ++i) {
+            const double v = fitp[i];
+            s += v; sq += v * v; tmin = std::min(tmin, v); tmax = std::max(tmax, v);
+        }
+        const double mu = s / (double)plane, sd = std::sqrt(std::max(sq / (double)plane - mu * mu, 0.0));
+        mn = tmin; mx = std::min(mu + 12 * sd, tmax);
+    }
+    if (fit_min_max) { fit_min_max[0] = mn; fit_min_max[1] = mx; }
+    const float alpha = (float)(255.0 / (mx - mn));
+    const double beta_d = -alpha * mn;                       /* float * double -> double (rslf_plot.cpp:106) */
+    const float a = (float)(double)alpha, b = (float)beta_d;
+    const float shadow = (float)(0.05 * 1.73205080757);      /* im_norm < _SHADOW_NORMALIZED_LEVEL on a CV_32F image */
+#pragma omp parallel for schedule(static)
+    for (int s = 0; s < S; ++s)
+        for (int v = 0; v < V; ++v)
+            for (int u = 0; u < U; ++u) {
+                const size_t o = (size_t)s * plane + (size_t)v * U + u;
+                float x = map[o] * a;
+                x = x + b;
+                int r = (int)std::nearbyint(x);              /* cvRound, then saturate_cast<uchar> */
+                r = r < 0 ? 0 : r > 255 ? 255 : r;
+                bool black = valid[o] == 0;
+                if (cut_shadows && norm_px(epis0 + epi_off(g, v, s, u), C) < shadow) black = true;
+                for (int c = 0; c < 3; ++c) out[o * 3 + c] = black ? 0 : lut[3 * r + c];
+            }
+}
+
 /* Input normalisation of the computers' ctors (dc.hpp:442-477, 668-704). */
 float normalise(const void* raw, int cv_depth, size_t n, float scale_factor, float* out) {
     if (cv_depth == RSLF_DEPTH_8U) {
@@ -908,6 +962,12 @@ void orc_set_bounds(const float* depth_up, const uint8_t* valid_up, int S, int V
 void orc_fuse(int levels, int S, const int* Vp, const int* Up, const float* const* disp, const uint8_t* const* valid,
               float* out_map, uint8_t* out_valid) {
     fuse(levels, S, Vp, Up, disp, valid, out_map, out_valid);
+}
+
+void orc_colour_maps(const float* map_svu, const uint8_t* valid_svu, const float* epis0_norm, int V, int S, int U, int C,
+                     const uint8_t* lut_bgr, int saturate, int cut_shadows, uint8_t* out_bgr, double* fit_min_max) {
+    Dims g{V, S, U, C};
+    colour_maps(map_svu, valid_svu, epis0_norm, g, lut_bgr, saturate != 0, cut_shadows != 0, out_bgr, fit_min_max);
 }
 
 void orc_resize_linear(const float* src, int Vs, int Us, float* dst, int Vd, int Ud) { resize_linear(src, Vs, Us, dst, Vd, Ud); }
