@@ -198,6 +198,16 @@ int rslf_cuda_fine_to_coarse_get_level(rslf_ctx* ctx, int level,
                                        uint8_t* edge_mask_svu, float* disp_conf_svu,
                                        float* dmin_svu, float* dmax_svu);
 
+/* FineToCoarse::get_coloured_depth_maps(plots, cv_colormap, saturate) (rslf_fine_to_coarse.hpp:324-377) of the last
+ * fine-to-coarse run: ImageConverter_uchar::fit on the fused map of view round(S / 2) (src/rslf_plot.cpp:66-98; the 2 %
+ * and 98 % order statistics), copy_and_scale to uchar (:100-107), colour table, pixels black where invalid or (with
+ * params->cut_shadows) darker than _SHADOW_NORMALIZED_LEVEL.  lut_bgr_256x3: the table cv::applyColorMap would use
+ * (apply it to the ramp 0..255 once; OpenCV's tables are not embedded here).  out_bgr_svu3: S x V x U x 3 uint8.
+ * fit_min_max (optional): the fitted range.  saturate = 0 (mean + 12 std) returns RSLF_ERR_UNSUPPORTED. */
+int rslf_cuda_fine_to_coarse_get_coloured(rslf_ctx* ctx, const uint8_t* lut_bgr_256x3, int saturate,
+                                          const rslf_params* params, uint8_t* out_bgr_svu3,
+                                          double* fit_min_max);
+
 /* ---- free functions of the reference (each one its own entry point) ------ */
 /* rslf::downsample_EPIs (src/rslf_fine_to_coarse_core.cpp:14-60), float32 stacks.
  * in: dense [V][S][U][C]; out: dense [V2][S][U2][C], V2 = cvRound(V/2). */

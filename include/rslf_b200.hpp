@@ -34,6 +34,10 @@
 #if __has_include(<opencv2/core.hpp>) && !defined(RSLF_B200_NO_OPENCV)
 #include <opencv2/core.hpp>
 #define RSLF_B200_HAVE_OPENCV 1
+#if __has_include(<opencv2/imgproc.hpp>)
+#include <opencv2/imgproc.hpp>              /* cv::applyColorMap, for get_coloured_depth_maps' colour table */
+#define RSLF_B200_HAVE_OPENCV_IMGPROC 1
+#endif
 #endif
 #endif
 
@@ -395,6 +399,32 @@ public:
         a_out_validity_s_v_u = detail::planes(m_dim_s, m_dim_v, m_dim_u, CV_8UC1);
         detail::scatter(map, a_out_map_s_v_u, m_dim_v, (size_t)m_dim_u);
         detail::scatter(valid, a_out_validity_s_v_u, m_dim_v, (size_t)m_dim_u);
+    }
+    /* coloured disparity maps, one CV_8UC3 (BGR) image per view (ftc.hpp:324-377).  With OpenCV the colour table is
+     * the one cv::applyColorMap(…, a_cv_colormap) uses; without it the caller supplies the 256 x 3 table. */
+    void get_coloured_depth_maps(Vec<Mat>& a_out_plot_depth_s_v_u, int a_cv_colormap = 2 /* cv::COLORMAP_JET */,
+                                 bool a_saturate = true, const unsigned char* a_lut_bgr_256x3 = nullptr)
+    {
+        unsigned char lut[768];
+        if (a_lut_bgr_256x3) std::memcpy(lut, a_lut_bgr_256x3, sizeof(lut));
+        else {
+#ifdef RSLF_B200_HAVE_OPENCV_IMGPROC
+            cv::Mat ramp(256, 1, CV_8UC1), table;
+            for (int i = 0; i < 256; ++i) ramp.at<unsigned char>(i) = (unsigned char)i;
+            cv::applyColorMap(ramp, table, a_cv_colormap);
+            std::memcpy(lut, table.data, sizeof(lut));
+#else
+            (void)a_cv_colormap;
+            throw Error(RSLF_ERR_ARG, "get_coloured_depth_maps: built without OpenCV's imgproc, pass the colour table");
+#endif
+        }
+        const size_t px = (size_t)m_dim_s * m_dim_v * m_dim_u;
+        std::vector<unsigned char> bgr(px * 3);
+        const rslf_params p = m_parameters.to_abi();
+        m_device->check(rslf_cuda_fine_to_coarse_get_coloured(m_device->get(), lut, a_saturate ? 1 : 0, &p, bgr.data(), nullptr),
+                        "rslf_cuda_fine_to_coarse_get_coloured");
+        a_out_plot_depth_s_v_u = detail::planes(m_dim_s, m_dim_v, m_dim_u, CV_8UC3);
+        detail::scatter(bgr, a_out_plot_depth_s_v_u, m_dim_v, (size_t)m_dim_u * 3);
     }
     rslf_timing get_timing() const { rslf_timing t; rslf_cuda_last_timing(m_device->get(), &t); return t; }
 

@@ -210,6 +210,18 @@ class Context:
                    "rslf_cuda_fine_to_coarse_get")
         return out_map, out_valid
 
+    def fine_to_coarse_coloured(self, lut_bgr, params, saturate=True):
+        """FineToCoarse::get_coloured_depth_maps of the last run -> ([S][V][U][3] uint8 BGR, (fit min, fit max))."""
+        V, S, U, Cc = self.dims
+        lut = np.ascontiguousarray(lut_bgr, np.uint8)
+        if lut.size != 768:
+            raise RslfError("the colour table must hold 256 x 3 bytes")
+        out = np.empty((S, V, U, 3), np.uint8)
+        mm = (C.c_double * 2)()
+        self.check(lib().rslf_cuda_fine_to_coarse_get_coloured(self._h, _bp(lut), int(bool(saturate)), C.byref(params),
+                                                               _bp(out), mm), "rslf_cuda_fine_to_coarse_get_coloured")
+        return out, (mm[0], mm[1])
+
     def fine_to_coarse_levels(self):
         V, S, U, Cc = self.dims
         n = lib().rslf_cuda_fine_to_coarse_level_dims(self._h, 0, None, None)
@@ -490,6 +502,15 @@ class FineToCoarse:
     def get_results(self, out_map=None, out_valid=None):
         """-> (out_map_s_v_u [S][V][U] float32, out_validity_s_v_u [S][V][U] uint8)."""
         return self.m_ctx.fine_to_coarse_get(out_map, out_valid)
+
+    def get_coloured_depth_maps(self, cv_colormap=2, saturate=True, lut_bgr=None):
+        """FineToCoarse::get_coloured_depth_maps(out, cv_colormap = COLORMAP_JET, saturate) (ftc.hpp:324-377) ->
+        [S][V][U][3] uint8 (BGR).  The colour table is OpenCV's: taken from cv2.applyColorMap of the ramp 0..255 unless
+        a 256 x 3 table is given."""
+        if lut_bgr is None:
+            import cv2
+            lut_bgr = cv2.applyColorMap(np.arange(256, dtype=np.uint8).reshape(256, 1), int(cv_colormap)).reshape(256, 3)
+        return self.m_ctx.fine_to_coarse_coloured(lut_bgr, self.m_parameters, saturate)[0]
 
     def get_levels(self):
         return self.m_ctx.fine_to_coarse_levels()

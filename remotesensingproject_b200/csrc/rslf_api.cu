@@ -19,6 +19,7 @@
 #include "k_median.cuh"
 #include "k_propagate.cuh"
 #include "k_pyramid.cuh"
+#include "k_colour.cuh"
 #include "rslf_comm.cuh"
 #include "k_peak.cuh"
 
@@ -311,6 +312,7 @@ extern "C" void rslf_cuda_destroy(rslf_ctx* ctx)
     free_scratch(ctx);
     if (ctx->raw_in && !ctx->raw_borrowed) cudaFree(ctx->raw_in);
     dev_free(&ctx->count); dev_free(&ctx->total_px); dev_free(&ctx->minmax); dev_free(&ctx->rowwork);
+    dev_free(&ctx->colour_hist); dev_free(&ctx->colour_lut);
     if (ctx->l2_flush) cudaFree(ctx->l2_flush);
     for (auto e : ctx->clk.pool) cudaEventDestroy(e);
     if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
@@ -1140,6 +1142,70 @@ extern "C" int rslf_cuda_fine_to_coarse(rslf_ctx* ctx, float dmin, float dmax, i
 {
     RSLF_TRY(rslf_cuda_fine_to_coarse_run(ctx, dmin, dmax, dim_d, params, max_pyr_depth, accept_all_last_scale));
     return rslf_cuda_fine_to_coarse_get(ctx, out_map_svu, out_valid_svu);
+}
+
+/* FineToCoarse::get_coloured_depth_maps (ftc.hpp:324-377) of the last fine-to-coarse run; see k_colour.cuh */
+extern "C" int rslf_cuda_fine_to_coarse_get_coloured(rslf_ctx* ctx, const uint8_t* lut_bgr_256x3, int saturate,
+                                                     const rslf_params* params, uint8_t* out_bgr_svu3, double* fit_min_max)
+{
+    if (!ctx || !lut_bgr_256x3 || !params || !out_bgr_svu3) return RSLF_ERR_ARG;
+    if (ctx->last_kind != 3) { snprintf(ctx->err, sizeof(ctx->err), "no fine-to-coarse result"); return RSLF_ERR_STATE; }
+    if (ctx->world > 1) { snprintf(ctx->err, sizeof(ctx->err), "coloured maps are not implemented for row-sharded runs"); return RSLF_ERR_UNSUPPORTED; }
+    if (!saturate) {
+        snprintf(ctx->err, sizeof(ctx->err), "ImageConverter_uchar::fit without saturation (mean + 12 std) is not implemented");
+        return RSLF_ERR_UNSUPPORTED;
+    }
+    RSLF_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const int S = ctx->S, V = ctx->V, U = ctx->U, C = ctx->C;
+    const size_t plane = (size_t)V * U, px = plane * S;
+    const int s_fit = (int)std::round(S / 2.0);                       /* ftc.hpp:345 */
+    if (s_fit >= S) { snprintf(ctx->err, sizeof(ctx->err), "S = %d: the reference fits on view round(S / 2) = %d, which does not exist", S, s_fit); return RSLF_ERR_ARG; }
+    if (V > 65535 || S > 65535) return RSLF_ERR_UNSUPPORTED;
+    if (!ctx->colour_hist) RSLF_TRY(dev_alloc(ctx, &ctx->colour_hist, (size_t)3 * COLOUR_BINS));
+    if (!ctx->colour_lut) RSLF_TRY(dev_alloc(ctx, &ctx->colour_lut, (size_t)768));
+    unsigned* h_hi = ctx->colour_hist; unsigned* h_a = h_hi + COLOUR_BINS; unsigned* h_b = h_a + COLOUR_BINS;
+    const float* fit_plane = ctx->out_map + (size_t)s_fit * plane;
+    std::vector<unsigned> host((size_t)2 * COLOUR_BINS);
+    /* rslf_plot.cpp:73-79: ranks floor(0.02 N) and floor(0.98 N) of the sorted plane */
+    const size_t k_min = (size_t)std::floor(0.02 * (double)plane), k_max = (size_t)std::floor(0.98 * (double)plane);
+    RSLF_CUDA_TRY(ctx, cudaMemsetAsync(h_hi, 0, (size_t)3 * COLOUR_BINS * sizeof(unsigned), ctx->stream));
+    colour_hist_hi_kernel<<<stream_grid(ctx, plane), 256, 0, ctx->stream>>>(fit_plane, plane, h_hi);
+    RSLF_CUDA_TRY(ctx, cudaGetLastError());
+    RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(host.data(), h_hi, COLOUR_BINS * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+    RSLF_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    unsigned hi_a = 0, hi_b = 0, lo_a = 0, lo_b = 0; size_t r_a = 0, r_b = 0, dummy = 0;
+    if (!colour_find_bin(host.data(), k_min, &hi_a, &r_a) || !colour_find_bin(host.data(), k_max, &hi_b, &r_b)) {
+        snprintf(ctx->err, sizeof(ctx->err), "coloured maps: histogram does not cover the plane"); return RSLF_ERR_CUDA;
+    }
+    colour_hist_lo_kernel<<<stream_grid(ctx, plane), 256, 0, ctx->stream>>>(fit_plane, plane, hi_a, hi_b, h_a, h_b);
+    RSLF_CUDA_TRY(ctx, cudaGetLastError());
+    RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(host.data(), h_a, (size_t)2 * COLOUR_BINS * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+    RSLF_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (!colour_find_bin(host.data(), r_a, &lo_a, &dummy) || !colour_find_bin(host.data() + COLOUR_BINS, r_b, &lo_b, &dummy)) {
+        snprintf(ctx->err, sizeof(ctx->err), "coloured maps: second-level histogram does not cover the bin"); return RSLF_ERR_CUDA;
+    }
+    const double mn = colour_key_to_float((hi_a << 16) | lo_a), mx = colour_key_to_float((hi_b << 16) | lo_b);
+    if (fit_min_max) { fit_min_max[0] = mn; fit_min_max[1] = mx; }
+    /* rslf_plot.cpp:105-106: float alpha = 255.0 / (max - min); convertTo(dst, CV_8U, alpha, -alpha * min) */
+    const float alpha = (float)(255.0 / (mx - mn));
+    const double beta = -alpha * mn;
+    const float a = alpha, b = (float)beta;
+    const float shadow = (float)(0.05 * 1.73205080757);               /* _SHADOW_NORMALIZED_LEVEL (core.hpp:30), compared in float */
+    const double shadow_T = rslf_sq_threshold(shadow);
+    RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->colour_lut, lut_bgr_256x3, 768, cudaMemcpyHostToDevice, ctx->stream));
+    uint8_t* d_out = reinterpret_cast<uint8_t*>(ctx->fuse_a);          /* scratch of the fusion: 4 B per pixel >= 3 */
+    dim3 grid(rslf_div_up(U, 128), V, S);
+    if (C == 1)
+        colour_maps_kernel<1><<<grid, 128, 0, ctx->stream>>>(ctx->out_map, ctx->out_valid, ctx->lv[0].epi, V, S, U, a, b,
+                                                              params->cut_shadows, shadow, shadow_T, ctx->colour_lut, d_out);
+    else
+        colour_maps_kernel<3><<<grid, 128, 0, ctx->stream>>>(ctx->out_map, ctx->out_valid, ctx->lv[0].epi, V, S, U, a, b,
+                                                              params->cut_shadows, shadow, shadow_T, ctx->colour_lut, d_out);
+    RSLF_CUDA_TRY(ctx, cudaGetLastError());
+    ctx->timing.kernel_launches += 3;
+    RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(out_bgr_svu3, d_out, px * 3, cudaMemcpyDeviceToHost, ctx->stream));
+    RSLF_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return RSLF_OK;
 }
 
 extern "C" int rslf_cuda_fine_to_coarse_level_dims(const rslf_ctx* ctx, int level, int* V, int* U)

@@ -102,6 +102,8 @@ struct rslf_ctx {
     float* g_map = nullptr; float* g_map2 = nullptr; uint8_t* g_mk = nullptr; uint8_t* g_mk2 = nullptr;
     size_t g_map_cap = 0;        /* gathered fuse maps (two slots), S*Vtot*U each */
     float* pile_depth_raw = nullptr;  /* 1D pile: unfiltered depth plane                      */
+    unsigned* colour_hist = nullptr;  /* coloured maps: three 65536-bin key histograms (k_colour.cuh) */
+    uint8_t* colour_lut = nullptr;    /* coloured maps: 256 x 3 colour table                  */
 
     /* results state */
     int last_kind = 0;           /* 1 = pile, 2 = depth2d, 3 = fine-to-coarse                 */

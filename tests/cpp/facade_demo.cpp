@@ -4,7 +4,7 @@
  * test_depth_computation_pile.cpp:49-51) through the C++ facade of include/rslf_b200.hpp.
  * Reads a raw float32 [V][S][U][C] stack, runs the three computers and writes the
  * result maps as raw files, which tests/test_cpp_facade.py compares with the oracle.
- * usage: facade_demo in.bin V S U C D dmin dmax outprefix
+ * usage: facade_demo in.bin V S U C D dmin dmax outprefix [colour_table.bin (256 x 3 bytes, BGR)]
  */
 #include <cstdio>
 #include <cstdlib>
@@ -23,7 +23,7 @@ static void dump(const std::string& path, const Vec<Mat>& mats)
 }
 
 template <typename DataType>
-static int run_all(const Vec<Mat>& epis, int D, float dmin, float dmax, const std::string& out)
+static int run_all(const Vec<Mat>& epis, int D, float dmin, float dmax, const std::string& out, const unsigned char* lut)
 {
     Depth1DComputer_pile<DataType> pile(epis, dmin, dmax, D, -1, 1.0f);
     pile.run();
@@ -42,6 +42,11 @@ static int run_all(const Vec<Mat>& epis, int D, float dmin, float dmax, const st
     ftc.get_results(map, valid);
     dump(out + "_ftc_map.bin", map);
     dump(out + "_ftc_valid.bin", valid);
+    if (lut) {                       /* FineToCoarse::get_coloured_depth_maps (tests/test_fine_to_coarse.cpp:71) */
+        Vec<Mat> plots;
+        ftc.get_coloured_depth_maps(plots, 2, true, lut);
+        dump(out + "_ftc_bgr.bin", plots);
+    }
     rslf_timing t = ftc.get_timing();
     printf("fine-to-coarse: %d levels, %d passes, %.0f pixels, %.3f ms on device\n", t.levels, t.passes, t.computed_pixels, t.ms_total);
 
@@ -70,8 +75,17 @@ int main(int argc, char** argv)
         if (fread(epis[v].data, sizeof(float), (size_t)S * U * C, f) != (size_t)S * U * C) { fprintf(stderr, "short read\n"); return 2; }
     }
     fclose(f);
+    unsigned char lut[768];
+    bool have_lut = false;
+    if (argc > 10) {
+        FILE* g = fopen(argv[10], "rb");
+        have_lut = g && fread(lut, 1, sizeof(lut), g) == sizeof(lut);
+        if (g) fclose(g);
+        if (!have_lut) { fprintf(stderr, "cannot read the colour table\n"); return 2; }
+    }
     try {
-        return C == 3 ? run_all<Vec3f>(epis, D, dmin, dmax, argv[9]) : run_all<float>(epis, D, dmin, dmax, argv[9]);
+        const unsigned char* l = have_lut ? lut : nullptr;
+        return C == 3 ? run_all<Vec3f>(epis, D, dmin, dmax, argv[9], l) : run_all<float>(epis, D, dmin, dmax, argv[9], l);
     } catch (const Error& e) {
         fprintf(stderr, "rslf_b200 error %d: %s\n", e.code, e.what());
         return 1;

@@ -34,7 +34,10 @@ def test_facade_matches_oracle(tmp_path, C):
     inp = str(tmp_path / "in.bin")
     epis.tofile(inp)
     out = str(tmp_path / "out")
-    r = subprocess.run([exe, inp, str(V), str(S), str(U), str(C), str(D), "-1.0", "2.0", out],
+    lut = np.load(os.path.join(ROOT, "tests", "golden", "colormap_jet.npy"))
+    lut_path = str(tmp_path / "jet.bin")
+    lut.tofile(lut_path)
+    r = subprocess.run([exe, inp, str(V), str(S), str(U), str(C), str(D), "-1.0", "2.0", out, lut_path],
                        capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "expected failure" in r.stdout
@@ -50,3 +53,5 @@ def test_facade_matches_oracle(tmp_path, C):
     ftc = oracle.fine_to_coarse(epis, -1.0, 2.0, D, scale_factor=1.0)
     np.testing.assert_array_equal(np.fromfile(out + "_ftc_map.bin", np.float32).reshape(S, V, U), ftc["map"])
     np.testing.assert_array_equal(np.fromfile(out + "_ftc_valid.bin", np.uint8).reshape(S, V, U), ftc["valid"])
+    bgr, _ = oracle.colour_maps(ftc["map"], ftc["valid"], norm, lut)
+    np.testing.assert_array_equal(np.fromfile(out + "_ftc_bgr.bin", np.uint8).reshape(S, V, U, 3), bgr)

@@ -170,3 +170,50 @@ def test_uint16_images_upload(gpu_ctx):
     ce_o, m_o = oracle.edge_confidence(oracle.normalise(raw, -1.0), 2)
     same(m, m_o, "u16 images mask")
     same(ce, ce_o, "u16 images C_e")
+
+
+# --------------------------------------------------------------------------- coloured disparity maps
+@pytest.mark.parametrize("S,V,U,C,kw", [(6, 24, 64, 3, {}), (5, 45, 90, 1, {}), (7, 24, 64, 3, dict(cut_shadows=0)),
+                                        (2, 24, 40, 1, {}), (5, 130, 300, 3, {})])
+def test_coloured_depth_maps(gpu_ctx, golden_dir, S, V, U, C, kw):
+    """FineToCoarse::get_coloured_depth_maps (ftc.hpp:324-377): quantile fit by radix select, uchar scaling, colour
+    table, invalid / shadow pixels black."""
+    import os
+    lut = np.load(os.path.join(golden_dir, "colormap_jet.npy"))
+    epis = lf(S, V, U, C, seed=50 + V, dark_fraction=0.2)
+    p, po = api.default_params(**kw), oracle.default_params(**kw)
+    f = api.FineToCoarse(epis, -1.0, 2.0, 16, epi_scale_factor=1.0, parameters=p, ctx=gpu_ctx).run()
+    got, fit = gpu_ctx.fine_to_coarse_coloured(lut, p, saturate=True)
+    o = oracle.fine_to_coarse(epis, -1.0, 2.0, 16, scale_factor=1.0, params=po)
+    want, fit_o = oracle.colour_maps(o["map"], o["valid"], oracle.normalise(epis, 1.0), lut, cut_shadows=po.cut_shadows)
+    assert fit == fit_o, (fit, fit_o)
+    same(got, want, "coloured maps")
+    same(f.get_coloured_depth_maps(lut_bgr=lut), want, "coloured maps (mirror class)")
+    m, v = f.get_results()                                   # the fused results are untouched by the colouring
+    same(m, o["map"], "ftc map after colouring")
+    same(v, o["valid"], "ftc valid after colouring")
+
+
+def test_coloured_depth_maps_negative_disparities(gpu_ctx, golden_dir):
+    """Order statistics over negative values (the integer keys of the radix select reverse their order)."""
+    import os
+    lut = np.load(os.path.join(golden_dir, "colormap_jet.npy"))
+    epis = lf(4, 24, 48, 3, seed=9, dmin=-3.0, dmax=-1.0)
+    f = api.FineToCoarse(epis, -3.0, -1.0, 12, epi_scale_factor=1.0, ctx=gpu_ctx).run()
+    got, fit = gpu_ctx.fine_to_coarse_coloured(lut, api.default_params())
+    o = oracle.fine_to_coarse(epis, -3.0, -1.0, 12, scale_factor=1.0)
+    want, fit_o = oracle.colour_maps(o["map"], o["valid"], oracle.normalise(epis, 1.0), lut)
+    assert fit == fit_o and fit[0] < 0
+    same(got, want, "coloured maps, negative disparities")
+
+
+def test_coloured_depth_maps_rejects(gpu_ctx, golden_dir):
+    import os
+    lut = np.load(os.path.join(golden_dir, "colormap_jet.npy"))
+    epis = lf(4, 24, 48, 3, seed=9)
+    api.FineToCoarse(epis, -1.0, 2.0, 12, epi_scale_factor=1.0, ctx=gpu_ctx).run()
+    with pytest.raises(api.RslfError):
+        gpu_ctx.fine_to_coarse_coloured(lut, api.default_params(), saturate=False)       # mean + 12 std fit: not implemented
+    api.Depth2DComputer(epis, -1.0, 2.0, 12, epi_scale_factor=1.0, ctx=gpu_ctx).run()
+    with pytest.raises(api.RslfError):
+        gpu_ctx.fine_to_coarse_coloured(lut, api.default_params())                       # no fine-to-coarse result

@@ -125,3 +125,31 @@ def test_downsample_uint16_matches_cv2():
                 np.testing.assert_array_equal(out[:, s], r, err_msg="%dx%dx%d" % (V, U, C))
     finally:
         cv2.ipp.setUseIPP(ipp)
+
+
+def test_coloured_maps_match_cv2_sort_and_colormap(golden_dir):
+    """ImageConverter_uchar::fit's cv::sort quantiles and cv::applyColorMap(COLORMAP_JET) of the real OpenCV; the
+    committed colour table (tests/golden/colormap_jet.npy) is the one cv2 produces."""
+    cv2 = pytest.importorskip("cv2")
+    import math
+    from remotesensingproject_b200.synth import make_light_field_np
+    lut = np.load(os.path.join(golden_dir, "colormap_jet.npy"))
+    ramp = np.arange(256, dtype=np.uint8).reshape(256, 1)
+    np.testing.assert_array_equal(cv2.applyColorMap(ramp, cv2.COLORMAP_JET).reshape(256, 3), lut)
+    S = 6
+    epis, _ = make_light_field_np(S, 48, 96, 3, dmin=-1.0, dmax=2.0, seed=3, layers=5, dark_fraction=0.2)
+    o = oracle.fine_to_coarse(epis, -1.0, 2.0, 16, scale_factor=1.0)
+    norm = oracle.normalise(epis, 1.0)
+    c, (mn, mx) = oracle.colour_maps(o["map"], o["valid"], norm, lut)
+    plane = o["map"][int(math.floor(S / 2.0 + 0.5))]
+    srt = cv2.sort(plane.reshape(-1, 1), cv2.SORT_EVERY_COLUMN + cv2.SORT_ASCENDING)
+    assert mn == float(srt[int(math.floor(0.02 * plane.size)), 0]) and mx == float(srt[int(math.floor(0.98 * plane.size)), 0])
+    alpha = np.float32(255.0 / (mx - mn))
+    beta = np.float32(-float(alpha) * mn)
+    for s in range(S):
+        u8 = np.clip(np.rint(o["map"][s] * alpha + beta), 0, 255).astype(np.uint8)      # convertTo(CV_8U, alpha, beta)
+        col = cv2.applyColorMap(u8, cv2.COLORMAP_JET)
+        col[o["valid"][s] == 0] = 0
+        nrm = np.sqrt((norm[:, s].astype(np.float64) ** 2).sum(-1)).astype(np.float32)
+        col[nrm < np.float32(0.05 * 1.73205080757)] = 0
+        np.testing.assert_array_equal(col, c[s])

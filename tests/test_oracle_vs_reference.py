@@ -212,6 +212,24 @@ def test_16_bit_input(S, V, U, C, scale):
     assert_same(r, o, ["valid", "map"], "u16 fused")
 
 
+@needs_ref
+@pytest.mark.parametrize("S,V,U,C,saturate,kw", [
+    (6, 24, 64, 3, True, {}), (5, 45, 90, 1, True, {}), (4, 24, 50, 3, False, {}),
+    (7, 24, 64, 3, True, dict(cut_shadows=0)), (2, 24, 40, 1, True, {})])
+def test_coloured_depth_maps(golden_dir, S, V, U, C, saturate, kw):
+    """FineToCoarse::get_coloured_depth_maps (ftc.hpp:324-377; ImageConverter_uchar, rslf_plot.cpp:66-107) of the
+    reference build, with OpenCV's JET table handed to the stand-in applyColorMap."""
+    lut = np.load(os.path.join(golden_dir, "colormap_jet.npy"))
+    epis = lf(S, V, U, C, seed=50 + V, dark_fraction=0.2)
+    p = oracle.default_params(**kw)
+    r = ref.fine_to_coarse_coloured(epis, -1.0, 2.0, 16, lut, scale_factor=1.0, params=p, saturate=saturate)
+    o = oracle.fine_to_coarse(epis, -1.0, 2.0, 16, scale_factor=1.0, params=p)
+    c, (mn, mx) = oracle.colour_maps(o["map"], o["valid"], oracle.normalise(epis, 1.0), lut, saturate=saturate,
+                                     cut_shadows=p.cut_shadows)
+    assert mx > mn and c.any()
+    np.testing.assert_array_equal(r, c)
+
+
 GOLDEN = ["ref_pile_c3", "ref_pile_c1_u8", "ref_2d_c3", "ref_ftc_c1", "ref_ftc_c3_u8"]
 
 
