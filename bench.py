@@ -197,6 +197,7 @@ def main():
     ap.add_argument("--config", default=os.environ.get("RSLF_BENCH_CONFIG", "c3"), choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-fast", action="store_true", help="skip the extra leg with the opt-in contracted (FMA) mean shift")
     ap.add_argument("--even-rows", action="store_true", help="multi-GPU: equal row counts instead of work-balanced blocks")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200" and args.config != "tiny":
@@ -315,6 +316,39 @@ def main():
     # waits for the neighbours' halo rows); the host clock between the two barriers is kept beside it as a cross-check
     value = samples / (dev_ms * 1e-3)
 
+    # ---- extra leg: the opt-in contracted (FMA) mean shift (rslf_cuda_set_fast_math), same steps, reported beside the
+    # headline, never instead of it: its results are within the north star's tolerance but not bit-identical ----------
+    fast = None
+    if not args.no_fast and C == 3:
+        ctx.set_fast_math(True)
+        ctx.flush_l2()
+        run_once()
+        barrier()
+        facc = {}
+        for _ in range(args.steps):
+            ctx.flush_l2()
+            t = run_once()
+            for k, v in t.items():
+                facc[k] = facc.get(k, 0.0) + v
+        barrier()
+        ctx.set_fast_math(False)
+        fst = torch.tensor([facc["ms_total"], facc["samples"], facc["ms_depth"]], dtype=torch.float64, device="cuda")
+        if world > 1:
+            fmx = fst.clone()
+            dist.all_reduce(fmx, op=dist.ReduceOp.MAX)
+            fsm = fst.clone()
+            dist.all_reduce(fsm, op=dist.ReduceOp.SUM)
+            f_ms, f_samples = float(fmx[0]), float(fsm[1])
+        else:
+            f_ms, f_samples = facc["ms_total"], facc["samples"]
+        fast = {"value": f_samples / (f_ms * 1e-3), "unit": "samples/s", "ms_per_step": f_ms / args.steps,
+                "ms_depth_per_step_rank0": facc["ms_depth"] / args.steps,
+                "depth_kernel_tflops_rank0": facc["samples"] * FLOPS_PER_SAMPLE[C] / (facc["ms_depth"] * 1e-3) * 1e-12,
+                "note": "opt-in (rslf_cuda_set_fast_math / RSLF_FAST_MATH=1): fused multiply-adds in the mean shift, 12 instead "
+                        "of 20 FP32 instructions per view and iteration; same masks, same disparity index where the winning "
+                        "margin exceeds 1e-5, confidences within 1e-4 relative (tests/test_gpu_widening.py); NOT bit-identical "
+                        "to the reference, so not the headline"}
+
     # ---- e2e: pinned host stack in, result maps out, through the mirror classes -----------------------------
     e2e = None
     if not args.no_e2e:
@@ -376,6 +410,8 @@ def main():
             traffic = bps * acc["samples"] / max(1.0, acc["depth_launches"])
             traffic_note = ("%.4f B/sample (dram__bytes_read+write of profiles/depth_kernel_capture_r01c.json) x samples_per_launch; "
                             "algorithmic HBM bytes are the scanline segments, shared by neighbouring pixels through L2" % bps)
+        if fast is not None:
+            fast["depth_kernel_frac_of_fma_peak_rank0"] = fast["depth_kernel_tflops_rank0"] / (fma * 1e-3)
         roofline = {
             "kernel": "depth_kernel_tm / depth_kernel (radiance sampling + mean shift + score + argmax)",
             "bound": "fp32", "unit": "TFLOP/s", "achieved": achieved, "peak": fma * 1e-3,
@@ -417,7 +453,7 @@ def main():
                        "ms_per_disparity_result_device": acc["ms_total"] / args.steps},
             "stages_ms_per_step": {k: acc[k] / args.steps for k in ("ms_edge", "ms_depth", "ms_reduce", "ms_median",
                                                                      "ms_propagate", "ms_pyramid")},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "fast_math": fast,
             "gpu_launches": int(launches), "clocks": sampler.summary(),
         }
         print(json.dumps(line), flush=True)

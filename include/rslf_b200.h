@@ -279,6 +279,13 @@ int rslf_cuda_measure_fp32x2_peak(rslf_ctx* ctx, double* gops_nofma_packed);
  * blocks (optional, 2 ints per 4-view block) = {staging offset in floats inside its round, floats per staged view}. */
 int rslf_plan_depth_tm(int S, int C, int D, int s_hat, float dmin, float dmax, float slope, size_t smem_limit,
                        int* out8, int* rounds, int* blocks);
+/* Opt-in contracted arithmetic for the mean shift (core.hpp:577-625) of RGB stacks: fused multiply-adds instead of the
+ * reference's separately rounded OpenCV operations (20 -> 12 instructions per view, hypothesis and iteration).  Results
+ * are then NOT bit-identical to the reference: scores move by a few 1e-7 relative, which stays inside the tolerance the
+ * port is specified to (same disparity index wherever the winning score margin exceeds 1e-5, 1e-4 relative on scores and
+ * confidences); a pixel inside that margin may pick the neighbouring hypothesis and propagate it.  Default: off (exact).
+ * The environment variable RSLF_FAST_MATH=1 sets it at context creation. */
+int rslf_cuda_set_fast_math(rslf_ctx* ctx, int on);
 /* Writes >126 MB on the device so the next timed step starts with a cold L2. */
 int rslf_cuda_flush_l2(rslf_ctx* ctx);
 int rslf_cuda_sync(rslf_ctx* ctx);

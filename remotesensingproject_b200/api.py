@@ -318,6 +318,10 @@ class Context:
     def set_stage_timing(self, on):
         lib().rslf_cuda_set_stage_timing(self._h, int(bool(on)))
 
+    def set_fast_math(self, on):
+        """Opt-in contracted (FMA) mean shift for RGB stacks: faster, within the specified tolerance, not bit-identical."""
+        self.check(lib().rslf_cuda_set_fast_math(self._h, int(bool(on))), "rslf_cuda_set_fast_math")
+
     def sync(self):
         self.check(lib().rslf_cuda_sync(self._h), "rslf_cuda_sync")
 

@@ -228,10 +228,36 @@ __device__ __forceinline__ void view_span(const depth_args& a, int s, float uf, 
 
 /* One view of the mean-shift sums for the lane's H hypotheses (core.hpp:591-603, kern.cpp:16-26 / 39-54,
  * core.cpp:25-38): K = max(1 - |(r - r_bar)/h|^2, 0); sum_K += K; sum_rK += max(r, 0) * K. */
-template <int C, int H, bool NONNEG>
+template <int C, int H, bool NONNEG, bool FAST = false>
 __device__ __forceinline__ void ms_accumulate(const float (&r)[C][H], const float (&rb)[C][H], float inv,
                                               float (&sR)[C][H], float (&sK)[H])
 {
+    if constexpr (FAST) {
+        /* Contracted form (opt-in, rslf_cuda_set_fast_math): the same sums with fused multiply-adds, 6 C + 2 -> 4 C
+         * operations per view and hypothesis (RGB: 20 -> 12 instructions).  NOT bit-identical to the reference: every
+         * fused operation drops one intermediate rounding, scores move by a few 1e-7 relative, inside the north star's
+         * tolerance (indices where the winning margin exceeds 1e-5, 1e-4 relative on scores / confidences). */
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+            float t;
+            {
+                const float x0 = r[0][h] - rb[0][h];
+                t = x0 * x0;
+            }
+#pragma unroll
+            for (int c = 1; c < C; ++c) {
+                const float x = r[c][h] - rb[c][h];
+                t = __fmaf_rn(x, x, t);
+            }
+            const float kk = fmaxf(__fmaf_rn(-inv, t, 1.0f), 0.f);
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const float r0 = NONNEG ? r[c][h] : fmaxf(r[c][h], 0.f);
+                sR[c][h] = __fmaf_rn(r0, kk, sR[c][h]);
+            }
+            sK[h] = sK[h] + kk;
+        }
+    } else {
 #pragma unroll
     for (int h = 0; h < H; ++h) {
         float b;
@@ -255,6 +281,7 @@ __device__ __forceinline__ void ms_accumulate(const float (&r)[C][H], const floa
             sR[c][h] = sR[c][h] + p;
         }
         sK[h] = sK[h] + kk;
+    }
     }
 }
 
@@ -295,10 +322,14 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b, f32x2 nz) {
  *   C=3, H=1 : (c0, c1) of one view form a pair, c2 of the two views form a pair;
  *   C=1, H=1 : the two views form a pair (the two accumulations stay scalar and ordered).
  */
-template <int C, int H, bool NONNEG>
+template <int C, int H, bool NONNEG, bool FAST = false>
 __device__ __forceinline__ void ms_accumulate_pair(const float (&va)[C][H], const float (&vb)[C][H], const float (&rb)[C][H],
                                                    float inv, f32x2 NZ, float (&sR)[C][H], float (&sK)[H])
 {
+    if constexpr (FAST) {
+        ms_accumulate<C, H, NONNEG, true>(va, rb, inv, sR, sK);
+        ms_accumulate<C, H, NONNEG, true>(vb, rb, inv, sR, sK);
+    } else {
 #if RSLF_PACKED_FP32
     const f32x2 INV = pk2(inv, inv), ONE = pk2(1.0f, 1.0f);
     if (H % 2 == 0) {
@@ -373,6 +404,7 @@ __device__ __forceinline__ void ms_accumulate_pair(const float (&va)[C][H], cons
     ms_accumulate<C, H, NONNEG>(va, rb, inv, sR, sK);
     ms_accumulate<C, H, NONNEG>(vb, rb, inv, sR, sK);
 #endif
+    }
 }
 
 /*

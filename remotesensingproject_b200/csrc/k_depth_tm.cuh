@@ -218,7 +218,7 @@ __device__ __forceinline__ void tm_convert_round(const depth_args& a, const int4
     }
 }
 
-template <int C, bool NONNEG>
+template <int C, bool NONNEG, bool FAST>
 __global__ void __launch_bounds__(32 * DEPTH_TM_WARPS, 1)
 depth_kernel_tm(const depth_args a, const depth_tm_layout L)
 {
@@ -369,7 +369,7 @@ depth_kernel_tm(const depth_args a, const depth_tm_layout L)
                 const int kind = L.reg_last ? (2 - part) : part;
                 if (kind == TM_KIND_REG) {
 #pragma unroll
-                    for (int j = 0; j < RV; j += 2) ms_accumulate_pair<C, H, NONNEG>(rr[j], rr[j + 1], rb, inv, NZ, sR, sK);
+                    for (int j = 0; j < RV; j += 2) ms_accumulate_pair<C, H, NONNEG, FAST>(rr[j], rr[j + 1], rb, inv, NZ, sR, sK);
                 } else if (kind == TM_KIND_TMEM) {
                     if (nbT > 0) {
                         ldtm_block(0, ba);
@@ -379,17 +379,17 @@ depth_kernel_tm(const depth_args a, const depth_tm_layout L)
                         for (int n = nbT >> 1; n > 0; --n) {
                             ldtm_block(slot + 1, bb);
 #pragma unroll
-                            for (int j = 0; j < DEPTH_UNR; j += 2) ms_accumulate_pair<C, H, NONNEG>(ba[j], ba[j + 1], rb, inv, NZ, sR, sK);
+                            for (int j = 0; j < DEPTH_UNR; j += 2) ms_accumulate_pair<C, H, NONNEG, FAST>(ba[j], ba[j + 1], rb, inv, NZ, sR, sK);
                             slot += 2;
                             tmem_wait_ld();
                             ldtm_block(slot < nbT ? slot : nbT - 1, ba);
 #pragma unroll
-                            for (int j = 0; j < DEPTH_UNR; j += 2) ms_accumulate_pair<C, H, NONNEG>(bb[j], bb[j + 1], rb, inv, NZ, sR, sK);
+                            for (int j = 0; j < DEPTH_UNR; j += 2) ms_accumulate_pair<C, H, NONNEG, FAST>(bb[j], bb[j + 1], rb, inv, NZ, sR, sK);
                             tmem_wait_ld();
                         }
                         if (nbT & 1) {
 #pragma unroll
-                            for (int j = 0; j < DEPTH_UNR; j += 2) ms_accumulate_pair<C, H, NONNEG>(ba[j], ba[j + 1], rb, inv, NZ, sR, sK);
+                            for (int j = 0; j < DEPTH_UNR; j += 2) ms_accumulate_pair<C, H, NONNEG, FAST>(ba[j], ba[j + 1], rb, inv, NZ, sR, sK);
                         }
                     }
                 } else {
@@ -402,15 +402,15 @@ depth_kernel_tm(const depth_args a, const depth_tm_layout L)
                         for (int n = nbS >> 1; n > 0; --n) {
                             lds_block(p + BLK, bb);
 #pragma unroll
-                            for (int j = 0; j < DEPTH_UNR; j += 2) ms_accumulate_pair<C, H, NONNEG>(ba[j], ba[j + 1], rb, inv, NZ, sR, sK);
+                            for (int j = 0; j < DEPTH_UNR; j += 2) ms_accumulate_pair<C, H, NONNEG, FAST>(ba[j], ba[j + 1], rb, inv, NZ, sR, sK);
                             p += 2 * BLK;
                             lds_block(p < plast ? p : plast, ba);
 #pragma unroll
-                            for (int j = 0; j < DEPTH_UNR; j += 2) ms_accumulate_pair<C, H, NONNEG>(bb[j], bb[j + 1], rb, inv, NZ, sR, sK);
+                            for (int j = 0; j < DEPTH_UNR; j += 2) ms_accumulate_pair<C, H, NONNEG, FAST>(bb[j], bb[j + 1], rb, inv, NZ, sR, sK);
                         }
                         if (nbS & 1) {
 #pragma unroll
-                            for (int j = 0; j < DEPTH_UNR; j += 2) ms_accumulate_pair<C, H, NONNEG>(ba[j], ba[j + 1], rb, inv, NZ, sR, sK);
+                            for (int j = 0; j < DEPTH_UNR; j += 2) ms_accumulate_pair<C, H, NONNEG, FAST>(ba[j], ba[j + 1], rb, inv, NZ, sR, sK);
                         }
                     }
                 }
@@ -502,10 +502,10 @@ depth_kernel_tm(const depth_args a, const depth_tm_layout L)
     if (wid == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base_s), "n"(512));
 }
 
-template <int C, bool NONNEG>
+template <int C, bool NONNEG, bool FAST>
 static int launch_depth_tm_t(rslf_ctx* ctx, const depth_args& a, const depth_tm_layout& L)
 {
-    auto kern = depth_kernel_tm<C, NONNEG>;
+    auto kern = depth_kernel_tm<C, NONNEG, FAST>;
     static bool configured = false;
     if (!configured) {
         /* the kernel also has 16 bytes of static shared memory (the TMEM base address) */
@@ -521,10 +521,17 @@ static int launch_depth_tm_t(rslf_ctx* ctx, const depth_args& a, const depth_tm_
     return RSLF_OK;
 }
 
-static int launch_depth_tm(rslf_ctx* ctx, int C, bool nonneg, const depth_args& a, const depth_tm_layout& L)
+/* fast: the contracted (FMA) mean shift, see ms_accumulate; the default is the reference's separately rounded arithmetic */
+static int launch_depth_tm(rslf_ctx* ctx, int C, bool nonneg, const depth_args& a, const depth_tm_layout& L, bool fast = false)
 {
-    if (C == 3) return nonneg ? launch_depth_tm_t<3, true>(ctx, a, L) : launch_depth_tm_t<3, false>(ctx, a, L);
-    if (C == 1) return nonneg ? launch_depth_tm_t<1, true>(ctx, a, L) : launch_depth_tm_t<1, false>(ctx, a, L);
+    if (C == 3) {
+        if (fast) return nonneg ? launch_depth_tm_t<3, true, true>(ctx, a, L) : launch_depth_tm_t<3, false, true>(ctx, a, L);
+        return nonneg ? launch_depth_tm_t<3, true, false>(ctx, a, L) : launch_depth_tm_t<3, false, false>(ctx, a, L);
+    }
+    if (C == 1) {
+        if (fast) return nonneg ? launch_depth_tm_t<1, true, true>(ctx, a, L) : launch_depth_tm_t<1, false, true>(ctx, a, L);
+        return nonneg ? launch_depth_tm_t<1, true, false>(ctx, a, L) : launch_depth_tm_t<1, false, false>(ctx, a, L);
+    }
     snprintf(ctx->err, sizeof(ctx->err), "no tensor-memory depth kernel for C=%d", C);
     return RSLF_ERR_UNSUPPORTED;
 }

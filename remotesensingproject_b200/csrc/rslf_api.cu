@@ -298,6 +298,8 @@ extern "C" int rslf_cuda_create(int device, rslf_ctx** out)
     memset(&ctx->timing, 0, sizeof(ctx->timing));
     const char* st = getenv("RSLF_STAGE_TIMING");
     if (st) ctx->stage_timing = atoi(st);
+    const char* fm = getenv("RSLF_FAST_MATH");
+    if (fm) ctx->fast_math = atoi(fm) != 0;
     *out = ctx;
     return RSLF_OK;
 }
@@ -334,6 +336,13 @@ extern "C" int rslf_cuda_set_stage_timing(rslf_ctx* ctx, int on)
 {
     if (!ctx) return RSLF_ERR_ARG;
     ctx->stage_timing = on;
+    return RSLF_OK;
+}
+
+extern "C" int rslf_cuda_set_fast_math(rslf_ctx* ctx, int on)
+{
+    if (!ctx) return RSLF_ERR_ARG;
+    ctx->fast_math = on != 0;
     return RSLF_OK;
 }
 
@@ -593,7 +602,7 @@ static int run_depth_pass(rslf_ctx* ctx, const rslf_params& P, const pass_io& io
         {
             stage_scope sc(ctx, ST_DEPTH);
             depth_args ab = a; ab.items = items_b; ab.count = count2;
-            if (use_tm) RSLF_TRY(launch_depth_tm(ctx, C, L.nonneg != 0, ab, tml));
+            if (use_tm) RSLF_TRY(launch_depth_tm(ctx, C, L.nonneg != 0, ab, tml, ctx->fast_math != 0));
             else RSLF_TRY(launch_depth(ctx, C, L.nonneg != 0, ab, plan));
         }
         {
@@ -611,7 +620,7 @@ static int run_depth_pass(rslf_ctx* ctx, const rslf_params& P, const pass_io& io
     }
     {
         stage_scope sc(ctx, ST_DEPTH);
-        if (use_tm) RSLF_TRY(launch_depth_tm(ctx, C, L.nonneg != 0, a, tml));
+        if (use_tm) RSLF_TRY(launch_depth_tm(ctx, C, L.nonneg != 0, a, tml, ctx->fast_math != 0));
         else RSLF_TRY(launch_depth(ctx, C, L.nonneg != 0, a, plan));
     }
     {

@@ -112,6 +112,7 @@ struct rslf_ctx {
     /* timing */
     rslf_timing timing;
     int stage_timing = 1;
+    int fast_math = 0;           /* contracted (FMA) mean shift in the tensor-memory depth kernel; default: exact */
     rslf_stage_clock clk;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
 

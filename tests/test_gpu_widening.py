@@ -217,3 +217,57 @@ def test_coloured_depth_maps_rejects(gpu_ctx, golden_dir):
     api.Depth2DComputer(epis, -1.0, 2.0, 12, epi_scale_factor=1.0, ctx=gpu_ctx).run()
     with pytest.raises(api.RslfError):
         gpu_ctx.fine_to_coarse_coloured(lut, api.default_params())                       # no fine-to-coarse result
+
+
+# --------------------------------------------------------------------------- opt-in contracted arithmetic
+def _pile_maps(comp):
+    return dict(best_depth=comp.m_best_depth_v_u, edge_conf=comp.m_edge_confidence_v_u,
+                edge_mask=comp.m_edge_confidence_mask_v_u, disp_conf=comp.m_disp_confidence_v_u,
+                rbar=comp.m_rbar_v_u, raw_depth=comp.m_raw_depth_v_u)
+
+
+@pytest.mark.parametrize("S,C,D,s_hat,U", [(24, 3, 40, -1, 96), (60, 3, 100, 0, 64), (100, 3, 48, -1, 64), (37, 3, 33, 35, 48)])
+def test_fast_math_stays_within_the_specified_tolerance(gpu_ctx, monkeypatch, S, C, D, s_hat, U):
+    """rslf_cuda_set_fast_math: fused multiply-adds in the mean shift of the tensor-memory kernel.  Not bit-identical,
+    but inside the tolerance the port is specified to: same masks, the same disparity index wherever the reference's
+    winning score margin exceeds 1e-5, 1e-4 relative on the confidences."""
+    monkeypatch.delenv("RSLF_DEPTH_H", raising=False)
+    monkeypatch.delenv("RSLF_DEPTH_RV", raising=False)
+    monkeypatch.delenv("RSLF_DEPTH_TMEM", raising=False)
+    epis = lf(S, 6, U, C, seed=900 + S + D, dmin=-1.0, dmax=1.5)
+    ref = oracle.depth1d_pile(oracle.normalise(epis, 1.0), -1.0, 1.5, D, s_hat=s_hat)
+    exact = _pile_maps(api.Depth1DComputer_pile(epis, -1.0, 1.5, D, s_hat=s_hat, epi_scale_factor=1.0, ctx=gpu_ctx).run())
+    gpu_ctx.set_fast_math(True)
+    try:
+        fast = _pile_maps(api.Depth1DComputer_pile(epis, -1.0, 1.5, D, s_hat=s_hat, epi_scale_factor=1.0, ctx=gpu_ctx).run())
+    finally:
+        gpu_ctx.set_fast_math(False)
+    for k in ("edge_mask", "edge_conf", "raw_depth", "disp_conf", "rbar"):
+        same(exact[k], ref[k], "exact mode " + k)                       # the default path is untouched by the switch
+    same(fast["edge_mask"], ref["edge_mask"], "fast mode mask")
+    same(fast["edge_conf"], ref["edge_conf"], "fast mode C_e")
+    computed = ref["best_idx"] >= 0
+    safe = computed & (ref["margin"] > 1e-5)
+    assert safe.sum() > 0.5 * computed.sum() > 0
+    same(fast["raw_depth"][safe], ref["raw_depth"][safe], "fast mode disparity where the margin exceeds 1e-5")
+    agree = computed & (fast["raw_depth"] == ref["raw_depth"])
+    np.testing.assert_allclose(fast["disp_conf"][agree], ref["disp_conf"][agree], rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose(fast["rbar"][agree], ref["rbar"][agree], rtol=1e-4, atol=1e-6)
+    assert (fast["disp_conf"] != ref["disp_conf"]).any(), "the contracted kernel did not run"
+
+
+def test_fast_math_whole_pipeline_is_close(gpu_ctx):
+    """Through propagation and the pyramid a pixel inside the 1e-5 margin may flip to the neighbouring hypothesis and
+    paint others; masks stay identical and all but a small fraction of the fused map is unchanged."""
+    epis = lf(28, 30, 60, 3, seed=640)
+    r = oracle.fine_to_coarse(epis, -1.0, 2.0, 40, scale_factor=1.0)
+    gpu_ctx.set_fast_math(True)
+    try:
+        m, v = api.FineToCoarse(epis, -1.0, 2.0, 40, epi_scale_factor=1.0, ctx=gpu_ctx).run().get_results()
+    finally:
+        gpu_ctx.set_fast_math(False)
+    same(v, r["valid"], "fast mode validity")
+    frac = float((m != r["map"]).mean())
+    assert frac < 0.02, "fraction of fused-map pixels that differ: %g" % frac
+    m2, v2 = api.FineToCoarse(epis, -1.0, 2.0, 40, epi_scale_factor=1.0, ctx=gpu_ctx).run().get_results()
+    same(m2, r["map"], "exact mode after switching back")
