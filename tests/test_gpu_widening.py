@@ -226,7 +226,7 @@ def _pile_maps(comp):
                 rbar=comp.m_rbar_v_u, raw_depth=comp.m_raw_depth_v_u)
 
 
-@pytest.mark.parametrize("S,C,D,s_hat,U", [(24, 3, 40, -1, 96), (60, 3, 100, 0, 64), (100, 3, 48, -1, 64), (37, 3, 33, 35, 48)])
+@pytest.mark.parametrize("S,C,D,s_hat,U", [(24, 3, 40, -1, 96), (60, 3, 100, 0, 64), (100, 3, 128, -1, 64), (37, 3, 33, 35, 48)])
 def test_fast_math_stays_within_the_specified_tolerance(gpu_ctx, monkeypatch, S, C, D, s_hat, U):
     """rslf_cuda_set_fast_math: fused multiply-adds in the mean shift of the tensor-memory kernel.  Not bit-identical,
     but inside the tolerance the port is specified to: same masks, the same disparity index wherever the reference's
@@ -234,6 +234,11 @@ def test_fast_math_stays_within_the_specified_tolerance(gpu_ctx, monkeypatch, S,
     monkeypatch.delenv("RSLF_DEPTH_H", raising=False)
     monkeypatch.delenv("RSLF_DEPTH_RV", raising=False)
     monkeypatch.delenv("RSLF_DEPTH_TMEM", raising=False)
+    import ctypes
+    fits = (ctypes.c_int * 8)()
+    api.lib().rslf_plan_depth_tm(S, C, D, s_hat if s_hat >= 0 else S // 2, ctypes.c_float(-1.0), ctypes.c_float(1.5),
+                                 ctypes.c_float(1.0), ctypes.c_size_t(227 * 1024 - 64), fits, None, None)
+    assert fits[0] == 1, "the case must run on the tensor-memory kernel (the only one with a contracted variant)"
     epis = lf(S, 6, U, C, seed=900 + S + D, dmin=-1.0, dmax=1.5)
     ref = oracle.depth1d_pile(oracle.normalise(epis, 1.0), -1.0, 1.5, D, s_hat=s_hat)
     exact = _pile_maps(api.Depth1DComputer_pile(epis, -1.0, 1.5, D, s_hat=s_hat, epi_scale_factor=1.0, ctx=gpu_ctx).run())
