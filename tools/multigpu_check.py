@@ -28,7 +28,9 @@ def main():
              # boundary 50 is a multiple of 2 only: levels 0-1 sharded, levels 2-3 replicated on every rank
              dict(S=5, V=100, U=90, C=3, D=16, mode="ftc", scale=-1.0),
              dict(S=4, V=100, U=90, C=1, D=24, mode="ftc", scale=1.0, u8=True),
-             dict(S=6, V=96, U=80, C=3, D=24, mode="ftc", scale=1.0, border_first="1")]
+             dict(S=6, V=96, U=80, C=3, D=24, mode="ftc", scale=1.0, border_first="1"),
+             # 16-bit stack, scaled by its maximum: all-reduce of the per-rank maxima, 16-bit raw rows gathered for the blur
+             dict(S=5, V=96, U=80, C=3, D=16, mode="ftc", scale=-1.0, u16=True)]
     for i, c in enumerate(cases):
         os.environ.pop("RSLF_MEDIAN_GATHER", None)
         os.environ.pop("RSLF_HALO", None)
@@ -44,6 +46,8 @@ def main():
             epis = (epis * 200.0 + 5.0).astype(np.float32)
         if c.get("u8"):
             epis = np.clip(np.rint(epis * 255.0), 0, 255).astype(np.uint8)
+        if c.get("u16"):
+            epis = np.clip(np.rint(epis * 200.0), 0, 65535).astype(np.uint16)
         p = api.default_params()
         # single-GPU result (every rank computes it on its own device)
         ctx1 = api.Context(local)
