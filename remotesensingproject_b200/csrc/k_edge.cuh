@@ -204,7 +204,8 @@ static int launch_edge_confidence(rslf_ctx* ctx, const float* epi, int V, int S,
                      P.edge_confidence_opening_type, P.edge_confidence_opening_size, MORPH_MAX_K);
             return RSLF_ERR_UNSUPPORTED;
         }
-        if (!mask_tmp || V > 65535 || s_count > 65535) { snprintf(ctx->err, sizeof(ctx->err), "edge_confidence_opening: no scratch mask"); return RSLF_ERR_STATE; }
+        if (!mask_tmp) { snprintf(ctx->err, sizeof(ctx->err), "edge_confidence_opening: no scratch mask"); return RSLF_ERR_STATE; }
+        if (V > 65535 || s_count > 65535) { snprintf(ctx->err, sizeof(ctx->err), "edge_confidence_opening: more than 65535 rows or views"); return RSLF_ERR_UNSUPPORTED; }
     }
     int* rowdark_late = opening ? rowdark : nullptr;      /* counted on the opened mask instead */
     if (opening) rowdark = nullptr;
