@@ -143,7 +143,9 @@ int rslf_cuda_depth1d_pile_get(rslf_ctx* ctx, float* best_depth_vu,
                                float* edge_conf_vu, uint8_t* edge_mask_vu,
                                float* disp_conf_vu, float* rbar_vuc);
 /* The unfiltered argmax depths of the last pile run: m_best_depth_v_u as it is
- * before core.hpp:881-892 replaces it by the median-filtered map (diagnostic). */
+ * before core.hpp:881-892 replaces it by the median-filtered map.  A one-row pile read
+ * back this way is Depth1DComputer<T>::run() (rslf_depth_computation.hpp:26-68, 319-363:
+ * one EPI, one line, no median) — what the facade's Depth1DComputer does. */
 int rslf_cuda_depth1d_pile_get_raw_depth(rslf_ctx* ctx, float* raw_depth_vu);
 
 /* ---- Depth2DComputer<T>::run() -------------------------------------------

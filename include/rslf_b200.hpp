@@ -236,6 +236,55 @@ inline void scatter(const std::vector<T>& a_buf, Vec<Mat>& a_mats, int V, size_t
 }
 } // namespace detail
 
+/* ---------------------------------------------------------------- Depth1DComputer */
+/* rslf::Depth1DComputer<DataType> (dc.hpp:26-68, ctor :254-317, run :319-363): ONE EPI (S x U x C), edge confidence and
+ * depth of line s_hat, no selective median.  On the device it runs as a one-row pile (the per-line results coincide
+ * except for the median, so the unfiltered depth is read back); the opening of the pile wrapper (core.hpp:759) does
+ * not apply because the reference calls compute_1D_edge_confidence directly (dc.hpp:339). */
+template <typename DataType>
+class Depth1DComputer
+{
+public:
+    Depth1DComputer(const Mat& epi, float dmin, float dmax, int dim_d, int s_hat = -1, float epi_scale_factor = -1,
+                    const Depth1DParameters<DataType>& parameters = Depth1DParameters<DataType>::get_default(), int device = 0)
+        : m_parameters(parameters), m_device(new detail::Device(device)), m_dim_d(dim_d), m_dmin(dmin), m_dmax(dmax)
+    {
+        int one = 0;
+        m_device->upload(Vec<Mat>(1, epi), epi_scale_factor, channels_of<DataType>::value, one, m_dim_s, m_dim_u);
+        m_s_hat = (s_hat < 0 || s_hat > m_dim_s - 1) ? (int)std::floor((0.0 + m_dim_s) / 2) : s_hat;      /* dc.hpp:296-305 */
+    }
+    void run()
+    {
+        const int C = channels_of<DataType>::value;
+        rslf_params p = m_parameters.to_abi();
+        p.edge_confidence_opening_size = 1;
+        m_best_depth_u = Mat::zeros(1, m_dim_u, CV_32FC1);
+        m_edge_confidence_u = Mat::zeros(1, m_dim_u, CV_32FC1);
+        m_edge_confidence_mask_u = Mat::zeros(1, m_dim_u, CV_8UC1);
+        m_disp_confidence_u = Mat::zeros(1, m_dim_u, CV_32FC1);
+        m_rbar_u = Mat::zeros(1, m_dim_u, CV_MAKETYPE(CV_32F, C));
+        m_device->check(rslf_cuda_depth1d_pile(m_device->get(), m_dmin, m_dmax, m_dim_d, m_s_hat, &p, nullptr,
+                                               m_edge_confidence_u.template ptr<float>(),
+                                               m_edge_confidence_mask_u.template ptr<unsigned char>(),
+                                               m_disp_confidence_u.template ptr<float>(), m_rbar_u.template ptr<float>()),
+                        "rslf_cuda_depth1d_pile");
+        m_device->check(rslf_cuda_depth1d_pile_get_raw_depth(m_device->get(), m_best_depth_u.template ptr<float>()),
+                        "rslf_cuda_depth1d_pile_get_raw_depth");
+    }
+    int get_s_hat() const { return m_s_hat; }
+
+    /* private in the reference (dc.hpp:53-60); exposed here because they are the results */
+    Mat m_edge_confidence_u, m_edge_confidence_mask_u, m_disp_confidence_u, m_rbar_u, m_best_depth_u;
+
+private:
+    const Depth1DParameters<DataType>& m_parameters;
+    std::unique_ptr<detail::Device> m_device;
+    int m_dim_d, m_dim_s = 0, m_dim_u = 0, m_s_hat = 0;
+    float m_dmin, m_dmax;
+};
+using Depth1DComputer_1ch = Depth1DComputer<float>;
+using Depth1DComputer_3ch = Depth1DComputer<Vec3f>;
+
 /* ---------------------------------------------------------------- Depth1DComputer_pile */
 template <typename DataType>
 class Depth1DComputer_pile

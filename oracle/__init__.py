@@ -162,6 +162,17 @@ def depth1d_pile(epis, dmin, dmax, D, s_hat=-1, params=None):
     return out
 
 
+def depth1d(epi, dmin, dmax, D, s_hat=-1, params=None):
+    """Depth1DComputer::run (dc.hpp:319-363) on ONE normalised EPI [S][U][C]: compute_1D_edge_confidence (no opening:
+    that belongs to the pile wrapper, core.hpp:759) and compute_1D_depth_epi of line s_hat; no selective median, so
+    best_depth is the argmax disparity itself."""
+    p = Params.from_buffer_copy(bytes(params)) if params is not None else default_params()
+    p.edge_confidence_opening_size = 1
+    r = depth1d_pile(_c32(epi)[None], dmin, dmax, D, s_hat=s_hat, params=p)
+    return dict(best_depth=r["raw_depth"][0], edge_conf=r["edge_conf"][0], edge_mask=r["edge_mask"][0],
+                disp_conf=r["disp_conf"][0], rbar=r["rbar"][0], computed_pixels=r["computed_pixels"])
+
+
 def visiting_order(S):
     buf = (C.c_int * (S + 1))()
     n = lib().orc_visiting_order(int(S), buf)

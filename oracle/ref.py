@@ -64,6 +64,23 @@ def _raw(raw):
     return raw, {np.dtype(np.uint8): 0, np.dtype(np.uint16): 2}.get(raw.dtype, 5)      # CV_8U, CV_16U, CV_32F
 
 
+def depth1d(raw_epi, dmin, dmax, D, s_hat=-1, scale_factor=-1.0, params=None):
+    """rslf::Depth1DComputer<T>(epi, dmin, dmax, D, s_hat, scale, params).run() on ONE raw EPI [S][U][C]
+    (dc.hpp:254-363): edge confidence and depth of line s_hat, no median."""
+    raw, depth = _raw(np.asarray(raw_epi)[None])
+    _, S, U, Cc = raw.shape
+    p = params or default_params()
+    out = dict(best_depth=np.zeros(U, np.float32), edge_conf=np.zeros(U, np.float32), edge_mask=np.zeros(U, np.uint8),
+               disp_conf=np.zeros(U, np.float32), rbar=np.zeros((U, Cc), np.float32))
+    rc = lib().ref_depth1d(raw.ctypes.data_as(C.c_void_p), depth, S, U, Cc, C.c_float(scale_factor), C.c_float(dmin),
+                           C.c_float(dmax), int(D), int(s_hat), C.byref(p), _f(out["best_depth"]), _f(out["edge_conf"]),
+                           _b(out["edge_mask"]), _f(out["disp_conf"]), _f(out["rbar"]))
+    if rc < 0:
+        raise ValueError("reference: unsupported channel count")
+    out["s_hat"] = rc
+    return out
+
+
 def depth1d_pile(raw, dmin, dmax, D, s_hat=-1, scale_factor=-1.0, params=None):
     """rslf::Depth1DComputer_pile<T>(epis, dmin, dmax, D, s_hat, scale, params).run() on a RAW [V][S][U][C] stack."""
     raw, depth = _raw(raw)

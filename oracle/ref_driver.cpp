@@ -6,6 +6,7 @@
  * TEST INFRASTRUCTURE ONLY: loaded by oracle/ref.py for tests/test_oracle_vs_reference.py (which pins the
  * restated oracle against the reference's own control flow), for the golden fixtures of tests/golden/ref_*.npz
  * and for the CPU legs of bench.py.  No reference source is copied into this repository: this file only calls
+ *   rslf::Depth1DComputer<T>       (include/rslf_depth_computation.hpp:26-68, 254-363)
  *   rslf::Depth1DComputer_pile<T>  (include/rslf_depth_computation.hpp:93-143, 424-565)
  *   rslf::Depth2DComputer<T>       (include/rslf_depth_computation.hpp:166-229, 652-915)
  *   rslf::FineToCoarse<T>          (include/rslf_fine_to_coarse.hpp:26-81, 103-322)
@@ -130,6 +131,26 @@ int pile_t(const void* raw, int cv_depth, int V, int S, int U, int C, float scal
     return comp.get_s_hat();
 }
 
+/* Depth1DComputer: one EPI, one line, no median (dc.hpp:254-363) */
+template <typename T>
+int single_t(const void* raw, int cv_depth, int S, int U, int C, float scale, float dmin, float dmax, int D, int s_hat,
+             const rslf_params* P, float* best_depth, float* edge_conf, uint8_t* edge_mask, float* disp_conf, float* rbar)
+{
+    rslf::Depth1DParameters<T> q;
+    fill_params(q, P);
+    RVec<Mat> epis = make_epis(raw, cv_depth, 1, S, U, C);
+    rslf::Depth1DComputer<T> comp(epis[0], dmin, dmax, D, s_hat, scale, q);
+    comp.run();
+    put_f32(comp.m_best_depth_u, best_depth);
+    put_f32(comp.m_edge_confidence_u, edge_conf);
+    put_u8(comp.m_edge_confidence_mask_u, edge_mask);
+    put_f32(comp.m_disp_confidence_u, disp_conf);
+    put_f32(comp.m_rbar_u, rbar, C);
+    delete q.par_interpolation_class;
+    delete q.par_kernel_class;
+    return comp.m_s_hat;
+}
+
 template <typename T>
 void depth2d_t(const void* raw, int cv_depth, int V, int S, int U, int C, float scale, float dmin, float dmax, int D,
                const rslf_params* P, const float* dmin_svu, const float* dmax_svu, int accept_all, float* best_depth,
@@ -201,6 +222,7 @@ template <typename T>
 int ftc_coloured_t(const void* raw, int cv_depth, int V, int S, int U, int C, float scale, float dmin, float dmax, int D,
                    const rslf_params* P, const uint8_t* lut_bgr, int saturate, uint8_t* out_bgr_svu3)
 {
+    QuietCout quiet;
     rslf::Depth1DParameters<T> q;
     fill_params(q, P);
     RVec<Mat> epis = make_epis(raw, cv_depth, V, S, U, C);
@@ -242,6 +264,16 @@ int ref_depth1d_pile(const void* raw, int cv_depth, int V, int S, int U, int C, 
     QuietCout q;
     if (C == 1) return pile_t<float>(raw, cv_depth, V, S, U, C, scale, dmin, dmax, D, s_hat, P, best_depth, edge_conf, edge_mask, disp_conf, rbar);
     if (C == 3) return pile_t<cv::Vec3f>(raw, cv_depth, V, S, U, C, scale, dmin, dmax, D, s_hat, P, best_depth, edge_conf, edge_mask, disp_conf, rbar);
+    return -1;
+}
+
+/* Depth1DComputer ctor + run on ONE EPI raw: [S][U][C].  Outputs: U values (rbar: U x C).  Returns the s_hat used. */
+int ref_depth1d(const void* raw, int cv_depth, int S, int U, int C, float scale, float dmin, float dmax, int D, int s_hat,
+                const rslf_params* P, float* best_depth, float* edge_conf, uint8_t* edge_mask, float* disp_conf, float* rbar)
+{
+    QuietCout q;
+    if (C == 1) return single_t<float>(raw, cv_depth, S, U, C, scale, dmin, dmax, D, s_hat, P, best_depth, edge_conf, edge_mask, disp_conf, rbar);
+    if (C == 3) return single_t<cv::Vec3f>(raw, cv_depth, S, U, C, scale, dmin, dmax, D, s_hat, P, best_depth, edge_conf, edge_mask, disp_conf, rbar);
     return -1;
 }
 

@@ -398,6 +398,39 @@ def _as_mats(epis):
 # ---------------------------------------------------------------------------
 # Mirrors of the reference classes
 # ---------------------------------------------------------------------------
+class Depth1DComputer:
+    """rslf::Depth1DComputer<T> (rslf_depth_computation.hpp:26-68, ctor :254-317, run :319-363): ONE EPI [S][U][C],
+    edge confidence and depth of line s_hat, no selective median.  The reference keeps the results private; they are
+    members here (m_best_depth_u, m_edge_confidence_u, m_edge_confidence_mask_u, m_disp_confidence_u, m_rbar_u).
+    Runs as a one-row pile on the device: the per-line results of the two classes coincide except for the median."""
+
+    def __init__(self, epi, dmin, dmax, dim_d, s_hat=-1, epi_scale_factor=-1.0, parameters=None, device=0, ctx=None):
+        self.m_ctx = ctx or Context(device)
+        # compute_1D_edge_confidence is called directly (dc.hpp:339): the opening of the pile wrapper does not apply
+        self.m_parameters = Params.from_buffer_copy(bytes(parameters)) if parameters is not None else default_params()
+        self.m_parameters.edge_confidence_opening_size = 1
+        epi = np.asarray(epi)
+        if epi.ndim == 2:
+            epi = epi[..., None]
+        self.m_ctx.upload_epis(epi[None], epi_scale_factor)
+        S = epi.shape[0]
+        self.m_dim_d = dim_d
+        self.m_dmin, self.m_dmax = dmin, dmax
+        if s_hat < 0 or s_hat > S - 1:
+            s_hat = int(np.floor((0.0 + S) / 2))
+        self.m_s_hat = s_hat
+
+    def run(self):
+        self.m_ctx.depth1d_pile_run(self.m_dmin, self.m_dmax, self.m_dim_d, self.m_s_hat, self.m_parameters)
+        r = self.m_ctx.depth1d_pile_get(want_raw=True)
+        self.m_best_depth_u = r["raw_depth"][0]
+        self.m_edge_confidence_u = r["edge_conf"][0]
+        self.m_edge_confidence_mask_u = r["edge_mask"][0]
+        self.m_disp_confidence_u = r["disp_conf"][0]
+        self.m_rbar_u = r["rbar"][0]
+        return self
+
+
 class Depth1DComputer_pile:
     """rslf::Depth1DComputer_pile<T> (rslf_depth_computation.hpp:93-143, ctor :425-511, run :513-565)."""
 

@@ -25,6 +25,11 @@ static void dump(const std::string& path, const Vec<Mat>& mats)
 template <typename DataType>
 static int run_all(const Vec<Mat>& epis, int D, float dmin, float dmax, const std::string& out, const unsigned char* lut)
 {
+    Depth1DComputer<DataType> single(epis[0], dmin, dmax, D, -1, 1.0f);      /* tests/test_depth_computation.cpp:47-48 */
+    single.run();
+    dump(out + "_1d_depth.bin", Vec<Mat>{single.m_best_depth_u});
+    dump(out + "_1d_cd.bin", Vec<Mat>{single.m_disp_confidence_u});
+
     Depth1DComputer_pile<DataType> pile(epis, dmin, dmax, D, -1, 1.0f);
     pile.run();
     dump(out + "_pile_depth.bin", Vec<Mat>{pile.m_best_depth_v_u});

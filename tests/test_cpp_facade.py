@@ -42,6 +42,9 @@ def test_facade_matches_oracle(tmp_path, C):
     assert r.returncode == 0, r.stdout + r.stderr
     assert "expected failure" in r.stdout
     norm = oracle.normalise(epis, 1.0)
+    one = oracle.depth1d(norm[0], -1.0, 2.0, D)
+    np.testing.assert_array_equal(np.fromfile(out + "_1d_depth.bin", np.float32), one["best_depth"])
+    np.testing.assert_array_equal(np.fromfile(out + "_1d_cd.bin", np.float32), one["disp_conf"])
     pile = oracle.depth1d_pile(norm, -1.0, 2.0, D)
     np.testing.assert_array_equal(np.fromfile(out + "_pile_depth.bin", np.float32).reshape(V, U), pile["best_depth"])
     np.testing.assert_array_equal(np.fromfile(out + "_pile_mask.bin", np.uint8).reshape(V, U), pile["edge_mask"])

@@ -276,3 +276,21 @@ def test_fast_math_whole_pipeline_is_close(gpu_ctx):
     assert frac < 0.02, "fraction of fused-map pixels that differ: %g" % frac
     m2, v2 = api.FineToCoarse(epis, -1.0, 2.0, 40, epi_scale_factor=1.0, ctx=gpu_ctx).run().get_results()
     same(m2, r["map"], "exact mode after switching back")
+
+
+# --------------------------------------------------------------------------- Depth1DComputer (one EPI)
+@pytest.mark.parametrize("S,U,C,D,s_hat,kw", [(9, 64, 3, 16, -1, {}), (8, 64, 1, 40, -1, {}), (7, 50, 3, 100, 2, {}),
+                                                (12, 33, 1, 33, 5, dict(edge_confidence_opening_size=3)),
+                                                (24, 96, 3, 40, -1, {})])
+def test_single_epi_computer(gpu_ctx, S, U, C, D, s_hat, kw):
+    """rslf::Depth1DComputer<T> (dc.hpp:254-363): one EPI, one line, no median; the opening parameter is ignored."""
+    epi = lf(S, 3, U, C, seed=100 + S + D)[1]
+    comp = api.Depth1DComputer(epi, -1.0, 2.0, D, s_hat=s_hat, epi_scale_factor=1.0, parameters=api.default_params(**kw),
+                               ctx=gpu_ctx).run()
+    o = oracle.depth1d(oracle.normalise(epi[None], 1.0)[0], -1.0, 2.0, D, s_hat=s_hat, params=oracle.default_params(**kw))
+    assert o["computed_pixels"] > 0
+    same(comp.m_edge_confidence_mask_u, o["edge_mask"], "1d mask")
+    same(comp.m_edge_confidence_u, o["edge_conf"], "1d C_e")
+    same(comp.m_best_depth_u, o["best_depth"], "1d depth")
+    same(comp.m_disp_confidence_u, o["disp_conf"], "1d C_d")
+    same(comp.m_rbar_u, o["rbar"], "1d rbar")

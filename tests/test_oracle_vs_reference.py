@@ -52,6 +52,22 @@ def test_pile(S, V, U, C, D, s_hat):
 
 
 @needs_ref
+@pytest.mark.parametrize("S,U,C,D,s_hat,kw", [(9, 64, 3, 16, -1, {}), (8, 64, 1, 40, -1, {}), (7, 50, 3, 100, 2, {}),
+                                                (12, 33, 1, 33, 5, dict(edge_confidence_opening_size=3))])
+def test_single_epi_computer(S, U, C, D, s_hat, kw):
+    """rslf::Depth1DComputer<T> (dc.hpp:254-363): one EPI, one line, no median, no opening (the parameter is ignored)."""
+    epi = lf(S, 3, U, C, seed=100 + S + D)[1]
+    p = oracle.default_params(**kw)
+    r = ref.depth1d(epi, -1.0, 2.0, D, s_hat=s_hat, scale_factor=1.0, params=p)
+    o = oracle.depth1d(oracle.normalise(epi[None], 1.0)[0], -1.0, 2.0, D, s_hat=s_hat, params=p)
+    assert o["computed_pixels"] > 0
+    assert_same(r, o, MAPS, "single EPI")
+    u8 = np.clip(np.rint(epi * 255.0), 0, 255).astype(np.uint8)
+    assert_same(ref.depth1d(u8, -1.0, 2.0, D, s_hat=s_hat), oracle.depth1d(oracle.normalise(u8[None])[0], -1.0, 2.0, D, s_hat=s_hat),
+                MAPS, "single EPI, 8-bit")
+
+
+@needs_ref
 def test_pile_input_normalisation():
     """8-bit input (x 1/255), float input divided by the stack maximum (scale < 0) or by a given factor (dc.hpp:442-477)."""
     epis = lf(7, 6, 48, 3, seed=5)
