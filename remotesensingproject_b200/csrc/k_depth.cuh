@@ -939,11 +939,13 @@ template <int C, int H, bool NONNEG, int RV>
 static int launch_depth_t(rslf_ctx* ctx, const depth_args& a, const depth_plan& p)
 {
     auto kern = depth_kernel<C, H, NONNEG, RV>;
-    static bool configured = false;
-    if (!configured) {
+    /* function attributes are per device: one flag per device a process drives (contexts on up to 64 devices) */
+    static unsigned long long configured = 0;
+    const unsigned long long dev_bit = 1ULL << (ctx->device & 63);
+    if (!(configured & dev_bit)) {
         RSLF_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin));
         RSLF_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        configured = true;
+        configured |= dev_bit;
     }
     int occ = 0;
     RSLF_CUDA_TRY(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 32, p.smem));

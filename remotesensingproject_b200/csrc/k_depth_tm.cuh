@@ -506,12 +506,14 @@ template <int C, bool NONNEG, bool FAST>
 static int launch_depth_tm_t(rslf_ctx* ctx, const depth_args& a, const depth_tm_layout& L)
 {
     auto kern = depth_kernel_tm<C, NONNEG, FAST>;
-    static bool configured = false;
-    if (!configured) {
+    /* function attributes are per device: one flag per device a process drives */
+    static unsigned long long configured = 0;
+    const unsigned long long dev_bit = 1ULL << (ctx->device & 63);
+    if (!(configured & dev_bit)) {
         /* the kernel also has 16 bytes of static shared memory (the TMEM base address) */
         RSLF_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->smem_optin - 64));
         RSLF_CUDA_TRY(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        configured = true;
+        configured |= dev_bit;
     }
     const size_t smem = (size_t)L.warp_bytes * DEPTH_TM_WARPS;
     kern<<<ctx->num_sm, 32 * DEPTH_TM_WARPS, smem, ctx->stream>>>(a, L);
