@@ -7,10 +7,8 @@
  * borders, restricted to masked neighbours whose colour on line s_hat is within
  * epsilon (norm) of the centre pixel's; unmasked outputs are 0.
  *
- * One block per MED_TILES_X-th part of an image row, threads striding over its pixels (a pass launches
- * V x MED_TILES_X blocks whatever U is: most passes are sparse, and with one block per 128 pixels the
- * launch was bound by scheduling 16 000 blocks that return at once); the window values sit in registers
- * (fully unrolled) and are sorted by a fixed compare-exchange network (Batcher), so no data-dependent
+ * One thread per pixel; the window values sit in registers (fully unrolled) and
+ * are sorted by a fixed compare-exchange network (Batcher), so no data-dependent
  * indexing is needed.  Colours are addressed through (colour, row_stride), and the rows
  * to filter through (v_begin, v_count), so that a row-sharded run filters its own rows
  * out of the gathered planes of line s_hat.
@@ -48,17 +46,15 @@ struct median_halo {
     const volatile unsigned* flag_top; const volatile unsigned* flag_bot; unsigned seq;
 };
 
-#define MED_THREADS 128
-#define MED_TILES_X 2
-
 template <int C, int WIDTH, bool HALO>
-__global__ void __launch_bounds__(MED_THREADS)
+__global__ void __launch_bounds__(128)
 selective_median_kernel(const float* __restrict__ src, const uint8_t* __restrict__ mask,
                         const float* __restrict__ colour, size_t colour_row_stride,
                         int V, int U, int v_begin, float eps, double eps_T, float* __restrict__ dst,
                         const uint8_t* __restrict__ fresh, const int* __restrict__ rowdark_v, const median_halo halo)
 {
     constexpr int N = (2 * WIDTH + 1) * (2 * WIDTH + 1);
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
     const int v = blockIdx.y + v_begin;            /* row in the (possibly gathered) planes */
     if (HALO && (halo.flag_top || halo.flag_bot)) {
         /* blocks whose window reaches a neighbour's rows wait until those rows have landed (bounded spin) */
@@ -71,56 +67,54 @@ selective_median_kernel(const float* __restrict__ src, const uint8_t* __restrict
         }
         __syncthreads();
     }
+    if (u >= U) return;
+    const size_t o = (size_t)v * U + u;
+    const size_t od = (size_t)blockIdx.y * U + u;     /* dst holds this rank's rows only */
+    if (!mask[o]) { dst[od] = 0.f; return; }
     /* the filtered value is only ever read by the propagation: needed for the pixels computed in this pass
      * (fresh: still flagged in the line's remaining mask) and, in rows that still hold dark targets, for the
      * pixels painted earlier (see k_propagate.cuh).  fresh == nullptr: filter every masked pixel. */
-    const bool row_all = !fresh || rowdark_v[blockIdx.y] > 0;
-    for (int u = blockIdx.x * MED_THREADS + threadIdx.x; u < U; u += gridDim.x * MED_THREADS) {
-        const size_t o = (size_t)v * U + u;
-        const size_t od = (size_t)blockIdx.y * U + u;     /* dst holds this rank's rows only */
-        if (!mask[o]) { dst[od] = 0.f; continue; }
-        if (!row_all && !fresh[od]) { dst[od] = 0.f; continue; }
-        float pc[C];
+    if (fresh && !fresh[od] && rowdark_v[blockIdx.y] <= 0) { dst[od] = 0.f; return; }
+    float pc[C];
 #pragma unroll
-        for (int c = 0; c < C; ++c) pc[c] = __ldg(colour + (size_t)v * colour_row_stride + (size_t)u * C + c);
-        float val[N];
-        int n = 0;
+    for (int c = 0; c < C; ++c) pc[c] = __ldg(colour + (size_t)v * colour_row_stride + (size_t)u * C + c);
+    float val[N];
+    int n = 0;
 #pragma unroll
-        for (int dk = -WIDTH; dk <= WIDTH; ++dk) {
-            const int k = v + dk;
-            /* the window row: inside the block, in a neighbour's halo rows, or outside the image */
-            const float* srow = nullptr; const uint8_t* mrow = nullptr; const float* crow = nullptr;
-            if (k >= 0 && k < V) {
-                srow = src + (size_t)k * U; mrow = mask + (size_t)k * U; crow = colour + (size_t)k * colour_row_stride;
-            } else if (HALO && k < 0 && k >= -2 && halo.top_depth) {
-                srow = halo.top_depth + (size_t)(k + 2) * U; mrow = halo.top_mask + (size_t)(k + 2) * U;
-                crow = halo.top_colour + (size_t)(k + 2) * U * C;
-            } else if (HALO && k >= V && k < V + 2 && halo.bot_depth) {
-                srow = halo.bot_depth + (size_t)(k - V) * U; mrow = halo.bot_mask + (size_t)(k - V) * U;
-                crow = halo.bot_colour + (size_t)(k - V) * U * C;
-            }
-#pragma unroll
-            for (int dl = -WIDTH; dl <= WIDTH; ++dl) {
-                const int l = u + dl;
-                float x = CUDART_INF_F;
-                if (srow && l >= 0 && l < U && mrow[l]) {
-                    float q[C];
-#pragma unroll
-                    for (int c = 0; c < C; ++c) q[c] = __ldg(crow + (size_t)l * C + c);
-                    if (rslf_norm_diff_lt<C>(pc, q, eps, eps_T)) { x = srow[l]; ++n; }
-                }
-                val[(dk + WIDTH) * (2 * WIDTH + 1) + (dl + WIDTH)] = x;
-            }
+    for (int dk = -WIDTH; dk <= WIDTH; ++dk) {
+        const int k = v + dk;
+        /* the window row: inside the block, in a neighbour's halo rows, or outside the image */
+        const float* srow = nullptr; const uint8_t* mrow = nullptr; const float* crow = nullptr;
+        if (k >= 0 && k < V) {
+            srow = src + (size_t)k * U; mrow = mask + (size_t)k * U; crow = colour + (size_t)k * colour_row_stride;
+        } else if (HALO && k < 0 && k >= -2 && halo.top_depth) {
+            srow = halo.top_depth + (size_t)(k + 2) * U; mrow = halo.top_mask + (size_t)(k + 2) * U;
+            crow = halo.top_colour + (size_t)(k + 2) * U * C;
+        } else if (HALO && k >= V && k < V + 2 && halo.bot_depth) {
+            srow = halo.bot_depth + (size_t)(k - V) * U; mrow = halo.bot_mask + (size_t)(k - V) * U;
+            crow = halo.bot_colour + (size_t)(k - V) * U * C;
         }
-        /* element of rank n/2 among the n selected values (std::nth_element at n/2, core.hpp:712-713): sort the
-         * window, the rejected slots are +inf and end up last.  Depths are finite, so +inf is unambiguous. */
-        sort_network<N>(val);
-        const int rank = n / 2;
-        float out = val[0];
 #pragma unroll
-        for (int i = 1; i <= N / 2; ++i) out = (rank == i) ? val[i] : out;
-        dst[od] = out;
+        for (int dl = -WIDTH; dl <= WIDTH; ++dl) {
+            const int l = u + dl;
+            float x = CUDART_INF_F;
+            if (srow && l >= 0 && l < U && mrow[l]) {
+                float q[C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) q[c] = __ldg(crow + (size_t)l * C + c);
+                if (rslf_norm_diff_lt<C>(pc, q, eps, eps_T)) { x = srow[l]; ++n; }
+            }
+            val[(dk + WIDTH) * (2 * WIDTH + 1) + (dl + WIDTH)] = x;
+        }
     }
+    /* element of rank n/2 among the n selected values (std::nth_element at n/2, core.hpp:712-713): sort the
+     * window, the rejected slots are +inf and end up last.  Depths are finite, so +inf is unambiguous. */
+    sort_network<N>(val);
+    const int rank = n / 2;
+    float out = val[0];
+#pragma unroll
+    for (int i = 1; i <= N / 2; ++i) out = (rank == i) ? val[i] : out;
+    dst[od] = out;
 }
 
 static int launch_selective_median(rslf_ctx* ctx, const float* src, const uint8_t* mask, const float* colour,
@@ -130,15 +124,15 @@ static int launch_selective_median(rslf_ctx* ctx, const float* src, const uint8_
 {
     const int width = (size - 1) / 2;
     if (v_count < 0) v_count = V;
-    dim3 grid(std::min(MED_TILES_X, rslf_div_up(U, MED_THREADS)), v_count);
+    dim3 grid(rslf_div_up(U, 128), v_count);
     const double T = rslf_sq_threshold(eps);
     median_halo h; memset(&h, 0, sizeof(h));
     if (halo) h = *halo;
 #define RSLF_MED_CASE(CC, WW)                                                                              \
     if (C == CC && width == WW) {                                                                          \
-        if (halo) selective_median_kernel<CC, WW, true><<<grid, MED_THREADS, 0, ctx->stream>>>(                    \
+        if (halo) selective_median_kernel<CC, WW, true><<<grid, 128, 0, ctx->stream>>>(                    \
             src, mask, colour, colour_row_stride, V, U, v_begin, eps, T, dst, fresh, rowdark_v, h);        \
-        else selective_median_kernel<CC, WW, false><<<grid, MED_THREADS, 0, ctx->stream>>>(                        \
+        else selective_median_kernel<CC, WW, false><<<grid, 128, 0, ctx->stream>>>(                        \
             src, mask, colour, colour_row_stride, V, U, v_begin, eps, T, dst, fresh, rowdark_v, h);        \
         RSLF_CUDA_TRY(ctx, cudaGetLastError());                                                            \
         ctx->timing.kernel_launches += 1;                                                                  \

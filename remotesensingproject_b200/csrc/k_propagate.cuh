@@ -37,7 +37,7 @@ struct prop_args {
     float* depth; float* cd; uint8_t* remaining; int* winner;   /* [S][V][U] */
     const int* items; const int* count;                         /* work list of the pass */
     const int* items2; const int* count2;                       /* second part of the list (row-sharded runs), or nullptr */
-    int* rowdark;                                                /* [S][V] confident-and-dark pixels still unpainted (upper bound), then [V]: their sums over s at the start of the level */
+    int* rowdark;                                                /* [S][V] confident-and-dark pixels still unpainted (upper bound) */
 };
 
 /* one (source, view) pair; PHASE 0: arbitration, PHASE 1: commit */
@@ -73,11 +73,8 @@ __device__ __forceinline__ void propagate_one(const prop_args& a, int v, int u, 
 }
 
 /* One launch per phase: the first list_blocks blocks walk the pass's work list (kind 1: one warp per list
- * entry, whose source data is loaded once, lanes over views); the remaining V blocks take one image row each for the
- * pixels painted earlier (kind 2: r_bar == 0): a row whose level-wide count of dark targets (rowdark[S][v], written
- * once per level) is zero returns after one load — almost every row of almost every pass — otherwise the block walks
- * the groups of PROP_SG views that still hold a dark target, threads over u.  (One block per (row, group) made
- * 14 000 blocks per launch for C3, and scheduling them cost more than the work of a sparse pass.) */
+ * entry, whose source data is loaded once, lanes over views), the remaining blocks are (row v, group of PROP_SG
+ * views) pairs for the pixels painted earlier (kind 2: r_bar == 0), threads over u. */
 template <int C, int PHASE>
 __global__ void __launch_bounds__(PROP_THREADS)
 propagate_kernel(const prop_args a, int list_blocks)
@@ -99,32 +96,30 @@ propagate_kernel(const prop_args a, int list_blocks)
         }
         return;
     }
-    const int v = (int)blockIdx.x - list_blocks;
-    if (a.rowdark[(size_t)a.S * a.V + v] <= 0) return;      /* no dark target in this row in any view of the level */
-    for (int s_begin = 0; s_begin < a.S; s_begin += PROP_SG) {
-        const int s_end = min(a.S, s_begin + PROP_SG);
-        unsigned live = 0;                                  /* views of the group that still hold a dark target */
-        for (int s = s_begin; s < s_end; ++s) live |= (a.rowdark[(size_t)s * a.V + v] > 0) ? (1u << (s - s_begin)) : 0u;
-        if (!live) continue;
-        for (int u = threadIdx.x; u < a.U; u += PROP_THREADS) {
-            const size_t o = (size_t)v * a.U + u;
-            if (!a.emask_p[o]) continue;
-            float rb[C]; bool zero = true;
+    const int idx = (int)blockIdx.x - list_blocks;
+    const int v = idx % a.V;
+    const int s_begin = (idx / a.V) * PROP_SG, s_end = min(a.S, s_begin + PROP_SG);
+    unsigned live = 0;                                      /* views of the group that still hold a dark target */
+    for (int s = s_begin; s < s_end; ++s) live |= (a.rowdark[(size_t)s * a.V + v] > 0) ? (1u << (s - s_begin)) : 0u;
+    if (!live) return;
+    for (int u = threadIdx.x; u < a.U; u += PROP_THREADS) {
+        const size_t o = (size_t)v * a.U + u;
+        if (!a.emask_p[o]) continue;
+        float rb[C]; bool zero = true;
 #pragma unroll
-            for (int c = 0; c < C; ++c) { rb[c] = a.rbar_p[o * C + c]; zero = zero && (rb[c] == 0.f); }
-            if (!zero) continue;
-            const float cur = a.filtered[o];
-            const float cdv = PHASE ? a.cd_p[o] : 0.f;
-            for (int s = s_begin; s < s_end; ++s)
-                if (live & (1u << (s - s_begin))) propagate_one<C, PHASE>(a, v, u, s, cur, rb, cdv);
-        }
+        for (int c = 0; c < C; ++c) { rb[c] = a.rbar_p[o * C + c]; zero = zero && (rb[c] == 0.f); }
+        if (!zero) continue;
+        const float cur = a.filtered[o];
+        const float cdv = PHASE ? a.cd_p[o] : 0.f;
+        for (int s = s_begin; s < s_end; ++s)
+            if (live & (1u << (s - s_begin))) propagate_one<C, PHASE>(a, v, u, s, cur, rb, cdv);
     }
 }
 
 static int launch_propagate(rslf_ctx* ctx, int C, const prop_args& a)
 {
     const int lb = ctx->num_sm * 16;
-    const int grid = lb + a.V;
+    const int grid = lb + a.V * rslf_div_up(a.S, PROP_SG);
     if (C == 1) {
         propagate_kernel<1, 0><<<grid, PROP_THREADS, 0, ctx->stream>>>(a, lb);
         propagate_kernel<1, 1><<<grid, PROP_THREADS, 0, ctx->stream>>>(a, lb);
