@@ -78,8 +78,60 @@ def run_case(name, epis, side="ref", oracle_side=False, ctx=None):
     return dict(map=m, valid=v)
 
 
+# ---- rows added after the first fixtures: options and entry points either side of the hot path --------------------------
+# name -> (kind, S, V, U, C, D, seed); inputs are float32 in [0, 1] unless the kind says otherwise
+LATE_CASES = {
+    "ref_opening_pile_c3": ("opening", 7, 14, 60, 3, 24, 911),      # MORPH_ELLIPSE 3x3 opening of the edge mask (core.hpp:759-769)
+    "ref_u16_ftc_c3": ("u16", 5, 44, 70, 3, 16, 912),               # CV_16U stack scaled by its maximum, 16-bit pyramid
+    "ref_coloured_c3": ("coloured", 6, 24, 64, 3, 16, 913),         # FineToCoarse::get_coloured_depth_maps (ftc.hpp:324-377)
+    "ref_single_epi_c1": ("single", 8, 1, 64, 1, 40, 914),          # Depth1DComputer on one EPI (dc.hpp:254-363)
+}
+
+
+def make_late_input(name):
+    from remotesensingproject_b200.synth import make_light_field_np
+    kind, S, V, U, C, D, seed = LATE_CASES[name]
+    epis, _ = make_light_field_np(S, V, U, C, dmin=-1.0, dmax=2.0, seed=seed, layers=5, dark_fraction=0.2)
+    if kind == "u16":
+        return np.clip(np.rint(epis * 60000.0), 0, 65535).astype(np.uint16)
+    return epis
+
+
+def run_late_case(name, epis, side="ref"):
+    """side "ref": the reference build; "oracle": oracle/rslf_oracle.cpp.  (The CUDA path is compared with the oracle on
+    the same rows in tests/test_gpu_widening.py.)"""
+    import oracle
+    from oracle import ref
+    kind, S, V, U, C, D, seed = LATE_CASES[name]
+    here = os.path.dirname(os.path.abspath(__file__))
+    if kind == "opening":
+        p = oracle.default_params(edge_confidence_opening_type=2, edge_confidence_opening_size=3)
+        r = ref.depth1d_pile(epis, -1.0, 2.0, D, scale_factor=1.0, params=p) if side == "ref" else \
+            oracle.depth1d_pile(oracle.normalise(epis, 1.0), -1.0, 2.0, D, params=p)
+        return {k: r[k] for k in PILE_KEYS}
+    if kind == "u16":
+        r = ref.fine_to_coarse(epis, -1.0, 2.0, D, scale_factor=-1.0, dims=oracle.pyramid_dims(V, U)) if side == "ref" else \
+            oracle.fine_to_coarse(epis, -1.0, 2.0, D, scale_factor=-1.0)
+        return dict(map=r["map"], valid=r["valid"])
+    if kind == "coloured":
+        lut = np.load(os.path.join(here, "colormap_jet.npy"))
+        if side == "ref":
+            return dict(bgr=ref.fine_to_coarse_coloured(epis, -1.0, 2.0, D, lut, scale_factor=1.0))
+        o = oracle.fine_to_coarse(epis, -1.0, 2.0, D, scale_factor=1.0)
+        return dict(bgr=oracle.colour_maps(o["map"], o["valid"], oracle.normalise(epis, 1.0), lut)[0])
+    r = ref.depth1d(epis[0], -1.0, 2.0, D, scale_factor=1.0) if side == "ref" else \
+        oracle.depth1d(oracle.normalise(epis, 1.0)[0], -1.0, 2.0, D)
+    return {k: r[k] for k in PILE_KEYS}
+
+
 def main():
     here = os.path.dirname(os.path.abspath(__file__))
+    for name in LATE_CASES:
+        epis = make_late_input(name)
+        out = run_late_case(name, epis, side="ref")
+        path = os.path.join(here, name + ".npz")
+        np.savez_compressed(path, epis=epis, **out)
+        print("%s: %d bytes" % (path, os.path.getsize(path)))
     for name in CASES:
         epis = make_input(name)
         out = run_case(name, epis, side="ref")

@@ -263,3 +263,19 @@ def test_oracle_matches_reference_fixtures(golden_dir, name):
         if k == "epis":
             continue
         np.testing.assert_array_equal(out[k], g[k], err_msg="%s:%s" % (name, k))
+
+
+@pytest.mark.parametrize("name", ["ref_opening_pile_c3", "ref_u16_ftc_c3", "ref_coloured_c3", "ref_single_epi_c1"])
+def test_oracle_matches_reference_fixtures_of_the_late_rows(golden_dir, name):
+    """Fixtures written by the reference build for the rows added late (edge-mask opening, CV_16U input, coloured maps,
+    the single-EPI computer): the pin survives where the reference tree is absent."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_ref_golden", os.path.join(golden_dir, "make_ref_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    out = mod.run_late_case(name, g["epis"], side="oracle")
+    assert set(out) == set(g.files) - {"epis"}
+    for k in out:
+        np.testing.assert_array_equal(out[k], g[k], err_msg="%s:%s" % (name, k))
+
