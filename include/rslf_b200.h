@@ -40,7 +40,8 @@ enum {
     RSLF_ERR_STATE      = -3,   /* call order violated (e.g. run before upload)       */
     RSLF_ERR_UNSUPPORTED= -4,   /* valid in the reference, not implemented here       */
     RSLF_ERR_NCCL       = -5,   /* NCCL error                                         */
-    RSLF_ERR_NOMEM      = -6
+    RSLF_ERR_NOMEM      = -6,
+    RSLF_ERR_PEER       = -7    /* a peer GPU of a row-sharded run did not answer in time  */
 };
 
 /*

@@ -135,6 +135,12 @@ struct PixelScratch {
  * multi-channel multiply/divide helpers (core.cpp:25-51), score (:616-625).
  * Leaves score[d], rbar[c][d], Dv[d] in the scratch.
  */
+/* Optional statistics (off by default; orc_ms_stats_*): at which mean-shift iteration r_bar reaches a bitwise
+ * fixed point, per hypothesis and per group of 32 consecutive hypotheses (a GPU warp).  Once r_bar(t+1) == r_bar(t)
+ * every later iteration and the score repeat exactly, which is what the CUDA kernel's early exit relies on. */
+bool g_ms_stats = false;
+long long g_ms_hist_lane[33], g_ms_hist_warp[33], g_ms_flat_pixels, g_ms_pixels;
+
 void pixel_scores(const float* epi /* [S][U][C] */, int S, int U, int C, int D,
                   int s_hat, int u, float dmin, float dmax, const rslf_params& P,
                   PixelScratch& w) {
@@ -197,6 +203,8 @@ void pixel_scores(const float* epi /* [S][U][C] */, int S, int U, int C, int D,
     float* sumK = w.sumK.data();
     float* sumrK = w.sumrK.data();
     const int iters = P.mean_shift_max_iter;
+    std::vector<int> fixed_at;                           /* statistics only: iterations a hypothesis needs */
+    if (g_ms_stats) fixed_at.assign(D, iters);
     for (int it = 0; it < iters; ++it) {
         for (int d = 0; d < D; ++d) sumK[d] = 0.f;
         for (int i = 0; i < C * D; ++i) sumrK[i] = 0.f;
@@ -236,12 +244,49 @@ void pixel_scores(const float* epi /* [S][U][C] */, int S, int U, int C, int D,
             }
         }
         /* core.hpp:606-609: r_bar = sum_rK / sum_K (OpenCV 3 divide: x/0 = 0), then max(.,0) */
+        if (g_ms_stats) std::memcpy(w.x.data(), rbar, sizeof(float) * C * D);
         for (int c = 0; c < C; ++c)
             for (int d = 0; d < D; ++d) {
                 float den = sumK[d];
                 float q = (den != 0.f) ? (sumrK[(size_t)c * D + d] / den) : 0.f;
                 rbar[(size_t)c * D + d] = (q > 0.f) ? q : 0.f;
             }
+        if (g_ms_stats) {
+            for (int d = 0; d < D; ++d) {
+                if (fixed_at[d] < iters) continue;
+                bool same = true;
+                for (int c = 0; c < C; ++c) {
+                    uint32_t a, b;
+                    std::memcpy(&a, &w.x[(size_t)c * D + d], 4); std::memcpy(&b, &rbar[(size_t)c * D + d], 4);
+                    same = same && (a == b);
+                }
+                if (same) fixed_at[d] = it + 1;          /* iterations executed when the sweep stops here */
+            }
+        }
+    }
+    if (g_ms_stats && iters > 0 && iters <= 32) {
+        long long hl[33] = {0}, hw[33] = {0};
+        for (int d0 = 0; d0 < D; d0 += 32) {
+            int mx = 0;
+            for (int d = d0; d < std::min(D, d0 + 32); ++d) { hl[fixed_at[d]]++; mx = std::max(mx, fixed_at[d]); }
+            hw[mx]++;
+        }
+        for (int i = 0; i <= iters; ++i) {
+            if (hl[i]) {
+#pragma omp atomic
+                g_ms_hist_lane[i] += hl[i];
+            }
+            if (hw[i]) {
+#pragma omp atomic
+                g_ms_hist_warp[i] += hw[i];
+            }
+        }
+#pragma omp atomic
+        g_ms_pixels += 1;
+        if (dmin == dmax) {
+#pragma omp atomic
+            g_ms_flat_pixels += 1;
+        }
     }
     /* core.hpp:616-622: K is re-evaluated from the stale r - r_bar of the last
      * iteration, i.e. it equals that iteration's K; score = sum_K / card_R, max(.,0). */
@@ -820,6 +865,17 @@ float normalise(const void* raw, int cv_depth, size_t n, float scale_factor, flo
 }  // namespace
 
 extern "C" {
+
+/* statistics of the mean-shift fixed point (see pixel_scores): enable + reset, read back */
+void orc_ms_stats_enable(int on) {
+    g_ms_stats = on != 0;
+    std::memset(g_ms_hist_lane, 0, sizeof(g_ms_hist_lane)); std::memset(g_ms_hist_warp, 0, sizeof(g_ms_hist_warp));
+    g_ms_flat_pixels = 0; g_ms_pixels = 0;
+}
+void orc_ms_stats_read(long long* lane33, long long* warp33, long long* pixels, long long* flat_pixels) {
+    std::memcpy(lane33, g_ms_hist_lane, sizeof(g_ms_hist_lane)); std::memcpy(warp33, g_ms_hist_warp, sizeof(g_ms_hist_warp));
+    *pixels = g_ms_pixels; *flat_pixels = g_ms_flat_pixels;
+}
 
 int orc_num_threads(void) {
 #ifdef _OPENMP

@@ -47,6 +47,7 @@
  */
 #pragma once
 #include "rslf_common.cuh"
+#include "k_balance.cuh"
 
 #define RSLF_RAD_SENTINEL 1.0e18f
 
@@ -80,50 +81,130 @@ struct depth_args {
     float negzero;                /* -0.0f, opaque to the compiler: addend of the packed multiplies */
     int wpv_q16;                  /* pixels a chunk's hypotheses spread per view step, 16.16 fixed point (row sizing) */
     int reg_last;                 /* register-resident views: 0 = the first RV views, 1 = the last RV (padded) views */
-    const int* items; const int* count;
-    const float* dmin_map; const float* dmax_map; float dmin_c, dmax_c;
-    float* ce; uint8_t* emask; float* cd; float* depth; float* rbar;   /* planes of line s_hat */
+    const int4* rec;              /* work records of the pass: {pixel index in the stack `epi`, dmin, dmax, C_e} (k_balance.cuh) */
+    const int* count;             /* number of records (direct mode) */
+    int* queue;                   /* work queue of the launch: next unclaimed warp item (zero when the kernel starts) */
+    int pix_off;                  /* direct mode: record pixel - pix_off = pixel index in the result planes below */
+    float* ce; uint8_t* emask; float* cd; float* depth; float* rbar;   /* planes of line s_hat (direct mode) */
     float raw_thr;
     int chunks; rslf_partial* partials; int* arrive;
+    depth_bal bal;                /* pass-balanced multi-GPU mode (bal.n > 0): records / results of all ranks */
 };
 
-/* remaining &= emask (in place) and list the survivors; remaining == nullptr: list emask.
- * rowwork (optional): per level-0 row of this rank, the number of pixels evaluated so far in the run — row v
- * of this level counts for level-0 row ((v + v0) << shift) - v0_base (load balancing of row-sharded runs). */
-__global__ void compact_kernel(const uint8_t* __restrict__ emask, uint8_t* __restrict__ remaining, int n,
-                               int* __restrict__ items, int* __restrict__ count,
-                               unsigned long long* __restrict__ total,
-                               unsigned* __restrict__ rowwork, int U, int v0, int shift, int v0_base, int rows_base,
-                               int V, int border_lo, int border_hi, int select)
+/* one warp item from the launch's work queue (lane 0 claims, the warp learns) */
+__device__ __forceinline__ int depth_claim(int* queue, int lane)
+{
+    int w = 0;
+    if (lane == 0) w = atomicAdd(queue, 1);
+    return __shfl_sync(0xffffffffu, w, 0);
+}
+
+/* Outputs of one pixel (core.hpp:630-657), written by one lane: the result planes in direct mode, a result
+ * record in the owner's list in balanced mode (applied by bal_apply_kernel). */
+template <int C>
+__device__ __forceinline__ void depth_emit(const depth_args& a, int rec_pix, float ce, int owner, int ridx, float best, float bdv,
+                                           double sum, const float (&brb)[C])
+{
+    const double maxVal = (double)best;
+    const bool ok = maxVal > (double)a.raw_thr;
+    const double mean = sum / (double)a.D;                         /* cv::mean (core.hpp:641) */
+    const float cdv = (float)((double)ce * fabs(maxVal - mean));
+    if (a.bal.n) {
+        float4* r = a.bal.res[owner] + 2 * (size_t)ridx;
+        r[0] = make_float4(bdv, cdv, brb[0], brb[C > 1 ? 1 : 0]);
+        r[1] = make_float4(brb[C > 2 ? 2 : 0], __int_as_float(ok ? 1 : 0), 0.f, 0.f);
+        return;
+    }
+    const int pix = rec_pix - a.pix_off;
+    if (ok) {
+        a.depth[pix] = bdv;
+        a.cd[pix] = cdv;
+#pragma unroll
+        for (int c = 0; c < C; ++c) a.rbar[(size_t)pix * C + c] = brb[c];
+    } else {
+        a.ce[pix] = 0.f;                                           /* core.hpp:655-656 */
+        a.emask[pix] = 0;
+    }
+}
+
+/* end of a depth kernel in balanced mode: once every block's result stores are visible system-wide, the last
+ * block raises this rank's done flag on every peer */
+__device__ __forceinline__ void depth_bal_finish(const depth_args& a)
+{
+    if (!a.bal.n) return;
+    __threadfence_system();
+    bal_last_block_signal(a.bal.blocks_done, a.bal.done, a.bal.n, a.bal.seq, 0u);
+}
+
+/* remaining &= emask (in place) and list the survivors (core.hpp:510-516); remaining == nullptr: list emask.
+ * Every listed pixel gets its work record (k_balance.cuh).  rowwork (optional): per level-0 row of this rank,
+ * the number of pixels evaluated so far in the run — row v of this level counts for level-0 row
+ * ((v + v0) << shift) - v0_base.  Balanced multi-GPU mode (bal_n > 0): the last block publishes the count. */
+struct compact_args {
+    const uint8_t* emask; uint8_t* remaining; int n;
+    int* items; int4* rec; int* count; unsigned long long* total;
+    unsigned* rowwork; int U, v0, shift, v0_base, rows_base;
+    int V, border_lo, border_hi, select;
+    const float* dmin_map; const float* dmax_map; float dmin_c, dmax_c; const float* ce;
+    int pix_off;                                   /* record pixel = local pixel + pix_off (first row of the block in the stack) */
+    int bal_n; unsigned seq; unsigned long long* counts_peer[RSLF_MAX_PEERS]; int* blocks_done;
+};
+
+__global__ void compact_kernel(const compact_args a)
 {
     /* select 0: every row; 1: only the border rows (v < border_lo or v >= V - border_hi); 2: only the others */
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, n = a.n;
     for (int base = (blockIdx.x * blockDim.x + threadIdx.x) - lane; base < n; base += gridDim.x * blockDim.x) {
         int i = base + lane;
         uint8_t m = 0;
-        if (i < n && select) {
-            const int v = i / U;
-            const bool border = (v < border_lo) || (v >= V - border_hi);
-            if (border != (select == 1)) i = n;                  /* not this launch's row */
+        if (i < n && a.select) {
+            const int v = i / a.U;
+            const bool border = (v < a.border_lo) || (v >= a.V - a.border_hi);
+            if (border != (a.select == 1)) i = n;                  /* not this launch's row */
         }
         if (i < n) {
-            m = emask[i];
-            if (remaining) { m &= remaining[i]; remaining[i] = m; }
+            m = a.emask[i];
+            if (a.remaining) { m &= a.remaining[i]; a.remaining[i] = m; }
         }
         unsigned bal = __ballot_sync(0xffffffffu, m != 0);
         if (bal) {
             int pos = 0;
             if (lane == 0) {
                 int c = __popc(bal);
-                pos = atomicAdd(count, c);
-                atomicAdd(total, (unsigned long long)c);
+                pos = atomicAdd(a.count, c);
+                atomicAdd(a.total, (unsigned long long)c);
             }
             pos = __shfl_sync(0xffffffffu, pos, 0);
-            if (m) items[pos + __popc(bal & ((1u << lane) - 1u))] = i;
-            if (rowwork && m) {
-                int r = (((i / U) + v0) << shift) - v0_base;
-                r = min(max(r, 0), rows_base - 1);
-                atomicAdd(rowwork + r, 1u);
+            if (m) {
+                const int at = pos + __popc(bal & ((1u << lane) - 1u));
+                a.items[at] = i;
+                int4 r;
+                r.x = i + a.pix_off;
+                r.y = __float_as_int(a.dmin_map ? a.dmin_map[i] : a.dmin_c);
+                r.z = __float_as_int(a.dmax_map ? a.dmax_map[i] : a.dmax_c);
+                r.w = __float_as_int(a.ce[i]);
+                a.rec[at] = r;
+            }
+            if (a.rowwork && m) {
+                int r = (((i / a.U) + a.v0) << a.shift) - a.v0_base;
+                r = min(max(r, 0), a.rows_base - 1);
+                atomicAdd(a.rowwork + r, 1u);
+            }
+        }
+    }
+    if (a.bal_n) {
+        /* records and list are read by the peers once the count is published */
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            const int old = atomicAdd(a.blocks_done, 1);
+            if (old == (int)gridDim.x - 1) {
+                *a.blocks_done = 0;
+                __threadfence_system();
+                const unsigned cnt = (unsigned)*reinterpret_cast<volatile int*>(a.count);
+                const unsigned long long v = ((unsigned long long)a.seq << 32) | (unsigned long long)cnt;
+                for (int r = 0; r < a.bal_n; ++r) *reinterpret_cast<volatile unsigned long long*>(a.counts_peer[r]) = v;
             }
         }
     }
@@ -511,7 +592,6 @@ depth_kernel(const depth_args a)
     int4* meta = reinterpret_cast<int4*>(blk_off1 + ((nblk + 1 + 3) & ~3));
     float* rows = reinterpret_cast<float*>(meta + nrows);
     const unsigned bar = smem_u32(smem_raw);
-    const long long total = (long long)(*a.count) * a.chunks;
     const float inv = a.inv;
     const f32x2 NZ = pk2(a.negzero, a.negzero);          /* -0.0 the compiler cannot see (see mul2) */
     const float Um1f = (float)(U - 1);
@@ -543,31 +623,28 @@ depth_kernel(const depth_args a)
     __syncwarp();
     unsigned phase = 0;                                     /* mbarrier phase parity */
 
-#if RSLF_PREFETCH_ITEM
-    /* the list entry and the bounds of the NEXT item are loaded while the current one is computed */
-    int pix_n = 0; float dmin_n = a.dmin_c, dmax_n = a.dmax_c;
-    if ((long long)blockIdx.x < total) {
-        pix_n = a.items[(int)((long long)blockIdx.x / a.chunks)];
-        if (a.dmin_map) dmin_n = a.dmin_map[pix_n];
-        if (a.dmax_map) dmax_n = a.dmax_map[pix_n];
-    }
-#endif
-    for (long long w = blockIdx.x; w < total; w += gridDim.x) {
-        const int item = (int)(w / a.chunks);
-        const int chunk = (int)(w - (long long)item * a.chunks);
-#if RSLF_PREFETCH_ITEM
-        const int pix = pix_n;
-        const float dmin = dmin_n, dmax = dmax_n;
-        if (w + gridDim.x < total) {
-            pix_n = a.items[(int)((w + gridDim.x) / a.chunks)];
-            if (a.dmin_map) dmin_n = a.dmin_map[pix_n];
-            if (a.dmax_map) dmax_n = a.dmax_map[pix_n];
-        }
-#else
-        const int pix = a.items[item];
-        const float dmin = a.dmin_map ? a.dmin_map[pix] : a.dmin_c;
-        const float dmax = a.dmax_map ? a.dmax_map[pix] : a.dmax_c;
-#endif
+    /* this launch's warp items: (record, chunk) pairs, claimed from the launch's work queue.  Balanced mode: the
+     * records of this rank's share of the pass, fetched from their owners. */
+    bal_slice sl; sl.lo = 0; sl.n = 0; sl.pre_excl = 0; sl.pre_incl = 0;
+    int total;
+    if (a.bal.n) { sl = bal_begin(a.bal, lane); total = sl.n * a.chunks; }
+    else total = (*a.count) * a.chunks;
+    int w = depth_claim(a.queue, lane);
+    while (w < total) {
+        int w_next = 0;
+        if (lane == 0) w_next = atomicAdd(a.queue, 1);          /* claimed now, needed after this item */
+        const int item = w / a.chunks;
+        const int chunk = w - item * a.chunks;
+        int owner = 0, ridx = item;
+        int4 rec;
+        if (a.bal.n) { bal_locate(sl, sl.lo + item, a.bal.n, lane, owner, ridx); rec = ld_cv_int4(a.bal.rec[owner] + ridx); }
+        else rec = a.rec[item];
+        const int pix = rec.x;
+        const float dmin = __int_as_float(rec.y), dmax = __int_as_float(rec.z);
+        /* dmin == dmax (bounds of a coarser level that met, ftc.hpp:201-294): all D hypotheses are the same EPI
+         * line, so every score equals the first one: d* = 0, C_d = 0.  Chunk 0 evaluates it, the others are void. */
+        const bool flat = (a.chunks > 1) && (dmin == dmax);
+        if (flat && chunk > 0) { w = __shfl_sync(0xffffffffu, w_next, 0); continue; }
         const int v = pix / U, u = pix - v * U;
         const int dbase = chunk * W + lane * H;
         const float uf = (float)u;
@@ -812,7 +889,9 @@ RSLF_PRAGMA(unroll RSLF_MS_UNROLL)
         }
         /* ---- merge the chunks of this pixel (last arriver), then the outputs (core.hpp:630-657) ---- */
         bool finalise = true;
-        if (a.chunks > 1) {
+        if (flat) {
+            sum = (double)best * (double)D;                              /* D equal scores: their double sum is exact */
+        } else if (a.chunks > 1) {
             if (lane == 0) {
                 rslf_partial p;
                 p.mx = best; p.idx = bidx; p.dv = bdv; p.sum = sum;
@@ -839,20 +918,10 @@ RSLF_PRAGMA(unroll RSLF_MS_UNROLL)
                 }
             }
         }
-        if (lane == 0 && finalise) {
-            const double maxVal = (double)best;
-            if (maxVal > (double)a.raw_thr) {
-                a.depth[pix] = bdv;
-                const double mean = sum / (double)D;                     /* cv::mean (core.hpp:641) */
-                a.cd[pix] = (float)((double)a.ce[pix] * fabs(maxVal - mean));
-#pragma unroll
-                for (int c = 0; c < C; ++c) a.rbar[(size_t)pix * C + c] = brb[c];
-            } else {
-                a.ce[pix] = 0.f;                                         /* core.hpp:655-656 */
-                a.emask[pix] = 0;
-            }
-        }
+        if (lane == 0 && finalise) depth_emit<C>(a, pix, __int_as_float(rec.w), owner, ridx, best, bdv, sum, brb);
+        w = __shfl_sync(0xffffffffu, w_next, 0);
     }
+    depth_bal_finish(a);
 }
 
 struct depth_plan { int H; int RV; int reg_last; int blocks_per_sm; size_t smem; int chunks; int wpv_q16; };

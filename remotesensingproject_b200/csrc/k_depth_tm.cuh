@@ -251,21 +251,34 @@ depth_kernel_tm(const depth_args a, const depth_tm_layout L)
     __syncwarp();
     unsigned phase = 0;
 
-    const long long total = (long long)(*a.count) * a.chunks;
     const float inv = a.inv;
     const f32x2 NZ = pk2(a.negzero, a.negzero);
     const float Um1f = (float)(U - 1);
     const int nbT = L.TV / DEPTH_UNR, nbS = L.SV / DEPTH_UNR;
 
-    /* consecutive items go to different SMs (and, within a CTA, to different schedulers): a pass with few items then
-     * spreads over the whole GPU instead of filling the twelve warps of a few CTAs */
-    for (long long w = (long long)blockIdx.x + (long long)gridDim.x * wid; w < total; w += (long long)gridDim.x * DEPTH_TM_WARPS) {
-        const int item = (int)(w / a.chunks);
-        const int chunk = (int)(w - (long long)item * a.chunks);
-        const int pix = a.items[item];
+    /* warp items = (record, chunk) pairs claimed from the launch's work queue: a pass with few items spreads over the
+     * whole GPU, and the void items of flat pixels (below) cost nothing.  Balanced mode: this rank's share of the pass,
+     * records fetched from their owners (k_balance.cuh). */
+    bal_slice sl; sl.lo = 0; sl.n = 0; sl.pre_excl = 0; sl.pre_incl = 0;
+    int total;
+    if (a.bal.n) { sl = bal_begin(a.bal, lane); total = sl.n * a.chunks; }
+    else total = (*a.count) * a.chunks;
+    int w = depth_claim(a.queue, lane);
+    while (w < total) {
+        int w_next = 0;
+        if (lane == 0) w_next = atomicAdd(a.queue, 1);          /* claimed now, needed after this item */
+        const int item = w / a.chunks;
+        const int chunk = w - item * a.chunks;
+        int owner = 0, ridx = item;
+        int4 rec;
+        if (a.bal.n) { bal_locate(sl, sl.lo + item, a.bal.n, lane, owner, ridx); rec = ld_cv_int4(a.bal.rec[owner] + ridx); }
+        else rec = a.rec[item];
+        const int pix = rec.x;
+        const float dmin = __int_as_float(rec.y), dmax = __int_as_float(rec.z);
+        /* dmin == dmax: all D hypotheses are the same EPI line (see depth_kernel): chunk 0 evaluates it, the others are void */
+        const bool flat = (a.chunks > 1) && (dmin == dmax);
+        if (flat && chunk > 0) { w = __shfl_sync(0xffffffffu, w_next, 0); continue; }
         const int v = pix / U, u = pix - v * U;
-        const float dmin = a.dmin_map ? a.dmin_map[pix] : a.dmin_c;
-        const float dmax = a.dmax_map ? a.dmax_map[pix] : a.dmax_c;
         const int dbase = chunk * W + lane;
         const float uf = (float)u;
         const float ufl = (dbase < D) ? uf : __int_as_float(0x7fc00000);   /* NaN for padding hypotheses */
@@ -454,7 +467,9 @@ depth_kernel_tm(const depth_args a, const depth_tm_layout L)
             }
         }
         bool finalise = true;
-        if (a.chunks > 1) {
+        if (flat) {
+            sum = (double)best * (double)D;                              /* D equal scores: their double sum is exact */
+        } else if (a.chunks > 1) {
             if (lane == 0) {
                 rslf_partial p;
                 p.mx = best; p.idx = bidx; p.dv = bdv; p.sum = sum;
@@ -481,25 +496,16 @@ depth_kernel_tm(const depth_args a, const depth_tm_layout L)
                 }
             }
         }
-        if (lane == 0 && finalise) {
-            const double maxVal = (double)best;
-            if (maxVal > (double)a.raw_thr) {
-                a.depth[pix] = bdv;
-                const double mean = sum / (double)D;
-                a.cd[pix] = (float)((double)a.ce[pix] * fabs(maxVal - mean));
-#pragma unroll
-                for (int c = 0; c < C; ++c) a.rbar[(size_t)pix * C + c] = brb[c];
-            } else {
-                a.ce[pix] = 0.f;
-                a.emask[pix] = 0;
-            }
-        }
+        if (lane == 0 && finalise) depth_emit<C>(a, pix, __int_as_float(rec.w), owner, ridx, best, bdv, sum, brb);
+        w = __shfl_sync(0xffffffffu, w_next, 0);
     }
+    if (a.bal.n) __threadfence_system();
     /* every tcgen05.ld / st of the CTA is complete (each warp waited on its own); free the columns */
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
     if (wid == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base_s), "n"(512));
+    if (a.bal.n) bal_last_block_signal(a.bal.blocks_done, a.bal.done, a.bal.n, a.bal.seq, 0u);
 }
 
 template <int C, bool NONNEG, bool FAST>

@@ -15,6 +15,7 @@
  */
 #pragma once
 #include "rslf_common.cuh"
+#include "k_balance.cuh"
 #include <math_constants.h>
 
 /* compare-exchange on registers */
@@ -41,9 +42,11 @@ __device__ __forceinline__ void sort_network(float (&a)[N])
 struct median_halo {
     const float* top_depth; const float* top_colour; const uint8_t* top_mask;     /* rows v = -2, -1 */
     const float* bot_depth; const float* bot_colour; const uint8_t* bot_mask;     /* rows v = V, V + 1 */
-    /* peer-to-peer exchange: the neighbours store the rows into this rank's buffer and then raise these
-     * flags to `seq`; the kernel waits for them before it touches a halo row (nullptr: NCCL path, no wait) */
-    const volatile unsigned* flag_top; const volatile unsigned* flag_bot; unsigned seq;
+    size_t colour_halo_stride;     /* floats between the two colour rows of a halo (U * C in a receive area, the stack's row stride in place) */
+    /* peer-to-peer exchange: the neighbours store the rows into this rank's arena and then raise these
+     * flags to `seq`; the kernel waits for them before it touches a halo row (nullptr: NCCL path, no wait).
+     * The wait is bounded by the global timer and raises *err instead of trapping (k_balance.cuh). */
+    const volatile unsigned* flag_top; const volatile unsigned* flag_bot; unsigned seq; int* err;
 };
 
 template <int C, int WIDTH, bool HALO>
@@ -60,9 +63,8 @@ selective_median_kernel(const float* __restrict__ src, const uint8_t* __restrict
         /* blocks whose window reaches a neighbour's rows wait until those rows have landed (bounded spin) */
         const bool need_top = halo.flag_top && v < WIDTH, need_bot = halo.flag_bot && v >= V - WIDTH;
         if ((need_top || need_bot) && threadIdx.x == 0) {
-            int spin = 0;
-            while ((need_top && (int)(*halo.flag_top - halo.seq) < 0) || (need_bot && (int)(*halo.flag_bot - halo.seq) < 0))
-                if (++spin > (1 << 26)) __trap();
+            if (need_top) peer_wait32(halo.flag_top, halo.seq, halo.err);
+            if (need_bot) peer_wait32(halo.flag_bot, halo.seq, halo.err);
             __threadfence_system();
         }
         __syncthreads();
@@ -89,20 +91,24 @@ selective_median_kernel(const float* __restrict__ src, const uint8_t* __restrict
             srow = src + (size_t)k * U; mrow = mask + (size_t)k * U; crow = colour + (size_t)k * colour_row_stride;
         } else if (HALO && k < 0 && k >= -2 && halo.top_depth) {
             srow = halo.top_depth + (size_t)(k + 2) * U; mrow = halo.top_mask + (size_t)(k + 2) * U;
-            crow = halo.top_colour + (size_t)(k + 2) * U * C;
+            crow = halo.top_colour + (size_t)(k + 2) * halo.colour_halo_stride;
         } else if (HALO && k >= V && k < V + 2 && halo.bot_depth) {
             srow = halo.bot_depth + (size_t)(k - V) * U; mrow = halo.bot_mask + (size_t)(k - V) * U;
-            crow = halo.bot_colour + (size_t)(k - V) * U * C;
+            crow = halo.bot_colour + (size_t)(k - V) * halo.colour_halo_stride;
         }
 #pragma unroll
         for (int dl = -WIDTH; dl <= WIDTH; ++dl) {
             const int l = u + dl;
             float x = CUDART_INF_F;
-            if (srow && l >= 0 && l < U && mrow[l]) {
+            if (srow && l >= 0 && l < U &&
+                ((HALO && (k < 0 || k >= V)) ? *reinterpret_cast<const volatile uint8_t*>(mrow + l) : mrow[l])) {
                 float q[C];
 #pragma unroll
-                for (int c = 0; c < C; ++c) q[c] = __ldg(crow + (size_t)l * C + c);
-                if (rslf_norm_diff_lt<C>(pc, q, eps, eps_T)) { x = srow[l]; ++n; }
+                for (int c = 0; c < C; ++c) q[c] = (HALO && (k < 0 || k >= V)) ? crow[(size_t)l * C + c] : __ldg(crow + (size_t)l * C + c);
+                if (rslf_norm_diff_lt<C>(pc, q, eps, eps_T)) {
+                    x = (HALO && (k < 0 || k >= V)) ? *reinterpret_cast<const volatile float*>(srow + l) : srow[l];
+                    ++n;
+                }
             }
             val[(dk + WIDTH) * (2 * WIDTH + 1) + (dl + WIDTH)] = x;
         }

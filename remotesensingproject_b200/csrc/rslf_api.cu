@@ -79,7 +79,7 @@ static void clk_resolve(rslf_ctx* ctx)
 static void free_level(rslf_level& L, bool keep_raw_borrowed_ptr = false)
 {
     (void)keep_raw_borrowed_ptr;
-    dev_free(&L.raw); dev_free(&L.epi); dev_free(&L.ce); dev_free(&L.cd); dev_free(&L.depth); dev_free(&L.rbar);
+    dev_free(&L.raw); dev_free(&L.epi_full); L.epi = nullptr; dev_free(&L.ce); dev_free(&L.cd); dev_free(&L.depth); dev_free(&L.rbar);
     dev_free(&L.dmin); dev_free(&L.dmax); dev_free(&L.emask); dev_free(&L.remaining); dev_free(&L.valid); dev_free(&L.rowdark);
     L.cap_px = 0; L.cap_stack = 0; L.V = L.U = 0; L.C = 0; L.have_bounds = false;
 }
@@ -87,6 +87,7 @@ static void free_level(rslf_level& L, bool keep_raw_borrowed_ptr = false)
 static void free_scratch(rslf_ctx* ctx)
 {
     dev_free(&ctx->items); dev_free(&ctx->filtered); dev_free(&ctx->winner); dev_free(&ctx->arrive);
+    dev_free(&ctx->rec_own); ctx->rec = nullptr;
     if (ctx->partials) { cudaFree(ctx->partials); ctx->partials = nullptr; }
     ctx->partials_cap = 0;
     dev_free(&ctx->nearest_l); dev_free(&ctx->nearest_r);
@@ -105,13 +106,19 @@ static int ensure_scratch(rslf_ctx* ctx, bool need_2d, bool need_ftc, size_t pla
      * the rank's share of level 0) */
     const size_t plane = plane_override ? plane_override : (size_t)ctx->V * ctx->U;
     const size_t px = plane * ctx->S;
-    if (ctx->scratch_px != px || ctx->scratch_plane != plane) {
+    if (ctx->scratch_px != px || ctx->scratch_plane != plane || ctx->scratch_world != ctx->world) {
+        ctx->scratch_world = ctx->world;
         free_scratch(ctx);
-        RSLF_TRY(dev_alloc(ctx, &ctx->items, plane + 4 * (size_t)ctx->U));     /* + the border list of sharded passes */
+        RSLF_TRY(dev_alloc(ctx, &ctx->items, plane));
+        RSLF_TRY(dev_alloc(ctx, &ctx->rec_own, plane));
         RSLF_TRY(dev_alloc(ctx, &ctx->filtered, plane));
-        RSLF_TRY(dev_alloc(ctx, &ctx->arrive, plane));
+        /* a rank of a pass-balanced run evaluates 1/world of the pass's pixels of ALL ranks: its share can
+         * exceed its own plane when the row blocks are unequal */
+        ctx->share_cap = plane;
+        if (ctx->world > 1) ctx->share_cap = std::max(plane, ((size_t)ctx->V_total * ctx->U + ctx->world - 1) / ctx->world + 64);
+        RSLF_TRY(dev_alloc(ctx, &ctx->arrive, ctx->share_cap));
         RSLF_TRY(dev_alloc(ctx, &ctx->pile_depth_raw, plane));
-        RSLF_CUDA_TRY(ctx, cudaMemsetAsync(ctx->arrive, 0, plane * sizeof(int), ctx->stream));
+        RSLF_CUDA_TRY(ctx, cudaMemsetAsync(ctx->arrive, 0, ctx->share_cap * sizeof(int), ctx->stream));
         ctx->scratch_px = px; ctx->scratch_plane = plane;
     }
     if (need_2d && !ctx->winner) {
@@ -144,18 +151,20 @@ static int ensure_partials(rslf_ctx* ctx, size_t n)
     return RSLF_OK;
 }
 
-/* per-level maps; `full` = all S lines (2D), else one plane (pile) */
-static int ensure_level(rslf_ctx* ctx, int p, int V, int U, bool full, bool with_bounds)
+/* per-level maps; `full` = all S lines (2D), else one plane (pile).  V rows of maps from global row v0 on; the
+ * EPI stack of the level holds all Vtot rows on every rank (Vtot < 0: V, a single-rank level). */
+static int ensure_level(rslf_ctx* ctx, int p, int V, int U, bool full, bool with_bounds, int v0 = 0, int Vtot = -1)
 {
     rslf_level& L = ctx->lv[p];
+    if (Vtot < 0) { Vtot = V; v0 = 0; }
     const size_t planes = full ? (size_t)ctx->S : 1;
     const size_t px = planes * V * U;
-    const size_t stack = (size_t)V * ctx->S * U * ctx->C + 64;     /* + slack: TMA segments end on 16-byte boundaries */
+    const size_t stack = (size_t)Vtot * ctx->S * U * ctx->C + 64;     /* + slack: TMA segments end on 16-byte boundaries */
     if (L.V != V || L.U != U || L.cap_px != px || L.C != ctx->C) {
-        float* raw = L.raw; float* epi = L.epi; size_t cap_stack = L.cap_stack;   /* stacks survive a map re-allocation */
-        L.raw = nullptr; L.epi = nullptr;
+        float* raw = L.raw; float* epi = L.epi_full; size_t cap_stack = L.cap_stack;   /* stacks survive a map re-allocation */
+        L.raw = nullptr; L.epi_full = nullptr;
         free_level(L);
-        L.raw = raw; L.epi = epi; L.cap_stack = cap_stack;
+        L.raw = raw; L.epi_full = epi; L.cap_stack = cap_stack;
         L.V = V; L.U = U; L.C = ctx->C;
         RSLF_TRY(dev_alloc(ctx, &L.ce, px)); RSLF_TRY(dev_alloc(ctx, &L.cd, px));
         RSLF_TRY(dev_alloc(ctx, &L.depth, px)); RSLF_TRY(dev_alloc(ctx, &L.rbar, px * ctx->C));
@@ -165,10 +174,12 @@ static int ensure_level(rslf_ctx* ctx, int p, int V, int U, bool full, bool with
         L.cap_px = px;
     }
     if (L.cap_stack < stack) {
-        RSLF_TRY(dev_alloc(ctx, &L.epi, stack));
+        RSLF_TRY(dev_alloc(ctx, &L.epi_full, stack));
         if (p > 0) RSLF_TRY(dev_alloc(ctx, &L.raw, stack));
         L.cap_stack = stack;
     }
+    L.v0 = v0; L.Vtot = Vtot;
+    L.epi = L.epi_full + (size_t)v0 * ctx->S * U * ctx->C;
     if (with_bounds && !L.dmin) {
         RSLF_TRY(dev_alloc(ctx, &L.dmin, px)); RSLF_TRY(dev_alloc(ctx, &L.dmax, px));
     }
@@ -193,31 +204,34 @@ static float kernel_inv(const rslf_params& P, int C)
     return inv;
 }
 
-/* Normalises the raw stack of level p into L.epi (ctor scaling, dc.hpp:442-477). */
+/* bytes of one value of a raw stack */
+static inline size_t depth_esz(int cv_depth) { return cv_depth == RSLF_DEPTH_8U ? 1 : cv_depth == RSLF_DEPTH_16U ? 2 : 4; }
+
+/* Normalises the raw stack of level p (all Vtot rows: every rank holds the whole stack, so the stack maximum
+ * needs no collective) into L.epi_full (ctor scaling, dc.hpp:442-477). */
 static int normalise_level(rslf_ctx* ctx, int p, const void* raw, int cv_depth)
 {
     rslf_level& L = ctx->lv[p];
     stage_scope sc(ctx, ST_PYR);
-    const size_t n = (size_t)L.V * ctx->S * L.U * ctx->C;
+    const size_t n = (size_t)L.Vtot * ctx->S * L.U * ctx->C;
     if (cv_depth == RSLF_DEPTH_8U) {
-        normalise_u8_kernel<<<stream_grid(ctx, n), 256, 0, ctx->stream>>>((const uint8_t*)raw, n, L.epi);
+        normalise_u8_kernel<<<stream_grid(ctx, n), 256, 0, ctx->stream>>>((const uint8_t*)raw, n, L.epi_full);
         L.nonneg = 1;
         ctx->timing.kernel_launches += 1;
     } else if (cv_depth == RSLF_DEPTH_16U) {
         float sf = ctx->scale_factor;
         if (sf < 0.f) {
-            /* the stack maximum over all ranks (start value = the scale factor, dc.hpp:445) */
+            /* the stack maximum (start value = the scale factor, dc.hpp:445) */
             float init[2] = {sf, 0.f}, mx = sf;
             RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->minmax, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
             stack_max_u16_kernel<<<stream_grid(ctx, n), 256, 0, ctx->stream>>>((const uint16_t*)raw, n, ctx->minmax);
             RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(&mx, ctx->minmax, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
             RSLF_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-            if (ctx->world > 1 && !L.replicated) RSLF_TRY(comm_allreduce_max(ctx, ctx->minmax, 1, &mx));
             sf = mx;
             ctx->timing.kernel_launches += 1;
         }
         L.nonneg = (sf > 0.f) ? 1 : 0;
-        normalise_u16_kernel<<<stream_grid(ctx, n), 256, 0, ctx->stream>>>((const uint16_t*)raw, n, sf, L.epi);
+        normalise_u16_kernel<<<stream_grid(ctx, n), 256, 0, ctx->stream>>>((const uint16_t*)raw, n, sf, L.epi_full);
         ctx->timing.kernel_launches += 1;
     } else {
         /* max (start value = the scale factor, dc.hpp:445) and min of the stack */
@@ -228,21 +242,37 @@ static int normalise_level(rslf_ctx* ctx, int p, const void* raw, int cv_depth)
         RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(mm, ctx->minmax, sizeof(mm), cudaMemcpyDeviceToHost, ctx->stream));
         RSLF_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
         float sf = ctx->scale_factor;
-        if (sf < 0.f) {
-            if (ctx->world > 1 && !L.replicated) RSLF_TRY(comm_allreduce_max(ctx, ctx->minmax, 1, &mm[0]));
-            sf = mm[0];
-        }
-        if (ctx->world > 1 && !L.replicated) { /* a shard may hold no negative value while another does: agree */
-            float neg = (mm[1] < 0.f) ? 1.f : 0.f, out = neg;
-            RSLF_TRY(comm_allreduce_max_host(ctx, neg, &out));
-            if (out > 0.f) mm[1] = -1.f;
-        }
+        if (sf < 0.f) sf = mm[0];
         /* sign of a normalised value: sign(x) * sign(1/sf) */
         L.nonneg = ((mm[1] >= 0.f && sf > 0.f)) ? 1 : 0;
-        normalise_f32_kernel<<<stream_grid(ctx, n), 256, 0, ctx->stream>>>((const float*)raw, n, nullptr, sf, L.epi);
+        normalise_f32_kernel<<<stream_grid(ctx, n), 256, 0, ctx->stream>>>((const float*)raw, n, nullptr, sf, L.epi_full);
         ctx->timing.kernel_launches += 2;
     }
     RSLF_CUDA_TRY(ctx, cudaGetLastError());
+    return RSLF_OK;
+}
+
+/* The raw level-0 stack with ALL rows: the uploaded stack itself on one GPU; in a row-sharded run every rank
+ * uploads its block and the blocks are all-gathered over NVLink once per input (cached until the next upload). */
+static int full_input(rslf_ctx* ctx, const void** out)
+{
+    if (ctx->world <= 1 || !ctx->have_shards) { *out = ctx->raw_in; return RSLF_OK; }
+    if (ctx->raw_full_epoch != ctx->input_epoch) {
+        const size_t row_bytes = (size_t)ctx->S * ctx->U * ctx->C * depth_esz(ctx->cv_depth);
+        const size_t bytes = row_bytes * ctx->V_total + 256;
+        if (ctx->raw_full_cap < bytes) {
+            if (ctx->raw_full) cudaFree(ctx->raw_full);
+            ctx->raw_full = nullptr; ctx->raw_full_cap = 0;
+            cudaError_t e = cudaMalloc(&ctx->raw_full, bytes);
+            if (e != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "cudaMalloc(full raw stack %zu): %s", bytes, cudaGetErrorString(e)); return RSLF_ERR_NOMEM; }
+            ctx->raw_full_cap = bytes;
+        }
+        shard_tab t; t.n = ctx->world;
+        for (int r = 0; r <= ctx->world; ++r) t.b[r] = ctx->row_starts[r];
+        RSLF_TRY(comm_gather_rows(ctx, ctx->raw_in, row_bytes, t, ctx->raw_full));
+        ctx->raw_full_epoch = ctx->input_epoch;
+    }
+    *out = ctx->raw_full;
     return RSLF_OK;
 }
 
@@ -271,6 +301,7 @@ extern "C" const char* rslf_cuda_strerror(int code)
         case RSLF_ERR_UNSUPPORTED: return "not implemented in the CUDA path";
         case RSLF_ERR_NCCL: return "NCCL error";
         case RSLF_ERR_NOMEM: return "out of device memory";
+        case RSLF_ERR_PEER: return "a peer GPU did not answer in time";
         default: return "unknown error";
     }
 }
@@ -291,6 +322,9 @@ extern "C" int rslf_cuda_create(int device, rslf_ctx** out)
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return RSLF_ERR_CUDA; }
     cudaEventCreate(&ctx->ev_a); cudaEventCreate(&ctx->ev_b);
     if (cudaMalloc((void**)&ctx->count, RSLF_COUNT_SLOTS * sizeof(int)) != cudaSuccess ||
+        cudaMalloc((void**)&ctx->queue, RSLF_COUNT_SLOTS * sizeof(int)) != cudaSuccess ||
+        cudaMalloc((void**)&ctx->dev_err, sizeof(int)) != cudaSuccess ||
+        cudaMemset(ctx->dev_err, 0, sizeof(int)) != cudaSuccess ||
         cudaMalloc((void**)&ctx->total_px, 2 * sizeof(unsigned long long)) != cudaSuccess ||
         cudaMalloc((void**)&ctx->minmax, 4 * sizeof(float)) != cudaSuccess) {
         rslf_cuda_destroy(ctx); return RSLF_ERR_CUDA;
@@ -300,6 +334,8 @@ extern "C" int rslf_cuda_create(int device, rslf_ctx** out)
     if (st) ctx->stage_timing = atoi(st);
     const char* fm = getenv("RSLF_FAST_MATH");
     if (fm) ctx->fast_math = atoi(fm) != 0;
+    const char* bl = getenv("RSLF_BALANCE");
+    if (bl) ctx->balance = atoi(bl) != 0;
     *out = ctx;
     return RSLF_OK;
 }
@@ -313,6 +349,8 @@ extern "C" void rslf_cuda_destroy(rslf_ctx* ctx)
     for (int p = 0; p < RSLF_MAX_LEVELS; ++p) free_level(ctx->lv[p]);
     free_scratch(ctx);
     if (ctx->raw_in && !ctx->raw_borrowed) cudaFree(ctx->raw_in);
+    if (ctx->raw_full) cudaFree(ctx->raw_full);
+    dev_free(&ctx->queue); dev_free(&ctx->dev_err);
     dev_free(&ctx->count); dev_free(&ctx->total_px); dev_free(&ctx->minmax); dev_free(&ctx->rowwork);
     dev_free(&ctx->colour_hist); dev_free(&ctx->colour_lut);
     if (ctx->l2_flush) cudaFree(ctx->l2_flush);
@@ -373,12 +411,10 @@ static int set_dims(rslf_ctx* ctx, int V, int S, int U, int C, int cv_depth, flo
     }
     if ((size_t)S * 4 > RSLF_COUNT_SLOTS / RSLF_MAX_LEVELS) { snprintf(ctx->err, sizeof(ctx->err), "S too large"); return RSLF_ERR_UNSUPPORTED; }
     ctx->V = V; ctx->S = S; ctx->U = U; ctx->C = C; ctx->cv_depth = cv_depth; ctx->scale_factor = scale;
+    ++ctx->input_epoch;                                      /* the gathered copy of the stack (full_input) is stale */
     if (ctx->V_total == 0 || ctx->world == 1) { ctx->v0 = 0; ctx->V_total = V; }
     return RSLF_OK;
 }
-
-/* bytes of one value of a raw stack */
-static inline size_t depth_esz(int cv_depth) { return cv_depth == RSLF_DEPTH_8U ? 1 : cv_depth == RSLF_DEPTH_16U ? 2 : 4; }
 
 static int own_raw(rslf_ctx* ctx, size_t bytes)
 {
@@ -524,8 +560,24 @@ struct pass_io {
     int count_slot;
 };
 
+/* Peer memory for the row-sharded run: the arena of every rank (rslf_comm.cuh), sized for the largest level-0
+ * block.  Collective; RSLF_ERR_UNSUPPORTED (on every rank) when peer memory is unavailable. */
+static int ensure_arena(rslf_ctx* ctx)
+{
+    if (ctx->world <= 1) return RSLF_ERR_UNSUPPORTED;
+    int max_rows = 1;
+    for (int q = 0; q < ctx->world; ++q) max_rows = std::max(max_rows, ctx->row_starts[q + 1] - ctx->row_starts[q]);
+    return comm_arena_setup(ctx, ctx->U, ctx->C, (size_t)max_rows * ctx->U);
+}
+
 /* compute_1D_depth_epi_pile (core.hpp:772-893) on line s_hat of level L: compaction,
- * depth kernel, selective median into ctx->filtered. */
+ * depth kernel, selective median into ctx->filtered.
+ *
+ * Row-sharded level, three ways to cross the block borders:
+ *   balanced  (default): pass-balanced depth kernel + median halo through peer memory (k_balance.cuh)
+ *   lock-step (RSLF_BALANCE=0, or the 1D pile): every rank evaluates its own rows, median halo through peer memory
+ *                        or, without peer memory, one small all-gather
+ *   gather               thin blocks / windows wider than 5x5: all-gather of the planes of line s_hat */
 static int run_depth_pass(rslf_ctx* ctx, const rslf_params& P, const pass_io& io)
 {
     rslf_level& L = ctx->lv[io.level];
@@ -533,30 +585,45 @@ static int run_depth_pass(rslf_ctx* ctx, const rslf_params& P, const pass_io& io
     const size_t plane = (size_t)V * U;
     const size_t po = io.pile ? 0 : (size_t)io.s_hat * plane;
     int* count = ctx->count + io.count_slot;
-    int* count2 = ctx->count + RSLF_COUNT_SLOTS / 2 + io.count_slot;
+    int* queue = ctx->queue + io.count_slot;
     const bool sharded = (ctx->world > 1 && !L.replicated);
     const float* colour0 = L.epi + (size_t)io.s_hat * U * C;      /* colours of line s_hat: row v at + v * S*U*C */
+    const size_t colour_stride = (size_t)S * U * C;
     const uint8_t* fresh = io.pile ? nullptr : L.remaining + po;
     const int* rdv = io.pile ? nullptr : L.rowdark + (size_t)S * V;
     /* row-sharded level: how the rows next to the block reach the neighbours */
-    shard_tab t; bool halo_path = false;
+    shard_tab t; bool halo_path = false, p2p = false, balanced = false;
     if (sharded) {
         t = level_shards(ctx, io.level, L.Vtot);
         int min_rows = L.Vtot;
         for (int q = 0; q < t.n; ++q) min_rows = std::min(min_rows, t.b[q + 1] - t.b[q]);
         const char* force_full = getenv("RSLF_MEDIAN_GATHER");         /* "full": test hook for the fallback */
         halo_path = (P.median_filter_size - 1) / 2 <= 2 && min_rows >= 2 && !(force_full && force_full[0] == 'f');
+        p2p = (ensure_arena(ctx) == RSLF_OK);
+        balanced = p2p && halo_path && ctx->balance && !io.pile && ctx->world <= RSLF_MAX_PEERS;
     }
-    auto compact = [&](int select, int* items, int* cnt) -> int {
+    const arena_layout al = p2p ? arena_current(ctx) : arena_layout();
+    int4* rec = balanced ? reinterpret_cast<int4*>(ctx->arena + al.off_rec) : ctx->rec_own;
+    const unsigned seq = balanced ? ++ctx->bal_seq : 0u;
+    {
         stage_scope sc(ctx, ST_REDUCE);
-        compact_kernel<<<stream_grid(ctx, plane), 256, 0, ctx->stream>>>(
-            L.emask + po, io.pile ? nullptr : L.remaining + po, (int)plane, items, cnt, ctx->total_px + (L.replicated ? 1 : 0),
-            L.replicated ? nullptr : ctx->rowwork, U, L.v0, io.level, ctx->v0, ctx->V,
-            V, (sharded && ctx->rank > 0) ? 2 : 0, (sharded && ctx->rank + 1 < ctx->world) ? 2 : 0, select);
+        compact_args c; memset(&c, 0, sizeof(c));
+        c.emask = L.emask + po; c.remaining = io.pile ? nullptr : L.remaining + po; c.n = (int)plane;
+        c.items = ctx->items; c.rec = rec; c.count = count; c.total = ctx->total_px + (L.replicated ? 1 : 0);
+        c.rowwork = L.replicated ? nullptr : ctx->rowwork; c.U = U; c.v0 = L.v0; c.shift = io.level; c.v0_base = ctx->v0; c.rows_base = ctx->V;
+        c.V = V; c.select = 0;
+        c.dmin_map = io.use_bound_maps ? L.dmin + po : nullptr; c.dmax_map = io.use_bound_maps ? L.dmax + po : nullptr;
+        c.dmin_c = io.dmin; c.dmax_c = io.dmax; c.ce = L.ce + po;
+        c.pix_off = L.v0 * U;                                    /* records address the level's full stack */
+        if (balanced) {
+            c.bal_n = ctx->world; c.seq = seq; c.blocks_done = ctx->p2p_done + 1;
+            for (int q = 0; q < ctx->world; ++q)
+                c.counts_peer[q] = reinterpret_cast<unsigned long long*>(ctx->arena_peer[q] + al.off_counts) + ctx->rank;
+        }
+        compact_kernel<<<stream_grid(ctx, plane), 256, 0, ctx->stream>>>(c);
         RSLF_CUDA_TRY(ctx, cudaGetLastError());
         ctx->timing.kernel_launches += 1;
-        return RSLF_OK;
-    };
+    }
     depth_plan plan = plan_depth(ctx, S, C, io.D, io.s_hat, io.dmin, io.dmax, P.slope_factor);
     /* tensor-memory variant (k_depth_tm.cuh): RSLF_DEPTH_TMEM = 0 off, 1 RGB stacks (the planner's H = 1 case), 2 every stack */
     depth_tm_layout tml; bool use_tm = false;
@@ -573,50 +640,31 @@ static int run_depth_pass(rslf_ctx* ctx, const rslf_params& P, const pass_io& io
             }
         }
     }
-    if (plan.chunks > 1) RSLF_TRY(ensure_partials(ctx, plane * plan.chunks));
-    depth_args a;
-    a.epi = L.epi; a.V = V; a.S = S; a.U = U; a.D = io.D; a.s_hat = io.s_hat; a.slope = P.slope_factor;
+    if (ctx->fast_math && !use_tm) {
+        snprintf(ctx->err, sizeof(ctx->err), "fast_math: the contracted mean shift exists only in the tensor-memory depth kernel, "
+                 "which does not take this pass (C=%d S=%d D=%d)", C, S, io.D);
+        return RSLF_ERR_UNSUPPORTED;
+    }
+    if (plan.chunks > 1) RSLF_TRY(ensure_partials(ctx, ctx->share_cap * plan.chunks));
+    depth_args a; memset(&a, 0, sizeof(a));
+    a.epi = L.epi_full; a.V = L.Vtot; a.S = S; a.U = U; a.D = io.D; a.s_hat = io.s_hat; a.slope = P.slope_factor;
     a.inv = kernel_inv(P, C); a.iters = P.mean_shift_max_iter; a.negzero = -0.0f;
-    a.items = ctx->items; a.count = count;
-    a.dmin_map = io.use_bound_maps ? L.dmin + po : nullptr;
-    a.dmax_map = io.use_bound_maps ? L.dmax + po : nullptr;
-    a.dmin_c = io.dmin; a.dmax_c = io.dmax;
+    a.rec = rec; a.count = count; a.queue = queue; a.pix_off = L.v0 * U;
     a.ce = L.ce + po; a.emask = L.emask + po; a.cd = L.cd + po;
     a.depth = io.pile ? ctx->pile_depth_raw : L.depth + po;
     a.rbar = L.rbar + po * C;
     a.raw_thr = P.raw_score_threshold;
     a.wpv_q16 = plan.wpv_q16; a.reg_last = plan.reg_last;
     a.chunks = plan.chunks; a.partials = (rslf_partial*)ctx->partials; a.arrive = ctx->arrive;
-    median_halo halo; memset(&halo, 0, sizeof(halo));
-    ctx->pass_items2 = nullptr; ctx->pass_count2 = nullptr;
-    const char* bf = getenv("RSLF_BORDER_FIRST");
-    const bool border_first = halo_path && bf && bf[0] == '1';
-    if (border_first) {
-        /* Border rows first (optional, RSLF_BORDER_FIRST=1; measured on 4 GPUs it does not pay: the ranks stay in
-         * lock-step through the largest pass anyway and the extra launches cost 4 %).  The only cross-row step of a pass is the 5x5 selective median (core.hpp:698-709),
-         * which reads the two rows next to the block.  Those rows are computed by a first small launch and sent to
-         * the neighbours at once, so that a neighbour's median never waits for this rank's whole depth kernel:
-         * the ranks may then drift by up to a pass instead of advancing in lock-step. */
-        int* items_b = ctx->items + ctx->scratch_plane;             /* the tail of the list buffer holds the border list */
-        RSLF_TRY(compact(1, items_b, count2));
-        {
-            stage_scope sc(ctx, ST_DEPTH);
-            depth_args ab = a; ab.items = items_b; ab.count = count2;
-            if (use_tm) RSLF_TRY(launch_depth_tm(ctx, C, L.nonneg != 0, ab, tml, ctx->fast_math != 0));
-            else RSLF_TRY(launch_depth(ctx, C, L.nonneg != 0, ab, plan));
+    if (balanced) {
+        a.bal.n = ctx->world; a.bal.rank = ctx->rank; a.bal.seq = seq;
+        for (int q = 0; q < ctx->world; ++q) {
+            a.bal.rec[q] = reinterpret_cast<const int4*>(ctx->arena_peer[q] + al.off_rec);
+            a.bal.res[q] = reinterpret_cast<float4*>(ctx->arena_peer[q] + al.off_res);
+            a.bal.done[q] = reinterpret_cast<unsigned long long*>(ctx->arena_peer[q] + al.off_done) + ctx->rank;
         }
-        {
-            stage_scope sc(ctx, ST_MEDIAN);
-            /* peer-to-peer stores over NVLink when CUDA IPC between the ranks works, else one small all-gather */
-            if (comm_p2p_setup(ctx, ctx->U, C) == RSLF_OK)
-                RSLF_TRY(comm_p2p_exchange_median_halo(ctx, a.depth, L.emask + po, colour0, (size_t)S * U * C, U, C, t, &halo));
-            else
-                RSLF_TRY(comm_exchange_median_halo(ctx, a.depth, L.emask + po, colour0, (size_t)S * U * C, U, C, t, &halo));
-        }
-        RSLF_TRY(compact(2, ctx->items, count));
-        ctx->pass_items2 = items_b; ctx->pass_count2 = count2;
-    } else {
-        RSLF_TRY(compact(0, ctx->items, count));
+        a.bal.counts = reinterpret_cast<const volatile unsigned long long*>(ctx->arena + al.off_counts);
+        a.bal.blocks_done = ctx->p2p_done + 2; a.bal.err = ctx->dev_err;
     }
     {
         stage_scope sc(ctx, ST_DEPTH);
@@ -625,25 +673,42 @@ static int run_depth_pass(rslf_ctx* ctx, const rslf_params& P, const pass_io& io
     }
     {
         stage_scope sc(ctx, ST_MEDIAN);
-        if (halo_path && !border_first) {
+        median_halo halo; memset(&halo, 0, sizeof(halo));
+        if (balanced) {
+            /* the owner applies the result records of its rows, then its first / last rows go to the neighbours;
+             * colours are read in place: every rank holds the whole stack */
+            bal_apply_args g; memset(&g, 0, sizeof(g));
+            g.items = ctx->items; g.count = count; g.res = reinterpret_cast<const float4*>(ctx->arena + al.off_res); g.C = C;
+            g.depth = a.depth; g.cd = a.cd; g.rbar = a.rbar; g.ce = a.ce; g.emask = a.emask;
+            g.done = reinterpret_cast<const volatile unsigned long long*>(ctx->arena + al.off_done);
+            g.n = ctx->world; g.seq = seq; g.err = ctx->dev_err; g.blocks_done = ctx->p2p_done + 3; g.do_push = 1;
+            p2p_prepare_halo(ctx, a.depth, L.emask + po, nullptr, colour_stride, U, C, t, &g.push, &halo);
+            bal_apply_kernel<<<ctx->num_sm, 256, 0, ctx->stream>>>(g);
+            RSLF_CUDA_TRY(ctx, cudaGetLastError());
+            ctx->timing.kernel_launches += 1;
+        } else if (halo_path) {
             /* the rows next to the block go to the neighbours: peer-to-peer stores over NVLink when CUDA IPC between
              * the ranks works, else one small all-gather */
-            if (comm_p2p_setup(ctx, ctx->U, C) == RSLF_OK)
-                RSLF_TRY(comm_p2p_exchange_median_halo(ctx, a.depth, L.emask + po, colour0, (size_t)S * U * C, U, C, t, &halo));
-            else
-                RSLF_TRY(comm_exchange_median_halo(ctx, a.depth, L.emask + po, colour0, (size_t)S * U * C, U, C, t, &halo));
+            if (p2p) RSLF_TRY(comm_p2p_exchange_median_halo(ctx, a.depth, L.emask + po, nullptr, colour_stride, U, C, t, &halo));
+            else RSLF_TRY(comm_exchange_median_halo(ctx, a.depth, L.emask + po, colour0, colour_stride, U, C, t, &halo));
+        }
+        if (halo_path && p2p) {
+            /* colour rows of the neighbours: in place in this rank's copy of the stack */
+            halo.colour_halo_stride = colour_stride;
+            if (halo.top_depth) halo.top_colour = colour0 - 2 * colour_stride;
+            if (halo.bot_depth) halo.bot_colour = colour0 + (size_t)V * colour_stride;
         }
         if (halo_path) {
-            RSLF_TRY(launch_selective_median(ctx, a.depth, L.emask + po, colour0, (size_t)S * U * C, V, U, C,
+            RSLF_TRY(launch_selective_median(ctx, a.depth, L.emask + po, colour0, colour_stride, V, U, C,
                                              P.median_filter_size, P.median_filter_epsilon, ctx->filtered, 0, -1, fresh, rdv, &halo));
         } else if (sharded) {
-            /* thin blocks or wide windows: gather the whole planes of line s_hat */
+            /* thin blocks or wide windows: gather the depth / mask planes of line s_hat (colours: the whole stack is here) */
             RSLF_TRY(ensure_gather_planes(ctx, (size_t)L.Vtot * U));
-            RSLF_TRY(comm_gather_median_planes(ctx, a.depth, L.emask + po, colour0, (size_t)S * U * C, U, C, t));
+            RSLF_TRY(comm_gather_median_planes(ctx, a.depth, L.emask + po, colour0, colour_stride, U, C, t));
             RSLF_TRY(launch_selective_median(ctx, ctx->g_depth, ctx->g_mask, ctx->g_colour, (size_t)U * C, L.Vtot, U, C,
                                              P.median_filter_size, P.median_filter_epsilon, ctx->filtered, L.v0, V, fresh, rdv));
         } else {
-            RSLF_TRY(launch_selective_median(ctx, a.depth, L.emask + po, colour0, (size_t)S * U * C,
+            RSLF_TRY(launch_selective_median(ctx, a.depth, L.emask + po, colour0, colour_stride,
                                              V, U, C, P.median_filter_size, P.median_filter_epsilon, ctx->filtered, 0, -1, fresh, rdv));
         }
     }
@@ -699,7 +764,7 @@ static int run_depth2d_level(rslf_ctx* ctx, int p, const rslf_params& P, float d
             a.rbar_p = L.rbar + (size_t)s_hat * plane * C; a.cd_p = L.cd + (size_t)s_hat * plane;
             a.depth = L.depth; a.cd = L.cd; a.remaining = L.remaining; a.winner = ctx->winner;
             a.items = ctx->items; a.count = ctx->count + io.count_slot; a.rowdark = L.rowdark;
-            a.items2 = ctx->pass_items2; a.count2 = ctx->pass_count2;
+            a.items2 = nullptr; a.count2 = nullptr;
             RSLF_TRY(launch_propagate(ctx, C, a));
         }
         ++pass;
@@ -716,6 +781,7 @@ static int begin_run(rslf_ctx* ctx)
     ctx->timing.ms_h2d = h2d;
     clk_reset(ctx);
     RSLF_CUDA_TRY(ctx, cudaMemsetAsync(ctx->count, 0, RSLF_COUNT_SLOTS * sizeof(int), ctx->stream));
+    RSLF_CUDA_TRY(ctx, cudaMemsetAsync(ctx->queue, 0, RSLF_COUNT_SLOTS * sizeof(int), ctx->stream));
     RSLF_CUDA_TRY(ctx, cudaMemsetAsync(ctx->total_px, 0, 2 * sizeof(unsigned long long), ctx->stream));
     if (ctx->rowwork_cap < (size_t)ctx->V) {
         RSLF_TRY(dev_alloc(ctx, &ctx->rowwork, (size_t)ctx->V));
@@ -730,8 +796,15 @@ static int end_run(rslf_ctx* ctx, int D)
 {
     RSLF_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_b, ctx->stream));
     unsigned long long both[2] = {0, 0};
+    int peer_err = 0;
     RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(both, ctx->total_px, sizeof(both), cudaMemcpyDeviceToHost, ctx->stream));
+    RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(&peer_err, ctx->dev_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     RSLF_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (peer_err) {
+        cudaMemsetAsync(ctx->dev_err, 0, sizeof(int), ctx->stream);
+        snprintf(ctx->err, sizeof(ctx->err), "rank %d: a wait for a peer GPU timed out (results of this run are invalid)", ctx->rank);
+        return RSLF_ERR_PEER;
+    }
     RSLF_CUDA_TRY(ctx, cudaEventElapsedTime(&ctx->timing.ms_total, ctx->ev_a, ctx->ev_b));
     if (ctx->stage_timing) clk_resolve(ctx);
     /* levels that every rank computes whole are counted once (by rank 0), so that the sum over ranks is the job's work */
@@ -759,14 +832,16 @@ extern "C" int rslf_cuda_depth1d_pile_run(rslf_ctx* ctx, float dmin, float dmax,
     RSLF_TRY(begin_run(ctx));
     const int V = ctx->V, U = ctx->U, S = ctx->S, C = ctx->C;
     if (s_hat < 0 || s_hat > S - 1) s_hat = (int)std::floor((0.0 + S) / 2);      /* dc.hpp:489-498 */
-    RSLF_TRY(ensure_scratch(ctx, false, false));
     RSLF_TRY(prepare_shards(ctx, 1));
-    RSLF_TRY(ensure_level(ctx, 0, V, U, false, false));
+    RSLF_TRY(ensure_scratch(ctx, false, false));
+    RSLF_TRY(ensure_level(ctx, 0, V, U, false, false, ctx->v0, ctx->V_total));
     ctx->n_levels = 1;
     rslf_level& L = ctx->lv[0];
-    L.v0 = ctx->v0; L.Vtot = ctx->V_total; L.replicated = false;
+    L.replicated = false;
     L.slope = P.slope_factor;
-    RSLF_TRY(normalise_level(ctx, 0, ctx->raw_in, ctx->cv_depth));
+    const void* raw0 = nullptr;
+    RSLF_TRY(full_input(ctx, &raw0));
+    RSLF_TRY(normalise_level(ctx, 0, raw0, ctx->cv_depth));
     const size_t plane = (size_t)V * U;
     RSLF_CUDA_TRY(ctx, cudaMemsetAsync(ctx->pile_depth_raw, 0, plane * sizeof(float), ctx->stream));
     RSLF_CUDA_TRY(ctx, cudaMemsetAsync(L.cd, 0, plane * sizeof(float), ctx->stream));
@@ -832,19 +907,21 @@ extern "C" int rslf_cuda_depth2d_run(rslf_ctx* ctx, float dmin, float dmax, int 
     const rslf_params& P = *params;
     const int V = ctx->V, U = ctx->U, S = ctx->S;
     RSLF_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    RSLF_TRY(ensure_scratch(ctx, true, false));
     RSLF_TRY(prepare_shards(ctx, 1));
-    RSLF_TRY(ensure_level(ctx, 0, V, U, true, dmin_svu != nullptr));
+    RSLF_TRY(ensure_scratch(ctx, true, false));
+    RSLF_TRY(ensure_level(ctx, 0, V, U, true, dmin_svu != nullptr, ctx->v0, ctx->V_total));
     ctx->n_levels = 1;
     rslf_level& L = ctx->lv[0];
-    L.v0 = ctx->v0; L.Vtot = ctx->V_total; L.replicated = false;
+    L.replicated = false;
     const size_t px = (size_t)S * V * U;
     if (dmin_svu) {
         RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(L.dmin, dmin_svu, px * 4, cudaMemcpyHostToDevice, ctx->stream));
         RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(L.dmax, dmax_svu, px * 4, cudaMemcpyHostToDevice, ctx->stream));
     }
+    const void* raw0 = nullptr;
+    RSLF_TRY(full_input(ctx, &raw0));
     RSLF_TRY(begin_run(ctx));
-    RSLF_TRY(normalise_level(ctx, 0, ctx->raw_in, ctx->cv_depth));
+    RSLF_TRY(normalise_level(ctx, 0, raw0, ctx->cv_depth));
     RSLF_TRY(run_depth2d_level(ctx, 0, P, dmin, dmax, dim_d, dmin_svu != nullptr));
     ctx->timing.levels = 1;
     ctx->last_kind = 2;
@@ -1042,8 +1119,8 @@ extern "C" int rslf_cuda_fine_to_coarse_run(rslf_ctx* ctx, float dmin, float dma
         max_plane = std::max(max_plane, (size_t)Vp[sharded_levels - 1] * Up[sharded_levels - 1]);
     RSLF_TRY(ensure_scratch(ctx, true, true, max_plane));
     for (int p = 0; p < levels; ++p) {
-        RSLF_TRY(ensure_level(ctx, p, Vl[p], Up[p], true, true));
-        ctx->lv[p].v0 = rep[p] ? 0 : tabs[p].b[r]; ctx->lv[p].Vtot = Vp[p]; ctx->lv[p].replicated = rep[p];
+        RSLF_TRY(ensure_level(ctx, p, Vl[p], Up[p], true, true, rep[p] ? 0 : tabs[p].b[r], Vp[p]));
+        ctx->lv[p].replicated = rep[p];
     }
     if (ctx->world > 1) {
         const size_t gpx = (size_t)S * Vp[0] * Up[0];
@@ -1052,16 +1129,16 @@ extern "C" int rslf_cuda_fine_to_coarse_run(rslf_ctx* ctx, float dmin, float dma
             RSLF_TRY(dev_alloc(ctx, &ctx->g_mk, gpx)); RSLF_TRY(dev_alloc(ctx, &ctx->g_mk2, gpx));
             ctx->g_map_cap = gpx;
         }
-        const size_t graw = (size_t)Vp[0] * S * Up[0] * C + 64;
-        if (levels > 1 && ctx->g_raw_cap < graw) { RSLF_TRY(dev_alloc(ctx, &ctx->g_raw, graw)); ctx->g_raw_cap = graw; }
     }
     ctx->n_levels = levels;
+    const void* raw0 = nullptr;
+    RSLF_TRY(full_input(ctx, &raw0));
     RSLF_TRY(begin_run(ctx));
     const rslf_params& P0 = *params;
     for (int p = 0; p < levels; ++p) {
         rslf_level& L = ctx->lv[p];
         const size_t px = (size_t)S * Vl[p] * Up[p];
-        const void* raw = (p == 0) ? ctx->raw_in : (const void*)L.raw;
+        const void* raw = (p == 0) ? raw0 : (const void*)L.raw;
         /* 8-bit / 16-bit stacks keep their depth between levels (OpenCV's integer blur / resize), float stacks stay float */
         RSLF_TRY(normalise_level(ctx, p, raw, ctx->cv_depth));
         rslf_params P = P0;
@@ -1082,21 +1159,15 @@ extern "C" int rslf_cuda_fine_to_coarse_run(rslf_ctx* ctx, float dmin, float dma
             if (p + 1 < levels) {
                 rslf_level& N = ctx->lv[p + 1];
                 const bool sh = (ctx->world > 1 && !rep[p]);             /* level p is sharded */
-                /* next level's raw stack (ftc.hpp:146): the 7x7 blur reads 3 rows beyond the rank's block, so a
-                 * sharded level first gathers its raw rows */
-                const size_t esz = depth_esz(ctx->cv_depth);
-                const void* ds_in = raw;
-                if (sh) {
-                    RSLF_TRY(comm_gather_rows(ctx, raw, (size_t)S * Up[p] * C * esz, tabs[p], ctx->g_raw));
-                    ds_in = ctx->g_raw;
-                }
+                /* next level's raw stack (ftc.hpp:146): every rank holds all rows of every level's stack, so the 7x7 blur
+                 * and the half-scale resize run on the whole level without any exchange */
                 const int ov0 = rep[p + 1] ? 0 : tabs[p + 1].b[r];
                 if (ctx->cv_depth == RSLF_DEPTH_8U)
-                    RSLF_TRY(launch_downsample_int<uint8_t>(ctx, (const uint8_t*)ds_in, Vp[p], S, Up[p], C, (uint8_t*)N.raw, Vp[p + 1], Up[p + 1], ov0, Vl[p + 1]));
+                    RSLF_TRY(launch_downsample_int<uint8_t>(ctx, (const uint8_t*)raw, Vp[p], S, Up[p], C, (uint8_t*)N.raw, Vp[p + 1], Up[p + 1]));
                 else if (ctx->cv_depth == RSLF_DEPTH_16U)
-                    RSLF_TRY(launch_downsample_int<uint16_t>(ctx, (const uint16_t*)ds_in, Vp[p], S, Up[p], C, (uint16_t*)N.raw, Vp[p + 1], Up[p + 1], ov0, Vl[p + 1]));
+                    RSLF_TRY(launch_downsample_int<uint16_t>(ctx, (const uint16_t*)raw, Vp[p], S, Up[p], C, (uint16_t*)N.raw, Vp[p + 1], Up[p + 1]));
                 else
-                    RSLF_TRY(launch_downsample(ctx, (const float*)ds_in, Vp[p], S, Up[p], C, N.raw, Vp[p + 1], Up[p + 1], ov0, Vl[p + 1]));
+                    RSLF_TRY(launch_downsample(ctx, (const float*)raw, Vp[p], S, Up[p], C, N.raw, Vp[p + 1], Up[p + 1]));
                 const size_t npx = (size_t)S * Vl[p + 1] * Up[p + 1];
                 fill_f32_kernel<<<stream_grid(ctx, npx), 256, 0, ctx->stream>>>(N.dmin, npx, dmin);
                 fill_f32_kernel<<<stream_grid(ctx, npx), 256, 0, ctx->stream>>>(N.dmax, npx, dmax);

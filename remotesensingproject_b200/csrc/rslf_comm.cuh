@@ -1,11 +1,12 @@
 /*
  * rslf_comm.cuh — NCCL plumbing for the row-sharded run (one process per GPU).
  * NCCL is resolved with dlopen at communicator creation, so the library loads
- * (and single-GPU runs work) on hosts without libnccl.  The path has two
- * exchange steps only: the per-pass all-gather of the depth / mask / colour rows
- * of line s_hat that the cross-row selective median reads
- * (rslf_depth_computation_core.hpp:698-709), and the scalar max of the input
- * normalisation (rslf_depth_computation.hpp:442-460).
+ * (and single-GPU runs work) on hosts without libnccl.  NCCL carries the one-off
+ * all-gather of the raw stack (every rank keeps the whole EPI stack, the result
+ * maps are sharded by rows), the gathers around the first replicated pyramid level
+ * and the fallbacks; the per-pass traffic — work / result records of the balanced
+ * depth kernel, the median halo rows (rslf_depth_computation_core.hpp:698-709) —
+ * goes through peer memory over NVLink (second half of this file, k_balance.cuh).
  */
 #pragma once
 #include <dlfcn.h>
@@ -64,14 +65,13 @@ static int nccl_load(char* err, size_t errlen)
         }                                                                                      \
     } while (0)
 
+static void arena_close(rslf_ctx* ctx);
+
 static void comm_destroy(rslf_ctx* ctx)
 {
-    if (ctx->p2p_up) cudaIpcCloseMemHandle(ctx->p2p_up);
-    if (ctx->p2p_dn) cudaIpcCloseMemHandle(ctx->p2p_dn);
-    ctx->p2p_up = ctx->p2p_dn = nullptr;
-    if (ctx->p2p_buf) cudaFree(ctx->p2p_buf);
+    arena_close(ctx);
     if (ctx->p2p_done) cudaFree(ctx->p2p_done);
-    ctx->p2p_buf = nullptr; ctx->p2p_done = nullptr; ctx->p2p_state = 0;
+    ctx->p2p_done = nullptr; ctx->p2p_state = 0;
     if (ctx->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->nccl_comm);
     ctx->nccl_comm = nullptr;
 }
@@ -251,6 +251,7 @@ static int comm_exchange_median_halo(rslf_ctx* ctx, const float* depth_plane, co
     ctx->timing.kernel_launches += 1;
     RSLF_NCCL_TRY(ctx, g_nccl.AllGather(ctx->g_send, ctx->g_recv, blockbytes, RSLF_NCCL_UINT8, ctx->nccl_comm, ctx->stream));
     memset(out, 0, sizeof(*out));
+    out->colour_halo_stride = (size_t)U * C;
     const char* recv = (const char*)ctx->g_recv;
     if (r0 > 0) {                                              /* rows 2, 3 of the rank above = its last two rows */
         const char* b = recv + (size_t)(r0 - 1) * blockbytes;
@@ -267,63 +268,105 @@ static int comm_exchange_median_halo(rslf_ctx* ctx, const float* depth_plane, co
     return RSLF_OK;
 }
 
-/* ---- peer-to-peer halo exchange (NVLink, CUDA IPC) ----------------------------------------------------
- * The per-pass median exchange is latency-bound (4 rows per rank).  Instead of a collective, every rank
- * stores its two first / two last rows of line s_hat straight into its neighbours' receive buffers with
- * ordinary global stores over NVLink and raises a sequence flag there; the neighbour's median kernel waits
- * for the flag.  No rank ever waits inside a producer, so there is no circular wait; two buffer slots
- * alternate because a rank can be at most one pass ahead of its neighbour (its next push comes after its
- * own median, which waited for the neighbour's push of the same pass).
- * Receive buffer of a rank: [slot 0 | slot 1] x [from above | from below] x area, then 4 flags.
+/* ---- peer memory over NVLink (CUDA IPC) -------------------------------------------------------------------
+ * Every rank allocates one ARENA with the same layout, exports it with cudaIpcGetMemHandle and maps the
+ * arenas of all peers.  It holds everything another GPU reads or writes during a run:
+ *
+ *   [halo areas: 2 slots x {from above, from below}]   rows next to the block for the 5x5 selective median
+ *   [halo flags]  [counts[r]]  [done[r]]                 sequence words raised by the peers (k_balance.cuh)
+ *   [records: cap x 16 B]  [results: cap x 32 B]         work / result records of the pass-balanced depth kernel
+ *
+ * Halo exchange: instead of a collective, every rank stores its two first / two last rows of line s_hat straight
+ * into its neighbours' areas with ordinary global stores over NVLink and raises a sequence flag there; the
+ * neighbour's median kernel waits for the flag.  No rank ever waits inside a producer, so there is no circular
+ * wait; two slots alternate because a rank can be at most one pass ahead of its neighbour.
  */
 static size_t p2p_area_bytes(int U, int C) { return (((size_t)2 * U * 4 + (size_t)2 * U * C * 4 + (size_t)2 * U) + 255) & ~(size_t)255; }
 
-static int comm_p2p_setup(rslf_ctx* ctx, int U, int C)
+struct arena_layout { size_t area, off_flags, off_counts, off_done, off_rec, off_res, total; };
+static arena_layout arena_make_layout(int U, int C, size_t cap_rec)
 {
-    if (ctx->p2p_state != 0 && ctx->p2p_area >= p2p_area_bytes(U, C)) return ctx->p2p_state > 0 ? RSLF_OK : RSLF_ERR_UNSUPPORTED;
+    arena_layout l;
+    l.area = p2p_area_bytes(U, C);
+    l.off_flags = 4 * l.area;
+    l.off_counts = l.off_flags + 256;
+    l.off_done = l.off_counts + 8 * RSLF_MAX_PEERS;
+    l.off_rec = (l.off_done + 8 * RSLF_MAX_PEERS + 255) & ~(size_t)255;
+    l.off_res = l.off_rec + ((cap_rec * 16 + 255) & ~(size_t)255);
+    l.total = l.off_res + cap_rec * 32 + 256;
+    return l;
+}
+
+static void arena_close(rslf_ctx* ctx)
+{
+    for (int r = 0; r < RSLF_MAX_RANKS; ++r) {
+        if (ctx->arena_peer[r] && ctx->arena_peer[r] != ctx->arena) cudaIpcCloseMemHandle(ctx->arena_peer[r]);
+        ctx->arena_peer[r] = nullptr;
+    }
+    if (ctx->arena) cudaFree(ctx->arena);
+    ctx->arena = nullptr; ctx->arena_bytes = 0; ctx->arena_cap_rec = 0;
+    ctx->p2p_up = ctx->p2p_dn = nullptr;
+}
+
+/* Collective over the ranks: (re)creates the arenas for rows of U x C values and cap_rec records per rank.
+ * Returns RSLF_ERR_UNSUPPORTED on EVERY rank when any rank cannot provide or map peer memory (the caller then
+ * uses the NCCL exchanges).  Local failures never leave the other ranks alone in a collective. */
+static int comm_arena_setup(rslf_ctx* ctx, int U, int C, size_t cap_rec)
+{
+    const arena_layout want = arena_make_layout(U, C, cap_rec);
+    if (ctx->p2p_state > 0 && ctx->p2p_area >= want.area && ctx->arena_cap_rec >= cap_rec) return RSLF_OK;
     if (ctx->p2p_state < 0) return RSLF_ERR_UNSUPPORTED;
     const char* mode = getenv("RSLF_HALO");
     if (mode && mode[0] == 'n') { ctx->p2p_state = -1; return RSLF_ERR_UNSUPPORTED; }
+    /* every rank that gets here takes part in the two collectives below, whatever fails locally */
+    float ok = (ctx->world <= RSLF_MAX_RANKS) ? 1.f : 0.f;
+    cudaStreamSynchronize(ctx->stream);
+    arena_close(ctx);
     ctx->p2p_state = -1;
-    /* all ranks must agree on using P2P: any failure below is reduced over the ranks before anyone commits */
-    const size_t area = p2p_area_bytes(U, C), total = 4 * area + 256;
-    float ok = 1.f;
-    if (ctx->p2p_buf) { cudaFree(ctx->p2p_buf); ctx->p2p_buf = nullptr; }
-    if (cudaMalloc((void**)&ctx->p2p_buf, total) != cudaSuccess) ok = 0.f;
-    if (!ctx->p2p_done && cudaMalloc((void**)&ctx->p2p_done, sizeof(int)) != cudaSuccess) ok = 0.f;
+    const arena_layout l = want;
+    if (ok > 0.f && cudaMalloc((void**)&ctx->arena, l.total) != cudaSuccess) { ctx->arena = nullptr; ok = 0.f; }
+    if (!ctx->p2p_done && cudaMalloc((void**)&ctx->p2p_done, 8 * sizeof(int)) != cudaSuccess) { ctx->p2p_done = nullptr; ok = 0.f; }
     cudaIpcMemHandle_t mine; memset(&mine, 0, sizeof(mine));
     if (ok > 0.f) {
-        cudaMemsetAsync(ctx->p2p_buf, 0, total, ctx->stream);
-        cudaMemsetAsync(ctx->p2p_done, 0, sizeof(int), ctx->stream);
-        if (cudaIpcGetMemHandle(&mine, ctx->p2p_buf) != cudaSuccess) ok = 0.f;
+        cudaMemsetAsync(ctx->arena, 0, l.total, ctx->stream);
+        cudaMemsetAsync(ctx->p2p_done, 0, 8 * sizeof(int), ctx->stream);
+        if (cudaIpcGetMemHandle(&mine, ctx->arena) != cudaSuccess) ok = 0.f;
     }
     cudaGetLastError();
     /* exchange the handles with one all-gather (through device staging) */
     const size_t hs = sizeof(cudaIpcMemHandle_t);
     std::vector<cudaIpcMemHandle_t> all(ctx->world);
-    {
-        RSLF_TRY(comm_ensure_stage(ctx, 256));
-        RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->g_send, &mine, hs, cudaMemcpyHostToDevice, ctx->stream));
-        RSLF_NCCL_TRY(ctx, g_nccl.AllGather(ctx->g_send, ctx->g_recv, hs, RSLF_NCCL_UINT8, ctx->nccl_comm, ctx->stream));
-        RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(all.data(), ctx->g_recv, hs * ctx->world, cudaMemcpyDeviceToHost, ctx->stream));
-        RSLF_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    bool coll_ok = true;
+    if (comm_ensure_stage(ctx, 256) != RSLF_OK) coll_ok = false;
+    if (coll_ok) {
+        coll_ok = cudaMemcpyAsync(ctx->g_send, &mine, hs, cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess &&
+                  g_nccl.AllGather(ctx->g_send, ctx->g_recv, hs, RSLF_NCCL_UINT8, ctx->nccl_comm, ctx->stream) == 0 &&
+                  cudaMemcpyAsync(all.data(), ctx->g_recv, hs * ctx->world, cudaMemcpyDeviceToHost, ctx->stream) == cudaSuccess &&
+                  cudaStreamSynchronize(ctx->stream) == cudaSuccess;
     }
-    char *up = nullptr, *dn = nullptr;
-    if (ok > 0.f && ctx->rank > 0 && cudaIpcOpenMemHandle((void**)&up, all[ctx->rank - 1], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) ok = 0.f;
-    if (ok > 0.f && ctx->rank + 1 < ctx->world && cudaIpcOpenMemHandle((void**)&dn, all[ctx->rank + 1], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) ok = 0.f;
+    if (!coll_ok) { snprintf(ctx->err, sizeof(ctx->err), "peer-memory setup: handle exchange failed"); cudaGetLastError(); return RSLF_ERR_NCCL; }
+    if (ok > 0.f) {
+        for (int r = 0; r < ctx->world && ok > 0.f; ++r) {
+            if (r == ctx->rank) { ctx->arena_peer[r] = ctx->arena; continue; }
+            void* ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0.f; break; }
+            ctx->arena_peer[r] = (char*)ptr;
+        }
+    }
     cudaGetLastError();
     float bad = (ok > 0.f) ? 0.f : 1.f, anybad = bad;
     RSLF_TRY(comm_allreduce_max_host(ctx, bad, &anybad));
     if (anybad > 0.f) {
-        if (up) cudaIpcCloseMemHandle(up);
-        if (dn) cudaIpcCloseMemHandle(dn);
-        return RSLF_ERR_UNSUPPORTED;                        /* every rank falls back to the NCCL halo exchange */
+        arena_close(ctx);
+        return RSLF_ERR_UNSUPPORTED;                        /* every rank falls back to the NCCL exchanges */
     }
-    if (ctx->p2p_up) cudaIpcCloseMemHandle(ctx->p2p_up);
-    if (ctx->p2p_dn) cudaIpcCloseMemHandle(ctx->p2p_dn);
-    ctx->p2p_up = up; ctx->p2p_dn = dn; ctx->p2p_area = area; ctx->p2p_seq = 0; ctx->p2p_state = 1;
+    ctx->p2p_up = ctx->rank > 0 ? ctx->arena_peer[ctx->rank - 1] : nullptr;
+    ctx->p2p_dn = ctx->rank + 1 < ctx->world ? ctx->arena_peer[ctx->rank + 1] : nullptr;
+    ctx->p2p_area = l.area; ctx->arena_bytes = l.total; ctx->arena_cap_rec = cap_rec; ctx->arena_U = U; ctx->arena_C = C;
+    ctx->p2p_seq = 0; ctx->bal_seq = 0; ctx->p2p_state = 1;
     return RSLF_OK;
 }
+static arena_layout arena_current(const rslf_ctx* ctx) { return arena_make_layout(ctx->arena_U, ctx->arena_C, ctx->arena_cap_rec); }
 
 struct p2p_push_args {
     const float* depth; const uint8_t* mask; const float* colour0; size_t colour_row_stride; int Vloc, U, C;
@@ -331,21 +374,27 @@ struct p2p_push_args {
     unsigned* up_flag; unsigned* dn_flag; unsigned seq; int* done; int nblocks;
 };
 
+/* rows j = 0, 1 (first rows -> rank above) and 2, 3 (last rows -> rank below), columns u0, u0 + ustep, ...;
+ * colour0 == nullptr: the receiver reads the colours from its own copy of the stack */
+__device__ __forceinline__ void p2p_push_rows(const p2p_push_args& a, int j, int u0, int ustep)
+{
+    char* dst = (j < 2) ? a.up_area : a.dn_area;
+    if (!dst) return;
+    const int v = (j < 2) ? j : a.Vloc - 4 + j, jj = j & 1;
+    float* d = reinterpret_cast<float*>(dst) + (size_t)jj * a.U;
+    float* c = reinterpret_cast<float*>(dst + (size_t)2 * a.U * 4) + (size_t)jj * a.U * a.C;
+    uint8_t* m = reinterpret_cast<uint8_t*>(dst + (size_t)2 * a.U * 4 + (size_t)2 * a.U * a.C * 4) + (size_t)jj * a.U;
+    for (int u = u0; u < a.U; u += ustep) {
+        d[u] = a.depth[(size_t)v * a.U + u];
+        m[u] = a.mask[(size_t)v * a.U + u];
+        if (a.colour0)
+            for (int cc = 0; cc < a.C; ++cc) c[(size_t)u * a.C + cc] = a.colour0[(size_t)v * a.colour_row_stride + (size_t)u * a.C + cc];
+    }
+}
+
 __global__ void p2p_push_halo_kernel(const p2p_push_args a)
 {
-    const int j = blockIdx.y;                                  /* 0,1: first rows -> rank above; 2,3: last rows -> rank below */
-    char* dst = (j < 2) ? a.up_area : a.dn_area;
-    if (dst) {
-        const int v = (j < 2) ? j : a.Vloc - 4 + j, jj = j & 1;
-        float* d = reinterpret_cast<float*>(dst) + (size_t)jj * a.U;
-        float* c = reinterpret_cast<float*>(dst + (size_t)2 * a.U * 4) + (size_t)jj * a.U * a.C;
-        uint8_t* m = reinterpret_cast<uint8_t*>(dst + (size_t)2 * a.U * 4 + (size_t)2 * a.U * a.C * 4) + (size_t)jj * a.U;
-        for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < a.U; u += gridDim.x * blockDim.x) {
-            d[u] = a.depth[(size_t)v * a.U + u];
-            m[u] = a.mask[(size_t)v * a.U + u];
-            for (int cc = 0; cc < a.C; ++cc) c[(size_t)u * a.C + cc] = a.colour0[(size_t)v * a.colour_row_stride + (size_t)u * a.C + cc];
-        }
-    }
+    p2p_push_rows(a, blockIdx.y, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
     /* the last block to finish raises the neighbours' flags, after every store of the grid is visible system-wide */
     __threadfence_system();
     __syncthreads();
@@ -360,45 +409,100 @@ __global__ void p2p_push_halo_kernel(const p2p_push_args a)
     }
 }
 
-/* layout helpers of a receive buffer: area(slot, side) with side 0 = from above, 1 = from below; flags after the areas */
+/* Balanced mode, owner side: waits for every rank's done flag of the pass, scatters the result records of this
+ * rank's pixels into its planes of line s_hat (core.hpp:630-657), and lets the last block push the halo rows. */
+struct bal_apply_args {
+    const int* items; const int* count; const float4* res; int C;
+    float* depth; float* cd; float* rbar; float* ce; uint8_t* emask;
+    const volatile unsigned long long* done; int n; unsigned seq; int* err; int* blocks_done;
+    int do_push; p2p_push_args push;
+};
+
+__global__ void __launch_bounds__(256) bal_apply_kernel(const bal_apply_args a)
+{
+    __shared__ int s_last;
+    if ((int)threadIdx.x < a.n) peer_wait64(a.done + threadIdx.x, a.seq, a.err);
+    __threadfence_system();
+    __syncthreads();
+    const int n = *a.count;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 r0 = ld_cv_float4(a.res + 2 * (size_t)i), r1 = ld_cv_float4(a.res + 2 * (size_t)i + 1);
+        const int pix = a.items[i];
+        if (__float_as_int(r1.y)) {
+            a.depth[pix] = r0.x; a.cd[pix] = r0.y;
+            a.rbar[(size_t)pix * a.C] = r0.z;
+            if (a.C == 3) { a.rbar[(size_t)pix * 3 + 1] = r0.w; a.rbar[(size_t)pix * 3 + 2] = r1.x; }
+        } else {
+            a.ce[pix] = 0.f; a.emask[pix] = 0;
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int old = atomicAdd(a.blocks_done, 1);
+        s_last = (old == (int)gridDim.x - 1);
+        if (s_last) *a.blocks_done = 0;
+    }
+    __syncthreads();
+    if (!s_last || !a.do_push) return;
+    __threadfence();
+    for (int j = 0; j < 4; ++j) p2p_push_rows(a.push, j, threadIdx.x, blockDim.x);
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (a.push.up_flag) *reinterpret_cast<volatile unsigned*>(a.push.up_flag) = a.push.seq;
+        if (a.push.dn_flag) *reinterpret_cast<volatile unsigned*>(a.push.dn_flag) = a.push.seq;
+    }
+}
+
+/* layout helpers of the halo part: area(slot, side) with side 0 = from above, 1 = from below; flags after the areas */
 static inline size_t p2p_area_off(const rslf_ctx* ctx, int slot, int side) { return ((size_t)slot * 2 + side) * ctx->p2p_area; }
 static inline size_t p2p_flag_off(const rslf_ctx* ctx, int slot, int side) { return 4 * ctx->p2p_area + ((size_t)slot * 2 + side) * sizeof(unsigned); }
 
-static int comm_p2p_exchange_median_halo(rslf_ctx* ctx, const float* depth_plane, const uint8_t* mask_plane, const float* colour0,
-                                         size_t colour_row_stride_floats, int U, int C, const shard_tab& t, median_halo* out)
+/* Fills the push arguments and the receiving side (median_halo) of one pass.  colour0 == nullptr: colours are read
+ * in place from the replicated stack by the receiver. */
+static void p2p_prepare_halo(rslf_ctx* ctx, const float* depth_plane, const uint8_t* mask_plane, const float* colour0,
+                             size_t colour_row_stride_floats, int U, int C, const shard_tab& t, p2p_push_args* push, median_halo* out)
 {
     const int r0 = ctx->rank, Vloc = t.b[r0 + 1] - t.b[r0];
     const unsigned seq = ++ctx->p2p_seq;
     const int slot = (int)(seq & 1u);
-    p2p_push_args a;
+    p2p_push_args& a = *push;
     a.depth = depth_plane; a.mask = mask_plane; a.colour0 = colour0; a.colour_row_stride = colour_row_stride_floats;
-    a.Vloc = Vloc; a.U = U; a.C = C; a.seq = seq; a.done = ctx->p2p_done;
+    a.Vloc = Vloc; a.U = U; a.C = C; a.seq = seq; a.done = ctx->p2p_done; a.nblocks = 0;
     /* my first rows are the rows BELOW the block of the rank above: its side 1; my last rows: side 0 of the rank below */
     a.up_area = ctx->p2p_up ? ctx->p2p_up + p2p_area_off(ctx, slot, 1) : nullptr;
     a.dn_area = ctx->p2p_dn ? ctx->p2p_dn + p2p_area_off(ctx, slot, 0) : nullptr;
     a.up_flag = ctx->p2p_up ? reinterpret_cast<unsigned*>(ctx->p2p_up + p2p_flag_off(ctx, slot, 1)) : nullptr;
     a.dn_flag = ctx->p2p_dn ? reinterpret_cast<unsigned*>(ctx->p2p_dn + p2p_flag_off(ctx, slot, 0)) : nullptr;
+    memset(out, 0, sizeof(*out));
+    out->seq = seq; out->err = ctx->dev_err; out->colour_halo_stride = (size_t)U * C;
+    if (r0 > 0) {
+        const char* b = ctx->arena + p2p_area_off(ctx, slot, 0);
+        out->top_depth = reinterpret_cast<const float*>(b);
+        out->top_colour = reinterpret_cast<const float*>(b + (size_t)2 * U * 4);
+        out->top_mask = reinterpret_cast<const uint8_t*>(b + (size_t)2 * U * 4 + (size_t)2 * U * C * 4);
+        out->flag_top = reinterpret_cast<const volatile unsigned*>(ctx->arena + p2p_flag_off(ctx, slot, 0));
+    }
+    if (r0 + 1 < t.n) {
+        const char* b = ctx->arena + p2p_area_off(ctx, slot, 1);
+        out->bot_depth = reinterpret_cast<const float*>(b);
+        out->bot_colour = reinterpret_cast<const float*>(b + (size_t)2 * U * 4);
+        out->bot_mask = reinterpret_cast<const uint8_t*>(b + (size_t)2 * U * 4 + (size_t)2 * U * C * 4);
+        out->flag_bot = reinterpret_cast<const volatile unsigned*>(ctx->arena + p2p_flag_off(ctx, slot, 1));
+    }
+}
+
+static int comm_p2p_exchange_median_halo(rslf_ctx* ctx, const float* depth_plane, const uint8_t* mask_plane, const float* colour0,
+                                         size_t colour_row_stride_floats, int U, int C, const shard_tab& t, median_halo* out)
+{
+    p2p_push_args a;
+    p2p_prepare_halo(ctx, depth_plane, mask_plane, colour0, colour_row_stride_floats, U, C, t, &a, out);
     dim3 grid(std::max(1, std::min(8, (U + 127) / 128)), 4);
     a.nblocks = (int)(grid.x * grid.y);
     p2p_push_halo_kernel<<<grid, 128, 0, ctx->stream>>>(a);
     RSLF_CUDA_TRY(ctx, cudaGetLastError());
     ctx->timing.kernel_launches += 1;
-    memset(out, 0, sizeof(*out));
-    out->seq = seq;
-    if (r0 > 0) {
-        const char* b = ctx->p2p_buf + p2p_area_off(ctx, slot, 0);
-        out->top_depth = reinterpret_cast<const float*>(b);
-        out->top_colour = reinterpret_cast<const float*>(b + (size_t)2 * U * 4);
-        out->top_mask = reinterpret_cast<const uint8_t*>(b + (size_t)2 * U * 4 + (size_t)2 * U * C * 4);
-        out->flag_top = reinterpret_cast<const volatile unsigned*>(ctx->p2p_buf + p2p_flag_off(ctx, slot, 0));
-    }
-    if (r0 + 1 < t.n) {
-        const char* b = ctx->p2p_buf + p2p_area_off(ctx, slot, 1);
-        out->bot_depth = reinterpret_cast<const float*>(b);
-        out->bot_colour = reinterpret_cast<const float*>(b + (size_t)2 * U * 4);
-        out->bot_mask = reinterpret_cast<const uint8_t*>(b + (size_t)2 * U * 4 + (size_t)2 * U * C * 4);
-        out->flag_bot = reinterpret_cast<const volatile unsigned*>(ctx->p2p_buf + p2p_flag_off(ctx, slot, 1));
-    }
     return RSLF_OK;
 }
 
@@ -435,5 +539,6 @@ extern "C" int rslf_cuda_set_row_shards(rslf_ctx* ctx, const int* row_starts, in
     for (int r = 0; r <= n_ranks; ++r) ctx->row_starts[r] = row_starts[r];
     ctx->v0 = row_starts[ctx->rank]; ctx->V_total = row_starts[n_ranks];
     ctx->have_shards = true;
+    ++ctx->input_epoch;                                  /* the gathered copy of the stack follows the shard table */
     return RSLF_OK;
 }

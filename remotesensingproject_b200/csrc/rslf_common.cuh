@@ -19,13 +19,15 @@
 #include "../../include/rslf_b200.h"
 
 #define RSLF_MAX_LEVELS 24
+#define RSLF_MAX_RANKS 16        /* ranks that can share peer memory (= RSLF_MAX_PEERS, k_balance.cuh) */
 
 struct rslf_level {
     int V = 0, U = 0;            /* rows held by this rank, columns                           */
     int v0 = 0, Vtot = 0;        /* first global row of this rank, global rows of the level   */
     bool replicated = false;     /* multi-rank run: this (coarse) level is computed whole by every rank */
-    float* raw = nullptr;        /* un-normalised stack of levels > 0 (float32, or uint8 for 8-bit input: raw8 aliases it) */
-    float* epi = nullptr;        /* normalised stack [V][S][U][C]                             */
+    float* raw = nullptr;        /* un-normalised stack of levels > 0 (float32, or uint8 for 8-bit input: raw8 aliases it); all Vtot rows */
+    float* epi_full = nullptr;   /* normalised stack [Vtot][S][U][C]: EVERY rank holds all rows of every level */
+    float* epi = nullptr;        /* = epi_full + v0 rows: the rows of this rank's block (the whole stack on one GPU) */
     float* ce = nullptr;         /* edge confidence            [S][V][U]                      */
     float* cd = nullptr;         /* disparity confidence       [S][V][U]                      */
     float* depth = nullptr;      /* best depth                 [S][V][U]                      */
@@ -63,10 +65,13 @@ struct rslf_ctx {
     /* input */
     int V = 0, S = 0, U = 0, C = 0, cv_depth = RSLF_DEPTH_32F;
     float scale_factor = -1.f;
-    void* raw_in = nullptr;      /* level-0 raw stack as uploaded (u8 or f32), owned unless borrowed */
+    void* raw_in = nullptr;      /* level-0 raw stack as uploaded (u8 or f32), owned unless borrowed: this rank's rows */
     bool raw_borrowed = false;
     size_t raw_cap = 0;
     bool have_input = false;
+    void* raw_full = nullptr;    /* multi-rank runs: all rows of the raw stack, gathered once per input */
+    size_t raw_full_cap = 0;
+    unsigned input_epoch = 1, raw_full_epoch = 0;
     int v0 = 0, V_total = 0;     /* row shard: first global row, global rows (level 0)        */
     int row_starts[65] = {0};    /* level-0 shard table, world + 1 entries                    */
     bool have_shards = false;
@@ -77,8 +82,11 @@ struct rslf_ctx {
 
     /* scratch */
     int* items = nullptr;        /* compacted pixel list of a pass                            */
-    int* count = nullptr;        /* list lengths, one slot per pass (second half: border lists) */
-    const int* pass_items2 = nullptr; const int* pass_count2 = nullptr;   /* border list of the current pass */
+    int* count = nullptr;        /* list lengths, one slot per pass                           */
+    int* queue = nullptr;        /* work-queue heads of the depth launches, one slot per pass */
+    int4* rec = nullptr;         /* work records of the pass (k_balance.cuh); in the arena when peers read them */
+    int4* rec_own = nullptr;     /* the cudaMalloc'ed record list of single-rank runs          */
+    int* dev_err = nullptr;      /* raised by a kernel whose wait for a peer timed out         */
     unsigned long long* total_px = nullptr;  /* [0] computed pixels of sharded levels, [1] of replicated levels */
     float* filtered = nullptr;   /* selective-median output plane [V][U]                      */
     int* winner = nullptr;       /* propagation arbitration [S][V][U], INT_MAX when idle      */
@@ -93,6 +101,8 @@ struct rslf_ctx {
     float* out_map = nullptr; uint8_t* out_valid = nullptr;
     size_t scratch_px = 0;       /* S*V*U the scratch was sized for                           */
     size_t scratch_plane = 0;    /* V*U the scratch was sized for                             */
+    int scratch_world = 0;       /* ranks the scratch was sized for                           */
+    size_t share_cap = 0;        /* pixels of a pass one rank may have to evaluate (arrive / partials)     */
     unsigned* rowwork = nullptr; size_t rowwork_cap = 0;   /* pixels evaluated per level-0 row of this rank (last run) */
     void* l2_flush = nullptr;
     /* row-sharded runs: gathered planes of line s_hat for the cross-row median, staging */
@@ -116,11 +126,15 @@ struct rslf_ctx {
     rslf_stage_clock clk;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
 
-    /* peer-to-peer halo exchange over NVLink (CUDA IPC): local receive buffer, the neighbours' buffers */
-    char* p2p_buf = nullptr; char* p2p_up = nullptr; char* p2p_dn = nullptr;
+    /* peer memory over NVLink (CUDA IPC, rslf_comm.cuh): this rank's arena, the mapped arenas of all ranks */
+    char* arena = nullptr; char* arena_peer[RSLF_MAX_RANKS] = {nullptr};
+    size_t arena_bytes = 0, arena_cap_rec = 0; int arena_U = 0, arena_C = 0;
+    char* p2p_up = nullptr; char* p2p_dn = nullptr;   /* arenas of the ranks above / below */
     size_t p2p_area = 0;         /* bytes of one halo area (2 rows of depth, colour, mask) */
     unsigned p2p_seq = 0; int p2p_state = 0;   /* 0 = not set up, 1 = ready, -1 = unavailable */
-    int* p2p_done = nullptr;     /* block completion counter of the push kernel */
+    unsigned bal_seq = 0;        /* sequence number of the last pass-balanced pass */
+    int balance = 1;             /* pass-balanced depth kernel in row-sharded runs (RSLF_BALANCE=0: lock-step row blocks) */
+    int* p2p_done = nullptr;     /* block completion counters: [0] push, [1] compact, [2] depth, [3] apply */
     /* NCCL (resolved lazily with dlopen; see rslf_comm.cuh) */
     void* nccl_lib = nullptr;
     void* nccl_comm = nullptr;

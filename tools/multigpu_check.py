@@ -28,15 +28,22 @@ def main():
              # boundary 50 is a multiple of 2 only: levels 0-1 sharded, levels 2-3 replicated on every rank
              dict(S=5, V=100, U=90, C=3, D=16, mode="ftc", scale=-1.0),
              dict(S=4, V=100, U=90, C=1, D=24, mode="ftc", scale=1.0, u8=True),
-             dict(S=6, V=96, U=80, C=3, D=24, mode="ftc", scale=1.0, border_first="1"),
+             # lock-step row blocks (every rank evaluates its own rows) instead of the pass-balanced depth kernel
+             dict(S=6, V=96, U=80, C=3, D=24, mode="ftc", scale=1.0, balance="0"),
+             dict(S=6, V=96, U=80, C=3, D=24, mode="ftc", scale=1.0, balance="0", halo="nccl"),
+             # unequal row blocks (cut by a made-up weight profile): shares of a pass span several owners
+             dict(S=7, V=128, U=80, C=3, D=40, mode="ftc", scale=1.0, skew=True),
+             # the geometry class of the bench: tensor-memory depth kernel (S >= 20, RGB), several chunks of hypotheses
+             dict(S=28, V=64, U=160, C=3, D=72, mode="ftc", scale=1.0),
+             dict(S=24, V=48, U=128, C=3, D=40, mode="depth2d", scale=1.0),
              # 16-bit stack, scaled by its maximum: all-reduce of the per-rank maxima, 16-bit raw rows gathered for the blur
              dict(S=5, V=96, U=80, C=3, D=16, mode="ftc", scale=-1.0, u16=True)]
     for i, c in enumerate(cases):
         os.environ.pop("RSLF_MEDIAN_GATHER", None)
         os.environ.pop("RSLF_HALO", None)
-        os.environ.pop("RSLF_BORDER_FIRST", None)
-        if c.get("border_first"):
-            os.environ["RSLF_BORDER_FIRST"] = c["border_first"]   # border rows computed and sent first
+        os.environ.pop("RSLF_BALANCE", None)
+        if c.get("balance"):
+            os.environ["RSLF_BALANCE"] = c["balance"]           # "0": lock-step row blocks
         if c.get("halo"):
             os.environ["RSLF_HALO"] = c["halo"]                 # "nccl": small all-gather instead of peer-to-peer stores
         if c.get("gather"):
@@ -62,7 +69,10 @@ def main():
         ref_samples = ctx1.timing()["samples"]
         ctx1.close()
         # sharded
-        starts = shard_table(c["V"], c["U"], world, pyramid=(c["mode"] == "ftc"))
+        weights = None
+        if c.get("skew"):
+            weights = [1.0 + 9.0 * (v < c["V"] // 4) for v in range(c["V"])]      # the first quarter of the rows weighs 10x
+        starts = shard_table(c["V"], c["U"], world, pyramid=(c["mode"] == "ftc"), weights=weights)
         v0, v1 = starts[rank], starts[rank + 1]
         ctx = api.Context(local)
         uid = [api.nccl_unique_id() if rank == 0 else None]
