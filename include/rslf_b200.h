@@ -102,6 +102,15 @@ int  rslf_cuda_last_timing(const rslf_ctx* ctx, rslf_timing* out);
 /* ABI version, bumped on any signature change. */
 int  rslf_cuda_abi_version(void);
 
+/* Which confidence gates the propagation sources and the validity maps.
+ * 0 (default) = the edge confidence: the reference as written — its `#elseif` lines (rslf_depth_computation_core.hpp:1099,
+ *     rslf_depth_computation.hpp:903) are not preprocessor directives, so the default build always takes the `#else` branch;
+ * 1 = the disparity confidence C_d > par_disp_score_threshold: the reference AS INTENDED with
+ *     -D_USE_DISP_CONFIDENCE_SCORE once `#elseif` reads `#elif` (core.hpp:1097-1098, dc.hpp:901-902; report section
+ *     "Disparity confidence score").  As written that macro does not compile.
+ * 2 (line confidence, core.hpp:1032-1081) -> RSLF_ERR_UNSUPPORTED. */
+int  rslf_cuda_set_confidence_criterion(rslf_ctx* ctx, int criterion);
+
 /* ---- input ---------------------------------------------------------------
  * Replaces the input handling of the computers' constructors
  * (rslf_depth_computation.hpp:425-477 Depth1DComputer_pile,

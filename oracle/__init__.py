@@ -76,6 +76,12 @@ def _cv_depth(a):
     return {np.dtype(np.uint8): 0, np.dtype(np.uint16): 2}.get(a.dtype, 5)
 
 
+def set_criterion(name):
+    """"edge": the reference as written (default build); "disp": -D_USE_DISP_CONFIDENCE_SCORE as intended (`#elseif` -> `#elif`):
+    propagation sources and validity maps are gated by C_d > par_disp_score_threshold (core.hpp:1097-1098, dc.hpp:901-902)."""
+    lib().orc_set_criterion({"edge": 0, "disp": 1}[name])
+
+
 def num_threads():
     return lib().orc_num_threads()
 

@@ -16,8 +16,23 @@ from . import Params, default_params  # noqa: F401  (same rslf_params layout)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_ref", "librslf_ref.so")
+# the reference built with -D_USE_DISP_CONFIDENCE_SCORE after `#elseif` -> `#elif` (oracle/Makefile, target ref_cd)
+LIB_CD_PATH = os.path.join(_HERE, "_ref", "librslf_ref_cd.so")
 REFERENCE_ROOT = "/root/reference/RSLightFields"
 _lib = None
+_lib_cd = None
+_criterion = "edge"
+
+
+def set_criterion(name):
+    """"edge": the default build; "disp": the disparity-confidence build (see LIB_CD_PATH)."""
+    global _criterion
+    assert name in ("edge", "disp")
+    _criterion = name
+
+
+def available_cd():
+    return os.path.exists(LIB_CD_PATH) or os.path.isdir(REFERENCE_ROOT)
 
 
 def build(force=False):
@@ -32,7 +47,15 @@ def available():
 
 
 def lib():
-    global _lib
+    global _lib, _lib_cd
+    if _criterion == "disp":
+        if _lib_cd is None:
+            if os.path.isdir(REFERENCE_ROOT) and not os.path.exists(LIB_CD_PATH):
+                subprocess.check_call(["make", "-C", _HERE, "-s", "ref_cd"])
+            if not os.path.exists(LIB_CD_PATH):
+                raise RuntimeError("oracle/_ref/librslf_ref_cd.so is missing and %s is not present to build it" % REFERENCE_ROOT)
+            _lib_cd = C.CDLL(LIB_CD_PATH)
+        return _lib_cd
     if _lib is None:
         build()
         if not os.path.exists(LIB_PATH):

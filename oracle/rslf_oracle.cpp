@@ -135,6 +135,12 @@ struct PixelScratch {
  * multi-channel multiply/divide helpers (core.cpp:25-51), score (:616-625).
  * Leaves score[d], rbar[c][d], Dv[d] in the scratch.
  */
+/* Which confidence gates the propagation and the validity maps: 0 = the edge confidence (the reference as written:
+ * the `#elseif` lines of core.hpp:1099 / dc.hpp:903 are not directives, so the default build always takes the `#else`
+ * branch), 1 = the disparity confidence C_d > par_disp_score_threshold (the reference AS INTENDED with
+ * -D_USE_DISP_CONFIDENCE_SCORE once `#elseif` reads `#elif`: core.hpp:1097-1098, dc.hpp:901-902).  orc_set_criterion. */
+int g_criterion = 0;
+
 /* Optional statistics (off by default; orc_ms_stats_*): at which mean-shift iteration r_bar reaches a bitwise
  * fixed point, per hypothesis and per group of 32 consecutive hypotheses (a GPU warp).  Once r_bar(t+1) == r_bar(t)
  * every later iteration and the score repeat exactly, which is what the CUDA kernel's early exit relies on. */
@@ -504,7 +510,9 @@ void depth2d(const float* epis, const Dims& g, int D, float dmin_c, float dmax_c
 #pragma omp parallel for schedule(dynamic, 4)
         for (int v = 0; v < V; ++v) {
             for (int u = 0; u < U; ++u) {
-                if (!em_p[(size_t)v * U + u]) continue;
+                if (g_criterion == 1) {                      /* core.hpp:1097-1098 (as intended) */
+                    if (!(cd_p[(size_t)v * U + u] > P.disp_score_threshold)) continue;
+                } else if (!em_p[(size_t)v * U + u]) continue;           /* core.hpp:1101-1102 */
                 float cur = filtered[(size_t)v * U + u];
                 const float* rb = rb_p + ((size_t)v * U + u) * C;
                 for (int s = 0; s < S; ++s) {
@@ -877,6 +885,9 @@ void orc_ms_stats_read(long long* lane33, long long* warp33, long long* pixels, 
     *pixels = g_ms_pixels; *flat_pixels = g_ms_flat_pixels;
 }
 
+void orc_set_criterion(int c) { g_criterion = c; }
+int orc_get_criterion(void) { return g_criterion; }
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();
@@ -1083,7 +1094,9 @@ double orc_fine_to_coarse(const void* raw, int cv_depth, int V, int S, int U, in
         valid[p].resize(n);
         bool accept_all = accept_all_last && (p == levels - 1);
         for (size_t i = 0; i < n; ++i)
-            valid[p][i] = accept_all ? (ce[p][i] > -1.f ? 255 : 0) : (ce[p][i] > P.edge_score_threshold ? 255 : 0);
+            valid[p][i] = accept_all ? (ce[p][i] > -1.f ? 255 : 0)
+                          : g_criterion == 1 ? (cd[p][i] > P.disp_score_threshold ? 255 : 0)      /* dc.hpp:901-902 */
+                                             : (ce[p][i] > P.edge_score_threshold ? 255 : 0);    /* dc.hpp:905-906 */
         if (p + 1 < levels) {
             /* next level's raw stack (ftc.hpp:146) and bounds (ftc.hpp:201-294) */
             if (cv_depth == RSLF_DEPTH_8U) {

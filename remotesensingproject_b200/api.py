@@ -318,6 +318,15 @@ class Context:
     def set_stage_timing(self, on):
         lib().rslf_cuda_set_stage_timing(self._h, int(bool(on)))
 
+    def set_confidence_criterion(self, name):
+        """"edge" (the reference's default build) or "disp" (-D_USE_DISP_CONFIDENCE_SCORE as intended: C_d > par_disp_score_threshold
+        gates propagation and validity)."""
+        self.check(lib().rslf_cuda_set_confidence_criterion(self._h, {"edge": 0, "disp": 1, "line": 2}[name]),
+                   "rslf_cuda_set_confidence_criterion")
+
+    def set_balance(self, on):
+        self.check(lib().rslf_cuda_set_balance(self._h, int(bool(on))), "rslf_cuda_set_balance")
+
     def set_fast_math(self, on):
         """Opt-in contracted (FMA) mean shift for RGB stacks: faster, within the specified tolerance, not bit-identical."""
         self.check(lib().rslf_cuda_set_fast_math(self._h, int(bool(on))), "rslf_cuda_set_fast_math")

@@ -20,7 +20,7 @@
  * initialised with (dc.hpp:744), so they can only paint targets whose own colour norm is below eps, i.e.
  * confident-but-dark pixels; per (s, v) row the edge-confidence kernel counted those (rowdark), and a block
  * of the dense kernel returns at once when its rows hold none.  A pixel computed in this pass whose r_bar
- * happens to be exactly zero is handled by both kinds; the arbitration makes that idempotent.
+ * happens to be exactly zero is handled by both kinds; the commit is exclusive (compare-and-swap on the arbitration entry).
  */
 #pragma once
 #include "rslf_common.cuh"
@@ -38,7 +38,14 @@ struct prop_args {
     const int* items; const int* count;                         /* work list of the pass */
     const int* items2; const int* count2;                       /* second part of the list (row-sharded runs), or nullptr */
     int* rowdark;                                                /* [S][V] confident-and-dark pixels still unpainted (upper bound) */
+    int criterion; float disp_thr;                               /* 1: sources are the pixels with C_d > disp_thr (core.hpp:1097-1098 as intended) */
 };
+
+/* "Only paint if the confidence threshold was high enough" (core.hpp:1096-1103) */
+__device__ __forceinline__ bool prop_source(const prop_args& a, size_t pix)
+{
+    return a.criterion == 1 ? (a.cd_p[pix] > a.disp_thr) : (a.emask_p[pix] != 0);
+}
 
 /* one (source, view) pair; PHASE 0: arbitration, PHASE 1: commit */
 template <int C, int PHASE>
@@ -56,12 +63,13 @@ __device__ __forceinline__ void propagate_one(const prop_args& a, int v, int u, 
 #pragma unroll
         for (int c = 0; c < C; ++c) ec[c] = __ldg(e + c);
         if (rslf_norm_diff_lt<C>(ec, rb, a.eps, a.eps_T)) atomicMin(a.winner + tgt, u);
-    } else if (a.winner[tgt] == u) {
-        /* the arbitration entry equals u only if this source passed every test in phase 0 and is the lowest */
+    } else if (a.winner[tgt] == u && atomicCAS(a.winner + tgt, u, 0x7fffffff) == u) {
+        /* the arbitration entry equals u only if this source passed every test in phase 0 and is the lowest; the
+         * compare-and-swap re-arms the entry and makes the commit exclusive: a source computed in this pass whose
+         * r_bar is exactly zero is seen by both kinds of blocks, and only one of them may count the dark target down */
         a.depth[tgt] = cur;
         a.cd[tgt] = cdv;
         a.remaining[tgt] = 0;
-        a.winner[tgt] = 0x7fffffff;
         if (a.rowdark) {
             const float* e = a.epi + (((size_t)v * a.S + s) * (size_t)a.U + q) * C;
             float ec[C], z[C];
@@ -85,7 +93,7 @@ propagate_kernel(const prop_args a, int list_blocks)
         const int warps = (list_blocks * PROP_THREADS) >> 5;
         for (int it = (blockIdx.x * PROP_THREADS + threadIdx.x) >> 5; it < n; it += warps) {
             const int pix = (it < n1) ? a.items[it] : a.items2[it - n1];
-            if (!a.emask_p[pix]) continue;                  /* score <= threshold: dropped by the depth kernel */
+            if (!prop_source(a, pix)) continue;             /* e.g. score <= threshold: dropped by the depth kernel */
             const int v = pix / a.U, u = pix - v * a.U;
             float rb[C];
 #pragma unroll
@@ -104,7 +112,7 @@ propagate_kernel(const prop_args a, int list_blocks)
     if (!live) return;
     for (int u = threadIdx.x; u < a.U; u += PROP_THREADS) {
         const size_t o = (size_t)v * a.U + u;
-        if (!a.emask_p[o]) continue;
+        if (!prop_source(a, o)) continue;
         float rb[C]; bool zero = true;
 #pragma unroll
         for (int c = 0; c < C; ++c) { rb[c] = a.rbar_p[o * C + c]; zero = zero && (rb[c] == 0.f); }

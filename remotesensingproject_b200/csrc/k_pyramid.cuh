@@ -210,14 +210,13 @@ downsample_int_kernel(const T* __restrict__ in, int V, int S, int U, T* __restri
     }
 }
 
-/* ---- validity mask ---- */
-__global__ void valid_mask_kernel(const float* __restrict__ ce, size_t n, float thr, int accept_all,
+/* ---- validity mask (Depth2DComputer::get_valid_depths_mask_s_v_u, dc.hpp:893-915): conf > thr with conf = C_e (default
+ * build, :905-906) or C_d (disparity-confidence criterion, :901-902); an accept-all level takes C_e > -1 ---- */
+__global__ void valid_mask_kernel(const float* __restrict__ ce, const float* __restrict__ conf, size_t n, float thr, int accept_all,
                                   uint8_t* __restrict__ valid)
 {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        float c = ce[i];
-        valid[i] = accept_all ? ((c > -1.f) ? 255 : 0) : ((c > thr) ? 255 : 0);
-    }
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        valid[i] = accept_all ? ((ce[i] > -1.f) ? 255 : 0) : ((conf[i] > thr) ? 255 : 0);
 }
 
 __global__ void fill_f32_kernel(float* __restrict__ x, size_t n, float v)
@@ -297,26 +296,53 @@ __global__ void set_bounds_kernel(const float* __restrict__ depth_up, const int*
     }
 }
 
+/* A [S][rows][U] map seen through a window of rows: the rank's own rows [r0, r0 + rows) in `mid` (plane stride
+ * mid_rows * U) plus H halo rows above / below them in `top` / `bot` (planes of H rows each: the neighbours' rows,
+ * pushed into this rank's arena).  A whole map is the window r0 = 0, rows = all, no halo. */
+template <typename T> struct svu_view { const T* mid; const T* top; const T* bot; int r0, rows, H; };
+template <typename T>
+__device__ __forceinline__ const T* svu_row(const svu_view<T>& w, int s, int r, int U)
+{
+    if (r < w.r0) return w.top + ((size_t)s * w.H + (r - (w.r0 - w.H))) * (size_t)U;
+    if (r >= w.r0 + w.rows) return w.bot + ((size_t)s * w.H + (r - (w.r0 + w.rows))) * (size_t)U;
+    return w.mid + ((size_t)s * w.rows + (r - w.r0)) * (size_t)U;
+}
+template <typename T> static svu_view<T> svu_whole(const T* p, int rows) { svu_view<T> w; w.mid = p; w.top = w.bot = nullptr; w.r0 = 0; w.rows = rows; w.H = 0; return w; }
+
+/* source row of the bilinear / nearest upsampling of fuse_disp_maps for destination row y (host and device agree) */
+static __host__ __device__ inline void fuse_src_rows(int y, int Vs, int Vd, int* iy0, int* iy1, float* fyo, int* ny)
+{
+    const double sy = (double)Vs / Vd;
+    float fy = (float)((y + 0.5) * sy - 0.5);
+    int iy = (int)floorf(fy); fy -= iy;
+    if (iy < 0) { iy = 0; fy = 0.f; }
+    if (iy >= Vs - 1) { iy = Vs - 1; fy = 0.f; }
+    *iy0 = iy; *iy1 = (iy + 1 < Vs - 1) ? iy + 1 : Vs - 1; *fyo = fy;
+    const int n = (int)floor(y * sy);
+    *ny = n < Vs - 1 ? n : Vs - 1;
+}
+
 /* ---- fuse one level: map = valid ? disp : bilinear(map_down); mask = valid | nearest(mask_down) ----
  * cv::resize INTER_LINEAR float32 (half-pixel centres, edge clamp, horizontal then vertical
  * interpolation) and INTER_NEAREST (src = min(floor(dst * scale), n - 1)).
  */
-__global__ void fuse_level_kernel(const float* __restrict__ map_down, const uint8_t* __restrict__ mask_down,
+__global__ void fuse_level_kernel(const svu_view<float> map_down, const svu_view<uint8_t> mask_down,
                                   int Vs, int Us, const float* __restrict__ disp, const uint8_t* __restrict__ valid,
                                   int Vd, int Ud, float* __restrict__ map_out, uint8_t* __restrict__ mask_out,
                                   int y0, int Vd_loc)
 {
-    /* map_down / mask_down: the whole coarser level; disp / valid / outputs: the Vd_loc local rows from
-     * global row y0 on (Vd = global rows of the finer level) */
+    /* map_down / mask_down: windows of the coarser level (Vs x Us); disp / valid / outputs: the Vd_loc local rows
+     * from global row y0 on (Vd = global rows of the finer level) */
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int yl = blockIdx.y, s = blockIdx.z;
     const int y = yl + y0;
     if (x >= Ud) return;
     const size_t o = ((size_t)s * Vd_loc + yl) * (size_t)Ud + x;
-    const double sx = (double)Us / Ud, sy = (double)Vs / Vd;
-    const uint8_t* mk = mask_down + (size_t)s * Vs * Us;
-    const int ny = min((int)floor(y * sy), Vs - 1), nx = min((int)floor(x * sx), Us - 1);
-    const uint8_t mup = mk[(size_t)ny * Us + nx];
+    const double sx = (double)Us / Ud;
+    int iy, y1, ny; float fy;
+    fuse_src_rows(y, Vs, Vd, &iy, &y1, &fy, &ny);
+    const int nx = min((int)floor(x * sx), Us - 1);
+    const uint8_t mup = svu_row(mask_down, s, ny, Us)[nx];
     const uint8_t vl = valid[o];
     mask_out[o] = vl | mup;
     if (vl) { map_out[o] = disp[o]; return; }
@@ -324,15 +350,12 @@ __global__ void fuse_level_kernel(const float* __restrict__ map_down, const uint
     int ix = (int)floorf(fx); fx -= ix;
     if (ix < 0) { ix = 0; fx = 0.f; }
     if (ix >= Us - 1) { ix = Us - 1; fx = 0.f; }
-    float fy = (float)((y + 0.5) * sy - 0.5);
-    int iy = (int)floorf(fy); fy -= iy;
-    if (iy < 0) { iy = 0; fy = 0.f; }
-    if (iy >= Vs - 1) { iy = Vs - 1; fy = 0.f; }
-    const float* src = map_down + (size_t)s * Vs * Us;
-    const int x1 = min(ix + 1, Us - 1), y1 = min(iy + 1, Vs - 1);
+    const float* r0 = svu_row(map_down, s, iy, Us);
+    const float* r1 = svu_row(map_down, s, y1, Us);
+    const int x1 = min(ix + 1, Us - 1);
     const float a1 = fx, a0 = 1.f - a1, b1 = fy, b0 = 1.f - b1;
-    float h0 = src[(size_t)iy * Us + ix] * a0; { float t = src[(size_t)iy * Us + x1] * a1; h0 = h0 + t; }
-    float h1 = src[(size_t)y1 * Us + ix] * a0; { float t = src[(size_t)y1 * Us + x1] * a1; h1 = h1 + t; }
+    float h0 = r0[ix] * a0; { float t = r0[x1] * a1; h0 = h0 + t; }
+    float h1 = r1[ix] * a0; { float t = r1[x1] * a1; h1 = h1 + t; }
     float r = h0 * b0; { float t = h1 * b1; r = r + t; }
     map_out[o] = 0.0f + r;
 }
@@ -340,21 +363,23 @@ __global__ void fuse_level_kernel(const float* __restrict__ map_down, const uint
 __device__ __forceinline__ void sort2(float& a, float& b) { float lo = fminf(a, b), hi = fmaxf(a, b); a = lo; b = hi; }
 
 /* cv::medianBlur(float32, 3): 3x3 median, BORDER_REPLICATE */
-__global__ void median3x3_kernel(const float* __restrict__ src, int V, int U, float* __restrict__ dst, int v0, int V_loc)
+__global__ void median3x3_kernel(const svu_view<float> src, int V, int U, float* __restrict__ dst, int v0, int V_loc)
 {
-    /* src: all V rows; dst: the V_loc local rows from global row v0 on */
+    /* src: window of the V-row map; dst: the V_loc local rows from global row v0 on */
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
     const int v = blockIdx.y + v0, s = blockIdx.z;
     if (u >= U) return;
-    const float* p = src + (size_t)s * V * U;
     float w[9]; int n = 0;
 #pragma unroll
-    for (int dv = -1; dv <= 1; ++dv)
+    for (int dv = -1; dv <= 1; ++dv) {
+        const int vv = min(max(v + dv, 0), V - 1);
+        const float* p = svu_row(src, s, vv, U);
 #pragma unroll
         for (int du = -1; du <= 1; ++du) {
-            const int vv = min(max(v + dv, 0), V - 1), uu = min(max(u + du, 0), U - 1);
-            w[n++] = p[(size_t)vv * U + uu];
+            const int uu = min(max(u + du, 0), U - 1);
+            w[n++] = p[uu];
         }
+    }
     /* median-of-9 exchange network */
     sort2(w[1], w[2]); sort2(w[4], w[5]); sort2(w[7], w[8]);
     sort2(w[0], w[1]); sort2(w[3], w[4]); sort2(w[6], w[7]);

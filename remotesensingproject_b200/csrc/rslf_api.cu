@@ -384,6 +384,25 @@ extern "C" int rslf_cuda_set_fast_math(rslf_ctx* ctx, int on)
     return RSLF_OK;
 }
 
+/* 0: edge confidence (the reference's default build); 1: disparity confidence, the reference as intended with
+ * -D_USE_DISP_CONFIDENCE_SCORE (`#elseif` read as `#elif`): core.hpp:1097-1098, dc.hpp:901-902 */
+extern "C" int rslf_cuda_set_confidence_criterion(rslf_ctx* ctx, int criterion)
+{
+    if (!ctx) return RSLF_ERR_ARG;
+    if (criterion == 2) { snprintf(ctx->err, sizeof(ctx->err), "the line-confidence criterion (core.hpp:1032-1081) is not implemented"); return RSLF_ERR_UNSUPPORTED; }
+    if (criterion != 0 && criterion != 1) return RSLF_ERR_ARG;
+    ctx->criterion = criterion;
+    return RSLF_OK;
+}
+
+/* 1 (default): pass-balanced depth kernel in row-sharded runs; 0: lock-step row blocks (k_balance.cuh) */
+extern "C" int rslf_cuda_set_balance(rslf_ctx* ctx, int on)
+{
+    if (!ctx) return RSLF_ERR_ARG;
+    ctx->balance = on != 0;
+    return RSLF_OK;
+}
+
 extern "C" int rslf_cuda_sync(rslf_ctx* ctx)
 {
     if (!ctx) return RSLF_ERR_ARG;
@@ -765,6 +784,7 @@ static int run_depth2d_level(rslf_ctx* ctx, int p, const rslf_params& P, float d
             a.depth = L.depth; a.cd = L.cd; a.remaining = L.remaining; a.winner = ctx->winner;
             a.items = ctx->items; a.count = ctx->count + io.count_slot; a.rowdark = L.rowdark;
             a.items2 = nullptr; a.count2 = nullptr;
+            a.criterion = ctx->criterion; a.disp_thr = P.disp_score_threshold;
             RSLF_TRY(launch_propagate(ctx, C, a));
         }
         ++pass;
@@ -971,7 +991,8 @@ extern "C" int rslf_cuda_depth2d_get_valid_mask(rslf_ctx* ctx, int accept_all, c
     RSLF_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     rslf_level& L = ctx->lv[0];
     const size_t px = (size_t)ctx->S * L.V * L.U;
-    valid_mask_kernel<<<stream_grid(ctx, px), 256, 0, ctx->stream>>>(L.ce, px, params->edge_score_threshold, accept_all, L.valid);
+    valid_mask_kernel<<<stream_grid(ctx, px), 256, 0, ctx->stream>>>(L.ce, ctx->criterion == 1 ? L.cd : L.ce, px,
+        ctx->criterion == 1 ? params->disp_score_threshold : params->edge_score_threshold, accept_all, L.valid);
     RSLF_CUDA_TRY(ctx, cudaGetLastError());
     RSLF_TRY(copy_out(ctx, valid_svu, L.valid, px));
     RSLF_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1006,43 +1027,69 @@ static int launch_downsample_int(rslf_ctx* ctx, const T* in, int V, int S, int U
     return RSLF_OK;
 }
 
+/* Rows of level p (Vs rows) that rank r's rows [y0, y1) of the finer level (Vd rows) read when upsampling: all inside
+ * its own block of level p plus FUSE_HALO rows either side? (same arithmetic as the kernel: fuse_src_rows) */
+static bool fuse_halo_suffices(const shard_tab& coarse, const shard_tab& fine, int Vs, int Vd)
+{
+    for (int r = 0; r < fine.n; ++r) {
+        const int lo = coarse.b[r] - FUSE_HALO, hi = coarse.b[r + 1] + FUSE_HALO;       /* rows available: [lo, hi) */
+        if (coarse.b[r + 1] - coarse.b[r] < FUSE_HALO) return false;                     /* the neighbour sends what it owns */
+        for (int y = fine.b[r]; y < fine.b[r + 1]; ++y) {
+            int iy0, iy1, ny; float fy;
+            fuse_src_rows(y, Vs, Vd, &iy0, &iy1, &fy, &ny);
+            if (iy0 < lo || iy1 >= hi || ny < lo || ny >= hi) return false;
+        }
+    }
+    return true;
+}
+
 /* fuse_disp_maps (ftc_core.cpp:69-135).  Vp: GLOBAL rows per level; disp / valid / outputs of a sharded level hold
- * the rank's rows (tabs[p]); a replicated level (rep[p]) is whole on every rank. */
+ * the rank's rows (tabs[p]); a replicated level (rep[p]) is whole on every rank.  Across the block borders the
+ * upsampling and the final 3x3 median read FUSE_HALO rows of the neighbours, sent through peer memory
+ * (comm_svu_halo); without peer memory, or when a block is thinner than the halo, the maps are all-gathered. */
 static int launch_fuse(rslf_ctx* ctx, int levels, const int* Vp, const int* Up, const shard_tab* tabs, const bool* rep,
                        const float* const* disp, const uint8_t* const* valid, float* out_map, uint8_t* out_valid)
 {
     const int S = ctx->S, r = ctx->rank;
     auto whole = [&](int p) { return ctx->world <= 1 || rep[p]; };
-    const float* map_down = disp[levels - 1]; const uint8_t* mask_down = valid[levels - 1];
-    if (!whole(levels - 1)) {
-        RSLF_TRY(global_svu_f32(ctx, disp[levels - 1], S, Up[levels - 1], tabs[levels - 1], 0, &map_down));
-        RSLF_TRY(global_svu_u8(ctx, valid[levels - 1], S, Up[levels - 1], tabs[levels - 1], 0, &mask_down));
-    }
+    const bool p2p = ctx->world > 1 && ctx->p2p_state > 0 && levels <= FUSE_SLOTS + 64 && getenv("RSLF_FUSE_GATHER") == nullptr;
+    if (p2p) ++ctx->fuse_seq;
+    /* the view of a level's (fused) map for the kernels that read across block borders */
+    auto view_of = [&](int p, const float* m, const uint8_t* k, bool need_halo_ok, svu_view<float>* vm, svu_view<uint8_t>* vk, int slot) -> int {
+        if (whole(p)) { *vm = svu_whole(m, Vp[p]); if (vk) *vk = svu_whole(k, Vp[p]); return RSLF_OK; }
+        if (p2p && need_halo_ok && p < FUSE_SLOTS) return comm_svu_halo(ctx, p, m, k, S, Up[p], tabs[p], vm, vk);
+        const float* gm = nullptr; const uint8_t* gk = nullptr;
+        RSLF_TRY(global_svu_f32(ctx, m, S, Up[p], tabs[p], slot, &gm));
+        *vm = svu_whole(gm, Vp[p]);
+        if (vk) { RSLF_TRY(global_svu_u8(ctx, k, S, Up[p], tabs[p], slot, &gk)); *vk = svu_whole(gk, Vp[p]); }
+        return RSLF_OK;
+    };
+    const float* map_cur = disp[levels - 1]; const uint8_t* mask_cur = valid[levels - 1];
     float* fa = ctx->fuse_a; float* fb = ctx->fuse_b; uint8_t* ma = ctx->fuse_ma; uint8_t* mb = ctx->fuse_mb;
     for (int p = levels - 1; p > 0; --p) {
         const int Vn = Vp[p - 1], Un = Up[p - 1];
         const int y0 = whole(p - 1) ? 0 : tabs[p - 1].b[r], Vn_loc = whole(p - 1) ? Vn : tabs[p - 1].b[r + 1] - y0;
+        svu_view<float> vm; svu_view<uint8_t> vk;
+        const bool halo_ok = !whole(p) && !whole(p - 1) && fuse_halo_suffices(tabs[p], tabs[p - 1], Vp[p], Vn);
+        RSLF_TRY(view_of(p, map_cur, mask_cur, halo_ok, &vm, &vk, p & 1));
         dim3 grid(rslf_div_up(Un, 128), Vn_loc, S);
         uint8_t* mout = (p == 1) ? out_valid : ma;
-        fuse_level_kernel<<<grid, 128, 0, ctx->stream>>>(map_down, mask_down, Vp[p], Up[p], disp[p - 1], valid[p - 1], Vn, Un, fa, mout, y0, Vn_loc);
+        fuse_level_kernel<<<grid, 128, 0, ctx->stream>>>(vm, vk, Vp[p], Up[p], disp[p - 1], valid[p - 1], Vn, Un, fa, mout, y0, Vn_loc);
         RSLF_CUDA_TRY(ctx, cudaGetLastError());
         ctx->timing.kernel_launches += 1;
-        /* the next (finer) level interpolates across rank borders, the final median reads +-1 row */
-        map_down = fa; mask_down = mout;
-        if (!whole(p - 1)) {
-            RSLF_TRY(global_svu_f32(ctx, fa, S, Un, tabs[p - 1], p & 1, &map_down));
-            if (p > 1) RSLF_TRY(global_svu_u8(ctx, mout, S, Un, tabs[p - 1], p & 1, &mask_down));
-        }
+        map_cur = fa; mask_cur = mout;
         std::swap(fa, fb); std::swap(ma, mb);
     }
     const int v0 = whole(0) ? 0 : tabs[0].b[r], V_loc = whole(0) ? Vp[0] : tabs[0].b[r + 1] - v0;
     const size_t px = (size_t)S * V_loc * Up[0];
-    if (levels == 1) {
-        RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(out_valid, valid[0], px, cudaMemcpyDeviceToDevice, ctx->stream));
-        if (!whole(0)) RSLF_TRY(global_svu_f32(ctx, disp[0], S, Up[0], tabs[0], 0, &map_down));
-    }
+    if (levels == 1) RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(out_valid, valid[0], px, cudaMemcpyDeviceToDevice, ctx->stream));
+    /* the final 3x3 median reads +-1 row */
+    svu_view<float> vm;
+    bool thick = true;
+    if (!whole(0)) for (int q = 0; q < tabs[0].n; ++q) thick = thick && (tabs[0].b[q + 1] - tabs[0].b[q] >= FUSE_HALO);
+    RSLF_TRY(view_of(0, map_cur, nullptr, thick, &vm, nullptr, 0));
     dim3 grid(rslf_div_up(Up[0], 128), V_loc, S);
-    median3x3_kernel<<<grid, 128, 0, ctx->stream>>>(map_down, Vp[0], Up[0], out_map, v0, V_loc);
+    median3x3_kernel<<<grid, 128, 0, ctx->stream>>>(vm, Vp[0], Up[0], out_map, v0, V_loc);
     RSLF_CUDA_TRY(ctx, cudaGetLastError());
     ctx->timing.kernel_launches += 1;
     return RSLF_OK;
@@ -1154,7 +1201,8 @@ extern "C" int rslf_cuda_fine_to_coarse_run(rslf_ctx* ctx, float dmin, float dma
         {
             stage_scope sc(ctx, ST_PYR);
             const int accept_all = (accept_all_last_scale && p == levels - 1) ? 1 : 0;   /* ftc.hpp:157-158 */
-            valid_mask_kernel<<<stream_grid(ctx, px), 256, 0, ctx->stream>>>(L.ce, px, P.edge_score_threshold, accept_all, L.valid);
+            valid_mask_kernel<<<stream_grid(ctx, px), 256, 0, ctx->stream>>>(L.ce, ctx->criterion == 1 ? L.cd : L.ce, px,
+                ctx->criterion == 1 ? P.disp_score_threshold : P.edge_score_threshold, accept_all, L.valid);
             ctx->timing.kernel_launches += 1;
             if (p + 1 < levels) {
                 rslf_level& N = ctx->lv[p + 1];

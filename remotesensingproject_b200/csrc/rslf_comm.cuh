@@ -283,17 +283,22 @@ static int comm_exchange_median_halo(rslf_ctx* ctx, const float* depth_plane, co
  */
 static size_t p2p_area_bytes(int U, int C) { return (((size_t)2 * U * 4 + (size_t)2 * U * C * 4 + (size_t)2 * U) + 255) & ~(size_t)255; }
 
-struct arena_layout { size_t area, off_flags, off_counts, off_done, off_rec, off_res, total; };
-static arena_layout arena_make_layout(int U, int C, size_t cap_rec)
+#define FUSE_HALO 2               /* rows of a fused map a neighbour may need (bilinear upsampling, 3x3 median) */
+#define FUSE_SLOTS 8              /* sharded pyramid levels whose fused maps travel through the arena */
+
+struct arena_layout { size_t area, off_flags, off_counts, off_done, off_rec, off_res, off_fuse, fuse_area, total; };
+static arena_layout arena_make_layout(int U, int C, size_t cap_rec, int S)
 {
     arena_layout l;
     l.area = p2p_area_bytes(U, C);
-    l.off_flags = 4 * l.area;
+    l.off_flags = 4 * l.area;                     /* 4 median-halo flags, then at + 64: FUSE_SLOTS x 2 fuse-halo flags */
     l.off_counts = l.off_flags + 256;
     l.off_done = l.off_counts + 8 * RSLF_MAX_PEERS;
     l.off_rec = (l.off_done + 8 * RSLF_MAX_PEERS + 255) & ~(size_t)255;
     l.off_res = l.off_rec + ((cap_rec * 16 + 255) & ~(size_t)255);
-    l.total = l.off_res + cap_rec * 32 + 256;
+    l.off_fuse = (l.off_res + cap_rec * 32 + 255) & ~(size_t)255;
+    l.fuse_area = ((size_t)S * FUSE_HALO * U * 5 + 255) & ~(size_t)255;     /* [S][H][U] float map, then [S][H][U] mask */
+    l.total = l.off_fuse + (size_t)FUSE_SLOTS * 2 * l.fuse_area + 256;
     return l;
 }
 
@@ -313,8 +318,9 @@ static void arena_close(rslf_ctx* ctx)
  * uses the NCCL exchanges).  Local failures never leave the other ranks alone in a collective. */
 static int comm_arena_setup(rslf_ctx* ctx, int U, int C, size_t cap_rec)
 {
-    const arena_layout want = arena_make_layout(U, C, cap_rec);
-    if (ctx->p2p_state > 0 && ctx->p2p_area >= want.area && ctx->arena_cap_rec >= cap_rec) return RSLF_OK;
+    const arena_layout want = arena_make_layout(U, C, cap_rec, ctx->S);
+    if (ctx->p2p_state > 0 && ctx->arena_U == U && ctx->arena_C == C && ctx->arena_S == ctx->S && ctx->arena_cap_rec >= cap_rec) return RSLF_OK;
+    if (ctx->p2p_state > 0) ctx->p2p_state = 0;             /* other geometry: rebuild (collective: every rank sees the same change) */
     if (ctx->p2p_state < 0) return RSLF_ERR_UNSUPPORTED;
     const char* mode = getenv("RSLF_HALO");
     if (mode && mode[0] == 'n') { ctx->p2p_state = -1; return RSLF_ERR_UNSUPPORTED; }
@@ -362,11 +368,11 @@ static int comm_arena_setup(rslf_ctx* ctx, int U, int C, size_t cap_rec)
     }
     ctx->p2p_up = ctx->rank > 0 ? ctx->arena_peer[ctx->rank - 1] : nullptr;
     ctx->p2p_dn = ctx->rank + 1 < ctx->world ? ctx->arena_peer[ctx->rank + 1] : nullptr;
-    ctx->p2p_area = l.area; ctx->arena_bytes = l.total; ctx->arena_cap_rec = cap_rec; ctx->arena_U = U; ctx->arena_C = C;
-    ctx->p2p_seq = 0; ctx->bal_seq = 0; ctx->p2p_state = 1;
+    ctx->p2p_area = l.area; ctx->arena_bytes = l.total; ctx->arena_cap_rec = cap_rec; ctx->arena_U = U; ctx->arena_C = C; ctx->arena_S = ctx->S;
+    ctx->p2p_seq = 0; ctx->bal_seq = 0; ctx->fuse_seq = 0; ctx->p2p_state = 1;
     return RSLF_OK;
 }
-static arena_layout arena_current(const rslf_ctx* ctx) { return arena_make_layout(ctx->arena_U, ctx->arena_C, ctx->arena_cap_rec); }
+static arena_layout arena_current(const rslf_ctx* ctx) { return arena_make_layout(ctx->arena_U, ctx->arena_C, ctx->arena_cap_rec, ctx->arena_S); }
 
 struct p2p_push_args {
     const float* depth; const uint8_t* mask; const float* colour0; size_t colour_row_stride; int Vloc, U, C;
@@ -503,6 +509,85 @@ static int comm_p2p_exchange_median_halo(rslf_ctx* ctx, const float* depth_plane
     p2p_push_halo_kernel<<<grid, 128, 0, ctx->stream>>>(a);
     RSLF_CUDA_TRY(ctx, cudaGetLastError());
     ctx->timing.kernel_launches += 1;
+    return RSLF_OK;
+}
+
+/* ---- halo rows of a row-sharded [S][Vloc][U] map + mask (fuse_disp_maps: bilinear upsampling across the block border,
+ * final 3x3 median): the first / last FUSE_HALO rows of every plane go into the neighbours' per-level areas ---- */
+struct svu_push_args {
+    const float* map; const uint8_t* mask; int S, Vloc, U, H;
+    char* up_area; char* dn_area; unsigned* up_flag; unsigned* dn_flag; unsigned seq; int* done; int nblocks;
+};
+__global__ void svu_push_halo_kernel(const svu_push_args a)
+{
+    const int j = blockIdx.y, s = blockIdx.z;                      /* j < H: my row j -> rank above; else my row Vloc - 2H + j -> rank below */
+    char* dst = (j < a.H) ? a.up_area : a.dn_area;
+    const int jj = (j < a.H) ? j : j - a.H;
+    const int v = (j < a.H) ? j : a.Vloc - 2 * a.H + j;
+    if (dst && v >= 0 && v < a.Vloc) {
+        float* dm = reinterpret_cast<float*>(dst) + ((size_t)s * a.H + jj) * a.U;
+        uint8_t* dk = reinterpret_cast<uint8_t*>(dst + (size_t)a.S * a.H * a.U * 4) + ((size_t)s * a.H + jj) * a.U;
+        const float* sm = a.map + ((size_t)s * a.Vloc + v) * a.U;
+        const uint8_t* sk = a.mask ? a.mask + ((size_t)s * a.Vloc + v) * a.U : nullptr;
+        for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < a.U; u += gridDim.x * blockDim.x) {
+            dm[u] = sm[u];
+            if (sk) dk[u] = sk[u];
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int old = atomicAdd(a.done, 1);
+        if (old == a.nblocks - 1) {
+            *a.done = 0;
+            __threadfence_system();
+            if (a.up_flag) *reinterpret_cast<volatile unsigned*>(a.up_flag) = a.seq;
+            if (a.dn_flag) *reinterpret_cast<volatile unsigned*>(a.dn_flag) = a.seq;
+        }
+    }
+}
+__global__ void peer_wait_kernel(const volatile unsigned* f0, const volatile unsigned* f1, unsigned seq, int* err)
+{
+    if (threadIdx.x == 0 && f0) peer_wait32(f0, seq, err);
+    if (threadIdx.x == 1 && f1) peer_wait32(f1, seq, err);
+    __threadfence_system();
+}
+
+static inline size_t fuse_area_off(const arena_layout& l, int slot, int side) { return l.off_fuse + ((size_t)slot * 2 + side) * l.fuse_area; }
+static inline size_t fuse_flag_off(const arena_layout& l, int slot, int side) { return l.off_flags + 64 + ((size_t)slot * 2 + side) * sizeof(unsigned); }
+
+/* Sends this rank's border rows of `map` / `mask` ([S][Vloc][U], level slot `slot`) to the neighbours, waits for
+ * theirs, and returns the windows (own rows + halo rows in the arena) for the kernels that read across the border. */
+static int comm_svu_halo(rslf_ctx* ctx, int slot, const float* map, const uint8_t* mask, int S, int U, const shard_tab& t,
+                         svu_view<float>* vm, svu_view<uint8_t>* vk)
+{
+    const arena_layout l = arena_current(ctx);
+    const int r0 = ctx->rank, Vloc = t.b[r0 + 1] - t.b[r0], H = FUSE_HALO;
+    const unsigned seq = ctx->fuse_seq;
+    svu_push_args a;
+    a.map = map; a.mask = mask; a.S = S; a.Vloc = Vloc; a.U = U; a.H = H; a.seq = seq; a.done = ctx->p2p_done + 4;
+    a.up_area = ctx->p2p_up ? ctx->p2p_up + fuse_area_off(l, slot, 1) : nullptr;
+    a.dn_area = ctx->p2p_dn ? ctx->p2p_dn + fuse_area_off(l, slot, 0) : nullptr;
+    a.up_flag = ctx->p2p_up ? reinterpret_cast<unsigned*>(ctx->p2p_up + fuse_flag_off(l, slot, 1)) : nullptr;
+    a.dn_flag = ctx->p2p_dn ? reinterpret_cast<unsigned*>(ctx->p2p_dn + fuse_flag_off(l, slot, 0)) : nullptr;
+    dim3 grid(std::max(1, std::min(4, (U + 255) / 256)), 2 * H, S);
+    a.nblocks = (int)(grid.x * grid.y * grid.z);
+    svu_push_halo_kernel<<<grid, 256, 0, ctx->stream>>>(a);
+    RSLF_CUDA_TRY(ctx, cudaGetLastError());
+    const volatile unsigned* f_top = r0 > 0 ? reinterpret_cast<const volatile unsigned*>(ctx->arena + fuse_flag_off(l, slot, 0)) : nullptr;
+    const volatile unsigned* f_bot = r0 + 1 < t.n ? reinterpret_cast<const volatile unsigned*>(ctx->arena + fuse_flag_off(l, slot, 1)) : nullptr;
+    peer_wait_kernel<<<1, 32, 0, ctx->stream>>>(f_top, f_bot, seq, ctx->dev_err);
+    RSLF_CUDA_TRY(ctx, cudaGetLastError());
+    ctx->timing.kernel_launches += 2;
+    const char* top = ctx->arena + fuse_area_off(l, slot, 0);
+    const char* bot = ctx->arena + fuse_area_off(l, slot, 1);
+    vm->mid = map; vm->top = reinterpret_cast<const float*>(top); vm->bot = reinterpret_cast<const float*>(bot);
+    vm->r0 = t.b[r0]; vm->rows = Vloc; vm->H = H;
+    if (vk) {
+        vk->mid = mask; vk->top = reinterpret_cast<const uint8_t*>(top + (size_t)S * H * U * 4);
+        vk->bot = reinterpret_cast<const uint8_t*>(bot + (size_t)S * H * U * 4);
+        vk->r0 = t.b[r0]; vk->rows = Vloc; vk->H = H;
+    }
     return RSLF_OK;
 }
 

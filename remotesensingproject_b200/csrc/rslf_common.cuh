@@ -122,19 +122,21 @@ struct rslf_ctx {
     /* timing */
     rslf_timing timing;
     int stage_timing = 1;
+    int criterion = 0;           /* 0: edge confidence gates propagation / validity (default build), 1: disparity confidence (as intended) */
     int fast_math = 0;           /* contracted (FMA) mean shift in the tensor-memory depth kernel; default: exact */
     rslf_stage_clock clk;
     cudaEvent_t ev_a = nullptr, ev_b = nullptr;
 
     /* peer memory over NVLink (CUDA IPC, rslf_comm.cuh): this rank's arena, the mapped arenas of all ranks */
     char* arena = nullptr; char* arena_peer[RSLF_MAX_RANKS] = {nullptr};
-    size_t arena_bytes = 0, arena_cap_rec = 0; int arena_U = 0, arena_C = 0;
+    size_t arena_bytes = 0, arena_cap_rec = 0; int arena_U = 0, arena_C = 0, arena_S = 0;
+    unsigned fuse_seq = 0;       /* sequence number of the last fusion that sent halo rows */
     char* p2p_up = nullptr; char* p2p_dn = nullptr;   /* arenas of the ranks above / below */
     size_t p2p_area = 0;         /* bytes of one halo area (2 rows of depth, colour, mask) */
     unsigned p2p_seq = 0; int p2p_state = 0;   /* 0 = not set up, 1 = ready, -1 = unavailable */
     unsigned bal_seq = 0;        /* sequence number of the last pass-balanced pass */
     int balance = 1;             /* pass-balanced depth kernel in row-sharded runs (RSLF_BALANCE=0: lock-step row blocks) */
-    int* p2p_done = nullptr;     /* block completion counters: [0] push, [1] compact, [2] depth, [3] apply */
+    int* p2p_done = nullptr;     /* block completion counters: [0] push, [1] compact, [2] depth, [3] apply, [4] fuse halo */
     /* NCCL (resolved lazily with dlopen; see rslf_comm.cuh) */
     void* nccl_lib = nullptr;
     void* nccl_comm = nullptr;

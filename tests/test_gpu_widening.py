@@ -2,6 +2,8 @@
 input formats either side of the hot path), through the C ABI against the CPU oracle.  Same bar as
 tests/test_gpu_parity.py: every map identical.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -294,3 +296,43 @@ def test_single_epi_computer(gpu_ctx, S, U, C, D, s_hat, kw):
     same(comp.m_best_depth_u, o["best_depth"], "1d depth")
     same(comp.m_disp_confidence_u, o["disp_conf"], "1d C_d")
     same(comp.m_rbar_u, o["rbar"], "1d rbar")
+
+
+# --------------------------------------------------------------------------- disparity-confidence criterion
+@pytest.mark.parametrize("S,V,U,C,D,thr", [(7, 24, 64, 3, 24, 0.01), (6, 44, 70, 1, 32, 0.01), (24, 23, 96, 3, 40, 0.05), (5, 23, 50, 3, 40, 0.0)])
+def test_disp_confidence_criterion(gpu_ctx, S, V, U, C, D, thr):
+    """rslf_cuda_set_confidence_criterion(1): the reference as intended with -D_USE_DISP_CONFIDENCE_SCORE (propagation and
+    validity gated by C_d > par_disp_score_threshold).  Checked against the oracle's restatement, which
+    tests/test_oracle_vs_reference.py pins to the reference built that way, and against that build itself when shipped."""
+    from oracle import ref
+    epis, _ = make_light_field_np(S, V, U, C, dmin=-1.0, dmax=2.0, seed=500 + S + V, layers=5)
+    p = api.default_params(disp_score_threshold=thr)
+    po = oracle.default_params(disp_score_threshold=thr)
+    gpu_ctx.set_confidence_criterion("disp")
+    oracle.set_criterion("disp")
+    try:
+        f = api.FineToCoarse(epis, -1.0, 2.0, D, epi_scale_factor=1.0, parameters=p, ctx=gpu_ctx).run()
+        out_map, out_valid = f.get_results()
+        levels = f.get_levels()
+        o = oracle.fine_to_coarse(epis, -1.0, 2.0, D, scale_factor=1.0, params=po)
+        np.testing.assert_array_equal(out_valid, o["valid"])
+        np.testing.assert_array_equal(out_map, o["map"])
+        for g, l in zip(levels, o["levels"]):
+            for k in ("edge_mask", "best_depth", "dmin", "dmax"):
+                np.testing.assert_array_equal(g[k], l[k], err_msg=k)
+        assert gpu_ctx.timing()["computed_pixels"] == o["computed_pixels"]
+        c = api.Depth2DComputer(epis, -1.0, 2.0, D, epi_scale_factor=1.0, parameters=p, ctx=gpu_ctx).run()
+        o2 = oracle.depth2d(oracle.normalise(epis, 1.0), -1.0, 2.0, D, params=po)
+        np.testing.assert_array_equal(c.m_best_depth_s_v_u, o2["best_depth"])
+        np.testing.assert_array_equal(c.get_valid_depths_mask_s_v_u(), (o2["disp_conf"] > np.float32(thr)).astype(np.uint8) * 255)
+        if os.path.exists(ref.LIB_CD_PATH):
+            ref.set_criterion("disp")
+            r = ref.fine_to_coarse(epis, -1.0, 2.0, D, scale_factor=1.0, params=po)
+            np.testing.assert_array_equal(out_map, r["map"])
+            np.testing.assert_array_equal(out_valid, r["valid"])
+    finally:
+        gpu_ctx.set_confidence_criterion("edge")
+        oracle.set_criterion("edge")
+        ref.set_criterion("edge")
+    with pytest.raises(api.RslfError):
+        gpu_ctx.set_confidence_criterion("line")

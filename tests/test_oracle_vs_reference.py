@@ -279,3 +279,40 @@ def test_oracle_matches_reference_fixtures_of_the_late_rows(golden_dir, name):
     for k in out:
         np.testing.assert_array_equal(out[k], g[k], err_msg="%s:%s" % (name, k))
 
+
+
+# --------------------------------------------------------------------------- the disparity-confidence criterion
+needs_ref_cd = pytest.mark.skipif(not ref.available_cd(), reason="oracle/_ref/librslf_ref_cd.so not built and no reference tree")
+
+
+@pytest.fixture
+def disp_criterion():
+    oracle.set_criterion("disp")
+    ref.set_criterion("disp")
+    yield
+    oracle.set_criterion("edge")
+    ref.set_criterion("edge")
+
+
+@needs_ref_cd
+@pytest.mark.parametrize("S,V,U,C,D,thr", [(7, 24, 64, 3, 24, 0.01), (6, 44, 70, 1, 32, 0.01), (9, 12, 80, 3, 16, 0.05), (5, 23, 50, 3, 40, 0.0)])
+def test_disp_confidence_criterion_as_intended(disp_criterion, S, V, U, C, D, thr):
+    """The reference with -D_USE_DISP_CONFIDENCE_SCORE does not compile as written (`#elseif` is no directive); built
+    with `#elseif` -> `#elif` (oracle/Makefile, target ref_cd) it gates the propagation sources and the validity maps
+    by C_d > par_disp_score_threshold (core.hpp:1097-1098, dc.hpp:901-902).  The oracle's restatement of that variant
+    must equal it bit for bit, and it must differ from the default build (otherwise the test tests nothing)."""
+    epis = lf(S, V, U, C, seed=500 + S + V)
+    p = oracle.default_params(disp_score_threshold=thr)
+    o = oracle.fine_to_coarse(epis, -1.0, 2.0, D, scale_factor=1.0, params=p)
+    r = ref.fine_to_coarse(epis, -1.0, 2.0, D, scale_factor=1.0, params=p, dims=o["dims"])
+    assert_same(r, o, ["map", "valid"], "ftc disp")
+    for lo, lr in zip(o["levels"], r["levels"]):
+        assert_same(lr, lo, ["edge_mask", "edge_conf", "best_depth", "disp_conf", "dmin", "dmax"], "ftc disp level")
+    o2 = oracle.depth2d(oracle.normalise(epis, 1.0), -1.0, 2.0, D, params=p)
+    r2 = ref.depth2d(epis, -1.0, 2.0, D, scale_factor=1.0, params=p)
+    assert_same(r2, o2, MAPS, "2d disp")
+    oracle.set_criterion("edge")
+    e2 = oracle.depth2d(oracle.normalise(epis, 1.0), -1.0, 2.0, D, params=p)
+    oracle.set_criterion("disp")
+    if thr > 0:
+        assert e2["computed_pixels"] != o2["computed_pixels"] or not np.array_equal(e2["best_depth"], o2["best_depth"])
