@@ -358,14 +358,25 @@ def main():
     for w in range(args.warmup):
         ctx.flush_l2()
         run_once()
-        if w == 0 and world > 1 and not batch and not balanced and not args.even_rows:
-            # lock-step mode: the heaviest block sets the pace; re-cut the blocks once from the work measured in this
-            # first warm-up step (rslf_cuda_get_row_work).  Results do not depend on the cut.
+        if w == 0 and world > 1 and not batch and not args.even_rows:
+            # The ranks advance in lock-step (two flag exchanges + the median halo per pass), so the slowest rank sets
+            # the pace.  Lock-step mode: a rank's time is the pixels of its rows.  Pass-balanced mode: the depth kernel's
+            # work is split evenly whatever the cut, but the row-local stages (compaction, median, propagation) scale
+            # with the pixels a rank OWNS and with its rows.  Re-cut the blocks once from the work measured in this first
+            # warm-up step (rslf_cuda_get_row_work).  Results do not depend on the cut.
             mine_w = torch.zeros(V, dtype=torch.float64, device="cuda")
             mine_w[starts[rank]:starts[rank + 1]] = torch.from_numpy(ctx.row_work().astype(np.float64)).cuda()
             dist.all_reduce(mine_w)
+            if balanced:
+                mine_w = mine_w + mine_w.mean()         # rows count as much as an average row's pixels
+                if full is None:
+                    full, _ = make_light_field(S, V, U, C, dmin=DMIN, dmax=DMAX, seed=cfg["seed"], value_range=cfg["rng"], device="cuda")
             cut_blocks((mine_w + 1.0).cpu().tolist() if rank == 0 else None,
-                       "lock-step, balanced by the per-row work measured in the first warm-up step")
+                       ("pass-balanced depth kernel; rows cut by owned pixels + rows, measured in the first warm-up step" if balanced
+                        else "lock-step, balanced by the per-row work measured in the first warm-up step"))
+            if balanced:
+                full = None
+                torch.cuda.empty_cache()
     Vloc = epis.shape[0] if epis is not None else 0
     sampler = ClockSampler(local)
     sampler.start()
@@ -385,14 +396,23 @@ def main():
     # waits for its peers); the host clock between the two barriers is kept beside it as a cross-check
     value = samples / (dev_ms * 1e-3)
 
-    # ---- the same steps without the per-stage CUDA events (what do they cost?) ---------------------------------
-    no_stage = None
+    # ---- extra steps (a) with CUDA events around EVERY stage, for the per-stage breakdown (the timed steps above carry
+    # events around the dominant depth kernel only: about twelve event records per pass would serialise the stream),
+    # (b) without any event inside the run: what the depth-kernel events of the timed steps cost ----------------------
+    no_stage, stages = None, None
     if not args.no_stage_check:
-        ctx.set_stage_timing(False)
-        a2, w2 = timed(max(1, min(2, args.steps)))
-        ctx.set_stage_timing(True)
+        k2 = max(1, min(2, args.steps))
+        ctx.set_stage_timing(2)
+        a3, w3 = timed(k2)
+        r3 = reduce_stats(a3, w3)
+        stages = {k: a3[k] / k2 for k in ("ms_edge", "ms_depth", "ms_reduce", "ms_median", "ms_propagate", "ms_pyramid")}
+        stages["ms_per_step_with_all_stage_events"] = r3["dev_ms"] / k2
+        stages["note"] = "rank 0, %d extra steps with rslf_cuda_set_stage_timing(2); a stage includes its waits for peer GPUs" % k2
+        ctx.set_stage_timing(0)
+        a2, w2 = timed(k2)
+        ctx.set_stage_timing(1)
         r2 = reduce_stats(a2, w2)
-        no_stage = {"ms_per_step": r2["dev_ms"] / max(1, min(2, args.steps)),
+        no_stage = {"ms_per_step": r2["dev_ms"] / k2,
                     "note": "same steps with rslf_cuda_set_stage_timing(0): no event records inside the run"}
 
     # ---- extra leg: the opt-in contracted (FMA) mean shift (rslf_cuda_set_fast_math), same steps, reported beside the
@@ -581,9 +601,7 @@ def main():
                        "ms_per_step_wall": wall / args.steps * 1e3,
                        "ms_per_disparity_result_device": acc["ms_total"] / args.steps / (batch and len(fields) or 1),
                        "fields_per_s": (batch * args.steps / (dev_ms * 1e-3)) if batch else None},
-            "stages_ms_per_step": {k: acc[k] / args.steps for k in ("ms_edge", "ms_depth", "ms_reduce", "ms_median",
-                                                                     "ms_propagate", "ms_pyramid")},
-            "without_stage_events": no_stage,
+            "stages_ms_per_step": stages, "without_stage_events": no_stage,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "fast_math": fast,
             "result_digest": result_digest, "parity_check": parity,
             "gpu_launches": int(launches), "clocks": sampler.summary(),

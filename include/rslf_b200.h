@@ -92,6 +92,19 @@ typedef struct rslf_timing {
 
 typedef struct rslf_ctx rslf_ctx;
 
+/* One evaluated pixel of a run (diagnostics, rslf_cuda_set_decision_log): what the depth kernel decided for pixel
+ * `pix` (= v * U + u in the level's image) of line s_hat of pyramid level `level` (core.hpp:630-657). */
+typedef struct rslf_decision {
+    int   level, s_hat, pix;
+    int   index;            /* d*: first maximum of the score over the hypotheses                */
+    float score;            /* its score                                                         */
+    float rbar[3];          /* mean-shift radiance of that hypothesis                            */
+    float disp_conf;        /* C_d                                                               */
+    float disparity;        /* D[d*]                                                             */
+    int   accepted;         /* score > par_raw_score_threshold                                   */
+    int   reserved;
+} rslf_decision;
+
 /* ---- lifetime ------------------------------------------------------------ */
 int  rslf_cuda_create(int device, rslf_ctx** out);
 void rslf_cuda_destroy(rslf_ctx* ctx);
@@ -298,6 +311,21 @@ int rslf_plan_depth_tm(int S, int C, int D, int s_hat, float dmin, float dmax, f
  * confidences); a pixel inside that margin may pick the neighbouring hypothesis and propagate it.  Default: off (exact).
  * The environment variable RSLF_FAST_MATH=1 sets it at context creation. */
 int rslf_cuda_set_fast_math(rslf_ctx* ctx, int on);
+/* Diagnostics: records every pixel decision of the following runs (up to `capacity` records; 0 switches the log
+ * off) so that a test can replay them through the CPU oracle — the way the contracted (fast_math) mode is checked
+ * against the tolerance it is specified to (tests/test_gpu_tolerance.py).  rslf_cuda_get_decision_log copies the
+ * records of the last run out and returns their number in *count (clipped to max_records in out). */
+int rslf_cuda_set_decision_log(rslf_ctx* ctx, size_t capacity);
+int rslf_cuda_get_decision_log(rslf_ctx* ctx, rslf_decision* out, size_t max_records, size_t* count);
+/* CUDA events inside a run: 0 = none (only ms_total is measured), 1 (default) = around the launches of the dominant
+ * depth kernel (ms_depth, the roofline's denominator; two records per s_hat pass), 2 = around every stage (ms_edge ...
+ * ms_pyramid; about twelve records per pass, which serialise the stream: +2 % on one GPU, +10 % on eight). */
+int rslf_cuda_set_stage_timing(rslf_ctx* ctx, int level);
+/* Row-sharded runs: 1 (default) = the pixels of every s_hat pass are split evenly over the ranks whatever rows they
+ * lie in (every rank holds the whole EPI stack, the result maps stay sharded by rows; work / result records travel
+ * through peer memory over NVLink); 0 = lock-step row blocks: every rank evaluates the pixels of its own rows (the
+ * reference's OpenMP axis, core.hpp:799).  Results are identical either way.  RSLF_BALANCE=0 sets it at creation. */
+int rslf_cuda_set_balance(rslf_ctx* ctx, int on);
 /* Writes >126 MB on the device so the next timed step starts with a cold L2. */
 int rslf_cuda_flush_l2(rslf_ctx* ctx);
 int rslf_cuda_sync(rslf_ctx* ctx);

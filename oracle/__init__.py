@@ -76,6 +76,35 @@ def _cv_depth(a):
     return {np.dtype(np.uint8): 0, np.dtype(np.uint16): 2}.get(a.dtype, 5)
 
 
+class Decision(C.Structure):
+    """rslf_decision (include/rslf_b200.h)."""
+    _fields_ = [("level", C.c_int), ("s_hat", C.c_int), ("pix", C.c_int), ("index", C.c_int), ("score", C.c_float),
+                ("rbar", C.c_float * 3), ("disp_conf", C.c_float), ("disparity", C.c_float), ("accepted", C.c_int),
+                ("reserved", C.c_int)]
+
+
+class replay:
+    """with oracle.replay(records, n): ... runs the oracle entry points with the recorded decisions adopted after the
+    tolerance check (see `Replay` in rslf_oracle.cpp); .report holds the counters afterwards."""
+
+    def __init__(self, records, n, margin_tol=1e-5, rel_tol=1e-4):
+        self.records, self.n, self.margin_tol, self.rel_tol = records, int(n), margin_tol, rel_tol
+        self.report = None
+
+    def __enter__(self):
+        lib().orc_replay_begin(self.records, C.c_longlong(self.n), C.c_float(self.margin_tol), C.c_float(self.rel_tol))
+        return self
+
+    def __exit__(self, *exc):
+        out = (C.c_longlong * 10)()
+        worst = (C.c_double * 2)()
+        lib().orc_replay_end(out, worst)
+        keys = ("looked_up", "missing", "index_changed", "bad_margin", "bad_score", "bad_rbar", "bad_cd", "bad_disparity", "records")
+        self.report = dict(zip(keys, out[:9]))
+        self.report["worst_margin"], self.report["worst_rel_score"] = worst[0], worst[1]
+        return False
+
+
 def set_criterion(name):
     """"edge": the reference as written (default build); "disp": -D_USE_DISP_CONFIDENCE_SCORE as intended (`#elseif` -> `#elif`):
     propagation sources and validity maps are gated by C_d > par_disp_score_threshold (core.hpp:1097-1098, dc.hpp:901-902)."""

@@ -33,6 +33,7 @@
 #include <cstdint>
 #include <cstring>
 #include <limits>
+#include <unordered_map>
 #include <vector>
 #ifdef _OPENMP
 #include <omp.h>
@@ -140,6 +141,25 @@ struct PixelScratch {
  * branch), 1 = the disparity confidence C_d > par_disp_score_threshold (the reference AS INTENDED with
  * -D_USE_DISP_CONFIDENCE_SCORE once `#elseif` reads `#elif`: core.hpp:1097-1098, dc.hpp:901-902).  orc_set_criterion. */
 int g_criterion = 0;
+
+/* REPLAY of recorded decisions (orc_replay_*): checks a run whose arithmetic is only specified to a tolerance — the
+ * CUDA path's contracted (FMA) mode — against the reference's rule (north star): same disparity index wherever the
+ * winning score margin exceeds margin_tol (1e-5), scores / r_bar / C_d within rel_tol (1e-4).  For every pixel this
+ * oracle evaluates, the recorded decision of the same (level, line, pixel) is looked up; it must pick a hypothesis whose
+ * exact score is within margin_tol of the exact maximum, and its floats must be within rel_tol of the exact ones for
+ * that hypothesis.  The decision is then ADOPTED (index, r_bar, C_d, acceptance), so that everything downstream —
+ * median, propagation, the remaining masks and thereby the set of pixels evaluated later, bounds, fusion — follows the
+ * recorded run exactly: any remaining difference between the two runs' maps is a genuine error, not tolerance. */
+struct Replay {
+    bool on = false;
+    std::unordered_map<uint64_t, const rslf_decision*> map;
+    float margin_tol = 1e-5f, rel_tol = 1e-4f;
+    int level = 0;
+    long long looked_up = 0, missing = 0, index_changed = 0, bad_margin = 0, bad_score = 0, bad_rbar = 0, bad_cd = 0, bad_disp = 0;
+    double worst_margin = 0, worst_rel = 0;
+} g_replay;
+inline uint64_t replay_key(int level, int s_hat, int pix) { return ((uint64_t)level << 56) | ((uint64_t)s_hat << 36) | (uint64_t)(uint32_t)pix; }
+inline bool close_rel(float a, float b, float rel, float abs_floor) { return std::fabs((double)a - (double)b) <= (double)rel * std::max((double)std::fabs(b), (double)abs_floor); }
 
 /* Optional statistics (off by default; orc_ms_stats_*): at which mean-shift iteration r_bar reaches a bitwise
  * fixed point, per hypothesis and per group of 32 consecutive hypotheses (a GPU warp).  Once r_bar(t+1) == r_bar(t)
@@ -318,7 +338,7 @@ long depth_row(const float* epi, int S, int U, int C, int D, int s_hat,
                const float* dmin_u, const float* dmax_u, float dmin_c, float dmax_c,
                float* ce, uint8_t* emask, float* cd, float* depth, float* rbar_out,
                uint8_t* remaining, const rslf_params& P, PixelScratch& w,
-               float* margin, int32_t* best_idx) {
+               float* margin, int32_t* best_idx, int v = 0) {
     long computed = 0;
     for (int u = 0; u < U; ++u) {
         uint8_t m;
@@ -338,6 +358,48 @@ long depth_row(const float* epi, int S, int U, int C, int D, int s_hat,
             margin[u] = mx - second;
         }
         if (best_idx) best_idx[u] = best;
+        if (g_replay.on) {
+            /* adopt the recorded decision of this pixel after checking it against the tolerance (see Replay) */
+            auto it = g_replay.map.find(replay_key(g_replay.level, s_hat, v * U + u));
+#pragma omp atomic
+            g_replay.looked_up += 1;
+            if (it == g_replay.map.end()) {
+#pragma omp atomic
+                g_replay.missing += 1;
+            } else {
+                const rslf_decision& r = *it->second;
+                const int gi = (r.index >= 0 && r.index < D) ? r.index : best;
+                const float gap = mx - w.score[gi];                        /* >= 0: exact score margin of the recorded choice */
+                bool okm = gap <= g_replay.margin_tol, oks = close_rel(r.score, w.score[gi], g_replay.rel_tol, 1e-3f), okr = true;
+                for (int c = 0; c < C; ++c) okr = okr && close_rel(r.rbar[c], w.rbar[(size_t)c * D + gi], g_replay.rel_tol, 1e-2f);
+                double sum = 0.0;
+                for (int d = 0; d < D; ++d) sum += (double)w.score[d];
+                const float cd_exact = (float)((double)ce[u] * std::fabs((double)w.score[gi] - sum / (double)D));
+                const bool accepted = r.accepted != 0;
+                /* C_d = C_e |max - mean|: a difference of two scores, so its tolerance is rel_tol of the scores' scale */
+                const bool okc = !accepted || std::fabs((double)r.disp_conf - (double)cd_exact) <= (double)g_replay.rel_tol * std::max((double)ce[u] * (double)std::max(mx, 1e-3f), 1e-9);
+                const bool okd = r.disparity == w.Dv[gi];
+#pragma omp critical(replay_stats)
+                {
+                    if (gi != best) g_replay.index_changed += 1;
+                    if (!okm) g_replay.bad_margin += 1;
+                    if (!oks) g_replay.bad_score += 1;
+                    if (!okr) g_replay.bad_rbar += 1;
+                    if (!okc) g_replay.bad_cd += 1;
+                    if (!okd) g_replay.bad_disp += 1;
+                    g_replay.worst_margin = std::max(g_replay.worst_margin, (double)gap);
+                    if (w.score[gi] > 1e-3f) g_replay.worst_rel = std::max(g_replay.worst_rel, std::fabs((double)r.score - (double)w.score[gi]) / (double)w.score[gi]);
+                }
+                if (accepted) {
+                    depth[u] = w.Dv[gi];
+                    cd[u] = r.disp_conf;
+                    for (int c = 0; c < C; ++c) rbar_out[(size_t)u * C + c] = r.rbar[c];
+                } else {
+                    ce[u] = 0.f; emask[u] = 0;
+                }
+                continue;
+            }
+        }
         double maxVal = (double)mx;
         if (maxVal > (double)P.raw_score_threshold) {
             depth[u] = w.Dv[best];
@@ -496,7 +558,7 @@ void depth2d(const float* epis, const Dims& g, int D, float dmin_c, float dmax_c
                                       dmin_c, dmax_c,
                                       ce_p + (size_t)v * U, em_p + (size_t)v * U, cd_p + (size_t)v * U,
                                       dp_p + (size_t)v * U, rb_p + (size_t)v * U * C,
-                                      rem_p + (size_t)v * U, P, w, nullptr, nullptr);
+                                      rem_p + (size_t)v * U, P, w, nullptr, nullptr, v);
             }
         }
         total += (double)computed;
@@ -885,6 +947,23 @@ void orc_ms_stats_read(long long* lane33, long long* warp33, long long* pixels, 
     *pixels = g_ms_pixels; *flat_pixels = g_ms_flat_pixels;
 }
 
+/* replay of recorded decisions (see Replay): load `n` records, run any of the entry points below, read the report */
+void orc_replay_begin(const rslf_decision* recs, long long n, float margin_tol, float rel_tol) {
+    g_replay = Replay();
+    g_replay.map.reserve((size_t)n * 2);
+    for (long long i = 0; i < n; ++i) g_replay.map[replay_key(recs[i].level, recs[i].s_hat, recs[i].pix)] = recs + i;
+    g_replay.margin_tol = margin_tol; g_replay.rel_tol = rel_tol; g_replay.on = true;
+}
+/* out[0..9] = looked up, missing, index changed, bad margin, bad score, bad r_bar, bad C_d, bad disparity value,
+ * records loaded, 0; worst[0..1] = largest exact margin of an adopted choice, largest relative score error */
+void orc_replay_end(long long* out10, double* worst2) {
+    out10[0] = g_replay.looked_up; out10[1] = g_replay.missing; out10[2] = g_replay.index_changed; out10[3] = g_replay.bad_margin;
+    out10[4] = g_replay.bad_score; out10[5] = g_replay.bad_rbar; out10[6] = g_replay.bad_cd; out10[7] = g_replay.bad_disp;
+    out10[8] = (long long)g_replay.map.size(); out10[9] = 0;
+    worst2[0] = g_replay.worst_margin; worst2[1] = g_replay.worst_rel;
+    g_replay = Replay();
+}
+
 void orc_set_criterion(int c) { g_criterion = c; }
 int orc_get_criterion(void) { return g_criterion; }
 
@@ -976,7 +1055,7 @@ double orc_depth1d_pile(const float* epis, int V, int S, int U, int C, float dmi
                                   ce + (size_t)v * U, emask + (size_t)v * U, cd + (size_t)v * U,
                                   depth.data() + (size_t)v * U, rbar + (size_t)v * U * C, nullptr, P, w,
                                   margin ? margin + (size_t)v * U : nullptr,
-                                  best_idx ? best_idx + (size_t)v * U : nullptr);
+                                  best_idx ? best_idx + (size_t)v * U : nullptr, v);
     }
     if (raw_depth) std::memcpy(raw_depth, depth.data(), plane * sizeof(float));
     selective_median(depth.data(), best_depth, epis, g, s_hat, P.median_filter_size, emask, P.median_filter_epsilon);
@@ -1076,6 +1155,7 @@ double orc_fine_to_coarse(const void* raw, int cv_depth, int V, int S, int U, in
     const void* cur_raw = raw;
     double total = 0;
     for (int p = 0; p < levels; ++p) {
+        g_replay.level = p;
         Dims g{Vp[p], S, Up[p], C};
         size_t n = (size_t)S * Vp[p] * Up[p];
         norm.resize((size_t)Vp[p] * S * Up[p] * C);

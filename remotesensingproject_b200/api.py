@@ -40,6 +40,13 @@ class Params(C.Structure):
     ]
 
 
+class Decision(C.Structure):
+    """rslf_decision (include/rslf_b200.h)."""
+    _fields_ = [("level", C.c_int), ("s_hat", C.c_int), ("pix", C.c_int), ("index", C.c_int), ("score", C.c_float),
+                ("rbar", C.c_float * 3), ("disp_conf", C.c_float), ("disparity", C.c_float), ("accepted", C.c_int),
+                ("reserved", C.c_int)]
+
+
 class Timing(C.Structure):
     """rslf_timing (include/rslf_b200.h)."""
     _fields_ = [
@@ -315,8 +322,23 @@ class Context:
         self.check(lib().rslf_cuda_last_timing(self._h, C.byref(t)), "rslf_cuda_last_timing")
         return t.as_dict()
 
-    def set_stage_timing(self, on):
-        lib().rslf_cuda_set_stage_timing(self._h, int(bool(on)))
+    def set_stage_timing(self, level):
+        """0: no CUDA events inside a run, 1 (default): around the depth kernel only, 2: around every stage."""
+        lib().rslf_cuda_set_stage_timing(self._h, int(level))
+
+    def set_decision_log(self, capacity):
+        """Diagnostics: record every pixel decision of the following runs (0: off)."""
+        self.check(lib().rslf_cuda_set_decision_log(self._h, C.c_size_t(int(capacity))), "rslf_cuda_set_decision_log")
+        self._dlog_cap = int(capacity)
+
+    def decision_log(self):
+        """(ctypes array of Decision, n) of the last run."""
+        buf = (Decision * max(1, self._dlog_cap))()
+        n = C.c_size_t(0)
+        self.check(lib().rslf_cuda_get_decision_log(self._h, buf, C.c_size_t(self._dlog_cap), C.byref(n)), "rslf_cuda_get_decision_log")
+        if n.value > self._dlog_cap:
+            raise RslfError("decision log overflow: %d records, capacity %d" % (n.value, self._dlog_cap))
+        return buf, n.value
 
     def set_confidence_criterion(self, name):
         """"edge" (the reference's default build) or "disp" (-D_USE_DISP_CONFIDENCE_SCORE as intended: C_d > par_disp_score_threshold

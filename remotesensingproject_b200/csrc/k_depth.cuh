@@ -89,6 +89,7 @@ struct depth_args {
     float raw_thr;
     int chunks; rslf_partial* partials; int* arrive;
     depth_bal bal;                /* pass-balanced multi-GPU mode (bal.n > 0): records / results of all ranks */
+    rslf_decision* log; int* log_count; int log_cap; int level;   /* diagnostics: decision log (rslf_cuda_set_decision_log) */
 };
 
 /* one warp item from the launch's work queue (lane 0 claims, the warp learns) */
@@ -102,13 +103,23 @@ __device__ __forceinline__ int depth_claim(int* queue, int lane)
 /* Outputs of one pixel (core.hpp:630-657), written by one lane: the result planes in direct mode, a result
  * record in the owner's list in balanced mode (applied by bal_apply_kernel). */
 template <int C>
-__device__ __forceinline__ void depth_emit(const depth_args& a, int rec_pix, float ce, int owner, int ridx, float best, float bdv,
-                                           double sum, const float (&brb)[C])
+__device__ __forceinline__ void depth_emit(const depth_args& a, int rec_pix, float ce, int owner, int ridx, float best, int bidx,
+                                           float bdv, double sum, const float (&brb)[C])
 {
     const double maxVal = (double)best;
     const bool ok = maxVal > (double)a.raw_thr;
     const double mean = sum / (double)a.D;                         /* cv::mean (core.hpp:641) */
     const float cdv = (float)((double)ce * fabs(maxVal - mean));
+    if (a.log) {
+        const int at = atomicAdd(a.log_count, 1);
+        if (at < a.log_cap) {
+            rslf_decision r;
+            r.level = a.level; r.s_hat = a.s_hat; r.pix = rec_pix; r.index = bidx; r.score = best;
+            r.rbar[0] = brb[0]; r.rbar[1] = brb[C > 1 ? 1 : 0]; r.rbar[2] = brb[C > 2 ? 2 : 0];
+            r.disp_conf = cdv; r.disparity = bdv; r.accepted = ok ? 1 : 0; r.reserved = 0;
+            a.log[at] = r;
+        }
+    }
     if (a.bal.n) {
         float4* r = a.bal.res[owner] + 2 * (size_t)ridx;
         r[0] = make_float4(bdv, cdv, brb[0], brb[C > 1 ? 1 : 0]);
@@ -918,7 +929,7 @@ RSLF_PRAGMA(unroll RSLF_MS_UNROLL)
                 }
             }
         }
-        if (lane == 0 && finalise) depth_emit<C>(a, pix, __int_as_float(rec.w), owner, ridx, best, bdv, sum, brb);
+        if (lane == 0 && finalise) depth_emit<C>(a, pix, __int_as_float(rec.w), owner, ridx, best, bidx, bdv, sum, brb);
         w = __shfl_sync(0xffffffffu, w_next, 0);
     }
     depth_bal_finish(a);

@@ -496,7 +496,7 @@ depth_kernel_tm(const depth_args a, const depth_tm_layout L)
                 }
             }
         }
-        if (lane == 0 && finalise) depth_emit<C>(a, pix, __int_as_float(rec.w), owner, ridx, best, bdv, sum, brb);
+        if (lane == 0 && finalise) depth_emit<C>(a, pix, __int_as_float(rec.w), owner, ridx, best, bidx, bdv, sum, brb);
         w = __shfl_sync(0xffffffffu, w_next, 0);
     }
     if (a.bal.n) __threadfence_system();

@@ -62,7 +62,10 @@ static size_t clk_mark(rslf_ctx* ctx)
 }
 struct stage_scope {
     rslf_ctx* ctx; int stage; size_t a; bool on;
-    stage_scope(rslf_ctx* c, int st) : ctx(c), stage(st), a(0), on(c->stage_timing != 0) { if (on) a = clk_mark(ctx); }
+    /* stage_timing 0: no events inside a run; 1 (default): only the dominant (depth) kernel is bracketed, two event
+     * records per pass; 2: every stage (diagnostics: ~12 records per pass, which cost ~2 % of a one-GPU step and ~10 % of
+     * an 8-GPU step, where a pass is a few hundred microseconds) */
+    stage_scope(rslf_ctx* c, int st) : ctx(c), stage(st), a(0), on(c->stage_timing >= 2 || (c->stage_timing == 1 && st == ST_DEPTH)) { if (on) a = clk_mark(ctx); }
     ~stage_scope() { if (on) { size_t b = clk_mark(ctx); ctx->clk.spans.push_back({stage, a, b}); } }
 };
 static void clk_resolve(rslf_ctx* ctx)
@@ -350,7 +353,7 @@ extern "C" void rslf_cuda_destroy(rslf_ctx* ctx)
     free_scratch(ctx);
     if (ctx->raw_in && !ctx->raw_borrowed) cudaFree(ctx->raw_in);
     if (ctx->raw_full) cudaFree(ctx->raw_full);
-    dev_free(&ctx->queue); dev_free(&ctx->dev_err);
+    dev_free(&ctx->queue); dev_free(&ctx->dev_err); dev_free(&ctx->dlog); dev_free(&ctx->dlog_count);
     dev_free(&ctx->count); dev_free(&ctx->total_px); dev_free(&ctx->minmax); dev_free(&ctx->rowwork);
     dev_free(&ctx->colour_hist); dev_free(&ctx->colour_lut);
     if (ctx->l2_flush) cudaFree(ctx->l2_flush);
@@ -381,6 +384,39 @@ extern "C" int rslf_cuda_set_fast_math(rslf_ctx* ctx, int on)
 {
     if (!ctx) return RSLF_ERR_ARG;
     ctx->fast_math = on != 0;
+    return RSLF_OK;
+}
+
+extern "C" int rslf_cuda_set_decision_log(rslf_ctx* ctx, size_t capacity)
+{
+    if (!ctx) return RSLF_ERR_ARG;
+    RSLF_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    RSLF_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->dlog) { cudaFree(ctx->dlog); ctx->dlog = nullptr; }
+    ctx->dlog_cap = 0;
+    if (capacity == 0) return RSLF_OK;
+    if (!ctx->dlog_count) RSLF_TRY(dev_alloc(ctx, &ctx->dlog_count, 1));
+    RSLF_CUDA_TRY(ctx, cudaMemsetAsync(ctx->dlog_count, 0, sizeof(int), ctx->stream));
+    RSLF_TRY(dev_alloc(ctx, &ctx->dlog, capacity));
+    ctx->dlog_cap = capacity;
+    return RSLF_OK;
+}
+
+extern "C" int rslf_cuda_get_decision_log(rslf_ctx* ctx, rslf_decision* out, size_t max_records, size_t* count)
+{
+    if (!ctx || !count) return RSLF_ERR_ARG;
+    *count = 0;
+    if (!ctx->dlog) { snprintf(ctx->err, sizeof(ctx->err), "no decision log (rslf_cuda_set_decision_log)"); return RSLF_ERR_STATE; }
+    RSLF_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    int n = 0;
+    RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(&n, ctx->dlog_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    RSLF_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    *count = (size_t)n;
+    const size_t m = std::min<size_t>(std::min<size_t>((size_t)n, ctx->dlog_cap), max_records);
+    if (out && m) {
+        RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(out, ctx->dlog, m * sizeof(rslf_decision), cudaMemcpyDeviceToHost, ctx->stream));
+        RSLF_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    }
     return RSLF_OK;
 }
 
@@ -675,6 +711,7 @@ static int run_depth_pass(rslf_ctx* ctx, const rslf_params& P, const pass_io& io
     a.raw_thr = P.raw_score_threshold;
     a.wpv_q16 = plan.wpv_q16; a.reg_last = plan.reg_last;
     a.chunks = plan.chunks; a.partials = (rslf_partial*)ctx->partials; a.arrive = ctx->arrive;
+    a.log = ctx->dlog; a.log_count = ctx->dlog_count; a.log_cap = (int)std::min<size_t>(ctx->dlog_cap, 0x7fffffff); a.level = io.level;
     if (balanced) {
         a.bal.n = ctx->world; a.bal.rank = ctx->rank; a.bal.seq = seq;
         for (int q = 0; q < ctx->world; ++q) {
@@ -803,6 +840,7 @@ static int begin_run(rslf_ctx* ctx)
     RSLF_CUDA_TRY(ctx, cudaMemsetAsync(ctx->count, 0, RSLF_COUNT_SLOTS * sizeof(int), ctx->stream));
     RSLF_CUDA_TRY(ctx, cudaMemsetAsync(ctx->queue, 0, RSLF_COUNT_SLOTS * sizeof(int), ctx->stream));
     RSLF_CUDA_TRY(ctx, cudaMemsetAsync(ctx->total_px, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    if (ctx->dlog_count) RSLF_CUDA_TRY(ctx, cudaMemsetAsync(ctx->dlog_count, 0, sizeof(int), ctx->stream));
     if (ctx->rowwork_cap < (size_t)ctx->V) {
         RSLF_TRY(dev_alloc(ctx, &ctx->rowwork, (size_t)ctx->V));
         ctx->rowwork_cap = (size_t)ctx->V;

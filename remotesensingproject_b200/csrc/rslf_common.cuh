@@ -87,6 +87,7 @@ struct rslf_ctx {
     int4* rec = nullptr;         /* work records of the pass (k_balance.cuh); in the arena when peers read them */
     int4* rec_own = nullptr;     /* the cudaMalloc'ed record list of single-rank runs          */
     int* dev_err = nullptr;      /* raised by a kernel whose wait for a peer timed out         */
+    rslf_decision* dlog = nullptr; int* dlog_count = nullptr; size_t dlog_cap = 0;   /* decision log (diagnostics) */
     unsigned long long* total_px = nullptr;  /* [0] computed pixels of sharded levels, [1] of replicated levels */
     float* filtered = nullptr;   /* selective-median output plane [V][U]                      */
     int* winner = nullptr;       /* propagation arbitration [S][V][U], INT_MAX when idle      */

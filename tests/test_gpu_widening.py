@@ -263,21 +263,8 @@ def test_fast_math_stays_within_the_specified_tolerance(gpu_ctx, monkeypatch, S,
     assert (fast["disp_conf"] != ref["disp_conf"]).any(), "the contracted kernel did not run"
 
 
-def test_fast_math_whole_pipeline_is_close(gpu_ctx):
-    """Through propagation and the pyramid a pixel inside the 1e-5 margin may flip to the neighbouring hypothesis and
-    paint others; masks stay identical and all but a small fraction of the fused map is unchanged."""
-    epis = lf(28, 30, 60, 3, seed=640)
-    r = oracle.fine_to_coarse(epis, -1.0, 2.0, 40, scale_factor=1.0)
-    gpu_ctx.set_fast_math(True)
-    try:
-        m, v = api.FineToCoarse(epis, -1.0, 2.0, 40, epi_scale_factor=1.0, ctx=gpu_ctx).run().get_results()
-    finally:
-        gpu_ctx.set_fast_math(False)
-    same(v, r["valid"], "fast mode validity")
-    frac = float((m != r["map"]).mean())
-    assert frac < 0.02, "fraction of fused-map pixels that differ: %g" % frac
-    m2, v2 = api.FineToCoarse(epis, -1.0, 2.0, 40, epi_scale_factor=1.0, ctx=gpu_ctx).run().get_results()
-    same(m2, r["map"], "exact mode after switching back")
+# The whole pipeline in contracted mode (propagation, pyramid, fusion) is checked by tests/test_gpu_tolerance.py: the
+# oracle replays the recorded decisions and every map must then be identical.
 
 
 # --------------------------------------------------------------------------- Depth1DComputer (one EPI)
