@@ -228,6 +228,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-fast", action="store_true", help="skip the extra leg with the opt-in contracted (FMA) mean shift")
     ap.add_argument("--no-stage-check", action="store_true", help="skip the extra steps timed without per-stage events")
+    ap.add_argument("--facade", action="store_true", help="also time the compiled C++ drop-in (include/rslf_b200.hpp) end to end on pageable Mats")
     ap.add_argument("--even-rows", action="store_true", help="lock-step multi-GPU mode: equal row counts instead of work-balanced blocks")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200" and not args.config.startswith("tiny"):
@@ -500,6 +501,25 @@ def main():
                "path": "api.FineToCoarse / api.Depth2DComputer (ctypes mirror of the C++ facade) -> C ABI, pinned host buffers"}
         if world > 1 and not batch:
             e2e["note"] = "includes the all-gather of the uploaded row blocks into every rank's copy of the stack"
+    # ---- the compiled C++ facade on pageable Mats (what a cv::Mat caller of the drop-in gets), optional -----------
+    facade = None
+    if args.facade and world == 1 and not batch and rank == 0:
+        tmp = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
+        exe, inp = os.path.join(tmp, "rslf_facade_e2e"), os.path.join(tmp, "rslf_facade_in.bin")
+        libdir = os.path.join(ROOT, "remotesensingproject_b200")
+        try:
+            subprocess.check_call(["g++", "-std=c++17", "-O2", "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tools", "facade_e2e.cpp"),
+                                   "-o", exe, "-L" + libdir, "-lrslf_b200", "-Wl,-rpath," + libdir])
+            epis.cpu().numpy().tofile(inp)
+            o = subprocess.run([exe, inp, str(V), str(S), str(U), str(C), str(D), str(DMIN), str(DMAX), str(cfg["scale"]), "2",
+                                "ftc" if cfg["mode"] == "ftc" else "2d"], capture_output=True, text=True, timeout=900)
+            facade = json.loads(o.stdout.strip().splitlines()[-1]) if o.returncode == 0 else {"failed": (o.stdout + o.stderr)[-300:]}
+        except Exception as e:                                    # no compiler on the box, no space: report, do not fail the bench
+            facade = {"unavailable": str(e)[:200]}
+        finally:
+            for f in (exe, inp):
+                if os.path.exists(f):
+                    os.remove(f)
     # result digest: sha256 over the per-row digests in global row (batch: field, row) order
     result_digest = None
     if digest_parts is not None:
@@ -602,7 +622,7 @@ def main():
                        "ms_per_disparity_result_device": acc["ms_total"] / args.steps / (batch and len(fields) or 1),
                        "fields_per_s": (batch * args.steps / (dev_ms * 1e-3)) if batch else None},
             "stages_ms_per_step": stages, "without_stage_events": no_stage,
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "fast_math": fast,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_facade": facade, "fast_math": fast,
             "result_digest": result_digest, "parity_check": parity,
             "gpu_launches": int(launches), "clocks": sampler.summary(),
         }

@@ -311,6 +311,24 @@ int rslf_plan_depth_tm(int S, int C, int D, int s_hat, float dmin, float dmax, f
  * confidences); a pixel inside that margin may pick the neighbouring hypothesis and propagate it.  Default: off (exact).
  * The environment variable RSLF_FAST_MATH=1 sets it at context creation. */
 int rslf_cuda_set_fast_math(rslf_ctx* ctx, int on);
+/* ---- host images (cv::Mat storage) ------------------------------------------------------------------------
+ * The reference's classes own S result Mats per map (rslf_depth_computation.hpp:170-228, rslf_fine_to_coarse.hpp:301-322).
+ * These getters write plane s of a result straight into the caller's image s (pointer = cv::Mat::data, step =
+ * cv::Mat::step), nullptr arrays / entries are skipped.  Page-locked destinations (rslf_host_alloc, cudaHostAlloc,
+ * cudaHostRegister) are filled by one strided DMA per image; pageable ones (an ordinary cv::Mat) through a ring of
+ * two pinned buffers, the host thread emptying one while the copy engine fills the other. */
+int rslf_cuda_depth2d_get_mats(rslf_ctx* ctx, float* const* best_depth_s, float* const* edge_conf_s,
+                               uint8_t* const* edge_mask_s, float* const* disp_conf_s, float* const* rbar_s,
+                               size_t step_f32, size_t step_u8, size_t step_rbar);
+int rslf_cuda_fine_to_coarse_get_mats(rslf_ctx* ctx, float* const* out_map_s, size_t map_step,
+                                      uint8_t* const* out_valid_s, size_t valid_step);
+/* Depth2DComputer::get_epis (rslf_depth_computation.hpp:207): the normalised float32 EPIs of the last run, V images
+ * of S rows x U x C. */
+int rslf_cuda_get_epis(rslf_ctx* ctx, float* const* epi_v, size_t step);
+/* Page-locked host memory for image storage that is uploaded / downloaded repeatedly (full PCIe rate, asynchronous). */
+void* rslf_host_alloc(size_t bytes);
+void  rslf_host_free(void* p);
+
 /* Diagnostics: records every pixel decision of the following runs (up to `capacity` records; 0 switches the log
  * off) so that a test can replay them through the CPU oracle — the way the contracted (fast_math) mode is checked
  * against the tolerance it is specified to (tests/test_gpu_tolerance.py).  rslf_cuda_get_decision_log copies the

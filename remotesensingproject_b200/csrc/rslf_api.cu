@@ -265,6 +265,10 @@ static int full_input(rslf_ctx* ctx, const void** out)
         const size_t bytes = row_bytes * ctx->V_total + 256;
         if (ctx->raw_full_cap < bytes) {
             if (ctx->raw_full) cudaFree(ctx->raw_full);
+    if (ctx->img_staging) cudaFree(ctx->img_staging);
+    for (int i = 0; i < 2; ++i) { if (ctx->ring[i]) cudaFreeHost(ctx->ring[i]); if (ctx->ring_ev[i]) cudaEventDestroy(ctx->ring_ev[i]); }
+    if (ctx->ev_img) cudaEventDestroy(ctx->ev_img);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
             ctx->raw_full = nullptr; ctx->raw_full_cap = 0;
             cudaError_t e = cudaMalloc(&ctx->raw_full, bytes);
             if (e != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "cudaMalloc(full raw stack %zu): %s", bytes, cudaGetErrorString(e)); return RSLF_ERR_NOMEM; }
@@ -353,6 +357,10 @@ extern "C" void rslf_cuda_destroy(rslf_ctx* ctx)
     free_scratch(ctx);
     if (ctx->raw_in && !ctx->raw_borrowed) cudaFree(ctx->raw_in);
     if (ctx->raw_full) cudaFree(ctx->raw_full);
+    if (ctx->img_staging) cudaFree(ctx->img_staging);
+    for (int i = 0; i < 2; ++i) { if (ctx->ring[i]) cudaFreeHost(ctx->ring[i]); if (ctx->ring_ev[i]) cudaEventDestroy(ctx->ring_ev[i]); }
+    if (ctx->ev_img) cudaEventDestroy(ctx->ev_img);
+    if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
     dev_free(&ctx->queue); dev_free(&ctx->dev_err); dev_free(&ctx->dlog); dev_free(&ctx->dlog_count);
     dev_free(&ctx->count); dev_free(&ctx->total_px); dev_free(&ctx->minmax); dev_free(&ctx->rowwork);
     dev_free(&ctx->colour_hist); dev_free(&ctx->colour_lut);
@@ -484,6 +492,9 @@ static int own_raw(rslf_ctx* ctx, size_t bytes)
     return RSLF_OK;
 }
 
+static int images_to_device(rslf_ctx* ctx, void* dev, int n_imgs, int rows, size_t row_bytes, const void* const* host, size_t step);
+static int planes_to_host(rslf_ctx* ctx, const void* dev, int planes, int rows, size_t row_bytes, void* const* host, size_t step);
+
 extern "C" int rslf_cuda_upload_epis(rslf_ctx* ctx, const void* const* epi_ptrs, int V, int S, int U, int C,
                                      int cv_depth, size_t row_step_bytes, float epi_scale_factor)
 {
@@ -496,17 +507,8 @@ extern "C" int rslf_cuda_upload_epis(rslf_ctx* ctx, const void* const* epi_ptrs,
     const size_t epi_bytes = row * S;
     RSLF_TRY(own_raw(ctx, epi_bytes * V));
     cudaEventRecord(ctx->ev_a, ctx->stream);
-    /* one dense copy when the V Mats are continuous and back to back, else one 2D copy per EPI */
-    bool dense = (row_step_bytes == row);
-    for (int v = 1; dense && v < V; ++v)
-        dense = ((const char*)epi_ptrs[v] == (const char*)epi_ptrs[0] + (size_t)v * epi_bytes);
-    if (dense) {
-        RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->raw_in, epi_ptrs[0], epi_bytes * V, cudaMemcpyHostToDevice, ctx->stream));
-    } else {
-        for (int v = 0; v < V; ++v)
-            RSLF_CUDA_TRY(ctx, cudaMemcpy2DAsync((char*)ctx->raw_in + (size_t)v * epi_bytes, row, epi_ptrs[v], row_step_bytes,
-                                                 row, S, cudaMemcpyHostToDevice, ctx->stream));
-    }
+    /* V images of S rows: pinned / registered memory by DMA, pageable cv::Mat storage through the pinned ring */
+    RSLF_TRY(images_to_device(ctx, ctx->raw_in, V, S, row, epi_ptrs, row_step_bytes));
     cudaEventRecord(ctx->ev_b, ctx->stream);
     RSLF_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     cudaEventElapsedTime(&ctx->timing.ms_h2d, ctx->ev_a, ctx->ev_b);
@@ -530,9 +532,9 @@ extern "C" int rslf_cuda_set_epis_device(rslf_ctx* ctx, const void* d_epis, int 
 
 /* [S][V][U][C] -> [V][S][U][C] (rslf::build_epis_from_imgs, src/rslf_io.cpp:194-227) */
 template <typename T>
-__global__ void build_epis_kernel(const T* __restrict__ imgs, int S, int V, size_t rowlen, T* __restrict__ epis)
+__global__ void build_epis_kernel(const T* __restrict__ imgs, int S, int V, size_t rowlen, T* __restrict__ epis, int s_first)
 {
-    const int s = blockIdx.y, v = blockIdx.z;
+    const int s = s_first + blockIdx.y, v = blockIdx.z;
     const T* src = imgs + ((size_t)s * V + v) * rowlen;
     T* dst = epis + ((size_t)v * S + s) * rowlen;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < rowlen; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
@@ -549,22 +551,34 @@ extern "C" int rslf_cuda_upload_images(rslf_ctx* ctx, const void* const* img_ptr
     if (row_step_bytes < row) return RSLF_ERR_ARG;
     const size_t img_bytes = row * V;
     RSLF_TRY(own_raw(ctx, img_bytes * S));
-    void* staging = nullptr;
-    RSLF_CUDA_TRY(ctx, cudaMalloc(&staging, img_bytes * S));
-    cudaEventRecord(ctx->ev_a, ctx->stream);
-    for (int s = 0; s < S; ++s) {
-        cudaError_t e = cudaMemcpy2DAsync((char*)staging + (size_t)s * img_bytes, row, img_ptrs[s], row_step_bytes, row, V,
-                                          cudaMemcpyHostToDevice, ctx->stream);
-        if (e != cudaSuccess) { cudaFree(staging); RSLF_CUDA_TRY(ctx, e); }
+    /* staging area for the image stack, kept for the next upload (no allocation per call) */
+    if (ctx->img_staging_cap < img_bytes * S) {
+        if (ctx->img_staging) cudaFree(ctx->img_staging);
+        ctx->img_staging = nullptr; ctx->img_staging_cap = 0;
+        cudaError_t e = cudaMalloc(&ctx->img_staging, img_bytes * S);
+        if (e != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "cudaMalloc(image staging %zu): %s", img_bytes * S, cudaGetErrorString(e)); return RSLF_ERR_NOMEM; }
+        ctx->img_staging_cap = img_bytes * S;
     }
-    dim3 grid(std::max(1, std::min(8, rslf_div_up((long long)U * C, 256))), S, V);
-    if (esz == 1) build_epis_kernel<uint8_t><<<grid, 256, 0, ctx->stream>>>((const uint8_t*)staging, S, V, (size_t)U * C, (uint8_t*)ctx->raw_in);
-    else if (esz == 2) build_epis_kernel<uint16_t><<<grid, 256, 0, ctx->stream>>>((const uint16_t*)staging, S, V, (size_t)U * C, (uint16_t*)ctx->raw_in);
-    else build_epis_kernel<float><<<grid, 256, 0, ctx->stream>>>((const float*)staging, S, V, (size_t)U * C, (float*)ctx->raw_in);
+    cudaEventRecord(ctx->ev_a, ctx->stream);
+    /* image by image: the transfer of image s + 1 (copy engine) overlaps the transposition of image s (SMs, second
+     * stream), which reads each staged image once and writes its V scanlines into the EPIs (rslf_io.cpp:203-219) */
+    if (!ctx->stream2) RSLF_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+    if (!ctx->ev_img) RSLF_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_img, cudaEventDisableTiming));
+    for (int s = 0; s < S; ++s) {
+        const void* one = img_ptrs[s];
+        RSLF_TRY(images_to_device(ctx, (char*)ctx->img_staging + (size_t)s * img_bytes, 1, V, row, &one, row_step_bytes));
+        RSLF_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_img, ctx->stream));
+        RSLF_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_img, 0));
+        dim3 grid(std::max(1, std::min(8, rslf_div_up((long long)U * C, 256))), 1, V);
+        if (esz == 1) build_epis_kernel<uint8_t><<<grid, 256, 0, ctx->stream2>>>((const uint8_t*)ctx->img_staging, S, V, (size_t)U * C, (uint8_t*)ctx->raw_in, s);
+        else if (esz == 2) build_epis_kernel<uint16_t><<<grid, 256, 0, ctx->stream2>>>((const uint16_t*)ctx->img_staging, S, V, (size_t)U * C, (uint16_t*)ctx->raw_in, s);
+        else build_epis_kernel<float><<<grid, 256, 0, ctx->stream2>>>((const float*)ctx->img_staging, S, V, (size_t)U * C, (float*)ctx->raw_in, s);
+    }
+    RSLF_CUDA_TRY(ctx, cudaGetLastError());
+    RSLF_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_img, ctx->stream2));
+    RSLF_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_img, 0));
     cudaEventRecord(ctx->ev_b, ctx->stream);
-    cudaError_t e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(staging);
-    RSLF_CUDA_TRY(ctx, e);
+    RSLF_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     cudaEventElapsedTime(&ctx->timing.ms_h2d, ctx->ev_a, ctx->ev_b);
     ctx->have_input = true;
     return RSLF_OK;
@@ -879,6 +893,113 @@ static int copy_out(rslf_ctx* ctx, void* host, const void* dev, size_t bytes)
     return RSLF_OK;
 }
 
+/* ---- host images (cv::Mat storage) <-> dense device arrays ------------------------------------------------
+ * A result map is [planes][rows][row_bytes] on the device; the caller's images are `planes` separate host
+ * buffers with `step` bytes between rows (cv::Mat::data / step).  Pinned (page-locked) or registered host
+ * memory is reached by one strided cudaMemcpy2DAsync per plane at full PCIe rate.  Pageable memory (an ordinary
+ * cv::Mat) cannot be the target of an asynchronous DMA: the rows go through a ring of two pinned buffers, the
+ * copy engine filling one while the host thread empties the other into the image rows — one CPU pass over the
+ * data, overlapped with the transfer (the driver's own pageable path would add a second one in the caller). */
+static const size_t RSLF_RING_BYTES = (size_t)32 << 20;
+
+static bool host_is_pinned(const void* p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+static int ensure_ring(rslf_ctx* ctx)
+{
+    for (int i = 0; i < 2; ++i) {
+        if (!ctx->ring[i] && cudaHostAlloc(&ctx->ring[i], RSLF_RING_BYTES, cudaHostAllocDefault) != cudaSuccess) {
+            snprintf(ctx->err, sizeof(ctx->err), "cudaHostAlloc(%zu) for the transfer ring failed", RSLF_RING_BYTES);
+            return RSLF_ERR_NOMEM;
+        }
+        if (!ctx->ring_ev[i]) RSLF_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ring_ev[i], cudaEventDisableTiming));
+    }
+    return RSLF_OK;
+}
+
+/* device [planes][rows][row_bytes] -> host planes (nullptr planes are skipped) */
+static int planes_to_host(rslf_ctx* ctx, const void* dev, int planes, int rows, size_t row_bytes, void* const* host, size_t step)
+{
+    if (!host) return RSLF_OK;
+    if (step < row_bytes) { snprintf(ctx->err, sizeof(ctx->err), "row step smaller than a row"); return RSLF_ERR_ARG; }
+    bool pinned = true;
+    for (int p = 0; p < planes && pinned; ++p) if (host[p]) pinned = host_is_pinned(host[p]);
+    if (pinned) {
+        for (int p = 0; p < planes; ++p)
+            if (host[p]) RSLF_CUDA_TRY(ctx, cudaMemcpy2DAsync(host[p], step, (const char*)dev + (size_t)p * rows * row_bytes, row_bytes,
+                                                             row_bytes, rows, cudaMemcpyDeviceToHost, ctx->stream));
+        return RSLF_OK;
+    }
+    RSLF_TRY(ensure_ring(ctx));
+    const int chunk_rows = (int)std::max<size_t>(1, RSLF_RING_BYTES / row_bytes);
+    struct job { int p, r0, n; };
+    std::vector<job> jobs;
+    for (int p = 0; p < planes; ++p)
+        if (host[p]) for (int r = 0; r < rows; r += chunk_rows) jobs.push_back({p, r, std::min(chunk_rows, rows - r)});
+    auto drain = [&](const job& j, int slot) -> int {
+        RSLF_CUDA_TRY(ctx, cudaEventSynchronize(ctx->ring_ev[slot]));
+        const char* src = (const char*)ctx->ring[slot];
+        char* dst = (char*)host[j.p] + (size_t)j.r0 * step;
+        if (step == row_bytes) memcpy(dst, src, (size_t)j.n * row_bytes);
+        else for (int r = 0; r < j.n; ++r) memcpy(dst + (size_t)r * step, src + (size_t)r * row_bytes, row_bytes);
+        return RSLF_OK;
+    };
+    for (size_t i = 0; i < jobs.size(); ++i) {
+        const int slot = (int)(i & 1);
+        if (i >= 2) RSLF_TRY(drain(jobs[i - 2], slot));                    /* the slot is free again after this */
+        const job& j = jobs[i];
+        RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->ring[slot], (const char*)dev + ((size_t)j.p * rows + j.r0) * row_bytes,
+                                           (size_t)j.n * row_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        RSLF_CUDA_TRY(ctx, cudaEventRecord(ctx->ring_ev[slot], ctx->stream));
+    }
+    for (size_t i = jobs.size() >= 2 ? jobs.size() - 2 : 0; i < jobs.size(); ++i) RSLF_TRY(drain(jobs[i], (int)(i & 1)));
+    return RSLF_OK;
+}
+
+/* host images -> device [n_imgs][rows][row_bytes] */
+static int images_to_device(rslf_ctx* ctx, void* dev, int n_imgs, int rows, size_t row_bytes, const void* const* host, size_t step)
+{
+    bool pinned = true;
+    for (int p = 0; p < n_imgs && pinned; ++p) pinned = host_is_pinned(host[p]);
+    if (pinned) {
+        /* one dense copy when the images are continuous and back to back, else one strided copy per image */
+        bool dense = (step == row_bytes);
+        for (int p = 1; dense && p < n_imgs; ++p) dense = ((const char*)host[p] == (const char*)host[0] + (size_t)p * rows * row_bytes);
+        if (dense) RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(dev, host[0], (size_t)n_imgs * rows * row_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        else for (int p = 0; p < n_imgs; ++p)
+            RSLF_CUDA_TRY(ctx, cudaMemcpy2DAsync((char*)dev + (size_t)p * rows * row_bytes, row_bytes, host[p], step, row_bytes, rows,
+                                                 cudaMemcpyHostToDevice, ctx->stream));
+        return RSLF_OK;
+    }
+    RSLF_TRY(ensure_ring(ctx));
+    const int chunk_rows = (int)std::max<size_t>(1, RSLF_RING_BYTES / row_bytes);
+    size_t i = 0;
+    for (int p = 0; p < n_imgs; ++p)
+        for (int r0 = 0; r0 < rows; r0 += chunk_rows, ++i) {
+            const int slot = (int)(i & 1), n = std::min(chunk_rows, rows - r0);
+            RSLF_CUDA_TRY(ctx, cudaEventSynchronize(ctx->ring_ev[slot]));     /* its previous transfer (this call's or an earlier one's) has left the buffer */
+            char* dst = (char*)ctx->ring[slot];
+            const char* src = (const char*)host[p] + (size_t)r0 * step;
+            if (step == row_bytes) memcpy(dst, src, (size_t)n * row_bytes);
+            else for (int r = 0; r < n; ++r) memcpy(dst + (size_t)r * row_bytes, src + (size_t)r * step, row_bytes);
+            RSLF_CUDA_TRY(ctx, cudaMemcpyAsync((char*)dev + ((size_t)p * rows + r0) * row_bytes, dst, (size_t)n * row_bytes,
+                                               cudaMemcpyHostToDevice, ctx->stream));
+            RSLF_CUDA_TRY(ctx, cudaEventRecord(ctx->ring_ev[slot], ctx->stream));
+        }
+    return RSLF_OK;
+}
+
+extern "C" void* rslf_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+extern "C" void rslf_host_free(void* p) { if (p) cudaFreeHost(p); }
+
 static int prepare_shards(rslf_ctx* ctx, int levels);
 
 /* ------------------------------------------------------------------ Depth1DComputer_pile */
@@ -1011,6 +1132,34 @@ extern "C" int rslf_cuda_depth2d_get(rslf_ctx* ctx, float* best_depth_svu, float
     if (ctx->last_kind != 2) { snprintf(ctx->err, sizeof(ctx->err), "no depth2d result"); return RSLF_ERR_STATE; }
     RSLF_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     return get_level_maps(ctx, 0, best_depth_svu, edge_conf_svu, edge_mask_svu, disp_conf_svu, rbar_svuc, nullptr, nullptr);
+}
+
+/* Results of the last depth2d / fine-to-coarse-level run straight into S host images per map (cv::Mat::data, step) */
+static int level_maps_to_mats(rslf_ctx* ctx, int p, float* const* best_depth, float* const* edge_conf, uint8_t* const* edge_mask,
+                              float* const* disp_conf, float* const* rbar, size_t step_f32, size_t step_u8, size_t step_rbar)
+{
+    rslf_level& L = ctx->lv[p];
+    const int S = ctx->S, V = L.V, U = L.U, C = ctx->C;
+    cudaEventRecord(ctx->ev_a, ctx->stream);
+    RSLF_TRY(planes_to_host(ctx, L.depth, S, V, (size_t)U * 4, (void* const*)best_depth, step_f32));
+    RSLF_TRY(planes_to_host(ctx, L.ce, S, V, (size_t)U * 4, (void* const*)edge_conf, step_f32));
+    RSLF_TRY(planes_to_host(ctx, L.emask, S, V, (size_t)U, (void* const*)edge_mask, step_u8));
+    RSLF_TRY(planes_to_host(ctx, L.cd, S, V, (size_t)U * 4, (void* const*)disp_conf, step_f32));
+    RSLF_TRY(planes_to_host(ctx, L.rbar, S, V, (size_t)U * 4 * C, (void* const*)rbar, step_rbar));
+    cudaEventRecord(ctx->ev_b, ctx->stream);
+    RSLF_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ctx->timing.ms_d2h, ctx->ev_a, ctx->ev_b);
+    return RSLF_OK;
+}
+
+extern "C" int rslf_cuda_depth2d_get_mats(rslf_ctx* ctx, float* const* best_depth_s, float* const* edge_conf_s,
+                                          uint8_t* const* edge_mask_s, float* const* disp_conf_s, float* const* rbar_s,
+                                          size_t step_f32, size_t step_u8, size_t step_rbar)
+{
+    if (!ctx) return RSLF_ERR_ARG;
+    if (ctx->last_kind != 2) { snprintf(ctx->err, sizeof(ctx->err), "no depth2d result"); return RSLF_ERR_STATE; }
+    RSLF_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    return level_maps_to_mats(ctx, 0, best_depth_s, edge_conf_s, edge_mask_s, disp_conf_s, rbar_s, step_f32, step_u8, step_rbar);
 }
 
 extern "C" int rslf_cuda_depth2d(rslf_ctx* ctx, float dmin, float dmax, int dim_d, const rslf_params* params,
@@ -1299,6 +1448,33 @@ extern "C" int rslf_cuda_fine_to_coarse_get(rslf_ctx* ctx, float* out_map_svu, u
     cudaEventRecord(ctx->ev_b, ctx->stream);
     RSLF_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     cudaEventElapsedTime(&ctx->timing.ms_d2h, ctx->ev_a, ctx->ev_b);
+    return RSLF_OK;
+}
+
+extern "C" int rslf_cuda_fine_to_coarse_get_mats(rslf_ctx* ctx, float* const* out_map_s, size_t map_step,
+                                                 uint8_t* const* out_valid_s, size_t valid_step)
+{
+    if (!ctx) return RSLF_ERR_ARG;
+    if (ctx->last_kind != 3) { snprintf(ctx->err, sizeof(ctx->err), "no fine-to-coarse result"); return RSLF_ERR_STATE; }
+    RSLF_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaEventRecord(ctx->ev_a, ctx->stream);
+    RSLF_TRY(planes_to_host(ctx, ctx->out_map, ctx->S, ctx->V, (size_t)ctx->U * 4, (void* const*)out_map_s, map_step));
+    RSLF_TRY(planes_to_host(ctx, ctx->out_valid, ctx->S, ctx->V, (size_t)ctx->U, (void* const*)out_valid_s, valid_step));
+    cudaEventRecord(ctx->ev_b, ctx->stream);
+    RSLF_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ctx->timing.ms_d2h, ctx->ev_a, ctx->ev_b);
+    return RSLF_OK;
+}
+
+/* The normalised EPIs the run worked on (Depth2DComputer::get_epis, dc.hpp:207; level 0 of a pyramid): V host
+ * images of S rows x U x C float32 */
+extern "C" int rslf_cuda_get_epis(rslf_ctx* ctx, float* const* epi_v, size_t step)
+{
+    if (!ctx || !epi_v) return RSLF_ERR_ARG;
+    if (ctx->last_kind == 0 || !ctx->lv[0].epi) { snprintf(ctx->err, sizeof(ctx->err), "no run yet"); return RSLF_ERR_STATE; }
+    RSLF_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    RSLF_TRY(planes_to_host(ctx, ctx->lv[0].epi, ctx->lv[0].V, ctx->S, (size_t)ctx->lv[0].U * ctx->C * 4, (void* const*)epi_v, step));
+    RSLF_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     return RSLF_OK;
 }
 

@@ -69,6 +69,9 @@ struct rslf_ctx {
     bool raw_borrowed = false;
     size_t raw_cap = 0;
     bool have_input = false;
+    void* img_staging = nullptr; size_t img_staging_cap = 0;   /* rslf_cuda_upload_images: the image stack before the transposition */
+    void* ring[2] = {nullptr, nullptr}; cudaEvent_t ring_ev[2] = {nullptr, nullptr};   /* pinned ring for pageable host images */
+    cudaStream_t stream2 = nullptr; cudaEvent_t ev_img = nullptr;
     void* raw_full = nullptr;    /* multi-rank runs: all rows of the raw stack, gathered once per input */
     size_t raw_full_cap = 0;
     unsigned input_epoch = 1, raw_full_epoch = 0;

@@ -52,6 +52,40 @@ static int run_all(const Vec<Mat>& epis, int D, float dmin, float dmax, const st
         ftc.get_coloured_depth_maps(plots, 2, true, lut);
         dump(out + "_ftc_bgr.bin", plots);
     }
+    /* the free functions with their Mat signatures (core.hpp:236-375, rslf_fine_to_coarse_core.hpp:28-49) */
+    {
+        Depth1DParameters<DataType> prm;
+        const Vec<Mat>& nepis = d2.get_epis();                       /* the normalised EPIs (dc.hpp:207) */
+        dump(out + "_epis.bin", nepis);
+        Mat ce, mask, med;
+        compute_1D_edge_confidence_pile<DataType>(nepis, 1, ce, mask, prm);
+        dump(out + "_fn_ce.bin", Vec<Mat>{ce});
+        dump(out + "_fn_mask.bin", Vec<Mat>{mask});
+        selective_median_filter<DataType>(d2.m_best_depth_s_v_u[2], med, nepis, 2, 5, d2.m_edge_confidence_mask_s_v_u[2], 0.1f);
+        dump(out + "_fn_median.bin", Vec<Mat>{med});
+        Vec<Mat> half;
+        downsample_EPIs(nepis, half);
+        dump(out + "_fn_down.bin", half);
+        /* a two-level pyramid by hand: level 1 = the 2D computer on the downsampled EPIs */
+        Depth2DComputer<DataType> d2b(half, dmin, dmax, D, 1.0f);
+        d2b.run();
+        d2b.set_accept_all(true);
+        Vec<Vec<Mat>> disp{d2.get_depths_s_v_u(), d2b.get_depths_s_v_u()};
+        Vec<Vec<Mat>> val{d2.get_valid_depths_mask_s_v_u(), d2b.get_valid_depths_mask_s_v_u()};
+        Vec<Mat> fmap, fval;
+        fuse_disp_maps(disp, val, fmap, fval);
+        dump(out + "_fn_fuse_map.bin", fmap);
+        dump(out + "_fn_fuse_valid.bin", fval);
+        dump(out + "_fn_l1_depth.bin", d2b.get_depths_s_v_u());
+        /* compute_2D_depth_epi with constant per-pixel bounds = the 2D computer */
+        Vec<Mat> lo(d2.get_depths_s_v_u().size()), hi(lo.size()), e1, e2, e3, e4, e5, e6;
+        for (size_t i = 0; i < lo.size(); ++i) {
+            lo[i] = Mat(nepis.size(), nepis[0].cols, CV_32FC1); hi[i] = Mat(nepis.size(), nepis[0].cols, CV_32FC1);
+            for (int r = 0; r < lo[i].rows; ++r) for (int c = 0; c < lo[i].cols; ++c) { lo[i].template at<float>(r, c) = dmin; hi[i].template at<float>(r, c) = dmax; }
+        }
+        compute_2D_depth_epi<DataType>(nepis, lo, hi, D, e1, e2, e3, e4, e5, e6, prm);
+        dump(out + "_fn_2d_depth.bin", e5);
+    }
     rslf_timing t = ftc.get_timing();
     printf("fine-to-coarse: %d levels, %d passes, %.0f pixels, %.3f ms on device\n", t.levels, t.passes, t.computed_pixels, t.ms_total);
 

@@ -58,3 +58,20 @@ def test_facade_matches_oracle(tmp_path, C):
     np.testing.assert_array_equal(np.fromfile(out + "_ftc_valid.bin", np.uint8).reshape(S, V, U), ftc["valid"])
     bgr, _ = oracle.colour_maps(ftc["map"], ftc["valid"], norm, lut)
     np.testing.assert_array_equal(np.fromfile(out + "_ftc_bgr.bin", np.uint8).reshape(S, V, U, 3), bgr)
+    # the free functions and get_epis
+    np.testing.assert_array_equal(np.fromfile(out + "_epis.bin", np.float32).reshape(V, S, U, C), norm)
+    ce, mask = oracle.edge_confidence(norm, 1)
+    np.testing.assert_array_equal(np.fromfile(out + "_fn_ce.bin", np.float32).reshape(V, U), ce)
+    np.testing.assert_array_equal(np.fromfile(out + "_fn_mask.bin", np.uint8).reshape(V, U), mask)
+    med = oracle.selective_median(d2["best_depth"][2], d2["edge_mask"][2], norm, 2, size=5, eps=0.1)
+    np.testing.assert_array_equal(np.fromfile(out + "_fn_median.bin", np.float32).reshape(V, U), med)
+    half = oracle.downsample(norm)
+    np.testing.assert_array_equal(np.fromfile(out + "_fn_down.bin", np.float32).reshape(half.shape), half)
+    d2b = oracle.depth2d(half, -1.0, 2.0, D)
+    np.testing.assert_array_equal(np.fromfile(out + "_fn_l1_depth.bin", np.float32).reshape(d2b["best_depth"].shape), d2b["best_depth"])
+    v0 = (d2["edge_conf"] > np.float32(0.02)).astype(np.uint8) * 255
+    v1 = np.full(d2b["edge_mask"].shape, 255, np.uint8)
+    fm, fv = oracle.fuse([d2["best_depth"], d2b["best_depth"]], [v0, v1])
+    np.testing.assert_array_equal(np.fromfile(out + "_fn_fuse_map.bin", np.float32).reshape(S, V, U), fm)
+    np.testing.assert_array_equal(np.fromfile(out + "_fn_fuse_valid.bin", np.uint8).reshape(S, V, U), fv)
+    np.testing.assert_array_equal(np.fromfile(out + "_fn_2d_depth.bin", np.float32).reshape(S, V, U), d2["best_depth"])
