@@ -136,6 +136,16 @@ int  rslf_cuda_set_confidence_criterion(rslf_ctx* ctx, int criterion);
 int rslf_cuda_upload_epis(rslf_ctx* ctx, const void* const* epi_ptrs,
                           int V, int S, int U, int C, int cv_depth,
                           size_t row_step_bytes, float epi_scale_factor);
+/* Ingest fused with the input handling and overlapped with the first stage: the EPIs are uploaded in
+ * chunks; while the next chunk crosses PCIe, the chunk that has arrived is normalised to float32
+ * (rslf_depth_computation.hpp:463-477) and, if `params` is given, its edge confidence and mask are computed for all
+ * views (rslf_depth_computation_core.hpp:901-931) on a second stream.  The next Depth2DComputer / FineToCoarse run on
+ * this input with the same edge parameters starts from those maps.  Falls back to rslf_cuda_upload_epis when the scale
+ * is only known after the upload (non-8-bit input with epi_scale_factor < 0), for row-sharded contexts and when the
+ * morphological opening is on. */
+int rslf_cuda_upload_epis_pipelined(rslf_ctx* ctx, const void* const* epi_ptrs,
+                                    int V, int S, int U, int C, int cv_depth,
+                                    size_t row_step_bytes, float epi_scale_factor, const rslf_params* params);
 /* Same, but the raw stack already lives on this ctx's device as one dense
  * [V][S][U][C] array (used to time the path with HBM-resident inputs). */
 int rslf_cuda_set_epis_device(rslf_ctx* ctx, const void* d_epis,

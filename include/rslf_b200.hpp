@@ -220,7 +220,7 @@ public:
         throw Error(a_rc, msg);
     }
     /* the reference ctors' input handling (dc.hpp:425-477, 651-704): V Mats of S x U x C */
-    void upload(const Vec<Mat>& a_epis, float a_scale, int a_channels, int& V, int& S, int& U)
+    void upload(const Vec<Mat>& a_epis, float a_scale, int a_channels, int& V, int& S, int& U, const rslf_params* a_params = nullptr)
     {
         if (a_epis.empty() || a_epis[0].empty()) throw Error(RSLF_ERR_ARG, "empty EPI vector");
         V = (int)a_epis.size(); S = a_epis[0].rows; U = a_epis[0].cols;
@@ -232,8 +232,11 @@ public:
                 throw Error(RSLF_ERR_ARG, "EPIs must share size, type and step, and match the class's channel count");
             ptrs[v] = m.data;
         }
-        check(rslf_cuda_upload_epis(m_ctx, ptrs.data(), V, S, U, a_channels, depth, (size_t)a_epis[0].step, a_scale),
-              "rslf_cuda_upload_epis");
+        /* with the computer's parameters: pipelined ingest (normalisation and level-0 edge confidence overlap the upload) */
+        if (a_params) check(rslf_cuda_upload_epis_pipelined(m_ctx, ptrs.data(), V, S, U, a_channels, depth, (size_t)a_epis[0].step, a_scale, a_params),
+                            "rslf_cuda_upload_epis_pipelined");
+        else check(rslf_cuda_upload_epis(m_ctx, ptrs.data(), V, S, U, a_channels, depth, (size_t)a_epis[0].step, a_scale),
+                   "rslf_cuda_upload_epis");
     }
     /* Row-sharded run, one process per GPU: this object was built from rows [row_starts[rank], row_starts[rank + 1])
      * of the light field; nccl_id = the 128 bytes of rslf_b200::nccl_unique_id() made by rank 0 and sent to all ranks. */
@@ -419,7 +422,8 @@ public:
         : m_parameters(parameters), m_device(detail::DevicePool::acquire(device)), m_dim_d(dim_d), m_dmin(dmin), m_dmax(dmax),
           m_verbose(verbose)
     {
-        m_device->upload(epis, epi_scale_factor, channels_of<DataType>::value, m_dim_v, m_dim_s, m_dim_u);
+        const rslf_params p = m_parameters.to_abi();
+        m_device->upload(epis, epi_scale_factor, channels_of<DataType>::value, m_dim_v, m_dim_s, m_dim_u, &p);
     }
     void run()
     {
@@ -520,7 +524,8 @@ public:
         : m_parameters(a_parameters), m_device(detail::DevicePool::acquire(a_device)), m_dim_d(a_dim_d), m_dmin(a_d_min),
           m_dmax(a_d_max), m_max_pyr_depth(a_max_pyr_depth), m_accept_all_last_scale(a_accept_all_last_scale)
     {
-        m_device->upload(a_epis, a_epi_scale_factor, channels_of<DataType>::value, m_dim_v, m_dim_s, m_dim_u);
+        const rslf_params p = m_parameters.to_abi();
+        m_device->upload(a_epis, a_epi_scale_factor, channels_of<DataType>::value, m_dim_v, m_dim_s, m_dim_u, &p);
     }
     void run()
     {

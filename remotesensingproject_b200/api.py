@@ -124,17 +124,23 @@ class Context:
                                                    lib().rslf_cuda_last_error_text(self._h).decode()))
 
     # ---- input ----------------------------------------------------------------
-    def upload_epis(self, epis, epi_scale_factor=-1.0):
+    def upload_epis(self, epis, epi_scale_factor=-1.0, params=None):
         """epis: the reference's Vec<Mat> — a [V][S][U][C] (or [V][S][U]) array or a list of V
-        [S][U][C] arrays; uint8, uint16 or float32 host memory (numpy, or a pinned CPU torch tensor)."""
+        [S][U][C] arrays; uint8, uint16 or float32 host memory (numpy, or a pinned CPU torch tensor).
+        params given: pipelined ingest (rslf_cuda_upload_epis_pipelined) — the stack is normalised and its level-0 edge
+        confidence computed chunk by chunk while the rest is still being uploaded."""
         mats = _as_mats(epis)
         V = len(mats)
         S, U, Cc = mats[0].shape
         depth = _DEPTH_OF[mats[0].dtype]
         ptrs = (C.c_void_p * V)(*[m.ctypes.data for m in mats])
         step = mats[0].strides[0]
-        self.check(lib().rslf_cuda_upload_epis(self._h, ptrs, V, S, U, Cc, depth, C.c_size_t(step),
-                                               C.c_float(epi_scale_factor)), "rslf_cuda_upload_epis")
+        if params is not None:
+            self.check(lib().rslf_cuda_upload_epis_pipelined(self._h, ptrs, V, S, U, Cc, depth, C.c_size_t(step),
+                                                             C.c_float(epi_scale_factor), C.byref(params)), "rslf_cuda_upload_epis_pipelined")
+        else:
+            self.check(lib().rslf_cuda_upload_epis(self._h, ptrs, V, S, U, Cc, depth, C.c_size_t(step),
+                                                   C.c_float(epi_scale_factor)), "rslf_cuda_upload_epis")
         self.dims = (V, S, U, Cc)
         self._keep = None
 
@@ -505,7 +511,7 @@ class Depth2DComputer:
         if hasattr(epis, "is_cuda") and epis.is_cuda:
             self.m_ctx.set_epis_device(epis, epi_scale_factor)
         else:
-            self.m_ctx.upload_epis(epis, epi_scale_factor)
+            self.m_ctx.upload_epis(epis, epi_scale_factor, params=self.m_parameters)      # pipelined ingest
         self.m_dim_d = dim_d
         self.m_dmin, self.m_dmax = dmin, dmax
         self.m_dmin_s_v_u = None
@@ -556,7 +562,7 @@ class FineToCoarse:
         if hasattr(epis, "is_cuda") and epis.is_cuda:
             self.m_ctx.set_epis_device(epis, epi_scale_factor)
         else:
-            self.m_ctx.upload_epis(epis, epi_scale_factor)
+            self.m_ctx.upload_epis(epis, epi_scale_factor, params=self.m_parameters)      # pipelined ingest
         self.m_dim_d = dim_d
         self.m_dmin, self.m_dmax = d_min, d_max
         self.m_max_pyr_depth = max_pyr_depth

@@ -29,12 +29,13 @@ __global__ void __launch_bounds__(EDGE_THREADS)
 edge_confidence_kernel(const float* __restrict__ epi, int V, int S, int U, int s_first, int s_count,
                        int fs, int cut_shadows, float shadow_level, double shadow_T, float thr,
                        float* __restrict__ ce_out, uint8_t* __restrict__ mask_out,
-                       float dark_eps, double dark_T, int* __restrict__ rowdark)
+                       float dark_eps, double dark_T, int* __restrict__ rowdark, int v_first)
 {
+    /* the grid covers rows v_first .. of the V-row planes (a chunk of EPIs during the pipelined ingest, else all) */
     extern __shared__ float seg[];                 /* (EDGE_TILE + fs - 1) * C floats */
     const int centre = (fs - 1) / 2;
-    const int row = blockIdx.x;                    /* row = v * s_count + si */
-    const int v = row / s_count, si = row % s_count;
+    const int row = blockIdx.x;                    /* row = (v - v_first) * s_count + si */
+    const int v = v_first + row / s_count, si = row % s_count;
     const int s = s_first + si;
     const int u0 = blockIdx.y * EDGE_TILE;
     const float* src = epi + ((size_t)v * S + s) * (size_t)U * C;
@@ -184,8 +185,46 @@ rowdark_count_kernel(const float* __restrict__ epi, const uint8_t* __restrict__ 
  * when the opening is enabled (edge_confidence_opening_size > 1). */
 static int launch_edge_confidence(rslf_ctx* ctx, const float* epi, int V, int S, int U, int C, int s_first,
                                   int s_count, const rslf_params& P, float* ce_out, uint8_t* mask_out,
-                                  int* rowdark = nullptr, uint8_t* mask_tmp = nullptr)
+                                  int* rowdark = nullptr, uint8_t* mask_tmp = nullptr, int rows_above = 0, int rows_below = 0)
 {
+    /* Row-sharded level with the opening switched on: the element reaches k/2 rows beyond the block in the erosion and
+     * again in the dilation.  Every rank holds the whole EPI stack, so it computes C_e and the mask on its rows PLUS
+     * 2 (k/2) rows either side (as far as the image goes: rows_above / rows_below say how many exist), opens that
+     * extended mask — whose outer 2 (k/2) rows are then wrong, and whose inner rows are exact — and keeps its rows.
+     * No exchange. */
+    if (P.edge_confidence_opening_size > 1 && (rows_above > 0 || rows_below > 0)) {
+        const int h = 2 * (P.edge_confidence_opening_size / 2);
+        const int ha = std::min(h, rows_above), hb = std::min(h, rows_below), Vx = V + ha + hb;
+        const size_t pxx = (size_t)s_count * Vx * U;
+        if (ctx->open_cap < pxx) {
+            if (ctx->open_ce) cudaFree(ctx->open_ce);
+            if (ctx->open_mask) cudaFree(ctx->open_mask);
+            if (ctx->open_tmp) cudaFree(ctx->open_tmp);
+            ctx->open_ce = nullptr; ctx->open_mask = ctx->open_tmp = nullptr; ctx->open_cap = 0;
+            if (cudaMalloc((void**)&ctx->open_ce, pxx * 4) != cudaSuccess || cudaMalloc((void**)&ctx->open_mask, pxx) != cudaSuccess ||
+                cudaMalloc((void**)&ctx->open_tmp, pxx) != cudaSuccess) {
+                snprintf(ctx->err, sizeof(ctx->err), "cudaMalloc(extended edge planes, %zu pixels)", pxx);
+                return RSLF_ERR_NOMEM;
+            }
+            ctx->open_cap = pxx;
+        }
+        const float* epi_x = epi - (size_t)ha * S * U * C;
+        RSLF_TRY(launch_edge_confidence(ctx, epi_x, Vx, S, U, C, s_first, s_count, P, ctx->open_ce, ctx->open_mask, nullptr, ctx->open_tmp, 0, 0));
+        /* keep rows [ha, ha + V) of every plane */
+        RSLF_CUDA_TRY(ctx, cudaMemcpy2DAsync(ce_out, (size_t)V * U * 4, ctx->open_ce + (size_t)ha * U, (size_t)Vx * U * 4, (size_t)V * U * 4, s_count,
+                                             cudaMemcpyDeviceToDevice, ctx->stream));
+        RSLF_CUDA_TRY(ctx, cudaMemcpy2DAsync(mask_out, (size_t)V * U, ctx->open_mask + (size_t)ha * U, (size_t)Vx * U, (size_t)V * U, s_count,
+                                             cudaMemcpyDeviceToDevice, ctx->stream));
+        if (rowdark) {
+            const double dT = rslf_sq_threshold(P.propagation_epsilon);
+            const unsigned rows = (unsigned)((size_t)V * s_count);
+            if (C == 1) rowdark_count_kernel<1><<<rows, EDGE_THREADS, 0, ctx->stream>>>(epi, mask_out, V, S, U, s_first, s_count, P.propagation_epsilon, dT, rowdark);
+            else rowdark_count_kernel<3><<<rows, EDGE_THREADS, 0, ctx->stream>>>(epi, mask_out, V, S, U, s_first, s_count, P.propagation_epsilon, dT, rowdark);
+            RSLF_CUDA_TRY(ctx, cudaGetLastError());
+            ctx->timing.kernel_launches += 1;
+        }
+        return RSLF_OK;
+    }
     int fs = P.edge_confidence_filter_size;
     if (fs < 1 || fs > EDGE_MAX_FS) {
         snprintf(ctx->err, sizeof(ctx->err), "edge_confidence_filter_size %d outside [1,%d]", fs, EDGE_MAX_FS);
@@ -194,11 +233,6 @@ static int launch_edge_confidence(rslf_ctx* ctx, const float* epi, int V, int S,
     const bool opening = P.edge_confidence_opening_size > 1;
     morph_elem elem;
     if (opening) {
-        if (ctx->world > 1) {
-            /* the element reaches k/2 rows beyond a rank's block in every view: not exchanged */
-            snprintf(ctx->err, sizeof(ctx->err), "morphological opening of the edge mask is not implemented for row-sharded runs");
-            return RSLF_ERR_UNSUPPORTED;
-        }
         if (!morph_build(elem, P.edge_confidence_opening_type, P.edge_confidence_opening_size)) {
             snprintf(ctx->err, sizeof(ctx->err), "edge_confidence_opening: type %d (0..2), size %d (<= %d)",
                      P.edge_confidence_opening_type, P.edge_confidence_opening_size, MORPH_MAX_K);
@@ -216,11 +250,11 @@ static int launch_edge_confidence(rslf_ctx* ctx, const float* epi, int V, int S,
     if (C == 1)
         edge_confidence_kernel<1><<<grid, EDGE_THREADS, smem, ctx->stream>>>(
             epi, V, S, U, s_first, s_count, fs, P.cut_shadows, P.shadow_level, T, P.edge_score_threshold, ce_out, mask_out,
-            P.propagation_epsilon, dT, rowdark);
+            P.propagation_epsilon, dT, rowdark, 0);
     else
         edge_confidence_kernel<3><<<grid, EDGE_THREADS, smem, ctx->stream>>>(
             epi, V, S, U, s_first, s_count, fs, P.cut_shadows, P.shadow_level, T, P.edge_score_threshold, ce_out, mask_out,
-            P.propagation_epsilon, dT, rowdark);
+            P.propagation_epsilon, dT, rowdark, 0);
     RSLF_CUDA_TRY(ctx, cudaGetLastError());
     ctx->timing.kernel_launches += 1;
     if (opening) {
@@ -236,5 +270,26 @@ static int launch_edge_confidence(rslf_ctx* ctx, const float* epi, int V, int S,
         }
         RSLF_CUDA_TRY(ctx, cudaGetLastError());
     }
+    return RSLF_OK;
+}
+
+/* Edge confidence of all S lines of the EPIs [v_first, v_first + v_count) on `stream` (pipelined ingest: a chunk of
+ * EPIs that has just been uploaded and normalised); planes are [S][V][U].  No opening (that needs the whole mask). */
+static int launch_edge_confidence_rows(rslf_ctx* ctx, cudaStream_t stream, const float* epi, int V, int S, int U, int C, int v_first,
+                                       int v_count, const rslf_params& P, float* ce_out, uint8_t* mask_out, int* rowdark)
+{
+    const int fs = P.edge_confidence_filter_size;
+    if (fs < 1 || fs > EDGE_MAX_FS) return RSLF_ERR_UNSUPPORTED;
+    dim3 grid((unsigned)((size_t)v_count * S), rslf_div_up(U, EDGE_TILE));
+    const size_t smem = (size_t)(EDGE_TILE + fs - 1) * C * sizeof(float);
+    const double T = rslf_sq_threshold(P.shadow_level), dT = rslf_sq_threshold(P.propagation_epsilon);
+    if (C == 1)
+        edge_confidence_kernel<1><<<grid, EDGE_THREADS, smem, stream>>>(epi, V, S, U, 0, S, fs, P.cut_shadows, P.shadow_level, T, P.edge_score_threshold,
+                                                                        ce_out, mask_out, P.propagation_epsilon, dT, rowdark, v_first);
+    else
+        edge_confidence_kernel<3><<<grid, EDGE_THREADS, smem, stream>>>(epi, V, S, U, 0, S, fs, P.cut_shadows, P.shadow_level, T, P.edge_score_threshold,
+                                                                        ce_out, mask_out, P.propagation_epsilon, dT, rowdark, v_first);
+    RSLF_CUDA_TRY(ctx, cudaGetLastError());
+    ctx->timing.kernel_launches += 1;
     return RSLF_OK;
 }

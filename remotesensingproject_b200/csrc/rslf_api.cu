@@ -23,7 +23,8 @@
 #include "rslf_comm.cuh"
 #include "k_peak.cuh"
 
-#define RSLF_ABI_VERSION 3
+#define RSLF_ABI_VERSION 4
+static const size_t RSLF_RING_BYTES = (size_t)32 << 20;   /* one buffer of the pinned transfer ring */
 #define RSLF_COUNT_SLOTS 65536
 
 /* ------------------------------------------------------------------ helpers */
@@ -217,6 +218,10 @@ static int normalise_level(rslf_ctx* ctx, int p, const void* raw, int cv_depth)
     rslf_level& L = ctx->lv[p];
     stage_scope sc(ctx, ST_PYR);
     const size_t n = (size_t)L.Vtot * ctx->S * L.U * ctx->C;
+    if (p == 0 && ctx->pre_norm_epoch == ctx->input_epoch && ctx->world <= 1) {
+        L.nonneg = ctx->pre_nonneg;                          /* normalised while it was uploaded (rslf_cuda_upload_epis_pipelined) */
+        return RSLF_OK;
+    }
     if (cv_depth == RSLF_DEPTH_8U) {
         normalise_u8_kernel<<<stream_grid(ctx, n), 256, 0, ctx->stream>>>((const uint8_t*)raw, n, L.epi_full);
         L.nonneg = 1;
@@ -266,6 +271,9 @@ static int full_input(rslf_ctx* ctx, const void** out)
         if (ctx->raw_full_cap < bytes) {
             if (ctx->raw_full) cudaFree(ctx->raw_full);
     if (ctx->img_staging) cudaFree(ctx->img_staging);
+    if (ctx->open_ce) cudaFree(ctx->open_ce);
+    if (ctx->open_mask) cudaFree(ctx->open_mask);
+    if (ctx->open_tmp) cudaFree(ctx->open_tmp);
     for (int i = 0; i < 2; ++i) { if (ctx->ring[i]) cudaFreeHost(ctx->ring[i]); if (ctx->ring_ev[i]) cudaEventDestroy(ctx->ring_ev[i]); }
     if (ctx->ev_img) cudaEventDestroy(ctx->ev_img);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
@@ -358,6 +366,9 @@ extern "C" void rslf_cuda_destroy(rslf_ctx* ctx)
     if (ctx->raw_in && !ctx->raw_borrowed) cudaFree(ctx->raw_in);
     if (ctx->raw_full) cudaFree(ctx->raw_full);
     if (ctx->img_staging) cudaFree(ctx->img_staging);
+    if (ctx->open_ce) cudaFree(ctx->open_ce);
+    if (ctx->open_mask) cudaFree(ctx->open_mask);
+    if (ctx->open_tmp) cudaFree(ctx->open_tmp);
     for (int i = 0; i < 2; ++i) { if (ctx->ring[i]) cudaFreeHost(ctx->ring[i]); if (ctx->ring_ev[i]) cudaEventDestroy(ctx->ring_ev[i]); }
     if (ctx->ev_img) cudaEventDestroy(ctx->ev_img);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
@@ -516,6 +527,80 @@ extern "C" int rslf_cuda_upload_epis(rslf_ctx* ctx, const void* const* epi_ptrs,
     return RSLF_OK;
 }
 
+/* min over a range, for the sign flag of the normalised stack (stack_minmax_kernel needs both slots initialised) */
+static bool edge_params_equal(const rslf_params& a, const rslf_params& b)
+{
+    return a.edge_score_threshold == b.edge_score_threshold && a.edge_confidence_filter_size == b.edge_confidence_filter_size &&
+           a.edge_confidence_opening_size == b.edge_confidence_opening_size && a.edge_confidence_opening_type == b.edge_confidence_opening_type &&
+           a.cut_shadows == b.cut_shadows && a.shadow_level == b.shadow_level && a.propagation_epsilon == b.propagation_epsilon;
+}
+
+/* Ingest fused with the computers' input handling: the V EPIs are uploaded in chunks and, while the
+ * next chunk is still crossing PCIe, the chunk that has arrived is normalised to float32 (dc.hpp:463-477) and —
+ * when `params` is given — its edge confidence C_e and mask are computed for all S lines (core.hpp:901-931) on a
+ * second stream.  The following Depth2DComputer / FineToCoarse run on the same input (and the same edge parameters)
+ * starts from those level-0 maps instead of recomputing them.  Needs the scale to be known up front (8-bit input, or
+ * epi_scale_factor >= 0: with scale < 0 the stack maximum is only known after the last byte) and a single-rank
+ * context without the opening; otherwise this is rslf_cuda_upload_epis. */
+extern "C" int rslf_cuda_upload_epis_pipelined(rslf_ctx* ctx, const void* const* epi_ptrs, int V, int S, int U, int C,
+                                               int cv_depth, size_t row_step_bytes, float epi_scale_factor, const rslf_params* params)
+{
+    if (!ctx || !epi_ptrs) return RSLF_ERR_ARG;
+    const bool scale_known = (cv_depth == RSLF_DEPTH_8U) || (epi_scale_factor >= 0.f);
+    if (!scale_known || ctx->world > 1 || (params && params->edge_confidence_opening_size > 1) || (epi_scale_factor == 0.f && cv_depth != RSLF_DEPTH_8U))
+        return rslf_cuda_upload_epis(ctx, epi_ptrs, V, S, U, C, cv_depth, row_step_bytes, epi_scale_factor);
+    RSLF_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    RSLF_TRY(set_dims(ctx, V, S, U, C, cv_depth, epi_scale_factor));
+    const size_t esz = depth_esz(cv_depth);
+    const size_t row = (size_t)U * C * esz;
+    if (row_step_bytes < row) { snprintf(ctx->err, sizeof(ctx->err), "row step smaller than a row"); return RSLF_ERR_ARG; }
+    const size_t epi_bytes = row * S, epi_vals = (size_t)S * U * C;
+    RSLF_TRY(own_raw(ctx, epi_bytes * V));
+    ctx->row_starts[0] = 0; ctx->row_starts[1] = V; ctx->v0 = 0; ctx->V_total = V;
+    RSLF_TRY(ensure_scratch(ctx, true, false));
+    RSLF_TRY(ensure_level(ctx, 0, V, U, true, false));
+    rslf_level& L = ctx->lv[0];
+    if (!ctx->stream2) RSLF_CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+    if (!ctx->ev_img) RSLF_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ev_img, cudaEventDisableTiming));
+    cudaEventRecord(ctx->ev_a, ctx->stream);
+    float init[2] = {0.f, std::numeric_limits<float>::infinity()};
+    RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->minmax, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+    if (params) RSLF_CUDA_TRY(ctx, cudaMemsetAsync(L.rowdark, 0, ((size_t)S + 1) * V * sizeof(int), ctx->stream));
+    const float sf = epi_scale_factor;
+    const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)V, RSLF_RING_BYTES / epi_bytes));
+    for (int v0 = 0; v0 < V; v0 += chunk) {
+        const int n = std::min(chunk, V - v0);
+        RSLF_TRY(images_to_device(ctx, (char*)ctx->raw_in + (size_t)v0 * epi_bytes, n, S, row, epi_ptrs + v0, row_step_bytes));
+        RSLF_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_img, ctx->stream));
+        RSLF_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_img, 0));
+        const size_t nv = (size_t)n * epi_vals;
+        float* out = L.epi_full + (size_t)v0 * epi_vals;
+        if (cv_depth == RSLF_DEPTH_8U)
+            normalise_u8_kernel<<<stream_grid(ctx, nv), 256, 0, ctx->stream2>>>((const uint8_t*)ctx->raw_in + (size_t)v0 * epi_vals, nv, out);
+        else if (cv_depth == RSLF_DEPTH_16U)
+            normalise_u16_kernel<<<stream_grid(ctx, nv), 256, 0, ctx->stream2>>>((const uint16_t*)ctx->raw_in + (size_t)v0 * epi_vals, nv, sf, out);
+        else {
+            stack_minmax_kernel<<<stream_grid(ctx, nv), 256, 0, ctx->stream2>>>((const float*)ctx->raw_in + (size_t)v0 * epi_vals, nv, ctx->minmax);
+            normalise_f32_kernel<<<stream_grid(ctx, nv), 256, 0, ctx->stream2>>>((const float*)ctx->raw_in + (size_t)v0 * epi_vals, nv, nullptr, sf, out);
+        }
+        ctx->timing.kernel_launches += 1;
+        if (params) RSLF_TRY(launch_edge_confidence_rows(ctx, ctx->stream2, L.epi_full, V, S, U, C, v0, n, *params, L.ce, L.emask, L.rowdark));
+    }
+    RSLF_CUDA_TRY(ctx, cudaGetLastError());
+    RSLF_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_img, ctx->stream2));
+    RSLF_CUDA_TRY(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_img, 0));
+    float mm[2] = {0.f, 0.f};
+    RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(mm, ctx->minmax, sizeof(mm), cudaMemcpyDeviceToHost, ctx->stream));
+    cudaEventRecord(ctx->ev_b, ctx->stream);
+    RSLF_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ctx->timing.ms_h2d, ctx->ev_a, ctx->ev_b);
+    ctx->have_input = true;
+    ctx->pre_norm_epoch = ctx->input_epoch;
+    ctx->pre_nonneg = (cv_depth == RSLF_DEPTH_8U) ? 1 : (cv_depth == RSLF_DEPTH_16U) ? (sf > 0.f ? 1 : 0) : ((mm[1] >= 0.f && sf > 0.f) ? 1 : 0);
+    if (params) { ctx->pre_edge_epoch = ctx->input_epoch; ctx->pre_params = *params; }
+    return RSLF_OK;
+}
+
 extern "C" int rslf_cuda_set_epis_device(rslf_ctx* ctx, const void* d_epis, int V, int S, int U, int C,
                                          int cv_depth, float epi_scale_factor)
 {
@@ -554,6 +639,9 @@ extern "C" int rslf_cuda_upload_images(rslf_ctx* ctx, const void* const* img_ptr
     /* staging area for the image stack, kept for the next upload (no allocation per call) */
     if (ctx->img_staging_cap < img_bytes * S) {
         if (ctx->img_staging) cudaFree(ctx->img_staging);
+    if (ctx->open_ce) cudaFree(ctx->open_ce);
+    if (ctx->open_mask) cudaFree(ctx->open_mask);
+    if (ctx->open_tmp) cudaFree(ctx->open_tmp);
         ctx->img_staging = nullptr; ctx->img_staging_cap = 0;
         cudaError_t e = cudaMalloc(&ctx->img_staging, img_bytes * S);
         if (e != cudaSuccess) { snprintf(ctx->err, sizeof(ctx->err), "cudaMalloc(image staging %zu): %s", img_bytes * S, cudaGetErrorString(e)); return RSLF_ERR_NOMEM; }
@@ -808,10 +896,21 @@ static int run_depth2d_level(rslf_ctx* ctx, int p, const rslf_params& P, float d
     RSLF_CUDA_TRY(ctx, cudaMemsetAsync(L.depth, 0, px * sizeof(float), ctx->stream));
     RSLF_CUDA_TRY(ctx, cudaMemsetAsync(L.cd, 0, px * sizeof(float), ctx->stream));
     RSLF_CUDA_TRY(ctx, cudaMemsetAsync(L.rbar, 0, px * C * sizeof(float), ctx->stream));
-    RSLF_CUDA_TRY(ctx, cudaMemsetAsync(L.rowdark, 0, ((size_t)S + 1) * V * sizeof(int), ctx->stream));
-    {
+    /* level 0 of an input whose edge confidence was computed while it was uploaded, with the same parameters? */
+    const bool pre_edge = (p == 0 && ctx->world <= 1 && ctx->pre_edge_epoch == ctx->input_epoch && edge_params_equal(ctx->pre_params, P));
+    if (!pre_edge) RSLF_CUDA_TRY(ctx, cudaMemsetAsync(L.rowdark, 0, ((size_t)S + 1) * V * sizeof(int), ctx->stream));
+    else RSLF_CUDA_TRY(ctx, cudaMemsetAsync(L.rowdark + (size_t)S * V, 0, (size_t)V * sizeof(int), ctx->stream));
+    if (pre_edge) {
         stage_scope sc(ctx, ST_EDGE);
-        RSLF_TRY(launch_edge_confidence(ctx, L.epi, V, S, U, C, 0, S, P, L.ce, L.emask, L.rowdark, L.remaining));   /* L.remaining is free until core.hpp:958-963 below */
+        row_sum_kernel<<<rslf_div_up(V, 256), 256, 0, ctx->stream>>>(L.rowdark, S, V, L.rowdark + (size_t)S * V);
+        RSLF_CUDA_TRY(ctx, cudaGetLastError());
+        ctx->timing.kernel_launches += 1;
+        ctx->pre_edge_epoch = 0;                             /* the run consumes the maps (the depth kernel clears C_e of rejected pixels) */
+    } else {
+        stage_scope sc(ctx, ST_EDGE);
+        const bool sh = ctx->world > 1 && !L.replicated;
+        RSLF_TRY(launch_edge_confidence(ctx, L.epi, V, S, U, C, 0, S, P, L.ce, L.emask, L.rowdark, L.remaining,   /* L.remaining is free until core.hpp:958-963 below */
+                                        sh ? L.v0 : 0, sh ? L.Vtot - L.v0 - V : 0));
         /* rows that hold a dark target in any view: rowdark[S][v] = sum over s (an upper bound for the whole level) */
         row_sum_kernel<<<rslf_div_up(V, 256), 256, 0, ctx->stream>>>(L.rowdark, S, V, L.rowdark + (size_t)S * V);
         RSLF_CUDA_TRY(ctx, cudaGetLastError());
@@ -900,8 +999,6 @@ static int copy_out(rslf_ctx* ctx, void* host, const void* dev, size_t bytes)
  * cv::Mat) cannot be the target of an asynchronous DMA: the rows go through a ring of two pinned buffers, the
  * copy engine filling one while the host thread empties the other into the image rows — one CPU pass over the
  * data, overlapped with the transfer (the driver's own pageable path would add a second one in the caller). */
-static const size_t RSLF_RING_BYTES = (size_t)32 << 20;
-
 static bool host_is_pinned(const void* p)
 {
     cudaPointerAttributes a;
@@ -1027,7 +1124,8 @@ extern "C" int rslf_cuda_depth1d_pile_run(rslf_ctx* ctx, float dmin, float dmax,
     RSLF_CUDA_TRY(ctx, cudaMemsetAsync(L.rbar, 0, plane * C * sizeof(float), ctx->stream));
     {
         stage_scope sc(ctx, ST_EDGE);
-        RSLF_TRY(launch_edge_confidence(ctx, L.epi, V, S, U, C, s_hat, 1, P, L.ce, L.emask, nullptr, L.remaining));
+        RSLF_TRY(launch_edge_confidence(ctx, L.epi, V, S, U, C, s_hat, 1, P, L.ce, L.emask, nullptr, L.remaining,
+                                        ctx->world > 1 ? L.v0 : 0, ctx->world > 1 ? L.Vtot - L.v0 - V : 0));
     }
     pass_io io;
     io.level = 0; io.s_hat = s_hat; io.D = dim_d; io.dmin = dmin; io.dmax = dmax; io.use_bound_maps = false;
@@ -1492,7 +1590,6 @@ extern "C" int rslf_cuda_fine_to_coarse_get_coloured(rslf_ctx* ctx, const uint8_
 {
     if (!ctx || !lut_bgr_256x3 || !params || !out_bgr_svu3) return RSLF_ERR_ARG;
     if (ctx->last_kind != 3) { snprintf(ctx->err, sizeof(ctx->err), "no fine-to-coarse result"); return RSLF_ERR_STATE; }
-    if (ctx->world > 1) { snprintf(ctx->err, sizeof(ctx->err), "coloured maps are not implemented for row-sharded runs"); return RSLF_ERR_UNSUPPORTED; }
     if (!saturate) {
         snprintf(ctx->err, sizeof(ctx->err), "ImageConverter_uchar::fit without saturation (mean + 12 std) is not implemented");
         return RSLF_ERR_UNSUPPORTED;
@@ -1500,6 +1597,11 @@ extern "C" int rslf_cuda_fine_to_coarse_get_coloured(rslf_ctx* ctx, const uint8_
     RSLF_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     const int S = ctx->S, V = ctx->V, U = ctx->U, C = ctx->C;
     const size_t plane = (size_t)V * U, px = plane * S;
+    /* row-sharded run: every rank colours its rows; the quantile fit is over the WHOLE plane of view s_fit: the
+     * key histograms of the radix select are summed over the ranks (NCCL all-reduce), the ranks of the quantiles
+     * count in the whole plane */
+    const bool sharded = ctx->world > 1 && ctx->have_shards;
+    const size_t plane_tot = sharded ? (size_t)ctx->V_total * U : plane;
     const int s_fit = (int)std::round(S / 2.0);                       /* ftc.hpp:345 */
     if (s_fit >= S) { snprintf(ctx->err, sizeof(ctx->err), "S = %d: the reference fits on view round(S / 2) = %d, which does not exist", S, s_fit); return RSLF_ERR_ARG; }
     if (V > 65535 || S > 65535) return RSLF_ERR_UNSUPPORTED;
@@ -1509,10 +1611,11 @@ extern "C" int rslf_cuda_fine_to_coarse_get_coloured(rslf_ctx* ctx, const uint8_
     const float* fit_plane = ctx->out_map + (size_t)s_fit * plane;
     std::vector<unsigned> host((size_t)2 * COLOUR_BINS);
     /* rslf_plot.cpp:73-79: ranks floor(0.02 N) and floor(0.98 N) of the sorted plane */
-    const size_t k_min = (size_t)std::floor(0.02 * (double)plane), k_max = (size_t)std::floor(0.98 * (double)plane);
+    const size_t k_min = (size_t)std::floor(0.02 * (double)plane_tot), k_max = (size_t)std::floor(0.98 * (double)plane_tot);
     RSLF_CUDA_TRY(ctx, cudaMemsetAsync(h_hi, 0, (size_t)3 * COLOUR_BINS * sizeof(unsigned), ctx->stream));
     colour_hist_hi_kernel<<<stream_grid(ctx, plane), 256, 0, ctx->stream>>>(fit_plane, plane, h_hi);
     RSLF_CUDA_TRY(ctx, cudaGetLastError());
+    if (sharded) RSLF_TRY(comm_allreduce_sum_u32(ctx, h_hi, COLOUR_BINS));
     RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(host.data(), h_hi, COLOUR_BINS * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
     RSLF_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     unsigned hi_a = 0, hi_b = 0, lo_a = 0, lo_b = 0; size_t r_a = 0, r_b = 0, dummy = 0;
@@ -1521,6 +1624,7 @@ extern "C" int rslf_cuda_fine_to_coarse_get_coloured(rslf_ctx* ctx, const uint8_
     }
     colour_hist_lo_kernel<<<stream_grid(ctx, plane), 256, 0, ctx->stream>>>(fit_plane, plane, hi_a, hi_b, h_a, h_b);
     RSLF_CUDA_TRY(ctx, cudaGetLastError());
+    if (sharded) RSLF_TRY(comm_allreduce_sum_u32(ctx, h_a, (size_t)2 * COLOUR_BINS));
     RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(host.data(), h_a, (size_t)2 * COLOUR_BINS * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
     RSLF_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     if (!colour_find_bin(host.data(), r_a, &lo_a, &dummy) || !colour_find_bin(host.data() + COLOUR_BINS, r_b, &lo_b, &dummy)) {

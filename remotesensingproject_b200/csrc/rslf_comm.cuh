@@ -34,7 +34,7 @@ struct rslf_nccl_api {
 static rslf_nccl_api g_nccl;
 
 /* ncclDataType_t / ncclRedOp_t values (stable across NCCL 2.x) */
-enum { RSLF_NCCL_UINT8 = 1, RSLF_NCCL_FLOAT = 7, RSLF_NCCL_MAX = 2 };
+enum { RSLF_NCCL_UINT8 = 1, RSLF_NCCL_UINT32 = 3, RSLF_NCCL_FLOAT = 7, RSLF_NCCL_SUM = 0, RSLF_NCCL_MAX = 2 };
 
 static int nccl_load(char* err, size_t errlen)
 {
@@ -85,6 +85,14 @@ static int comm_allreduce_max(rslf_ctx* ctx, float* dev, int n, float* host0)
         RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(host0, dev, sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
         RSLF_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     }
+    return RSLF_OK;
+}
+
+/* in-place sum over ranks of n device uint32 counters (histograms of the coloured maps' quantile fit) */
+static int comm_allreduce_sum_u32(rslf_ctx* ctx, unsigned* dev, size_t n)
+{
+    if (ctx->world <= 1 || !ctx->nccl_comm) return RSLF_OK;
+    RSLF_NCCL_TRY(ctx, g_nccl.AllReduce(dev, dev, n, RSLF_NCCL_UINT32, RSLF_NCCL_SUM, ctx->nccl_comm, ctx->stream));
     return RSLF_OK;
 }
 

@@ -69,12 +69,16 @@ struct rslf_ctx {
     bool raw_borrowed = false;
     size_t raw_cap = 0;
     bool have_input = false;
+    float* open_ce = nullptr; uint8_t* open_mask = nullptr; uint8_t* open_tmp = nullptr; size_t open_cap = 0;   /* extended planes of a sharded opening */
     void* img_staging = nullptr; size_t img_staging_cap = 0;   /* rslf_cuda_upload_images: the image stack before the transposition */
     void* ring[2] = {nullptr, nullptr}; cudaEvent_t ring_ev[2] = {nullptr, nullptr};   /* pinned ring for pageable host images */
     cudaStream_t stream2 = nullptr; cudaEvent_t ev_img = nullptr;
     void* raw_full = nullptr;    /* multi-rank runs: all rows of the raw stack, gathered once per input */
     size_t raw_full_cap = 0;
     unsigned input_epoch = 1, raw_full_epoch = 0;
+    /* pipelined ingest (rslf_cuda_upload_epis_pipelined): level 0 was normalised / its edge confidence computed while the
+     * stack was still arriving; valid for the input of that epoch (and, for the edge confidence, those parameters) */
+    unsigned pre_norm_epoch = 0, pre_edge_epoch = 0; int pre_nonneg = 1; rslf_params pre_params;
     int v0 = 0, V_total = 0;     /* row shard: first global row, global rows (level 0)        */
     int row_starts[65] = {0};    /* level-0 shard table, world + 1 entries                    */
     bool have_shards = false;

@@ -323,3 +323,39 @@ def test_disp_confidence_criterion(gpu_ctx, S, V, U, C, D, thr):
         ref.set_criterion("edge")
     with pytest.raises(api.RslfError):
         gpu_ctx.set_confidence_criterion("line")
+
+
+# --------------------------------------------------------------------------- pipelined ingest
+@pytest.mark.parametrize("dtype,scale", [(np.float32, 1.0), (np.uint8, -1.0), (np.uint16, 300.0), (np.float32, -1.0)])
+def test_pipelined_ingest_equals_plain_upload(gpu_ctx, dtype, scale):
+    """rslf_cuda_upload_epis_pipelined normalises the stack and computes the level-0 edge confidence chunk by chunk while
+    the rest is uploaded; the run that follows must give exactly what a plain upload gives — also when the parameters
+    change between the upload and the run (the precomputed maps are then discarded), and for a second run."""
+    epis, _ = make_light_field_np(7, 40, 90, 3, dmin=-1.0, dmax=2.0, seed=321, layers=5)
+    if dtype == np.uint8:
+        epis = np.clip(np.rint(epis * 255.0), 0, 255).astype(np.uint8)
+    elif dtype == np.uint16:
+        epis = np.clip(np.rint(epis * 300.0), 0, 65535).astype(np.uint16)
+    p = api.default_params()
+    ref = oracle.fine_to_coarse(epis, -1.0, 2.0, 24, scale_factor=scale)
+    gpu_ctx.upload_epis(epis, scale)                                        # plain
+    gpu_ctx.fine_to_coarse_run(-1.0, 2.0, 24, p)
+    m0, v0 = gpu_ctx.fine_to_coarse_get()
+    gpu_ctx.upload_epis(epis, scale, params=p)                              # pipelined
+    gpu_ctx.fine_to_coarse_run(-1.0, 2.0, 24, p)
+    m1, v1 = gpu_ctx.fine_to_coarse_get()
+    gpu_ctx.fine_to_coarse_run(-1.0, 2.0, 24, p)                            # again on the same input
+    m2, v2 = gpu_ctx.fine_to_coarse_get()
+    for m, v in ((m0, v0), (m1, v1), (m2, v2)):
+        np.testing.assert_array_equal(v, ref["valid"])
+        np.testing.assert_array_equal(m, ref["map"])
+    q = api.default_params(edge_score_threshold=0.05)
+    gpu_ctx.upload_epis(epis, scale, params=p)
+    gpu_ctx.fine_to_coarse_run(-1.0, 2.0, 24, q)                            # other edge parameters than at the upload
+    m3, v3 = gpu_ctx.fine_to_coarse_get()
+    r3 = oracle.fine_to_coarse(epis, -1.0, 2.0, 24, scale_factor=scale, params=oracle.default_params(edge_score_threshold=0.05))
+    np.testing.assert_array_equal(m3, r3["map"])
+    np.testing.assert_array_equal(v3, r3["valid"])
+    c = api.Depth1DComputer_pile(epis, -1.0, 2.0, 24, epi_scale_factor=scale, ctx=gpu_ctx).run()     # another computer afterwards
+    pile = oracle.depth1d_pile(oracle.normalise(epis, scale), -1.0, 2.0, 24)
+    np.testing.assert_array_equal(c.m_best_depth_v_u, pile["best_depth"])

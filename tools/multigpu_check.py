@@ -36,6 +36,10 @@ def main():
              # the geometry class of the bench: tensor-memory depth kernel (S >= 20, RGB), several chunks of hypotheses
              dict(S=28, V=64, U=160, C=3, D=72, mode="ftc", scale=1.0),
              dict(S=24, V=48, U=128, C=3, D=40, mode="depth2d", scale=1.0),
+             # morphological opening of the edge mask (5x5 ellipse, core.hpp:759-769): every rank opens its rows plus a
+             # margin taken from its own copy of the stack; coloured maps: quantile fit over the whole plane
+             dict(S=6, V=96, U=80, C=3, D=24, mode="ftc", scale=1.0, opening=5, coloured=True),
+             dict(S=5, V=64, U=72, C=1, D=16, mode="depth2d", scale=1.0, opening=3),
              # 16-bit stack, scaled by its maximum: all-reduce of the per-rank maxima, 16-bit raw rows gathered for the blur
              dict(S=5, V=96, U=80, C=3, D=16, mode="ftc", scale=-1.0, u16=True)]
     for i, c in enumerate(cases):
@@ -56,12 +60,16 @@ def main():
         if c.get("u16"):
             epis = np.clip(np.rint(epis * 200.0), 0, 65535).astype(np.uint16)
         p = api.default_params()
+        if c.get("opening"):
+            p.edge_confidence_opening_size = c["opening"]
+        lut = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "colormap_jet.npy"))
         # single-GPU result (every rank computes it on its own device)
         ctx1 = api.Context(local)
         ctx1.upload_epis(epis, c["scale"])
         if c["mode"] == "ftc":
             ctx1.fine_to_coarse_run(-1.0, 2.0, c["D"], p)
             ref_map, ref_valid = ctx1.fine_to_coarse_get()
+            ref_bgr = ctx1.fine_to_coarse_coloured(lut, p)[0] if c.get("coloured") else None
         else:
             ctx1.depth2d_run(-1.0, 2.0, c["D"], p)
             r = ctx1.depth2d_get()
@@ -83,13 +91,17 @@ def main():
         if c["mode"] == "ftc":
             ctx.fine_to_coarse_run(-1.0, 2.0, c["D"], p)
             m, k = ctx.fine_to_coarse_get()
+            bgr_ok = True
+            if c.get("coloured"):
+                bgr_ok = np.array_equal(ctx.fine_to_coarse_coloured(lut, p)[0], ref_bgr[:, v0:v1])
         else:
+            bgr_ok = True
             ctx.depth2d_run(-1.0, 2.0, c["D"], p)
             r = ctx.depth2d_get()
             m, k = r["best_depth"], r["edge_mask"]
         samples = torch.tensor([ctx.timing()["samples"]], dtype=torch.float64, device="cuda")
         dist.all_reduce(samples)
-        ok = np.array_equal(m, ref_map[:, v0:v1]) and np.array_equal(k, ref_valid[:, v0:v1]) and float(samples[0]) == ref_samples
+        ok = np.array_equal(m, ref_map[:, v0:v1]) and np.array_equal(k, ref_valid[:, v0:v1]) and float(samples[0]) == ref_samples and bgr_ok
         print("rank %d case %d rows [%d,%d): %s (samples %.0f vs %.0f)" % (rank, i, v0, v1, "OK" if ok else "MISMATCH",
                                                                           float(samples[0]), ref_samples), flush=True)
         failures += 0 if ok else 1
