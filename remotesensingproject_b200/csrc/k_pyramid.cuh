@@ -31,8 +31,15 @@ __device__ __forceinline__ void atomic_min_float(float* addr, float v) {
 __global__ void stack_minmax_kernel(const float* __restrict__ x, size_t n, float* __restrict__ mm)
 {
     float mx = -CUDART_INF_F, mn = CUDART_INF_F;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        float v = x[i];
+    /* 16-byte loads over the aligned body, scalar head / tail */
+    const size_t head = min(n, (size_t)((16 - ((uintptr_t)x & 15)) & 15) / 4), n4 = (n - head) / 4;
+    const float4* x4 = reinterpret_cast<const float4*>(x + head);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 v = x4[i];
+        mx = fmaxf(fmaxf(mx, v.x), fmaxf(v.y, fmaxf(v.z, v.w))); mn = fminf(fminf(mn, v.x), fminf(v.y, fminf(v.z, v.w)));
+    }
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n - 4 * n4; i += (size_t)gridDim.x * blockDim.x) {
+        const float v = (i < head) ? x[i] : x[4 * n4 + i];
         mx = fmaxf(mx, v); mn = fminf(mn, v);
     }
 #pragma unroll
@@ -49,12 +56,35 @@ __global__ void normalise_f32_kernel(const float* __restrict__ in, size_t n, con
 {
     const float sf = scale_dev ? *scale_dev : scale_host;
     const float a = (float)(1.0 / (double)sf);
+    if ((((uintptr_t)in | (uintptr_t)out) & 15) == 0) {
+        /* HBM-bound stream: 16-byte loads and stores */
+        const size_t n4 = n / 4;
+        const float4* in4 = reinterpret_cast<const float4*>(in);
+        float4* out4 = reinterpret_cast<float4*>(out);
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+            const float4 v = in4[i];
+            out4[i] = make_float4(v.x * a, v.y * a, v.z * a, v.w * a);
+        }
+        for (size_t i = 4 * n4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = in[i] * a;
+        return;
+    }
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         out[i] = in[i] * a;
 }
 __global__ void normalise_u8_kernel(const uint8_t* __restrict__ in, size_t n, float* __restrict__ out)
 {
     const float a = (float)(1.0 / 255.0);
+    if ((((uintptr_t)in & 3) | ((uintptr_t)out & 15)) == 0) {
+        const size_t n4 = n / 4;
+        const uchar4* in4 = reinterpret_cast<const uchar4*>(in);
+        float4* out4 = reinterpret_cast<float4*>(out);
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+            const uchar4 v = in4[i];
+            out4[i] = make_float4((float)v.x * a, (float)v.y * a, (float)v.z * a, (float)v.w * a);
+        }
+        for (size_t i = 4 * n4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = (float)in[i] * a;
+        return;
+    }
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         out[i] = (float)in[i] * a;
 }
@@ -263,8 +293,10 @@ __global__ void nearest_valid_kernel(const uint8_t* __restrict__ valid, int rows
 __global__ void set_bounds_kernel(const float* __restrict__ depth_up, const int* __restrict__ left,
                                   const int* __restrict__ right, int S, int Vu, int Uu, int Vd, int Ud,
                                   float* __restrict__ dmin_map, float* __restrict__ dmax_map,
-                                  int Vu_tot, int vu0, int vd0)
+                                  int Vu_tot, int vu0, int vd0, int write_default, float dmin_default, float dmax_default)
 {
+    /* write_default: pixels without a bound from the level above take the global bounds here (ftc.hpp:160-168 fills the
+     * maps first); otherwise the maps hold them already (rslf_cuda_set_bounds) */
     /* Vu / Vd: rows held locally (first global rows vu0 / vd0); Vu_tot: global rows of the upper level */
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
     const int v = blockIdx.y, s = blockIdx.z;
@@ -290,10 +322,9 @@ __global__ void set_bounds_kernel(const float* __restrict__ depth_up, const int*
             }
         }
     }
-    if (n > 1) {
-        const size_t o = ((size_t)s * Vd + v) * (size_t)Ud + u;
-        dmin_map[o] = mn; dmax_map[o] = mx;
-    }
+    const size_t o = ((size_t)s * Vd + v) * (size_t)Ud + u;
+    if (n > 1) { dmin_map[o] = mn; dmax_map[o] = mx; }
+    else if (write_default) { dmin_map[o] = dmin_default; dmax_map[o] = dmax_default; }
 }
 
 /* A [S][rows][U] map seen through a window of rows: the rank's own rows [r0, r0 + rows) in `mid` (plane stride

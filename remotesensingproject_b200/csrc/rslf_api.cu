@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <limits>
+#include <thread>
 
 #include "rslf_common.cuh"
 #include "k_edge.cuh"
@@ -24,7 +25,8 @@
 #include "k_peak.cuh"
 
 #define RSLF_ABI_VERSION 4
-static const size_t RSLF_RING_BYTES = (size_t)32 << 20;   /* one buffer of the pinned transfer ring */
+static const size_t RSLF_RING_BYTES = (size_t)64 << 20;   /* one buffer of the pinned transfer ring */
+static const size_t RSLF_COPY_THREADS = 6;                /* host threads that fill / empty a ring buffer */
 #define RSLF_COUNT_SLOTS 65536
 
 /* ------------------------------------------------------------------ helpers */
@@ -242,19 +244,25 @@ static int normalise_level(rslf_ctx* ctx, int p, const void* raw, int cv_depth)
         normalise_u16_kernel<<<stream_grid(ctx, n), 256, 0, ctx->stream>>>((const uint16_t*)raw, n, sf, L.epi_full);
         ctx->timing.kernel_launches += 1;
     } else {
-        /* max (start value = the scale factor, dc.hpp:445) and min of the stack */
-        float init[2] = {ctx->scale_factor, std::numeric_limits<float>::infinity()};
-        RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->minmax, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
-        stack_minmax_kernel<<<stream_grid(ctx, n), 256, 0, ctx->stream>>>((const float*)raw, n, ctx->minmax);
+        /* max (start value = the scale factor, dc.hpp:445) and min of the stack; those of the uploaded stack (level 0)
+         * are a property of the input: computed once per upload, not once per run */
         float mm[2];
-        RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(mm, ctx->minmax, sizeof(mm), cudaMemcpyDeviceToHost, ctx->stream));
-        RSLF_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        if (p == 0 && ctx->mm0_epoch == ctx->input_epoch) { mm[0] = ctx->mm0[0]; mm[1] = ctx->mm0[1]; }
+        else {
+            float init[2] = {ctx->scale_factor, std::numeric_limits<float>::infinity()};
+            RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->minmax, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+            stack_minmax_kernel<<<stream_grid(ctx, n), 256, 0, ctx->stream>>>((const float*)raw, n, ctx->minmax);
+            RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(mm, ctx->minmax, sizeof(mm), cudaMemcpyDeviceToHost, ctx->stream));
+            RSLF_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            ctx->timing.kernel_launches += 1;
+            if (p == 0) { ctx->mm0[0] = mm[0]; ctx->mm0[1] = mm[1]; ctx->mm0_epoch = ctx->input_epoch; }
+        }
         float sf = ctx->scale_factor;
         if (sf < 0.f) sf = mm[0];
         /* sign of a normalised value: sign(x) * sign(1/sf) */
         L.nonneg = ((mm[1] >= 0.f && sf > 0.f)) ? 1 : 0;
         normalise_f32_kernel<<<stream_grid(ctx, n), 256, 0, ctx->stream>>>((const float*)raw, n, nullptr, sf, L.epi_full);
-        ctx->timing.kernel_launches += 2;
+        ctx->timing.kernel_launches += 1;
     }
     RSLF_CUDA_TRY(ctx, cudaGetLastError());
     return RSLF_OK;
@@ -1017,6 +1025,60 @@ static int ensure_ring(rslf_ctx* ctx)
     return RSLF_OK;
 }
 
+/* A ring job: consecutive pieces of host images that map to ONE contiguous device range of at most a ring buffer. */
+struct ring_piece { char* host; int rows; };
+struct ring_job { size_t dev_off, bytes; std::vector<ring_piece> pieces; };
+
+static std::vector<ring_job> ring_jobs(int n_imgs, int rows, size_t row_bytes, void* const* host, size_t step)
+{
+    std::vector<ring_job> jobs;
+    const int max_rows = (int)std::max<size_t>(1, RSLF_RING_BYTES / row_bytes);
+    ring_job cur; cur.dev_off = 0; cur.bytes = 0;
+    auto flush = [&]() { if (!cur.pieces.empty()) jobs.push_back(cur); cur.pieces.clear(); cur.bytes = 0; };
+    for (int p = 0; p < n_imgs; ++p) {
+        if (!host[p]) { flush(); continue; }
+        for (int r0 = 0; r0 < rows; ) {
+            const int room = max_rows - (int)(cur.bytes / row_bytes);
+            if (room <= 0) { flush(); continue; }
+            const int n = std::min(room, rows - r0);
+            if (cur.pieces.empty()) cur.dev_off = ((size_t)p * rows + r0) * row_bytes;
+            cur.pieces.push_back({(char*)host[p] + (size_t)r0 * step, n});
+            cur.bytes += (size_t)n * row_bytes;
+            r0 += n;
+        }
+    }
+    flush();
+    return jobs;
+}
+
+/* moves the pieces of a job between the images and a ring buffer with a few host threads (pieces split by bytes) */
+static void ring_copy(const ring_job& j, char* ring, size_t row_bytes, size_t step, bool to_ring)
+{
+    int nt = (int)std::min<size_t>(RSLF_COPY_THREADS, std::max<size_t>(1, j.bytes >> 22));
+    unsigned hw = std::thread::hardware_concurrency();
+    if (hw && (int)hw < nt) nt = (int)hw;
+    const long long total_rows = (long long)(j.bytes / row_bytes);
+    auto part = [&j, ring, row_bytes, step, to_ring, total_rows](int t, int n) {
+        const long long a = total_rows * t / n, b = total_rows * (t + 1) / n;
+        long long at = 0;
+        for (const ring_piece& pc : j.pieces) {
+            const long long lo = std::max(a, at), hi = std::min(b, at + pc.rows);
+            for (long long r = lo; r < hi; ++r) {
+                char* h = pc.host + (size_t)(r - at) * step;
+                char* g = ring + (size_t)r * row_bytes;
+                if (to_ring) memcpy(g, h, row_bytes); else memcpy(h, g, row_bytes);
+            }
+            at += pc.rows;
+            if (at >= b) break;
+        }
+    };
+    if (nt <= 1) { part(0, 1); return; }
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) th.emplace_back(part, t, nt);
+    part(0, nt);
+    for (auto& x : th) x.join();
+}
+
 /* device [planes][rows][row_bytes] -> host planes (nullptr planes are skipped) */
 static int planes_to_host(rslf_ctx* ctx, const void* dev, int planes, int rows, size_t row_bytes, void* const* host, size_t step)
 {
@@ -1031,28 +1093,18 @@ static int planes_to_host(rslf_ctx* ctx, const void* dev, int planes, int rows, 
         return RSLF_OK;
     }
     RSLF_TRY(ensure_ring(ctx));
-    const int chunk_rows = (int)std::max<size_t>(1, RSLF_RING_BYTES / row_bytes);
-    struct job { int p, r0, n; };
-    std::vector<job> jobs;
-    for (int p = 0; p < planes; ++p)
-        if (host[p]) for (int r = 0; r < rows; r += chunk_rows) jobs.push_back({p, r, std::min(chunk_rows, rows - r)});
-    auto drain = [&](const job& j, int slot) -> int {
-        RSLF_CUDA_TRY(ctx, cudaEventSynchronize(ctx->ring_ev[slot]));
-        const char* src = (const char*)ctx->ring[slot];
-        char* dst = (char*)host[j.p] + (size_t)j.r0 * step;
-        if (step == row_bytes) memcpy(dst, src, (size_t)j.n * row_bytes);
-        else for (int r = 0; r < j.n; ++r) memcpy(dst + (size_t)r * step, src + (size_t)r * row_bytes, row_bytes);
-        return RSLF_OK;
-    };
-    for (size_t i = 0; i < jobs.size(); ++i) {
+    const std::vector<ring_job> jobs = ring_jobs(planes, rows, row_bytes, host, step);
+    for (size_t i = 0; i < jobs.size() + 2; ++i) {
         const int slot = (int)(i & 1);
-        if (i >= 2) RSLF_TRY(drain(jobs[i - 2], slot));                    /* the slot is free again after this */
-        const job& j = jobs[i];
-        RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->ring[slot], (const char*)dev + ((size_t)j.p * rows + j.r0) * row_bytes,
-                                           (size_t)j.n * row_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-        RSLF_CUDA_TRY(ctx, cudaEventRecord(ctx->ring_ev[slot], ctx->stream));
+        if (i >= 2) {                                                       /* empty the buffer filled two jobs ago */
+            RSLF_CUDA_TRY(ctx, cudaEventSynchronize(ctx->ring_ev[slot]));
+            ring_copy(jobs[i - 2], (char*)ctx->ring[slot], row_bytes, step, false);
+        }
+        if (i < jobs.size()) {
+            RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->ring[slot], (const char*)dev + jobs[i].dev_off, jobs[i].bytes, cudaMemcpyDeviceToHost, ctx->stream));
+            RSLF_CUDA_TRY(ctx, cudaEventRecord(ctx->ring_ev[slot], ctx->stream));
+        }
     }
-    for (size_t i = jobs.size() >= 2 ? jobs.size() - 2 : 0; i < jobs.size(); ++i) RSLF_TRY(drain(jobs[i], (int)(i & 1)));
     return RSLF_OK;
 }
 
@@ -1072,20 +1124,14 @@ static int images_to_device(rslf_ctx* ctx, void* dev, int n_imgs, int rows, size
         return RSLF_OK;
     }
     RSLF_TRY(ensure_ring(ctx));
-    const int chunk_rows = (int)std::max<size_t>(1, RSLF_RING_BYTES / row_bytes);
-    size_t i = 0;
-    for (int p = 0; p < n_imgs; ++p)
-        for (int r0 = 0; r0 < rows; r0 += chunk_rows, ++i) {
-            const int slot = (int)(i & 1), n = std::min(chunk_rows, rows - r0);
-            RSLF_CUDA_TRY(ctx, cudaEventSynchronize(ctx->ring_ev[slot]));     /* its previous transfer (this call's or an earlier one's) has left the buffer */
-            char* dst = (char*)ctx->ring[slot];
-            const char* src = (const char*)host[p] + (size_t)r0 * step;
-            if (step == row_bytes) memcpy(dst, src, (size_t)n * row_bytes);
-            else for (int r = 0; r < n; ++r) memcpy(dst + (size_t)r * row_bytes, src + (size_t)r * step, row_bytes);
-            RSLF_CUDA_TRY(ctx, cudaMemcpyAsync((char*)dev + ((size_t)p * rows + r0) * row_bytes, dst, (size_t)n * row_bytes,
-                                               cudaMemcpyHostToDevice, ctx->stream));
-            RSLF_CUDA_TRY(ctx, cudaEventRecord(ctx->ring_ev[slot], ctx->stream));
-        }
+    const std::vector<ring_job> jobs = ring_jobs(n_imgs, rows, row_bytes, (void* const*)host, step);
+    for (size_t i = 0; i < jobs.size(); ++i) {
+        const int slot = (int)(ctx->ring_next++ & 1u);                      /* alternates across calls too (chunked uploads) */
+        RSLF_CUDA_TRY(ctx, cudaEventSynchronize(ctx->ring_ev[slot]));       /* its previous transfer (this call's or an earlier one's) has left the buffer */
+        ring_copy(jobs[i], (char*)ctx->ring[slot], row_bytes, step, true);
+        RSLF_CUDA_TRY(ctx, cudaMemcpyAsync((char*)dev + jobs[i].dev_off, ctx->ring[slot], jobs[i].bytes, cudaMemcpyHostToDevice, ctx->stream));
+        RSLF_CUDA_TRY(ctx, cudaEventRecord(ctx->ring_ev[slot], ctx->stream));
+    }
     return RSLF_OK;
 }
 
@@ -1191,6 +1237,7 @@ extern "C" int rslf_cuda_depth2d_run(rslf_ctx* ctx, float dmin, float dmax, int 
     rslf_level& L = ctx->lv[0];
     L.replicated = false;
     const size_t px = (size_t)S * V * U;
+    L.bounds_const = false;
     if (dmin_svu) {
         RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(L.dmin, dmin_svu, px * 4, cudaMemcpyHostToDevice, ctx->stream));
         RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(L.dmax, dmax_svu, px * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -1216,7 +1263,14 @@ static int get_level_maps(rslf_ctx* ctx, int p, float* best_depth, float* edge_c
     RSLF_TRY(copy_out(ctx, edge_mask, L.emask, px));
     RSLF_TRY(copy_out(ctx, disp_conf, L.cd, px * 4));
     RSLF_TRY(copy_out(ctx, rbar, L.rbar, px * 4 * ctx->C));
-    if (L.dmin) { RSLF_TRY(copy_out(ctx, dmin_svu, L.dmin, px * 4)); RSLF_TRY(copy_out(ctx, dmax_svu, L.dmax, px * 4)); }
+    if (L.dmin) {
+        if (L.bounds_const && (dmin_svu || dmax_svu)) {
+            fill_f32_kernel<<<stream_grid(ctx, px), 256, 0, ctx->stream>>>(L.dmin, px, L.bounds_lo);
+            fill_f32_kernel<<<stream_grid(ctx, px), 256, 0, ctx->stream>>>(L.dmax, px, L.bounds_hi);
+            L.bounds_const = false;
+        }
+        RSLF_TRY(copy_out(ctx, dmin_svu, L.dmin, px * 4)); RSLF_TRY(copy_out(ctx, dmax_svu, L.dmax, px * 4));
+    }
     cudaEventRecord(ctx->ev_b, ctx->stream);
     RSLF_CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     cudaEventElapsedTime(&ctx->timing.ms_d2h, ctx->ev_a, ctx->ev_b);
@@ -1476,13 +1530,11 @@ extern "C" int rslf_cuda_fine_to_coarse_run(rslf_ctx* ctx, float dmin, float dma
         rslf_params P = P0;
         P.slope_factor = (float)((0.0 + Up[p]) / Up[0]);                        /* ftc.hpp:139 */
         L.slope = P.slope_factor;
-        if (p == 0) {
-            stage_scope sc(ctx, ST_PYR);
-            fill_f32_kernel<<<stream_grid(ctx, px), 256, 0, ctx->stream>>>(L.dmin, px, dmin);
-            fill_f32_kernel<<<stream_grid(ctx, px), 256, 0, ctx->stream>>>(L.dmax, px, dmax);
-            ctx->timing.kernel_launches += 2;
-        }
-        RSLF_TRY(run_depth2d_level(ctx, p, P, dmin, dmax, dim_d, true));
+        /* level 0 has the global bounds everywhere (ftc.hpp:160-168): they travel as constants in the work records; the
+         * maps are only filled if somebody asks for them (rslf_cuda_fine_to_coarse_get_level) */
+        if (p == 0) L.bounds_const = true, L.bounds_lo = dmin, L.bounds_hi = dmax;
+        else L.bounds_const = false;
+        RSLF_TRY(run_depth2d_level(ctx, p, P, dmin, dmax, dim_d, p > 0));
         {
             stage_scope sc(ctx, ST_PYR);
             const int accept_all = (accept_all_last_scale && p == levels - 1) ? 1 : 0;   /* ftc.hpp:157-158 */
@@ -1501,9 +1553,6 @@ extern "C" int rslf_cuda_fine_to_coarse_run(rslf_ctx* ctx, float dmin, float dma
                     RSLF_TRY(launch_downsample_int<uint16_t>(ctx, (const uint16_t*)raw, Vp[p], S, Up[p], C, (uint16_t*)N.raw, Vp[p + 1], Up[p + 1]));
                 else
                     RSLF_TRY(launch_downsample(ctx, (const float*)raw, Vp[p], S, Up[p], C, N.raw, Vp[p + 1], Up[p + 1]));
-                const size_t npx = (size_t)S * Vl[p + 1] * Up[p + 1];
-                fill_f32_kernel<<<stream_grid(ctx, npx), 256, 0, ctx->stream>>>(N.dmin, npx, dmin);
-                fill_f32_kernel<<<stream_grid(ctx, npx), 256, 0, ctx->stream>>>(N.dmax, npx, dmax);
                 /* bounds of level p+1 from level p (ftc.hpp:201-294): rows 2v, 2v+1 are local when both levels are
                  * sharded (aligned blocks); the first replicated level reads the gathered maps of level p */
                 const float* b_depth = L.depth; const uint8_t* b_valid = L.valid;
@@ -1517,8 +1566,8 @@ extern "C" int rslf_cuda_fine_to_coarse_run(rslf_ctx* ctx, float dmin, float dma
                 nearest_valid_kernel<<<rslf_div_up((long long)rows * 32, 256), 256, 0, ctx->stream>>>(b_valid, rows, Up[p], ctx->nearest_l, ctx->nearest_r);
                 dim3 grid(rslf_div_up(Up[p + 1], 128), Vl[p + 1], S);
                 set_bounds_kernel<<<grid, 128, 0, ctx->stream>>>(b_depth, ctx->nearest_l, ctx->nearest_r, S, b_rows, Up[p],
-                                                                 Vl[p + 1], Up[p + 1], N.dmin, N.dmax, Vp[p], b_v0, ov0);
-                ctx->timing.kernel_launches += 4;
+                                                                 Vl[p + 1], Up[p + 1], N.dmin, N.dmax, Vp[p], b_v0, ov0, 1, dmin, dmax);
+                ctx->timing.kernel_launches += 2;
             }
             RSLF_CUDA_TRY(ctx, cudaGetLastError());
         }
@@ -1801,7 +1850,7 @@ extern "C" int rslf_cuda_set_bounds(rslf_ctx* ctx, const float* depth_up, const 
         const int rows = S * Vu;
         nearest_valid_kernel<<<rslf_div_up((long long)rows * 32, 256), 256, 0, ctx->stream>>>(d_val, rows, Uu, d_l, d_r);
         dim3 grid(rslf_div_up(Ud, 128), Vd, S);
-        set_bounds_kernel<<<grid, 128, 0, ctx->stream>>>(d_dep, d_l, d_r, S, Vu, Uu, Vd, Ud, d_mn, d_mx, Vu, 0, 0);
+        set_bounds_kernel<<<grid, 128, 0, ctx->stream>>>(d_dep, d_l, d_r, S, Vu, Uu, Vd, Ud, d_mn, d_mx, Vu, 0, 0, 0, 0.f, 0.f);
         cudaMemcpyAsync(dmin_map, d_mn, nd * 4, cudaMemcpyDeviceToHost, ctx->stream);
         cudaMemcpyAsync(dmax_map, d_mx, nd * 4, cudaMemcpyDeviceToHost, ctx->stream);
         if (cudaStreamSynchronize(ctx->stream) != cudaSuccess || cudaGetLastError() != cudaSuccess) rc = RSLF_ERR_CUDA;

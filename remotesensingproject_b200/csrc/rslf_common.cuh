@@ -41,6 +41,7 @@ struct rslf_level {
     float slope = 1.f;
     int nonneg = 1;              /* normalised stack has no negative value                    */
     bool have_bounds = false;
+    bool bounds_const = false; float bounds_lo = 0.f, bounds_hi = 0.f;   /* dmin / dmax maps not filled: every pixel has these bounds */
     size_t cap_px = 0;           /* allocated S*V*U                                           */
     size_t cap_stack = 0;        /* allocated floats of epi (and raw, levels > 0)             */
     int C = 0;                   /* channels the maps were allocated for                      */
@@ -71,11 +72,13 @@ struct rslf_ctx {
     bool have_input = false;
     float* open_ce = nullptr; uint8_t* open_mask = nullptr; uint8_t* open_tmp = nullptr; size_t open_cap = 0;   /* extended planes of a sharded opening */
     void* img_staging = nullptr; size_t img_staging_cap = 0;   /* rslf_cuda_upload_images: the image stack before the transposition */
+    unsigned ring_next = 0;
     void* ring[2] = {nullptr, nullptr}; cudaEvent_t ring_ev[2] = {nullptr, nullptr};   /* pinned ring for pageable host images */
     cudaStream_t stream2 = nullptr; cudaEvent_t ev_img = nullptr;
     void* raw_full = nullptr;    /* multi-rank runs: all rows of the raw stack, gathered once per input */
     size_t raw_full_cap = 0;
     unsigned input_epoch = 1, raw_full_epoch = 0;
+    float mm0[2] = {0.f, 0.f}; unsigned mm0_epoch = 0;   /* max / min of the uploaded float stack, per input */
     /* pipelined ingest (rslf_cuda_upload_epis_pipelined): level 0 was normalised / its edge confidence computed while the
      * stack was still arriving; valid for the input of that epoch (and, for the edge confidence, those parameters) */
     unsigned pre_norm_epoch = 0, pre_edge_epoch = 0; int pre_nonneg = 1; rslf_params pre_params;
