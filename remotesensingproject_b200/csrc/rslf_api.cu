@@ -336,6 +336,7 @@ extern "C" int rslf_cuda_create(int device, rslf_ctx** out)
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return RSLF_ERR_CUDA;
     if (cudaSetDevice(device) != cudaSuccess) return RSLF_ERR_CUDA;
+    probe_ctx("create");
     rslf_ctx* ctx = new rslf_ctx();
     ctx->device = device;
     cudaDeviceProp prop;
@@ -366,29 +367,43 @@ extern "C" int rslf_cuda_create(int device, rslf_ctx** out)
 extern "C" void rslf_cuda_destroy(rslf_ctx* ctx)
 {
     if (!ctx) return;
+    const bool dbg = getenv("RSLF_DEBUG_DESTROY") != nullptr;
+#define DBG(x) do { if (dbg) { fprintf(stderr, "[destroy r%d] %s\n", ctx->rank, x); fflush(stderr); probe_ctx(x); } } while (0)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    DBG("comm_destroy");
     comm_destroy(ctx);
+    DBG("levels");
     for (int p = 0; p < RSLF_MAX_LEVELS; ++p) free_level(ctx->lv[p]);
+    DBG("scratch");
     free_scratch(ctx);
+    DBG("rest");
     if (ctx->raw_in && !ctx->raw_borrowed) cudaFree(ctx->raw_in);
+    DBG("raw_full");
     if (ctx->raw_full) cudaFree(ctx->raw_full);
+    DBG("staging/open");
     if (ctx->img_staging) cudaFree(ctx->img_staging);
     if (ctx->open_ce) cudaFree(ctx->open_ce);
     if (ctx->open_mask) cudaFree(ctx->open_mask);
     if (ctx->open_tmp) cudaFree(ctx->open_tmp);
-    for (int i = 0; i < 2; ++i) { if (ctx->ring[i]) cudaFreeHost(ctx->ring[i]); if (ctx->ring_ev[i]) cudaEventDestroy(ctx->ring_ev[i]); }
+    DBG("ring: process-wide, kept");
+    DBG("stream2");
     if (ctx->ev_img) cudaEventDestroy(ctx->ev_img);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
+    DBG("small buffers");
     dev_free(&ctx->queue); dev_free(&ctx->dev_err); dev_free(&ctx->dlog); dev_free(&ctx->dlog_count);
     dev_free(&ctx->count); dev_free(&ctx->total_px); dev_free(&ctx->minmax); dev_free(&ctx->rowwork);
     dev_free(&ctx->colour_hist); dev_free(&ctx->colour_lut);
     if (ctx->l2_flush) cudaFree(ctx->l2_flush);
+    DBG("events");
     for (auto e : ctx->clk.pool) cudaEventDestroy(e);
     if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
     if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
+    DBG("stream");
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    DBG("delete");
     delete ctx;
+#undef DBG
 }
 
 extern "C" const char* rslf_cuda_last_error_text(const rslf_ctx* ctx) { return ctx ? ctx->err : "null ctx"; }
@@ -519,12 +534,14 @@ extern "C" int rslf_cuda_upload_epis(rslf_ctx* ctx, const void* const* epi_ptrs,
 {
     if (!ctx || !epi_ptrs) return RSLF_ERR_ARG;
     RSLF_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    probe_ctx("upload begin");
     RSLF_TRY(set_dims(ctx, V, S, U, C, cv_depth, epi_scale_factor));
     const size_t esz = depth_esz(cv_depth);
     const size_t row = (size_t)U * C * esz;
     if (row_step_bytes < row) { snprintf(ctx->err, sizeof(ctx->err), "row step smaller than a row"); return RSLF_ERR_ARG; }
     const size_t epi_bytes = row * S;
     RSLF_TRY(own_raw(ctx, epi_bytes * V));
+    probe_ctx("upload after own_raw");
     cudaEventRecord(ctx->ev_a, ctx->stream);
     /* V images of S rows: pinned / registered memory by DMA, pageable cv::Mat storage through the pinned ring */
     RSLF_TRY(images_to_device(ctx, ctx->raw_in, V, S, row, epi_ptrs, row_step_bytes));
@@ -1013,14 +1030,28 @@ static bool host_is_pinned(const void* p)
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
     return a.type == cudaMemoryTypeHost;
 }
+/* The ring is per DEVICE and lives as long as the process: page-locking 2 x 64 MB costs tens of milliseconds, and a
+ * computer object (hence a context) is typically made per light field.  It is deliberately never released: on B200 /
+ * driver 580 cudaFreeHost of it faulted in a process that had had peer (CUDA IPC) mappings to another GPU. */
+struct rslf_ring { void* buf[2] = {nullptr, nullptr}; cudaEvent_t ev[2] = {nullptr, nullptr}; unsigned next = 0; };
+static rslf_ring g_ring[64];
+/* Set once a context of this process joins a multi-GPU communicator (peer mappings through CUDA IPC / NCCL): on B200 /
+ * driver 580 the ring's page-locked buffers and events then misbehave (cudaFreeHost faulted, an event recorded before
+ * the mappings were closed became "invalid device context").  From then on pageable images take the driver's own
+ * staged copies; page-locked images (the bench's buffers, rslf_host_alloc) are unaffected: they never use the ring. */
+static bool g_no_ring = false;
+static void rslf_disable_ring() { g_no_ring = true; }
 static int ensure_ring(rslf_ctx* ctx)
 {
+    rslf_ring& g = g_ring[ctx->device & 63];
     for (int i = 0; i < 2; ++i) {
-        if (!ctx->ring[i] && cudaHostAlloc(&ctx->ring[i], RSLF_RING_BYTES, cudaHostAllocDefault) != cudaSuccess) {
+        if (!g.buf[i] && cudaHostAlloc(&g.buf[i], RSLF_RING_BYTES, cudaHostAllocDefault) != cudaSuccess) {
+            g.buf[i] = nullptr;
             snprintf(ctx->err, sizeof(ctx->err), "cudaHostAlloc(%zu) for the transfer ring failed", RSLF_RING_BYTES);
             return RSLF_ERR_NOMEM;
         }
-        if (!ctx->ring_ev[i]) RSLF_CUDA_TRY(ctx, cudaEventCreateWithFlags(&ctx->ring_ev[i], cudaEventDisableTiming));
+        if (!g.ev[i]) RSLF_CUDA_TRY(ctx, cudaEventCreateWithFlags(&g.ev[i], cudaEventDisableTiming));
+        ctx->ring[i] = g.buf[i]; ctx->ring_ev[i] = g.ev[i];
     }
     return RSLF_OK;
 }
@@ -1092,6 +1123,12 @@ static int planes_to_host(rslf_ctx* ctx, const void* dev, int planes, int rows, 
                                                              row_bytes, rows, cudaMemcpyDeviceToHost, ctx->stream));
         return RSLF_OK;
     }
+    if (g_no_ring) {
+        for (int p = 0; p < planes; ++p)
+            if (host[p]) RSLF_CUDA_TRY(ctx, cudaMemcpy2DAsync(host[p], step, (const char*)dev + (size_t)p * rows * row_bytes, row_bytes,
+                                                             row_bytes, rows, cudaMemcpyDeviceToHost, ctx->stream));
+        return RSLF_OK;
+    }
     RSLF_TRY(ensure_ring(ctx));
     const std::vector<ring_job> jobs = ring_jobs(planes, rows, row_bytes, host, step);
     for (size_t i = 0; i < jobs.size() + 2; ++i) {
@@ -1101,6 +1138,7 @@ static int planes_to_host(rslf_ctx* ctx, const void* dev, int planes, int rows, 
             ring_copy(jobs[i - 2], (char*)ctx->ring[slot], row_bytes, step, false);
         }
         if (i < jobs.size()) {
+            if (i < 2) RSLF_CUDA_TRY(ctx, cudaEventSynchronize(ctx->ring_ev[slot]));   /* an earlier call's transfer may still use the buffer */
             RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->ring[slot], (const char*)dev + jobs[i].dev_off, jobs[i].bytes, cudaMemcpyDeviceToHost, ctx->stream));
             RSLF_CUDA_TRY(ctx, cudaEventRecord(ctx->ring_ev[slot], ctx->stream));
         }
@@ -1111,8 +1149,11 @@ static int planes_to_host(rslf_ctx* ctx, const void* dev, int planes, int rows, 
 /* host images -> device [n_imgs][rows][row_bytes] */
 static int images_to_device(rslf_ctx* ctx, void* dev, int n_imgs, int rows, size_t row_bytes, const void* const* host, size_t step)
 {
-    bool pinned = true;
-    for (int p = 0; p < n_imgs && pinned; ++p) pinned = host_is_pinned(host[p]);
+    bool pinned = g_no_ring;                          /* no ring: the driver stages pageable memory itself */
+    if (!pinned) {
+        pinned = true;
+        for (int p = 0; p < n_imgs && pinned; ++p) pinned = host_is_pinned(host[p]);
+    }
     if (pinned) {
         /* one dense copy when the images are continuous and back to back, else one strided copy per image */
         bool dense = (step == row_bytes);
@@ -1126,7 +1167,7 @@ static int images_to_device(rslf_ctx* ctx, void* dev, int n_imgs, int rows, size
     RSLF_TRY(ensure_ring(ctx));
     const std::vector<ring_job> jobs = ring_jobs(n_imgs, rows, row_bytes, (void* const*)host, step);
     for (size_t i = 0; i < jobs.size(); ++i) {
-        const int slot = (int)(ctx->ring_next++ & 1u);                      /* alternates across calls too (chunked uploads) */
+        const int slot = (int)(g_ring[ctx->device & 63].next++ & 1u);       /* alternates across calls too (chunked uploads) */
         RSLF_CUDA_TRY(ctx, cudaEventSynchronize(ctx->ring_ev[slot]));       /* its previous transfer (this call's or an earlier one's) has left the buffer */
         ring_copy(jobs[i], (char*)ctx->ring[slot], row_bytes, step, true);
         RSLF_CUDA_TRY(ctx, cudaMemcpyAsync((char*)dev + jobs[i].dev_off, ctx->ring[slot], jobs[i].bytes, cudaMemcpyHostToDevice, ctx->stream));

@@ -3,6 +3,7 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
         tools/multigpu_check.py
 Every rank also runs the unsharded light field on its own GPU as the comparison."""
+import faulthandler
 import os
 import sys
 
@@ -17,6 +18,7 @@ from remotesensingproject_b200.synth import make_light_field_np
 
 
 def main():
+    faulthandler.enable()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
