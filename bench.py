@@ -379,6 +379,15 @@ def main():
                 full = None
                 torch.cuda.empty_cache()
     Vloc = epis.shape[0] if epis is not None else 0
+    # CUDA events inside the timed steps: on one GPU the launches of the dominant depth kernel are bracketed (two event
+    # records per pass, +0.4 % of a step) and give the roofline's launch duration over the timed region itself.  On
+    # several GPUs a pass is a few hundred microseconds and every event record between two kernels costs the overlap of
+    # their launches (+3.5 % on two GPUs, about +10 % on eight): the timed steps then carry no event inside the run and
+    # the kernel's duration comes from the extra instrumented steps below.
+    timed_level = 1 if world == 1 else 0
+    if args.no_stage_check:
+        timed_level = 1
+    ctx.set_stage_timing(timed_level)
     sampler = ClockSampler(local)
     sampler.start()
     acc, wall = timed(args.steps)
@@ -409,12 +418,16 @@ def main():
         stages = {k: a3[k] / k2 for k in ("ms_edge", "ms_depth", "ms_reduce", "ms_median", "ms_propagate", "ms_pyramid")}
         stages["ms_per_step_with_all_stage_events"] = r3["dev_ms"] / k2
         stages["note"] = "rank 0, %d extra steps with rslf_cuda_set_stage_timing(2); a stage includes its waits for peer GPUs" % k2
-        ctx.set_stage_timing(0)
+        ctx.set_stage_timing(1 - timed_level)
         a2, w2 = timed(k2)
-        ctx.set_stage_timing(1)
+        ctx.set_stage_timing(timed_level)
         r2 = reduce_stats(a2, w2)
-        no_stage = {"ms_per_step": r2["dev_ms"] / k2,
-                    "note": "same steps with rslf_cuda_set_stage_timing(0): no event records inside the run"}
+        no_stage = {"ms_per_step": r2["dev_ms"] / k2, "stage_timing_level": 1 - timed_level,
+                    "note": ("same steps with rslf_cuda_set_stage_timing(0): no event records inside the run" if timed_level == 1 else
+                             "same steps with rslf_cuda_set_stage_timing(1): events around the depth kernel's launches only")}
+        if timed_level == 0:
+            # the depth kernel's launch times of this rank, measured in the instrumented steps (see timed_level above)
+            acc["ms_depth"] = a3["ms_depth"] * args.steps / k2
 
     # ---- extra leg: the opt-in contracted (FMA) mean shift (rslf_cuda_set_fast_math), same steps, reported beside the
     # headline, never instead of it: its results are within the north star's tolerance but not bit-identical ----------
@@ -618,6 +631,8 @@ def main():
                        "samples_per_step": samples / args.steps, "pixels_per_step": pixels / args.steps,
                        "timing": "CUDA events on the library stream around each run, summed per step, max over ranks; host clock "
                                  "between the barriers (L2 flushes included) in ms_per_step_wall",
+                       "events_inside_timed_runs": "around the depth kernel's launches" if timed_level == 1 else
+                                                   "none (roofline launch times from the extra instrumented steps)",
                        "ms_per_step_wall": wall / args.steps * 1e3,
                        "ms_per_disparity_result_device": acc["ms_total"] / args.steps / (batch and len(fields) or 1),
                        "fields_per_s": (batch * args.steps / (dev_ms * 1e-3)) if batch else None},
