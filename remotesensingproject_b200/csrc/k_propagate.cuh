@@ -26,7 +26,9 @@
 #include "rslf_common.cuh"
 
 #define PROP_THREADS 128
-#define PROP_SG 8
+#define PROP_SG 32              /* views per block of the dense kind (one bit each in the block's `live` word) */
+#define PROP_DENSE_MIN 8192     /* list entries from which the list kind walks sources by lane instead of views by lane */
+#define PROP_VS 4               /* view slices per group of 32 sources in that mode */
 
 struct prop_args {
     const float* epi; int V, S, U; int s_hat; float slope; float eps; double eps_T;
@@ -91,6 +93,29 @@ propagate_kernel(const prop_args a, int list_blocks)
         const int n1 = *a.count, n = n1 + (a.count2 ? *a.count2 : 0);
         const int lane = threadIdx.x & 31;
         const int warps = (list_blocks * PROP_THREADS) >> 5;
+        if (n >= PROP_DENSE_MIN) {
+            /* Dense list (the first passes of a level: up to a million sources): lanes over 32 CONSECUTIVE list entries —
+             * the compaction keeps the pixels of a 32-pixel stretch in order — and a loop over a slice of the views.  In
+             * one view the 32 lanes then touch neighbouring targets (sources that lie side by side mostly carry similar
+             * depths): the mask bytes and the colours of a warp's access fall into a few sectors instead of 32 planes. */
+            const int groups = (n + 31) >> 5;
+            for (int item = (blockIdx.x * PROP_THREADS + threadIdx.x) >> 5; item < groups * PROP_VS; item += warps) {
+                const int g = item / PROP_VS, vs = item - g * PROP_VS;
+                const int e = (g << 5) + lane;
+                int pix = 0; bool ok = false;
+                if (e < n) { pix = (e < n1) ? a.items[e] : a.items2[e - n1]; ok = prop_source(a, pix); }
+                const int v = pix / a.U, u = pix - v * a.U;
+                float rb[C];
+#pragma unroll
+                for (int c = 0; c < C; ++c) rb[c] = ok ? a.rbar_p[(size_t)pix * C + c] : 0.f;
+                const float cur = ok ? a.filtered[pix] : 0.f;
+                const float cdv = (PHASE && ok) ? a.cd_p[pix] : 0.f;
+                const int s0 = a.S * vs / PROP_VS, s1 = a.S * (vs + 1) / PROP_VS;
+                if (ok)
+                    for (int s = s0; s < s1; ++s) propagate_one<C, PHASE>(a, v, u, s, cur, rb, cdv);
+            }
+            return;
+        }
         for (int it = (blockIdx.x * PROP_THREADS + threadIdx.x) >> 5; it < n; it += warps) {
             const int pix = (it < n1) ? a.items[it] : a.items2[it - n1];
             if (!prop_source(a, pix)) continue;             /* e.g. score <= threshold: dropped by the depth kernel */
