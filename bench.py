@@ -418,6 +418,9 @@ def main():
         stages = {k: a3[k] / k2 for k in ("ms_edge", "ms_depth", "ms_reduce", "ms_median", "ms_propagate", "ms_pyramid")}
         stages["ms_per_step_with_all_stage_events"] = r3["dev_ms"] / k2
         stages["note"] = "rank 0, %d extra steps with rslf_cuda_set_stage_timing(2); a stage includes its waits for peer GPUs" % k2
+        if os.environ.get("RSLF_BENCH_SPANS") and rank == 0 and not batch:      # per-pass spans of the last instrumented step
+            with open(os.environ["RSLF_BENCH_SPANS"], "w") as f:
+                json.dump(ctx.last_spans(), f)
         ctx.set_stage_timing(1 - timed_level)
         a2, w2 = timed(k2)
         ctx.set_stage_timing(timed_level)

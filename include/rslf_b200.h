@@ -349,6 +349,9 @@ int rslf_cuda_get_decision_log(rslf_ctx* ctx, rslf_decision* out, size_t max_rec
  * depth kernel (ms_depth, the roofline's denominator; two records per s_hat pass), 2 = around every stage (ms_edge ...
  * ms_pyramid; about twelve records per pass, which serialise the stream: +2 % on one GPU, +10 % on eight). */
 int rslf_cuda_set_stage_timing(rslf_ctx* ctx, int level);
+/* Diagnostics: the event spans of the last run in issue order (stage 0 edge, 1 depth, 2 reduce / compaction, 3 median,
+ * 4 propagation, 5 pyramid; milliseconds): with level 2 one entry per stage and s_hat pass. */
+int rslf_cuda_last_spans(const rslf_ctx* ctx, int* stage, float* ms, size_t max_spans, size_t* count);
 /* Row-sharded runs: 1 (default) = the pixels of every s_hat pass are split evenly over the ranks whatever rows they
  * lie in (every rank holds the whole EPI stack, the result maps stay sharded by rows; work / result records travel
  * through peer memory over NVLink); 0 = lock-step row blocks: every rank evaluates the pixels of its own rows (the

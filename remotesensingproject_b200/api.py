@@ -355,6 +355,15 @@ class Context:
     def set_balance(self, on):
         self.check(lib().rslf_cuda_set_balance(self._h, int(bool(on))), "rslf_cuda_set_balance")
 
+    def last_spans(self):
+        """[(stage id, ms)] of the last run in issue order (see rslf_cuda_last_spans)."""
+        n = C.c_size_t(0)
+        self.check(lib().rslf_cuda_last_spans(self._h, None, None, C.c_size_t(0), C.byref(n)), "rslf_cuda_last_spans")
+        st = (C.c_int * max(1, n.value))()
+        ms = (C.c_float * max(1, n.value))()
+        self.check(lib().rslf_cuda_last_spans(self._h, st, ms, C.c_size_t(n.value), C.byref(n)), "rslf_cuda_last_spans")
+        return [(st[i], ms[i]) for i in range(n.value)]
+
     def set_fast_math(self, on):
         """Opt-in contracted (FMA) mean shift for RGB stacks: faster, within the specified tolerance, not bit-identical."""
         self.check(lib().rslf_cuda_set_fast_math(self._h, int(bool(on))), "rslf_cuda_set_fast_math")

@@ -29,7 +29,8 @@ __global__ void __launch_bounds__(EDGE_THREADS)
 edge_confidence_kernel(const float* __restrict__ epi, int V, int S, int U, int s_first, int s_count,
                        int fs, int cut_shadows, float shadow_level, double shadow_T, float thr,
                        float* __restrict__ ce_out, uint8_t* __restrict__ mask_out,
-                       float dark_eps, double dark_T, int* __restrict__ rowdark, int v_first)
+                       float dark_eps, double dark_T, int* __restrict__ rowdark, int v_first,
+                       int* __restrict__ dark_lo, int* __restrict__ dark_hi)
 {
     /* the grid covers rows v_first .. of the V-row planes (a chunk of EPIs during the pipelined ingest, else all) */
     extern __shared__ float seg[];                 /* (EDGE_TILE + fs - 1) * C floats */
@@ -48,7 +49,7 @@ edge_confidence_kernel(const float* __restrict__ epi, int V, int S, int U, int s
     }
     __syncthreads();
     const size_t out_row = ((size_t)si * V + v) * (size_t)U;
-    int ndark = 0;
+    int ndark = 0, dlo = 0x7fffffff, dhi = -1;         /* dark confident pixels of the row: count and column range */
 #pragma unroll
     for (int k = 0; k < EDGE_PPT; ++k) {
         /* pixel index inside the tile: consecutive threads take consecutive pixels (coalesced stores) */
@@ -83,12 +84,19 @@ edge_confidence_kernel(const float* __restrict__ epi, int V, int S, int U, int s
             if (C == 1) dk = rslf_norm1_lt(x[0], dark_eps);
             else dk = rslf_norm3_lt(x[0], x[C > 1 ? 1 : 0], x[C > 2 ? 2 : 0], dark_T);
             ndark += dk ? 1 : 0;
+            if (dk) { dlo = min(dlo, u); dhi = max(dhi, u); }
         }
     }
     if (rowdark) {
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) ndark += __shfl_xor_sync(0xffffffffu, ndark, off);
-        if ((threadIdx.x & 31) == 0 && ndark) atomicAdd(rowdark + (size_t)si * V + v, ndark);
+        for (int off = 16; off > 0; off >>= 1) {
+            ndark += __shfl_xor_sync(0xffffffffu, ndark, off);
+            dlo = min(dlo, __shfl_xor_sync(0xffffffffu, dlo, off)); dhi = max(dhi, __shfl_xor_sync(0xffffffffu, dhi, off));
+        }
+        if ((threadIdx.x & 31) == 0 && ndark) {
+            atomicAdd(rowdark + (size_t)si * V + v, ndark);
+            if (dark_lo) { atomicMin(dark_lo + (size_t)si * V + v, dlo); atomicMax(dark_hi + (size_t)si * V + v, dhi); }
+        }
     }
 }
 
@@ -158,13 +166,14 @@ morph_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int V, i
 template <int C>
 __global__ void __launch_bounds__(EDGE_THREADS)
 rowdark_count_kernel(const float* __restrict__ epi, const uint8_t* __restrict__ mask, int V, int S, int U, int s_first,
-                     int s_count, float dark_eps, double dark_T, int* __restrict__ rowdark)
+                     int s_count, float dark_eps, double dark_T, int* __restrict__ rowdark,
+                     int* __restrict__ dark_lo, int* __restrict__ dark_hi)
 {
     const int row = blockIdx.x;
     const int v = row / s_count, si = row % s_count;
     const float* src = epi + ((size_t)v * S + (s_first + si)) * (size_t)U * C;
     const uint8_t* m = mask + ((size_t)si * V + v) * (size_t)U;
-    int ndark = 0;
+    int ndark = 0, dlo = 0x7fffffff, dhi = -1;
     for (int u = threadIdx.x; u < U; u += EDGE_THREADS) {
         if (!m[u]) continue;
         float x[C];
@@ -174,10 +183,17 @@ rowdark_count_kernel(const float* __restrict__ epi, const uint8_t* __restrict__ 
         if (C == 1) dk = rslf_norm1_lt(x[0], dark_eps);
         else dk = rslf_norm3_lt(x[0], x[C > 1 ? 1 : 0], x[C > 2 ? 2 : 0], dark_T);
         ndark += dk ? 1 : 0;
+        if (dk) { dlo = min(dlo, u); dhi = max(dhi, u); }
     }
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) ndark += __shfl_xor_sync(0xffffffffu, ndark, off);
-    if ((threadIdx.x & 31) == 0 && ndark) atomicAdd(rowdark + (size_t)si * V + v, ndark);
+    for (int off = 16; off > 0; off >>= 1) {
+        ndark += __shfl_xor_sync(0xffffffffu, ndark, off);
+        dlo = min(dlo, __shfl_xor_sync(0xffffffffu, dlo, off)); dhi = max(dhi, __shfl_xor_sync(0xffffffffu, dhi, off));
+    }
+    if ((threadIdx.x & 31) == 0 && ndark) {
+        atomicAdd(rowdark + (size_t)si * V + v, ndark);
+        if (dark_lo) { atomicMin(dark_lo + (size_t)si * V + v, dlo); atomicMax(dark_hi + (size_t)si * V + v, dhi); }
+    }
 }
 
 /* Launch for lines [s_first, s_first + s_count) of every row; output planes are
@@ -185,7 +201,8 @@ rowdark_count_kernel(const float* __restrict__ epi, const uint8_t* __restrict__ 
  * when the opening is enabled (edge_confidence_opening_size > 1). */
 static int launch_edge_confidence(rslf_ctx* ctx, const float* epi, int V, int S, int U, int C, int s_first,
                                   int s_count, const rslf_params& P, float* ce_out, uint8_t* mask_out,
-                                  int* rowdark = nullptr, uint8_t* mask_tmp = nullptr, int rows_above = 0, int rows_below = 0)
+                                  int* rowdark = nullptr, uint8_t* mask_tmp = nullptr, int rows_above = 0, int rows_below = 0,
+                                  int* dark_lo = nullptr, int* dark_hi = nullptr)
 {
     /* Row-sharded level with the opening switched on: the element reaches k/2 rows beyond the block in the erosion and
      * again in the dilation.  Every rank holds the whole EPI stack, so it computes C_e and the mask on its rows PLUS
@@ -218,8 +235,8 @@ static int launch_edge_confidence(rslf_ctx* ctx, const float* epi, int V, int S,
         if (rowdark) {
             const double dT = rslf_sq_threshold(P.propagation_epsilon);
             const unsigned rows = (unsigned)((size_t)V * s_count);
-            if (C == 1) rowdark_count_kernel<1><<<rows, EDGE_THREADS, 0, ctx->stream>>>(epi, mask_out, V, S, U, s_first, s_count, P.propagation_epsilon, dT, rowdark);
-            else rowdark_count_kernel<3><<<rows, EDGE_THREADS, 0, ctx->stream>>>(epi, mask_out, V, S, U, s_first, s_count, P.propagation_epsilon, dT, rowdark);
+            if (C == 1) rowdark_count_kernel<1><<<rows, EDGE_THREADS, 0, ctx->stream>>>(epi, mask_out, V, S, U, s_first, s_count, P.propagation_epsilon, dT, rowdark, dark_lo, dark_hi);
+            else rowdark_count_kernel<3><<<rows, EDGE_THREADS, 0, ctx->stream>>>(epi, mask_out, V, S, U, s_first, s_count, P.propagation_epsilon, dT, rowdark, dark_lo, dark_hi);
             RSLF_CUDA_TRY(ctx, cudaGetLastError());
             ctx->timing.kernel_launches += 1;
         }
@@ -250,11 +267,11 @@ static int launch_edge_confidence(rslf_ctx* ctx, const float* epi, int V, int S,
     if (C == 1)
         edge_confidence_kernel<1><<<grid, EDGE_THREADS, smem, ctx->stream>>>(
             epi, V, S, U, s_first, s_count, fs, P.cut_shadows, P.shadow_level, T, P.edge_score_threshold, ce_out, mask_out,
-            P.propagation_epsilon, dT, rowdark, 0);
+            P.propagation_epsilon, dT, rowdark, 0, dark_lo, dark_hi);
     else
         edge_confidence_kernel<3><<<grid, EDGE_THREADS, smem, ctx->stream>>>(
             epi, V, S, U, s_first, s_count, fs, P.cut_shadows, P.shadow_level, T, P.edge_score_threshold, ce_out, mask_out,
-            P.propagation_epsilon, dT, rowdark, 0);
+            P.propagation_epsilon, dT, rowdark, 0, dark_lo, dark_hi);
     RSLF_CUDA_TRY(ctx, cudaGetLastError());
     ctx->timing.kernel_launches += 1;
     if (opening) {
@@ -264,8 +281,8 @@ static int launch_edge_confidence(rslf_ctx* ctx, const float* epi, int V, int S,
         ctx->timing.kernel_launches += 2;
         if (rowdark_late) {
             const unsigned rows = (unsigned)((size_t)V * s_count);
-            if (C == 1) rowdark_count_kernel<1><<<rows, EDGE_THREADS, 0, ctx->stream>>>(epi, mask_out, V, S, U, s_first, s_count, P.propagation_epsilon, dT, rowdark_late);
-            else rowdark_count_kernel<3><<<rows, EDGE_THREADS, 0, ctx->stream>>>(epi, mask_out, V, S, U, s_first, s_count, P.propagation_epsilon, dT, rowdark_late);
+            if (C == 1) rowdark_count_kernel<1><<<rows, EDGE_THREADS, 0, ctx->stream>>>(epi, mask_out, V, S, U, s_first, s_count, P.propagation_epsilon, dT, rowdark_late, dark_lo, dark_hi);
+            else rowdark_count_kernel<3><<<rows, EDGE_THREADS, 0, ctx->stream>>>(epi, mask_out, V, S, U, s_first, s_count, P.propagation_epsilon, dT, rowdark_late, dark_lo, dark_hi);
             ctx->timing.kernel_launches += 1;
         }
         RSLF_CUDA_TRY(ctx, cudaGetLastError());
@@ -276,7 +293,8 @@ static int launch_edge_confidence(rslf_ctx* ctx, const float* epi, int V, int S,
 /* Edge confidence of all S lines of the EPIs [v_first, v_first + v_count) on `stream` (pipelined ingest: a chunk of
  * EPIs that has just been uploaded and normalised); planes are [S][V][U].  No opening (that needs the whole mask). */
 static int launch_edge_confidence_rows(rslf_ctx* ctx, cudaStream_t stream, const float* epi, int V, int S, int U, int C, int v_first,
-                                       int v_count, const rslf_params& P, float* ce_out, uint8_t* mask_out, int* rowdark)
+                                       int v_count, const rslf_params& P, float* ce_out, uint8_t* mask_out, int* rowdark,
+                                       int* dark_lo, int* dark_hi)
 {
     const int fs = P.edge_confidence_filter_size;
     if (fs < 1 || fs > EDGE_MAX_FS) return RSLF_ERR_UNSUPPORTED;
@@ -285,10 +303,10 @@ static int launch_edge_confidence_rows(rslf_ctx* ctx, cudaStream_t stream, const
     const double T = rslf_sq_threshold(P.shadow_level), dT = rslf_sq_threshold(P.propagation_epsilon);
     if (C == 1)
         edge_confidence_kernel<1><<<grid, EDGE_THREADS, smem, stream>>>(epi, V, S, U, 0, S, fs, P.cut_shadows, P.shadow_level, T, P.edge_score_threshold,
-                                                                        ce_out, mask_out, P.propagation_epsilon, dT, rowdark, v_first);
+                                                                        ce_out, mask_out, P.propagation_epsilon, dT, rowdark, v_first, dark_lo, dark_hi);
     else
         edge_confidence_kernel<3><<<grid, EDGE_THREADS, smem, stream>>>(epi, V, S, U, 0, S, fs, P.cut_shadows, P.shadow_level, T, P.edge_score_threshold,
-                                                                        ce_out, mask_out, P.propagation_epsilon, dT, rowdark, v_first);
+                                                                        ce_out, mask_out, P.propagation_epsilon, dT, rowdark, v_first, dark_lo, dark_hi);
     RSLF_CUDA_TRY(ctx, cudaGetLastError());
     ctx->timing.kernel_launches += 1;
     return RSLF_OK;

@@ -40,6 +40,7 @@ struct prop_args {
     const int* items; const int* count;                         /* work list of the pass */
     const int* items2; const int* count2;                       /* second part of the list (row-sharded runs), or nullptr */
     int* rowdark;                                                /* [S][V] confident-and-dark pixels still unpainted (upper bound) */
+    const int* dark_lo; const int* dark_hi;                      /* [S][V] column range that holds them (a bound; nullptr: no range test) */
     int criterion; float disp_thr;                               /* 1: sources are the pixels with C_d > disp_thr (core.hpp:1097-1098 as intended) */
 };
 
@@ -132,8 +133,22 @@ propagate_kernel(const prop_args a, int list_blocks)
     const int idx = (int)blockIdx.x - list_blocks;
     const int v = idx % a.V;
     const int s_begin = (idx / a.V) * PROP_SG, s_end = min(a.S, s_begin + PROP_SG);
-    unsigned live = 0;                                      /* views of the group that still hold a dark target */
-    for (int s = s_begin; s < s_end; ++s) live |= (a.rowdark[(size_t)s * a.V + v] > 0) ? (1u << (s - s_begin)) : 0u;
+    /* views of the group that still hold a dark target in this row, and the column range those targets lie in: a source
+     * without r_bar can only paint such targets, so a (source, view) pair whose target column falls outside the range
+     * is rejected before any memory is touched */
+    __shared__ int s_lo[PROP_SG], s_hi[PROP_SG];
+    __shared__ unsigned s_live;
+    if (threadIdx.x == 0) s_live = 0;
+    __syncthreads();
+    if ((int)threadIdx.x < s_end - s_begin) {
+        const int s = s_begin + threadIdx.x;
+        const bool lv = a.rowdark[(size_t)s * a.V + v] > 0;
+        s_lo[threadIdx.x] = a.dark_lo ? a.dark_lo[(size_t)s * a.V + v] : 0;
+        s_hi[threadIdx.x] = a.dark_hi ? a.dark_hi[(size_t)s * a.V + v] : a.U - 1;
+        if (lv) atomicOr(&s_live, 1u << threadIdx.x);
+    }
+    __syncthreads();
+    const unsigned live = s_live;
     if (!live) return;
     for (int u = threadIdx.x; u < a.U; u += PROP_THREADS) {
         const size_t o = (size_t)v * a.U + u;
@@ -144,8 +159,14 @@ propagate_kernel(const prop_args a, int list_blocks)
         if (!zero) continue;
         const float cur = a.filtered[o];
         const float cdv = PHASE ? a.cd_p[o] : 0.f;
-        for (int s = s_begin; s < s_end; ++s)
-            if (live & (1u << (s - s_begin))) propagate_one<C, PHASE>(a, v, u, s, cur, rb, cdv);
+        for (int s = s_begin; s < s_end; ++s) {
+            if (!(live & (1u << (s - s_begin)))) continue;
+            float t = cur * (float)(a.s_hat - s);                       /* the target column, as in propagate_one */
+            t = t * a.slope;
+            const int q = u + (int)roundf(t);
+            if (q < s_lo[s - s_begin] || q > s_hi[s - s_begin]) continue;
+            propagate_one<C, PHASE>(a, v, u, s, cur, rb, cdv);
+        }
     }
 }
 

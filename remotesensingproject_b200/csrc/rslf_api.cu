@@ -74,9 +74,11 @@ struct stage_scope {
 static void clk_resolve(rslf_ctx* ctx)
 {
     float acc[ST_COUNT] = {0};
+    ctx->clk.span_ms.clear();
     for (auto& sp : ctx->clk.spans) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, ctx->clk.pool[sp.a], ctx->clk.pool[sp.b]) == cudaSuccess) acc[sp.stage] += ms;
+        ctx->clk.span_ms.push_back(ms);
     }
     ctx->timing.ms_edge = acc[ST_EDGE]; ctx->timing.ms_depth = acc[ST_DEPTH]; ctx->timing.ms_reduce = acc[ST_REDUCE];
     ctx->timing.ms_median = acc[ST_MEDIAN]; ctx->timing.ms_propagate = acc[ST_PROP]; ctx->timing.ms_pyramid = acc[ST_PYR];
@@ -86,7 +88,7 @@ static void free_level(rslf_level& L, bool keep_raw_borrowed_ptr = false)
 {
     (void)keep_raw_borrowed_ptr;
     dev_free(&L.raw); dev_free(&L.epi_full); L.epi = nullptr; dev_free(&L.ce); dev_free(&L.cd); dev_free(&L.depth); dev_free(&L.rbar);
-    dev_free(&L.dmin); dev_free(&L.dmax); dev_free(&L.emask); dev_free(&L.remaining); dev_free(&L.valid); dev_free(&L.rowdark);
+    dev_free(&L.dmin); dev_free(&L.dmax); dev_free(&L.emask); dev_free(&L.remaining); dev_free(&L.valid); dev_free(&L.rowdark); dev_free(&L.dark_lo); dev_free(&L.dark_hi);
     L.cap_px = 0; L.cap_stack = 0; L.V = L.U = 0; L.C = 0; L.have_bounds = false;
 }
 
@@ -177,6 +179,7 @@ static int ensure_level(rslf_ctx* ctx, int p, int V, int U, bool full, bool with
         RSLF_TRY(dev_alloc(ctx, &L.emask, px)); RSLF_TRY(dev_alloc(ctx, &L.remaining, px));
         RSLF_TRY(dev_alloc(ctx, &L.valid, px));
         RSLF_TRY(dev_alloc(ctx, &L.rowdark, (planes + 1) * (size_t)V));
+        RSLF_TRY(dev_alloc(ctx, &L.dark_lo, planes * (size_t)V)); RSLF_TRY(dev_alloc(ctx, &L.dark_hi, planes * (size_t)V));
         L.cap_px = px;
     }
     if (L.cap_stack < stack) {
@@ -415,6 +418,17 @@ extern "C" int rslf_cuda_last_timing(const rslf_ctx* ctx, rslf_timing* out)
     return RSLF_OK;
 }
 
+/* Diagnostics: the individual event spans of the last run in issue order (stage id 0 edge, 1 depth, 2 reduce, 3 median,
+ * 4 propagate, 5 pyramid; milliseconds); with rslf_cuda_set_stage_timing(2) that is one entry per stage and pass. */
+extern "C" int rslf_cuda_last_spans(const rslf_ctx* ctx, int* stage, float* ms, size_t max_spans, size_t* count)
+{
+    if (!ctx || !count) return RSLF_ERR_ARG;
+    const size_t n = std::min(ctx->clk.spans.size(), ctx->clk.span_ms.size());
+    *count = n;
+    for (size_t i = 0; i < n && i < max_spans; ++i) { if (stage) stage[i] = ctx->clk.spans[i].stage; if (ms) ms[i] = ctx->clk.span_ms[i]; }
+    return RSLF_OK;
+}
+
 extern "C" int rslf_cuda_set_stage_timing(rslf_ctx* ctx, int on)
 {
     if (!ctx) return RSLF_ERR_ARG;
@@ -590,7 +604,11 @@ extern "C" int rslf_cuda_upload_epis_pipelined(rslf_ctx* ctx, const void* const*
     cudaEventRecord(ctx->ev_a, ctx->stream);
     float init[2] = {0.f, std::numeric_limits<float>::infinity()};
     RSLF_CUDA_TRY(ctx, cudaMemcpyAsync(ctx->minmax, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
-    if (params) RSLF_CUDA_TRY(ctx, cudaMemsetAsync(L.rowdark, 0, ((size_t)S + 1) * V * sizeof(int), ctx->stream));
+    if (params) {
+        RSLF_CUDA_TRY(ctx, cudaMemsetAsync(L.rowdark, 0, ((size_t)S + 1) * V * sizeof(int), ctx->stream));
+        RSLF_CUDA_TRY(ctx, cudaMemsetAsync(L.dark_lo, 0x7f, (size_t)S * V * sizeof(int), ctx->stream));
+        RSLF_CUDA_TRY(ctx, cudaMemsetAsync(L.dark_hi, 0xff, (size_t)S * V * sizeof(int), ctx->stream));
+    }
     const float sf = epi_scale_factor;
     const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)V, RSLF_RING_BYTES / epi_bytes));
     for (int v0 = 0; v0 < V; v0 += chunk) {
@@ -609,7 +627,7 @@ extern "C" int rslf_cuda_upload_epis_pipelined(rslf_ctx* ctx, const void* const*
             normalise_f32_kernel<<<stream_grid(ctx, nv), 256, 0, ctx->stream2>>>((const float*)ctx->raw_in + (size_t)v0 * epi_vals, nv, nullptr, sf, out);
         }
         ctx->timing.kernel_launches += 1;
-        if (params) RSLF_TRY(launch_edge_confidence_rows(ctx, ctx->stream2, L.epi_full, V, S, U, C, v0, n, *params, L.ce, L.emask, L.rowdark));
+        if (params) RSLF_TRY(launch_edge_confidence_rows(ctx, ctx->stream2, L.epi_full, V, S, U, C, v0, n, *params, L.ce, L.emask, L.rowdark, L.dark_lo, L.dark_hi));
     }
     RSLF_CUDA_TRY(ctx, cudaGetLastError());
     RSLF_CUDA_TRY(ctx, cudaEventRecord(ctx->ev_img, ctx->stream2));
@@ -923,8 +941,11 @@ static int run_depth2d_level(rslf_ctx* ctx, int p, const rslf_params& P, float d
     RSLF_CUDA_TRY(ctx, cudaMemsetAsync(L.rbar, 0, px * C * sizeof(float), ctx->stream));
     /* level 0 of an input whose edge confidence was computed while it was uploaded, with the same parameters? */
     const bool pre_edge = (p == 0 && ctx->world <= 1 && ctx->pre_edge_epoch == ctx->input_epoch && edge_params_equal(ctx->pre_params, P));
-    if (!pre_edge) RSLF_CUDA_TRY(ctx, cudaMemsetAsync(L.rowdark, 0, ((size_t)S + 1) * V * sizeof(int), ctx->stream));
-    else RSLF_CUDA_TRY(ctx, cudaMemsetAsync(L.rowdark + (size_t)S * V, 0, (size_t)V * sizeof(int), ctx->stream));
+    if (!pre_edge) {
+        RSLF_CUDA_TRY(ctx, cudaMemsetAsync(L.rowdark, 0, ((size_t)S + 1) * V * sizeof(int), ctx->stream));
+        RSLF_CUDA_TRY(ctx, cudaMemsetAsync(L.dark_lo, 0x7f, (size_t)S * V * sizeof(int), ctx->stream));
+        RSLF_CUDA_TRY(ctx, cudaMemsetAsync(L.dark_hi, 0xff, (size_t)S * V * sizeof(int), ctx->stream));
+    } else RSLF_CUDA_TRY(ctx, cudaMemsetAsync(L.rowdark + (size_t)S * V, 0, (size_t)V * sizeof(int), ctx->stream));
     if (pre_edge) {
         stage_scope sc(ctx, ST_EDGE);
         row_sum_kernel<<<rslf_div_up(V, 256), 256, 0, ctx->stream>>>(L.rowdark, S, V, L.rowdark + (size_t)S * V);
@@ -935,7 +956,7 @@ static int run_depth2d_level(rslf_ctx* ctx, int p, const rslf_params& P, float d
         stage_scope sc(ctx, ST_EDGE);
         const bool sh = ctx->world > 1 && !L.replicated;
         RSLF_TRY(launch_edge_confidence(ctx, L.epi, V, S, U, C, 0, S, P, L.ce, L.emask, L.rowdark, L.remaining,   /* L.remaining is free until core.hpp:958-963 below */
-                                        sh ? L.v0 : 0, sh ? L.Vtot - L.v0 - V : 0));
+                                        sh ? L.v0 : 0, sh ? L.Vtot - L.v0 - V : 0, L.dark_lo, L.dark_hi));
         /* rows that hold a dark target in any view: rowdark[S][v] = sum over s (an upper bound for the whole level) */
         row_sum_kernel<<<rslf_div_up(V, 256), 256, 0, ctx->stream>>>(L.rowdark, S, V, L.rowdark + (size_t)S * V);
         RSLF_CUDA_TRY(ctx, cudaGetLastError());
@@ -958,6 +979,7 @@ static int run_depth2d_level(rslf_ctx* ctx, int p, const rslf_params& P, float d
             a.rbar_p = L.rbar + (size_t)s_hat * plane * C; a.cd_p = L.cd + (size_t)s_hat * plane;
             a.depth = L.depth; a.cd = L.cd; a.remaining = L.remaining; a.winner = ctx->winner;
             a.items = ctx->items; a.count = ctx->count + io.count_slot; a.rowdark = L.rowdark;
+            a.dark_lo = L.dark_lo; a.dark_hi = L.dark_hi;
             a.items2 = nullptr; a.count2 = nullptr;
             a.criterion = ctx->criterion; a.disp_thr = P.disp_score_threshold;
             RSLF_TRY(launch_propagate(ctx, C, a));

@@ -38,6 +38,7 @@ struct rslf_level {
     uint8_t* remaining = nullptr;/* "still to compute" mask    [S][V][U]                      */
     uint8_t* valid = nullptr;    /* validity mask for bounds / fuse [S][V][U]                 */
     int* rowdark = nullptr;      /* [S][V] confident-and-dark pixels not yet painted, then [V] row sums */
+    int* dark_lo = nullptr; int* dark_hi = nullptr;   /* [S][V] column range of those pixels (never shrinks: a bound) */
     float slope = 1.f;
     int nonneg = 1;              /* normalised stack has no negative value                    */
     bool have_bounds = false;
@@ -52,6 +53,7 @@ struct rslf_stage_clock {
     size_t used = 0;
     struct span { int stage; size_t a, b; };
     std::vector<span> spans;
+    std::vector<float> span_ms;
 };
 
 enum { ST_EDGE = 0, ST_DEPTH, ST_REDUCE, ST_MEDIAN, ST_PROP, ST_PYR, ST_COUNT };
