@@ -49,12 +49,20 @@ struct median_halo {
     const volatile unsigned* flag_top; const volatile unsigned* flag_bot; unsigned seq; int* err;
 };
 
+/* Which painted pixels of a row that still holds dark targets can reach one (k_propagate.cuh, second kind of source)?
+ * A source at column u paints column u + round(d k_s slope) in view s, with its filtered depth d somewhere in the level's
+ * disparity range [dlo, dhi]; the dark targets of (row, view s) lie in columns [lo_s, hi_s].  So only sources with
+ * u in the hull over the live views of [lo_s - max offset, hi_s - min offset] need a filtered value at all.
+ * on == 0 (user-edited bounds may leave the range): every painted pixel of such a row is filtered. */
+struct median_gate { const int* rowdark; const int* lo; const int* hi; int S, s_hat; float slope, dlo, dhi; int on; };
+
 template <int C, int WIDTH, bool HALO>
 __global__ void __launch_bounds__(128)
 selective_median_kernel(const float* __restrict__ src, const uint8_t* __restrict__ mask,
                         const float* __restrict__ colour, size_t colour_row_stride,
                         int V, int U, int v_begin, float eps, double eps_T, float* __restrict__ dst,
-                        const uint8_t* __restrict__ fresh, const int* __restrict__ rowdark_v, const median_halo halo)
+                        const uint8_t* __restrict__ fresh, const int* __restrict__ rowdark_v, const median_halo halo,
+                        const median_gate gate)
 {
     constexpr int N = (2 * WIDTH + 1) * (2 * WIDTH + 1);
     const int u = blockIdx.x * blockDim.x + threadIdx.x;
@@ -69,6 +77,25 @@ selective_median_kernel(const float* __restrict__ src, const uint8_t* __restrict
         }
         __syncthreads();
     }
+    __shared__ int s_ulo, s_uhi;
+    bool dark_row = false;
+    if (fresh) {
+        dark_row = rowdark_v[blockIdx.y] > 0;
+        if (dark_row && gate.on) {
+            if (threadIdx.x == 0) { s_ulo = 0x7fffffff; s_uhi = -1; }
+            __syncthreads();
+            for (int s = threadIdx.x; s < gate.S; s += blockDim.x) {
+                if (gate.rowdark[(size_t)blockIdx.y * gate.S + s] <= 0) continue;
+                const float k = (float)(gate.s_hat - s);
+                float t1 = gate.dlo * k; t1 = t1 * gate.slope;
+                float t2 = gate.dhi * k; t2 = t2 * gate.slope;
+                const int o1 = (int)roundf(fminf(t1, t2)) - 1, o2 = (int)roundf(fmaxf(t1, t2)) + 1;
+                atomicMin(&s_ulo, gate.lo[(size_t)blockIdx.y * gate.S + s] - o2);
+                atomicMax(&s_uhi, gate.hi[(size_t)blockIdx.y * gate.S + s] - o1);
+            }
+            __syncthreads();
+        }
+    }
     if (u >= U) return;
     const size_t o = (size_t)v * U + u;
     const size_t od = (size_t)blockIdx.y * U + u;     /* dst holds this rank's rows only */
@@ -76,7 +103,7 @@ selective_median_kernel(const float* __restrict__ src, const uint8_t* __restrict
     /* the filtered value is only ever read by the propagation: needed for the pixels computed in this pass
      * (fresh: still flagged in the line's remaining mask) and, in rows that still hold dark targets, for the
      * pixels painted earlier (see k_propagate.cuh).  fresh == nullptr: filter every masked pixel. */
-    if (fresh && !fresh[od] && rowdark_v[blockIdx.y] <= 0) { dst[od] = 0.f; return; }
+    if (fresh && !fresh[od] && (!dark_row || (gate.on && (u < s_ulo || u > s_uhi)))) { dst[od] = 0.f; return; }
     float pc[C];
 #pragma unroll
     for (int c = 0; c < C; ++c) pc[c] = __ldg(colour + (size_t)v * colour_row_stride + (size_t)u * C + c);
@@ -126,7 +153,7 @@ selective_median_kernel(const float* __restrict__ src, const uint8_t* __restrict
 static int launch_selective_median(rslf_ctx* ctx, const float* src, const uint8_t* mask, const float* colour,
                                    size_t colour_row_stride, int V, int U, int C, int size, float eps, float* dst,
                                    int v_begin = 0, int v_count = -1, const uint8_t* fresh = nullptr,
-                                   const int* rowdark_v = nullptr, const median_halo* halo = nullptr)
+                                   const int* rowdark_v = nullptr, const median_halo* halo = nullptr, const median_gate* gate = nullptr)
 {
     const int width = (size - 1) / 2;
     if (v_count < 0) v_count = V;
@@ -134,12 +161,14 @@ static int launch_selective_median(rslf_ctx* ctx, const float* src, const uint8_
     const double T = rslf_sq_threshold(eps);
     median_halo h; memset(&h, 0, sizeof(h));
     if (halo) h = *halo;
+    median_gate g; memset(&g, 0, sizeof(g));
+    if (gate) g = *gate;
 #define RSLF_MED_CASE(CC, WW)                                                                              \
     if (C == CC && width == WW) {                                                                          \
         if (halo) selective_median_kernel<CC, WW, true><<<grid, 128, 0, ctx->stream>>>(                    \
-            src, mask, colour, colour_row_stride, V, U, v_begin, eps, T, dst, fresh, rowdark_v, h);        \
+            src, mask, colour, colour_row_stride, V, U, v_begin, eps, T, dst, fresh, rowdark_v, h, g);     \
         else selective_median_kernel<CC, WW, false><<<grid, 128, 0, ctx->stream>>>(                        \
-            src, mask, colour, colour_row_stride, V, U, v_begin, eps, T, dst, fresh, rowdark_v, h);        \
+            src, mask, colour, colour_row_stride, V, U, v_begin, eps, T, dst, fresh, rowdark_v, h, g);     \
         RSLF_CUDA_TRY(ctx, cudaGetLastError());                                                            \
         ctx->timing.kernel_launches += 1;                                                                  \
         return RSLF_OK;                                                                                    \

@@ -58,7 +58,7 @@ __device__ __forceinline__ void propagate_one(const prop_args& a, int v, int u, 
     t = t * a.slope;
     const int q = u + (int)roundf(t);
     if (q < 0 || q >= a.U) return;
-    const size_t tgt = ((size_t)s * a.V + v) * (size_t)a.U + q;
+    const size_t tgt = ((size_t)v * a.S + s) * (size_t)a.U + q;
     if (!a.remaining[tgt]) return;
     if (PHASE == 0) {
         const float* e = a.epi + (((size_t)v * a.S + s) * (size_t)a.U + q) * C;
@@ -78,7 +78,7 @@ __device__ __forceinline__ void propagate_one(const prop_args& a, int v, int u, 
             float ec[C], z[C];
 #pragma unroll
             for (int c = 0; c < C; ++c) { ec[c] = __ldg(e + c); z[c] = 0.f; }
-            if (rslf_norm_diff_lt<C>(ec, z, a.eps, a.eps_T)) atomicSub(a.rowdark + (size_t)s * a.V + v, 1);
+            if (rslf_norm_diff_lt<C>(ec, z, a.eps, a.eps_T)) atomicSub(a.rowdark + (size_t)v * a.S + s, 1);
         }
     }
 }
@@ -142,9 +142,9 @@ propagate_kernel(const prop_args a, int list_blocks)
     __syncthreads();
     if ((int)threadIdx.x < s_end - s_begin) {
         const int s = s_begin + threadIdx.x;
-        const bool lv = a.rowdark[(size_t)s * a.V + v] > 0;
-        s_lo[threadIdx.x] = a.dark_lo ? a.dark_lo[(size_t)s * a.V + v] : 0;
-        s_hi[threadIdx.x] = a.dark_hi ? a.dark_hi[(size_t)s * a.V + v] : a.U - 1;
+        const bool lv = a.rowdark[(size_t)v * a.S + s] > 0;
+        s_lo[threadIdx.x] = a.dark_lo ? a.dark_lo[(size_t)v * a.S + s] : 0;
+        s_hi[threadIdx.x] = a.dark_hi ? a.dark_hi[(size_t)v * a.S + s] : a.U - 1;
         if (lv) atomicOr(&s_live, 1u << threadIdx.x);
     }
     __syncthreads();

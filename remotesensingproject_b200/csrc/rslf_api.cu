@@ -749,13 +749,14 @@ __global__ void row_sum_kernel(const int* __restrict__ rowdark, int S, int V, in
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= V) return;
     int t = 0;
-    for (int s = 0; s < S; ++s) t += rowdark[(size_t)s * V + v];
+    for (int s = 0; s < S; ++s) t += rowdark[(size_t)v * S + s];        /* [V][S]: the views of a row lie side by side */
     out[v] = t;
 }
 
 /* ------------------------------------------------------------------ one s_hat pass */
 struct pass_io {
     int level; int s_hat; int D; float dmin, dmax; bool use_bound_maps;
+    bool bounds_in_range;     /* every per-pixel bound lies inside [dmin, dmax] (always true for the pyramid's own bounds) */
     bool pile;                /* 1D pile: single-plane maps, no remaining mask */
     int count_slot;
 };
@@ -791,6 +792,10 @@ static int run_depth_pass(rslf_ctx* ctx, const rslf_params& P, const pass_io& io
     const size_t colour_stride = (size_t)S * U * C;
     const uint8_t* fresh = io.pile ? nullptr : L.remaining + po;
     const int* rdv = io.pile ? nullptr : L.rowdark + (size_t)S * V;
+    median_gate gate; memset(&gate, 0, sizeof(gate));
+    gate.rowdark = L.rowdark; gate.lo = L.dark_lo; gate.hi = L.dark_hi; gate.S = S; gate.s_hat = io.s_hat; gate.slope = P.slope_factor;
+    gate.dlo = std::min(io.dmin, io.dmax); gate.dhi = std::max(io.dmin, io.dmax);
+    gate.on = (!io.pile && io.bounds_in_range) ? 1 : 0;
     /* row-sharded level: how the rows next to the block reach the neighbours */
     shard_tab t; bool halo_path = false, p2p = false, balanced = false;
     if (sharded) {
@@ -901,7 +906,7 @@ static int run_depth_pass(rslf_ctx* ctx, const rslf_params& P, const pass_io& io
         }
         if (halo_path) {
             RSLF_TRY(launch_selective_median(ctx, a.depth, L.emask + po, colour0, colour_stride, V, U, C,
-                                             P.median_filter_size, P.median_filter_epsilon, ctx->filtered, 0, -1, fresh, rdv, &halo));
+                                             P.median_filter_size, P.median_filter_epsilon, ctx->filtered, 0, -1, fresh, rdv, &halo, &gate));
         } else if (sharded) {
             /* thin blocks or wide windows: gather the depth / mask planes of line s_hat (colours: the whole stack is here) */
             RSLF_TRY(ensure_gather_planes(ctx, (size_t)L.Vtot * U));
@@ -910,7 +915,7 @@ static int run_depth_pass(rslf_ctx* ctx, const rslf_params& P, const pass_io& io
                                              P.median_filter_size, P.median_filter_epsilon, ctx->filtered, L.v0, V, fresh, rdv));
         } else {
             RSLF_TRY(launch_selective_median(ctx, a.depth, L.emask + po, colour0, colour_stride,
-                                             V, U, C, P.median_filter_size, P.median_filter_epsilon, ctx->filtered, 0, -1, fresh, rdv));
+                                             V, U, C, P.median_filter_size, P.median_filter_epsilon, ctx->filtered, 0, -1, fresh, rdv, nullptr, &gate));
         }
     }
     return RSLF_OK;
@@ -930,7 +935,8 @@ static std::vector<int> visiting_order(int S)
 }
 
 /* Depth2DComputer::run (dc.hpp:748-805) on level p (stack already normalised in L.epi). */
-static int run_depth2d_level(rslf_ctx* ctx, int p, const rslf_params& P, float dmin, float dmax, int D, bool use_bound_maps)
+static int run_depth2d_level(rslf_ctx* ctx, int p, const rslf_params& P, float dmin, float dmax, int D, bool use_bound_maps,
+                             bool bounds_in_range = true)
 {
     rslf_level& L = ctx->lv[p];
     const int V = L.V, U = L.U, S = ctx->S, C = ctx->C;
@@ -968,7 +974,7 @@ static int run_depth2d_level(rslf_ctx* ctx, int p, const rslf_params& P, float d
     for (int s_hat : order) {
         pass_io io;
         io.level = p; io.s_hat = s_hat; io.D = D; io.dmin = dmin; io.dmax = dmax; io.use_bound_maps = use_bound_maps;
-        io.pile = false; io.count_slot = p * 2 * S + pass;
+        io.pile = false; io.count_slot = p * 2 * S + pass; io.bounds_in_range = bounds_in_range;
         RSLF_TRY(run_depth_pass(ctx, P, io));
         {
             stage_scope sc(ctx, ST_PROP);
@@ -1238,7 +1244,7 @@ extern "C" int rslf_cuda_depth1d_pile_run(rslf_ctx* ctx, float dmin, float dmax,
     }
     pass_io io;
     io.level = 0; io.s_hat = s_hat; io.D = dim_d; io.dmin = dmin; io.dmax = dmax; io.use_bound_maps = false;
-    io.pile = true; io.count_slot = 0;
+    io.pile = true; io.count_slot = 0; io.bounds_in_range = false;
     RSLF_TRY(run_depth_pass(ctx, P, io));
     ctx->timing.passes = 1; ctx->timing.levels = 1;
     ctx->last_kind = 1; ctx->pile_s_hat = s_hat;
@@ -1309,7 +1315,7 @@ extern "C" int rslf_cuda_depth2d_run(rslf_ctx* ctx, float dmin, float dmax, int 
     RSLF_TRY(full_input(ctx, &raw0));
     RSLF_TRY(begin_run(ctx));
     RSLF_TRY(normalise_level(ctx, 0, raw0, ctx->cv_depth));
-    RSLF_TRY(run_depth2d_level(ctx, 0, P, dmin, dmax, dim_d, dmin_svu != nullptr));
+    RSLF_TRY(run_depth2d_level(ctx, 0, P, dmin, dmax, dim_d, dmin_svu != nullptr, dmin_svu == nullptr));   /* user-edited bounds may leave [dmin, dmax] */
     ctx->timing.levels = 1;
     ctx->last_kind = 2;
     return end_run(ctx, dim_d);

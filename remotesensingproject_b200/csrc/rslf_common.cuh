@@ -37,8 +37,8 @@ struct rslf_level {
     uint8_t* emask = nullptr;    /* edge-confidence mask       [S][V][U]                      */
     uint8_t* remaining = nullptr;/* "still to compute" mask    [S][V][U]                      */
     uint8_t* valid = nullptr;    /* validity mask for bounds / fuse [S][V][U]                 */
-    int* rowdark = nullptr;      /* [S][V] confident-and-dark pixels not yet painted, then [V] row sums */
-    int* dark_lo = nullptr; int* dark_hi = nullptr;   /* [S][V] column range of those pixels (never shrinks: a bound) */
+    int* rowdark = nullptr;      /* [V][S] confident-and-dark pixels not yet painted, then [V] row sums */
+    int* dark_lo = nullptr; int* dark_hi = nullptr;   /* [V][S] column range of those pixels (never shrinks: a bound) */
     float slope = 1.f;
     int nonneg = 1;              /* normalised stack has no negative value                    */
     bool have_bounds = false;
