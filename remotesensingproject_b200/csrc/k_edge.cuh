@@ -48,7 +48,7 @@ edge_confidence_kernel(const float* __restrict__ epi, int V, int S, int U, int s
         seg[i] = __ldg(src + (size_t)q * C + c);
     }
     __syncthreads();
-    const size_t out_row = ((size_t)v * s_count + si) * (size_t)U;
+    const size_t out_row = ((size_t)si * V + v) * (size_t)U;
     int ndark = 0, dlo = 0x7fffffff, dhi = -1;         /* dark confident pixels of the row: count and column range */
 #pragma unroll
     for (int k = 0; k < EDGE_PPT; ++k) {
@@ -172,7 +172,7 @@ rowdark_count_kernel(const float* __restrict__ epi, const uint8_t* __restrict__ 
     const int row = blockIdx.x;
     const int v = row / s_count, si = row % s_count;
     const float* src = epi + ((size_t)v * S + (s_first + si)) * (size_t)U * C;
-    const uint8_t* m = mask + ((size_t)v * s_count + si) * (size_t)U;
+    const uint8_t* m = mask + ((size_t)si * V + v) * (size_t)U;
     int ndark = 0, dlo = 0x7fffffff, dhi = -1;
     for (int u = threadIdx.x; u < U; u += EDGE_THREADS) {
         if (!m[u]) continue;

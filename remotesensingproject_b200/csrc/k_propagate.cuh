@@ -58,7 +58,7 @@ __device__ __forceinline__ void propagate_one(const prop_args& a, int v, int u, 
     t = t * a.slope;
     const int q = u + (int)roundf(t);
     if (q < 0 || q >= a.U) return;
-    const size_t tgt = ((size_t)v * a.S + s) * (size_t)a.U + q;
+    const size_t tgt = ((size_t)s * a.V + v) * (size_t)a.U + q;
     if (!a.remaining[tgt]) return;
     if (PHASE == 0) {
         const float* e = a.epi + (((size_t)v * a.S + s) * (size_t)a.U + q) * C;

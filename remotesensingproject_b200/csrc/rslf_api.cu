@@ -796,6 +796,7 @@ static int run_depth_pass(rslf_ctx* ctx, const rslf_params& P, const pass_io& io
     gate.rowdark = L.rowdark; gate.lo = L.dark_lo; gate.hi = L.dark_hi; gate.S = S; gate.s_hat = io.s_hat; gate.slope = P.slope_factor;
     gate.dlo = std::min(io.dmin, io.dmax); gate.dhi = std::max(io.dmin, io.dmax);
     gate.on = (!io.pile && io.bounds_in_range) ? 1 : 0;
+    { const char* eg = getenv("RSLF_MEDIAN_GATE"); if (eg && eg[0] == '0') gate.on = 0; }      /* test hook */
     /* row-sharded level: how the rows next to the block reach the neighbours */
     shard_tab t; bool halo_path = false, p2p = false, balanced = false;
     if (sharded) {
