@@ -1903,6 +1903,7 @@ extern "C" int rslf_cuda_set_bounds(rslf_ctx* ctx, const float* depth_up, const 
                                     int Vd, int Ud, float* dmin_map, float* dmax_map)
 {
     if (!ctx || !depth_up || !valid_up || !dmin_map || !dmax_map) return RSLF_ERR_ARG;
+    if (S < 1 || Vu < 1 || Uu < 1 || Vd < 1 || Ud < 1) { snprintf(ctx->err, sizeof(ctx->err), "rslf_cuda_set_bounds: dimensions must be positive"); return RSLF_ERR_ARG; }
     RSLF_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     const size_t nu = (size_t)S * Vu * Uu, nd = (size_t)S * Vd * Ud;
     float *d_dep = nullptr, *d_mn = nullptr, *d_mx = nullptr; uint8_t* d_val = nullptr; int *d_l = nullptr, *d_r = nullptr;
@@ -1933,7 +1934,9 @@ extern "C" int rslf_cuda_fuse_disp_maps(rslf_ctx* ctx, int levels, int S, const 
                                         const float* const* disp_p, const uint8_t* const* valid_p,
                                         float* out_map_svu, uint8_t* out_valid_svu)
 {
-    if (!ctx || levels < 1 || levels > RSLF_MAX_LEVELS || !Vp || !Up || !disp_p || !valid_p) return RSLF_ERR_ARG;
+    if (!ctx || levels < 1 || levels > RSLF_MAX_LEVELS || !Vp || !Up || !disp_p || !valid_p || S < 1) return RSLF_ERR_ARG;
+    for (int p = 0; p < levels; ++p)
+        if (Vp[p] < 1 || Up[p] < 1 || !disp_p[p] || !valid_p[p]) { snprintf(ctx->err, sizeof(ctx->err), "rslf_cuda_fuse_disp_maps: level %d is empty", p); return RSLF_ERR_ARG; }
     RSLF_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     std::vector<float*> dd(levels, nullptr); std::vector<uint8_t*> dv(levels, nullptr);
     const size_t px0 = (size_t)S * Vp[0] * Up[0];
