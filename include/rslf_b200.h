@@ -339,6 +339,10 @@ int rslf_cuda_get_epis(rslf_ctx* ctx, float* const* epi_v, size_t step);
 void* rslf_host_alloc(size_t bytes);
 void  rslf_host_free(void* p);
 
+/* Host-only helper (no device needed): which part of a pass rank `rank` evaluates in the pass-balanced multi-GPU mode,
+ * given the lengths of every rank's work list: first pixel and number of pixels in the concatenated lists, and how many
+ * of them come from each owner (from_owner[world], may be NULL). */
+int rslf_balance_share(const int* counts, int world, int rank, long long* first, int* count, int* from_owner);
 /* Diagnostics: records every pixel decision of the following runs (up to `capacity` records; 0 switches the log
  * off) so that a test can replay them through the CPU oracle — the way the contracted (fast_math) mode is checked
  * against the tolerance it is specified to (tests/test_gpu_tolerance.py).  rslf_cuda_get_decision_log copies the

@@ -2000,6 +2000,29 @@ extern "C" int rslf_plan_depth_tm(int S, int C, int D, int s_hat, float dmin, fl
     return RSLF_OK;
 }
 
+/* Host-only: the share of a pass that rank `rank` of `world` evaluates when the ranks' work lists hold counts[0..world)
+ * pixels (pass-balanced multi-GPU mode, k_balance.cuh): first pixel and number of pixels in the concatenated lists,
+ * and for every owner how many of those pixels come from its list (from_owner[world], optional).  Same arithmetic as
+ * the device side (bal_share). */
+extern "C" int rslf_balance_share(const int* counts, int world, int rank, long long* first, int* count, int* from_owner)
+{
+    if (!counts || world < 1 || world > RSLF_MAX_PEERS || rank < 0 || rank >= world || !first || !count) return RSLF_ERR_ARG;
+    long long T = 0;
+    for (int r = 0; r < world; ++r) { if (counts[r] < 0) return RSLF_ERR_ARG; T += counts[r]; }
+    int lo = 0, n = 0;
+    bal_share(T, rank, world, &lo, &n);
+    *first = lo; *count = n;
+    if (from_owner) {
+        long long pre = 0;
+        for (int r = 0; r < world; ++r) {
+            const long long a = std::max<long long>(pre, lo), b = std::min<long long>(pre + counts[r], (long long)lo + n);
+            from_owner[r] = (int)std::max<long long>(0, b - a);
+            pre += counts[r];
+        }
+    }
+    return RSLF_OK;
+}
+
 extern "C" int rslf_cuda_measure_fp32_peak(rslf_ctx* ctx, double* gops_nofma, double* gflops_fma)
 {
     if (!ctx) return RSLF_ERR_ARG;

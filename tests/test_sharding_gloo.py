@@ -118,3 +118,35 @@ def test_median_exchange_with_gloo_world2():
         assert p.exitcode == 0
     assert all(ok for _, ok, _ in res), res
     assert not all(alone for _, _, alone in res), "the halo exchange made no difference: test field too plain"
+
+
+def test_pass_balanced_shares_partition_every_pass():
+    """Pass-balanced multi-GPU mode (k_balance.cuh): the ranks' shares of a pass tile the concatenated work lists exactly,
+    differ by at most one pixel, and every owner's list is fully covered (host restatement of the device arithmetic)."""
+    import ctypes as C
+    from remotesensingproject_b200 import api
+    lib = api.lib()
+    rng = np.random.default_rng(5)
+    for world in (1, 2, 3, 4, 8, 16):
+        for trial in range(20):
+            counts = rng.integers(0, 5000, size=world)
+            if trial % 5 == 0:
+                counts[rng.integers(0, world)] = 0
+            if trial == 7:
+                counts[:] = 0
+            arr = (C.c_int * world)(*[int(x) for x in counts])
+            T = int(counts.sum())
+            covered = np.zeros(world, dtype=np.int64)
+            nxt, sizes = 0, []
+            for r in range(world):
+                first, cnt = C.c_longlong(), C.c_int()
+                frm = (C.c_int * world)()
+                assert lib.rslf_balance_share(arr, world, r, C.byref(first), C.byref(cnt), frm) == 0
+                assert first.value == nxt                       # contiguous, in rank order
+                nxt += cnt.value
+                sizes.append(cnt.value)
+                assert sum(frm) == cnt.value
+                covered += np.array(list(frm), dtype=np.int64)
+            assert nxt == T and max(sizes) - min(sizes) <= 1
+            np.testing.assert_array_equal(covered, counts)
+    assert lib.rslf_balance_share(arr, 17, 0, C.byref(first), C.byref(cnt), None) != 0
