@@ -26,7 +26,7 @@
 #include "rslf_common.cuh"
 
 #define PROP_THREADS 128
-#define PROP_SG 32              /* views per block of the dense kind (one bit each in the block's `live` word) */
+#define PROP_SG 32              /* at most this many views per block of the dense kind (one bit each in the block's `live` word) */
 #define PROP_DENSE_MIN 8192     /* list entries from which the list kind walks sources by lane instead of views by lane */
 #define PROP_VS 4               /* view slices per group of 32 sources in that mode */
 
@@ -88,8 +88,9 @@ __device__ __forceinline__ void propagate_one(const prop_args& a, int v, int u, 
  * views) pairs for the pixels painted earlier (kind 2: r_bar == 0), threads over u. */
 template <int C, int PHASE>
 __global__ void __launch_bounds__(PROP_THREADS)
-propagate_kernel(const prop_args a, int list_blocks)
+propagate_kernel(const prop_args a, int list_blocks, int sg)
 {
+    /* sg: views per block of the second kind (<= PROP_SG) */
     if ((int)blockIdx.x < list_blocks) {
         const int n1 = *a.count, n = n1 + (a.count2 ? *a.count2 : 0);
         const int lane = threadIdx.x & 31;
@@ -132,7 +133,7 @@ propagate_kernel(const prop_args a, int list_blocks)
     }
     const int idx = (int)blockIdx.x - list_blocks;
     const int v = idx % a.V;
-    const int s_begin = (idx / a.V) * PROP_SG, s_end = min(a.S, s_begin + PROP_SG);
+    const int s_begin = (idx / a.V) * sg, s_end = min(a.S, s_begin + sg);
     /* views of the group that still hold a dark target in this row, and the column range those targets lie in: a source
      * without r_bar can only paint such targets, so a (source, view) pair whose target column falls outside the range
      * is rejected before any memory is touched */
@@ -173,13 +174,17 @@ propagate_kernel(const prop_args a, int list_blocks)
 static int launch_propagate(rslf_ctx* ctx, int C, const prop_args& a)
 {
     const int lb = ctx->num_sm * 16;
-    const int grid = lb + a.V * rslf_div_up(a.S, PROP_SG);
+    /* second kind: (row, group of sg views) blocks.  Many rows: 32 views per block keep the launch small (most blocks
+     * return at once); few rows (a rank's block of a row-sharded level, a coarse level): 8 views per block, so that the
+     * rows that do hold dark targets are spread over enough blocks */
+    const int sg = ((long long)a.V * rslf_div_up(a.S, PROP_SG) >= 2048) ? PROP_SG : 8;
+    const int grid = lb + a.V * rslf_div_up(a.S, sg);
     if (C == 1) {
-        propagate_kernel<1, 0><<<grid, PROP_THREADS, 0, ctx->stream>>>(a, lb);
-        propagate_kernel<1, 1><<<grid, PROP_THREADS, 0, ctx->stream>>>(a, lb);
+        propagate_kernel<1, 0><<<grid, PROP_THREADS, 0, ctx->stream>>>(a, lb, sg);
+        propagate_kernel<1, 1><<<grid, PROP_THREADS, 0, ctx->stream>>>(a, lb, sg);
     } else {
-        propagate_kernel<3, 0><<<grid, PROP_THREADS, 0, ctx->stream>>>(a, lb);
-        propagate_kernel<3, 1><<<grid, PROP_THREADS, 0, ctx->stream>>>(a, lb);
+        propagate_kernel<3, 0><<<grid, PROP_THREADS, 0, ctx->stream>>>(a, lb, sg);
+        propagate_kernel<3, 1><<<grid, PROP_THREADS, 0, ctx->stream>>>(a, lb, sg);
     }
     RSLF_CUDA_TRY(ctx, cudaGetLastError());
     ctx->timing.kernel_launches += 2;
