@@ -339,7 +339,6 @@ extern "C" int rslf_cuda_create(int device, rslf_ctx** out)
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return RSLF_ERR_CUDA;
     if (cudaSetDevice(device) != cudaSuccess) return RSLF_ERR_CUDA;
-    probe_ctx("create");
     rslf_ctx* ctx = new rslf_ctx();
     ctx->device = device;
     cudaDeviceProp prop;
@@ -370,43 +369,28 @@ extern "C" int rslf_cuda_create(int device, rslf_ctx** out)
 extern "C" void rslf_cuda_destroy(rslf_ctx* ctx)
 {
     if (!ctx) return;
-    const bool dbg = getenv("RSLF_DEBUG_DESTROY") != nullptr;
-#define DBG(x) do { if (dbg) { fprintf(stderr, "[destroy r%d] %s\n", ctx->rank, x); fflush(stderr); probe_ctx(x); } } while (0)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    DBG("comm_destroy");
     comm_destroy(ctx);
-    DBG("levels");
     for (int p = 0; p < RSLF_MAX_LEVELS; ++p) free_level(ctx->lv[p]);
-    DBG("scratch");
     free_scratch(ctx);
-    DBG("rest");
     if (ctx->raw_in && !ctx->raw_borrowed) cudaFree(ctx->raw_in);
-    DBG("raw_full");
     if (ctx->raw_full) cudaFree(ctx->raw_full);
-    DBG("staging/open");
     if (ctx->img_staging) cudaFree(ctx->img_staging);
     if (ctx->open_ce) cudaFree(ctx->open_ce);
     if (ctx->open_mask) cudaFree(ctx->open_mask);
     if (ctx->open_tmp) cudaFree(ctx->open_tmp);
-    DBG("ring: process-wide, kept");
-    DBG("stream2");
     if (ctx->ev_img) cudaEventDestroy(ctx->ev_img);
     if (ctx->stream2) cudaStreamDestroy(ctx->stream2);
-    DBG("small buffers");
     dev_free(&ctx->queue); dev_free(&ctx->dev_err); dev_free(&ctx->dlog); dev_free(&ctx->dlog_count);
     dev_free(&ctx->count); dev_free(&ctx->total_px); dev_free(&ctx->minmax); dev_free(&ctx->rowwork);
     dev_free(&ctx->colour_hist); dev_free(&ctx->colour_lut);
     if (ctx->l2_flush) cudaFree(ctx->l2_flush);
-    DBG("events");
     for (auto e : ctx->clk.pool) cudaEventDestroy(e);
     if (ctx->ev_a) cudaEventDestroy(ctx->ev_a);
     if (ctx->ev_b) cudaEventDestroy(ctx->ev_b);
-    DBG("stream");
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
-    DBG("delete");
     delete ctx;
-#undef DBG
 }
 
 extern "C" const char* rslf_cuda_last_error_text(const rslf_ctx* ctx) { return ctx ? ctx->err : "null ctx"; }
@@ -548,14 +532,12 @@ extern "C" int rslf_cuda_upload_epis(rslf_ctx* ctx, const void* const* epi_ptrs,
 {
     if (!ctx || !epi_ptrs) return RSLF_ERR_ARG;
     RSLF_CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    probe_ctx("upload begin");
     RSLF_TRY(set_dims(ctx, V, S, U, C, cv_depth, epi_scale_factor));
     const size_t esz = depth_esz(cv_depth);
     const size_t row = (size_t)U * C * esz;
     if (row_step_bytes < row) { snprintf(ctx->err, sizeof(ctx->err), "row step smaller than a row"); return RSLF_ERR_ARG; }
     const size_t epi_bytes = row * S;
     RSLF_TRY(own_raw(ctx, epi_bytes * V));
-    probe_ctx("upload after own_raw");
     cudaEventRecord(ctx->ev_a, ctx->stream);
     /* V images of S rows: pinned / registered memory by DMA, pageable cv::Mat storage through the pinned ring */
     RSLF_TRY(images_to_device(ctx, ctx->raw_in, V, S, row, epi_ptrs, row_step_bytes));

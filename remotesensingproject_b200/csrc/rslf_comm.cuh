@@ -68,30 +68,13 @@ static int nccl_load(char* err, size_t errlen)
 static void arena_close(rslf_ctx* ctx);
 static void rslf_disable_ring();
 
-static cudaEvent_t g_probe_ev = nullptr;
-static void probe_ctx(const char* where)
-{
-    if (!getenv("RSLF_DEBUG_DESTROY")) return;
-    if (!g_probe_ev) { cudaEventCreateWithFlags(&g_probe_ev, cudaEventDisableTiming); fprintf(stderr, "[probe] created at %s\n", where); }
-    cudaError_t e = cudaEventQuery(g_probe_ev);
-    fprintf(stderr, "[probe] %s: %s\n", where, cudaGetErrorString(e)); fflush(stderr);
-    cudaGetLastError();
-}
 static void comm_destroy(rslf_ctx* ctx)
 {
-    const bool dbg = getenv("RSLF_DEBUG_DESTROY") != nullptr;
-    probe_ctx("before arena_close");
-    if (dbg) { fprintf(stderr, "[destroy r%d] arena_close\n", ctx->rank); fflush(stderr); }
     arena_close(ctx);
-    probe_ctx("after arena_close");
-    if (dbg) { fprintf(stderr, "[destroy r%d] p2p_done\n", ctx->rank); fflush(stderr); }
     if (ctx->p2p_done) cudaFree(ctx->p2p_done);
     ctx->p2p_done = nullptr; ctx->p2p_state = 0;
-    if (dbg) { fprintf(stderr, "[destroy r%d] nccl\n", ctx->rank); fflush(stderr); }
     if (ctx->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->nccl_comm);
     ctx->nccl_comm = nullptr;
-    probe_ctx("after nccl destroy");
-    if (dbg) { fprintf(stderr, "[destroy r%d] comm done\n", ctx->rank); fflush(stderr); }
 }
 
 /* in-place max over ranks of n device floats; optionally read element 0 back */
@@ -341,12 +324,9 @@ static void arena_close(rslf_ctx* ctx)
         if (ctx->arena_peer[r] && ctx->arena_peer[r] != ctx->arena) { cudaIpcCloseMemHandle(ctx->arena_peer[r]); mapped = true; }
         ctx->arena_peer[r] = nullptr;
     }
-    probe_ctx("after ipc close");
     if (mapped && ctx->arena && ctx->nccl_comm && ctx->world > 1) { float out = 0.f; comm_allreduce_max_host(ctx, 0.f, &out); }
     cudaGetLastError();
-    probe_ctx("after barrier");
     if (ctx->arena) cudaFree(ctx->arena);
-    probe_ctx("after arena free");
     ctx->arena = nullptr; ctx->arena_bytes = 0; ctx->arena_cap_rec = 0;
     ctx->p2p_up = ctx->p2p_dn = nullptr;
 }
@@ -404,7 +384,6 @@ static int comm_arena_setup(rslf_ctx* ctx, int U, int C, size_t cap_rec)
         arena_close(ctx);
         return RSLF_ERR_UNSUPPORTED;                        /* every rank falls back to the NCCL exchanges */
     }
-    probe_ctx("after ipc open");
     ctx->p2p_up = ctx->rank > 0 ? ctx->arena_peer[ctx->rank - 1] : nullptr;
     ctx->p2p_dn = ctx->rank + 1 < ctx->world ? ctx->arena_peer[ctx->rank + 1] : nullptr;
     ctx->p2p_area = l.area; ctx->arena_bytes = l.total; ctx->arena_cap_rec = cap_rec; ctx->arena_U = U; ctx->arena_C = C; ctx->arena_S = ctx->S;
